@@ -1,0 +1,229 @@
+"""Host-side mirror of the reference's interface for the FMD-index hot path, over libfermi_b200.so.
+
+Names follow lh3/fermi (rld.h:45-58, fermi.h:61-104) so that the parity tests read like calls into
+the reference; every function is batched (NumPy arrays in, NumPy arrays out) and executes on the GPU
+through the C-ABI.  There is no CPU path here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import lib, u8p, u64p
+
+INTV = np.dtype([("x0", "<u8"), ("x1", "<u8"), ("x2", "<u8"), ("info", "<u8")])   # fmintv_t, fermi.h:13-16
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+class Fmd:
+    """Host .fmd container: rld_t (rld.h:20-39)."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise IOError("fermi_b200: could not create the .fmd container")
+        self.h = handle
+        o = np.zeros(17, np.uint64)
+        lib().fmg_fmd_info(self.h, _p(o, u64p))
+        self.mcnt = o[0:7].copy()
+        self.cnt = o[7:14].copy()
+        self.n_bytes, self.n_frames, self.ibits = int(o[14]), int(o[15]), int(o[16])
+
+    @classmethod
+    def restore(cls, fn):
+        """rld_restore (rld.c:288): accepts "RLD\\2" files and raw "RLE\\6" streams."""
+        return cls(lib().fmg_fmd_restore(str(fn).encode()))
+
+    @classmethod
+    def from_bwt(cls, bwt):
+        """fm_bwtenc (build.c:11)."""
+        bwt = np.ascontiguousarray(bwt, np.uint8)
+        return cls(lib().fmg_fmd_from_bwt(len(bwt), _p(bwt, u8p)))
+
+    @classmethod
+    def from_rle6(cls, rle):
+        rle = np.ascontiguousarray(rle, np.uint8)
+        return cls(lib().fmg_fmd_from_rle6(len(rle), _p(rle, u8p)))
+
+    def dump(self, fn):
+        """rld_dump (rld.c:242)."""
+        if lib().fmg_fmd_dump(self.h, str(fn).encode()) != 0:
+            raise IOError("fermi_b200: cannot write " + str(fn))
+
+    def decode_bwt(self):
+        out = np.zeros(int(self.mcnt[0]), np.uint8)
+        n = lib().fmg_fmd_decode_bwt(self.h, _p(out, u8p))
+        assert n == len(out)
+        return out
+
+    def close(self):
+        if self.h:
+            lib().fmg_fmd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FmdIndex:
+    """The index resident in the HBM of one GPU (replaces holding an rld_t for queries)."""
+
+    def __init__(self, fmd, device=0):
+        self.fmd = fmd
+        self.h = lib().fmg_index_upload(fmd.h, device)
+        if not self.h:
+            raise RuntimeError("fermi_b200: index upload failed (no CUDA device? see stderr); there is no CPU fallback")
+        self.device = device
+        self.mcnt, self.cnt = fmd.mcnt, fmd.cnt
+
+    @property
+    def nbytes(self):
+        return int(lib().fmg_index_bytes(self.h))
+
+    def close(self):
+        if self.h:
+            lib().fmg_index_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("fermi_b200: %s failed (rc=%d), see stderr" % (what, rc))
+
+
+def rld_rank2a(idx, k, l):
+    """n x rld_rank2a (rld.c:457): returns (ok[n,6], ol[n,6])."""
+    k = np.ascontiguousarray(k, np.uint64)
+    l = np.ascontiguousarray(l, np.uint64)
+    ok = np.zeros((len(k), 6), np.uint64)
+    ol = np.zeros((len(k), 6), np.uint64)
+    _check(lib().fmg_rank2a_batch(idx.h, len(k), _p(k, u64p), _p(l, u64p), _p(ok, u64p), _p(ol, u64p)), "rld_rank2a")
+    return ok, ol
+
+
+def fm6_extend(idx, ik, is_back):
+    """n x fm6_extend (exact.c:72): ik INTV[n] -> ok INTV[n,6] (info = 0)."""
+    ik = np.ascontiguousarray(ik, INTV)
+    is_back = np.ascontiguousarray(is_back, np.uint8)
+    ok = np.zeros((len(ik), 6), INTV)
+    _check(lib().fmg_extend_batch(idx.h, len(ik), ik.ctypes.data, _p(is_back, u8p), ok.ctypes.data), "fm6_extend")
+    return ok
+
+
+def fm_backward_search(idx, seq, off):
+    """n x fm_backward_search (exact.c:7): returns (sa_beg, sa_end, size); size 0 = no match."""
+    seq = np.ascontiguousarray(seq, np.uint8)
+    off = np.ascontiguousarray(off, np.uint64)
+    n = len(off) - 1
+    b, e, s = (np.zeros(n, np.uint64) for _ in range(3))
+    _check(lib().fmg_backward_search_batch(idx.h, n, _p(seq, u8p), _p(off, u64p), _p(b, u64p), _p(e, u64p), _p(s, u64p)),
+           "fm_backward_search")
+    return b, e, s
+
+
+def fm6_smem(idx, seq, off, self_match=0):
+    """n x fm6_smem (smem.c:397): returns (records INTV[], mem_off u64[n+1])."""
+    seq = np.ascontiguousarray(seq, np.uint8)
+    off = np.ascontiguousarray(off, np.uint64)
+    n = len(off) - 1
+    mo = np.zeros(n + 1, np.uint64)
+    mem = C.c_void_p()
+    _check(lib().fmg_smem_batch(idx.h, n, _p(seq, u8p), _p(off, u64p), int(self_match), C.byref(mem), _p(mo, u64p)), "fm6_smem")
+    tot = int(mo[-1])
+    rec = np.frombuffer(C.string_at(mem.value, tot * 32), dtype=INTV).copy() if tot else np.zeros(0, INTV)
+    lib().fmg_free(mem)
+    return rec, mo
+
+
+def fm6_smem_raw(idx, n, seq_ptr, off_ptr, mem_ptr, mem_cap, mem_off_ptr, self_match=0, batch_reads=0):
+    """fmg_smem_batch_into on raw host pointers (pinned torch tensors in bench.py). Returns n_records."""
+    got = C.c_uint64()
+    rc = lib().fmg_smem_batch_into(idx.h, n, seq_ptr, off_ptr, int(self_match), mem_ptr, mem_cap, mem_off_ptr,
+                                   C.byref(got), batch_reads)
+    if rc == 1:
+        raise RuntimeError("fermi_b200: record buffer too small (%d needed)" % got.value)
+    _check(rc, "fm6_smem")
+    return got.value
+
+
+class SmemSession:
+    """Device-resident SMEM session (fmg_smem_session_*): reads and results stay in HBM."""
+
+    def __init__(self, idx, max_reads, max_len):
+        self.idx = idx
+        self.h = lib().fmg_smem_session_create(idx.h, max_reads, max_len)
+        if not self.h:
+            raise RuntimeError("fermi_b200: cannot create the SMEM session")
+
+    def run(self, n, d_seq_ptr, d_off_ptr, self_match=0, stream=0):
+        _check(lib().fmg_smem_session_run(self.h, n, d_seq_ptr, d_off_ptr, int(self_match), stream), "smem session run")
+
+    def result(self):
+        """(n_records, device pointer of records, device pointer of offsets); synchronises the stream."""
+        n = C.c_uint64()
+        mem = C.c_void_p()
+        off = C.c_void_p()
+        _check(lib().fmg_smem_session_result(self.h, C.byref(n), C.byref(mem), C.byref(off)), "smem session result")
+        return n.value, mem.value, off.value
+
+    def close(self):
+        if self.h:
+            lib().fmg_smem_session_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def fm_build_bwt(text, device=0):
+    """BWT of the FMD text on the GPU (replaces fm_bwtgen/ksa_bwt, build.c:5, ksa.c:231)."""
+    text = np.ascontiguousarray(text, np.uint8)
+    bwt = np.zeros(len(text), np.uint8)
+    _check(lib().fmg_build_bwt(device, len(text), _p(text, u8p), _p(bwt, u8p)), "fm_build_bwt")
+    return bwt
+
+
+def fm_build(text, device=0):
+    """fm_build (build.c:33): text -> Fmd."""
+    return Fmd.from_bwt(fm_build_bwt(text, device))
+
+
+def launch_count():
+    return int(lib().fmg_launch_count())
+
+
+# ------------------------------------------------------------------ synthetic data (host helpers)
+def synth_genome(seed, n):
+    g = np.zeros(n, np.uint8)
+    lib().fmg_synth_genome(seed, n, _p(g, u8p))
+    return g
+
+
+def synth_reads(seed, genome, n_reads, length, err, out=None):
+    genome = np.ascontiguousarray(genome, np.uint8)
+    if out is None:
+        out = np.zeros((n_reads, length), np.uint8)
+    lib().fmg_synth_reads(seed, len(genome), _p(genome, u8p), n_reads, length, float(err), _p(out, u8p))
+    return out
+
+
+def fmd_text(seqs):
+    seqs = np.ascontiguousarray(seqs, np.uint8)
+    n, L = seqs.shape
+    total = lib().fmg_fmd_text(n, L, _p(seqs, u8p), None)
+    text = np.zeros(total, np.uint8)
+    lib().fmg_fmd_text(n, L, _p(seqs, u8p), _p(text, u8p))
+    return text

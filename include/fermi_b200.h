@@ -1,0 +1,118 @@
+/* fermi_b200.h -- C-ABI of libfermi_b200.so: the B200 (sm_100a) drop-in for the FMD-index hot
+ * path of lh3/fermi.  Plain C types only (pointers + sizes); no torch / C++ types cross this
+ * boundary.  Every entry point names the reference interface it replaces (file:line relative to
+ * the reference tree, lh3/fermi 1.1-r751-beta).  Host code (fermi's cmd.c mains, or any FFI)
+ * binds exactly these symbols; INTEGRATION.md shows the patch.
+ *
+ * Conventions (same as the reference):
+ *   - every function that can fail returns int, 0 = ok; on failure it prints "[E::fmg_*] ..." to
+ *     stderr (honouring fmg_verbose like fm_verbose, utils.c:8) and returns non-zero.  There is
+ *     NO CPU fallback: without a CUDA device every device entry point fails loudly.
+ *   - result arrays returned through `T **out` are malloc'd and owned by the caller
+ *     (release with fmg_free), like the kvec results of fm6_smem (fermi.h:21,102-104).
+ *   - handles are read-only and re-entrant during queries; one host thread per GPU.
+ */
+#ifndef FERMI_B200_H
+#define FERMI_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMG_VERSION "0.1-r1"
+
+extern int fmg_verbose;                                   /* fm_verbose, utils.c:8 */
+
+/* bi-interval, layout-identical to fmintv_t (fermi.h:13-16) */
+typedef struct { uint64_t x[3]; uint64_t info; } fmg_intv_t;
+
+/* ------------------------------------------------------------------ host .fmd container
+ * Mirror of rld_t (rld.h:20-39) restricted to the Makefile flavour: asize=6, sbits=3, Elias-delta
+ * codec.  The bit stream is one flat array instead of 64 MB chunks. */
+typedef struct fmg_fmd_s fmg_fmd_t;
+
+fmg_fmd_t *fmg_fmd_restore(const char *fn);               /* rld_restore, rld.c:288-325: "RLD\2" or raw "RLE\6" */
+fmg_fmd_t *fmg_fmd_from_bwt(int64_t n, const uint8_t *bwt);   /* fm_bwtenc, build.c:11-31 (nt6 BWT string) */
+fmg_fmd_t *fmg_fmd_from_rle6(int64_t n, const uint8_t *rle);  /* rld.c:295-309 (bytes len<<3|sym, bcr.c:20-126) */
+/* adopt the fields of an existing rld_t without copying semantics changes: z = n_chunks pointers to
+ * 2^23-word chunks (rld.h:9-11,31), frame = n_frames*7 words (rld.h:35-36), mcnt[0..6] (rld.h:33) */
+fmg_fmd_t *fmg_fmd_from_rld(int asize, int sbits, uint64_t n_bytes, int n_chunks, const uint64_t *const *z,
+                            const uint64_t *mcnt, uint64_t n_frames, const uint64_t *frame);
+int        fmg_fmd_dump(const fmg_fmd_t *e, const char *fn);  /* rld_dump, rld.c:242-263 (byte-identical .fmd) */
+void       fmg_fmd_destroy(fmg_fmd_t *e);                     /* rld_destroy, rld.c:81-94 */
+/* out[0..6]=mcnt, out[7..13]=cnt, out[14]=n_bytes, out[15]=n_frames, out[16]=ibits */
+void       fmg_fmd_info(const fmg_fmd_t *e, uint64_t out[17]);
+int64_t    fmg_fmd_decode_bwt(const fmg_fmd_t *e, uint8_t *out); /* main_chkbwt -p / unpack view, cmd.c:106 */
+
+/* ------------------------------------------------------------------ device index
+ * fmg_index_upload copies the .fmd image to the HBM of `device` and builds the query layout
+ * there ("occ lines": 128-byte lines of 256 symbols = mid-line cumulative counts + 3 bit planes).
+ * Replaces holding an rld_t for queries: rld_restore + rld_rank_index (rld.c:186-224,288). */
+typedef struct fmg_index_s fmg_index_t;
+
+fmg_index_t *fmg_index_upload(const fmg_fmd_t *e, int device);
+void         fmg_index_free(fmg_index_t *idx);
+uint64_t     fmg_index_bytes(const fmg_index_t *idx);         /* HBM bytes of the query layout */
+int          fmg_index_device(const fmg_index_t *idx);
+
+/* ------------------------------------------------------------------ batched queries, HOST buffers
+ * (host->device and device->host copies happen inside the call) */
+
+/* n x rld_rank2a (rld.c:457-492): ok/ol = n*6 counts; k = (uint64_t)-1 allowed */
+int fmg_rank2a_batch(const fmg_index_t *idx, int64_t n, const uint64_t *k, const uint64_t *l, uint64_t *ok, uint64_t *ol);
+/* n x fm6_extend (exact.c:72-88): ok6 = n*6 intervals; ok6[].info is set to 0 */
+int fmg_extend_batch(const fmg_index_t *idx, int64_t n, const fmg_intv_t *ik, const uint8_t *is_back, fmg_intv_t *ok6);
+/* n x fm_backward_search (exact.c:7-23): reads are nt6 bytes, read i = seq[off[i]..off[i+1]) */
+int fmg_backward_search_batch(const fmg_index_t *idx, int64_t n, const uint8_t *seq, const uint64_t *off,
+                              uint64_t *sa_beg, uint64_t *sa_end, uint64_t *size);
+/* n x fm6_smem (smem.c:397-410): *mem = all records ordered by read, then exactly as fm6_smem
+ * orders them; mem_off[n+1] = first record of each read.  self_match as in fm6_smem1 (smem.c:104). */
+int fmg_smem_batch(const fmg_index_t *idx, int64_t n, const uint8_t *seq, const uint64_t *off, int self_match,
+                   fmg_intv_t **mem, uint64_t *mem_off);
+/* same, into caller-owned host buffers (pinned memory makes the copies asynchronous): mem holds
+ * mem_cap records.  Reads are processed in batches of batch_reads (0 = default) with the host->device
+ * copy, the kernels and the device->host copy of consecutive batches overlapped on three streams.
+ * Returns 0, or 1 when mem_cap is too small (*n_records then holds the required capacity). */
+int fmg_smem_batch_into(const fmg_index_t *idx, int64_t n, const uint8_t *seq, const uint64_t *off, int self_match,
+                        fmg_intv_t *mem, uint64_t mem_cap, uint64_t *mem_off, uint64_t *n_records, int64_t batch_reads);
+void fmg_free(void *p);
+
+/* ------------------------------------------------------------------ device-resident SMEM session
+ * For callers that keep reads and results in HBM (bench.py's kernel-only figure, pipelines).
+ * A session owns the scratch for batches of up to max_reads reads of up to max_len bases.
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream). */
+typedef struct fmg_smem_session_s fmg_smem_session_t;
+
+fmg_smem_session_t *fmg_smem_session_create(const fmg_index_t *idx, int64_t max_reads, int max_len);
+void                fmg_smem_session_destroy(fmg_smem_session_t *s);
+/* d_seq/d_off are DEVICE pointers. Runs the SMEM kernel + compaction on `stream`; no host sync
+ * unless a read overflowed its record slots (then it is re-run with larger slots). */
+int fmg_smem_session_run(fmg_smem_session_t *s, int64_t n, const uint8_t *d_seq, const uint64_t *d_off,
+                         int self_match, void *stream);
+/* after the stream has been synchronised: device pointers to the compacted result of the last run */
+int fmg_smem_session_result(fmg_smem_session_t *s, uint64_t *n_records, const fmg_intv_t **d_mem, const uint64_t **d_mem_off);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+uint64_t fmg_launch_count(void);
+
+/* ------------------------------------------------------------------ index construction
+ * BWT of the FMD text  r0 $ rc(r0) $ r1 $ rc(r1) $ ...  (cmd.c:457-469) by prefix-doubling suffix
+ * sorting on the GPU; replaces fm_build / ksa_bwt (build.c:33-50, ksa.c:231-242) for texts that fit
+ * one GPU.  `text` = nt6 bytes with 0 sentinels (n < 2^32); `bwt` receives n symbols. */
+int fmg_build_bwt(int device, int64_t n, const uint8_t *text, uint8_t *bwt);
+
+/* ------------------------------------------------------------------ synthetic data
+ * Deterministic, seed-addressed generators shared by the GPU run, the CPU baseline and the tests. */
+void fmg_synth_genome(uint64_t seed, int64_t n, uint8_t *nt6);
+void fmg_synth_reads(uint64_t seed, int64_t genome_len, const uint8_t *genome, int64_t n_reads, int len,
+                     double err, uint8_t *reads);
+/* the text fermi indexes for a set of equal-length sequences (cmd.c:457-469); returns its length,
+ * text may be NULL to query the size */
+int64_t fmg_fmd_text(int64_t n_seq, int len, const uint8_t *seqs, uint8_t *text);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,91 @@
+// TEST INFRASTRUCTURE ONLY.
+// Compiles the product's device-side core (fermi_b200/csrc/fmd_device.cuh) for the HOST so that the
+// CPU-only test suite can check the exact code the kernels run (occ-line rank, fm6_extend, the SMEM
+// lane state machine) against the oracle without a GPU.  The product never links this file and has
+// no CPU execution path; libfermi_b200.so fails loudly without a CUDA device.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../fermi_b200/csrc/fmd_device.cuh"
+#include "../../fermi_b200/csrc/occ_layout.hpp"
+#include "../../include/fermi_b200.h"
+
+using namespace fmg;
+
+struct fmg_fmd_s { FmdImage img; };
+
+struct EmuIndex {
+    OccHost occ;
+    OccView view;
+};
+
+extern "C" {
+
+void *emu_index_build(const fmg_fmd_t *e) {
+    EmuIndex *x = new EmuIndex;
+    x->occ = build_occ_host(e->img);
+    x->view.lines = reinterpret_cast<const uint4 *>(x->occ.lines.data());
+    x->view.super = x->occ.super.empty() ? nullptr : x->occ.super.data();
+    x->view.n_sym = e->img.mcnt[0];
+    x->view.n_seq = e->img.mcnt[1];
+    for (int c = 0; c < 8; ++c) x->view.C[c] = e->img.cnt[c];
+    return x;
+}
+
+void emu_index_free(void *x) { delete static_cast<EmuIndex *>(x); }
+
+void emu_rank2a(const void *_x, int64_t n, const uint64_t *k, const uint64_t *l, uint64_t *ok, uint64_t *ol) {
+    const OccView &ix = static_cast<const EmuIndex *>(_x)->view;
+    for (int64_t i = 0; i < n; ++i) {
+        const uint64_t pk = k[i] + 1, pl = l[i] + 1;      // k == -1 -> p = 0
+        rank_from_line(ix, load_line(ix, pk), pk, ok + 6 * i);
+        rank_from_line(ix, load_line(ix, pl), pl, ol + 6 * i);
+    }
+}
+
+void emu_extend(const void *_x, int64_t n, const fmg_intv_t *ik, const uint8_t *is_back, fmg_intv_t *ok6) {
+    const OccView &ix = static_cast<const EmuIndex *>(_x)->view;
+    for (int64_t i = 0; i < n; ++i) {
+        const int b = is_back[i] != 0;
+        Ext6 e;
+        extend6(ix, ik[i].x[b], ik[i].x[!b], ik[i].x[2], e);
+        for (int c = 0; c < 6; ++c) {
+            fmg_intv_t &o = ok6[6 * i + c];
+            o.x[!b] = e.far[c]; o.x[b] = e.near[c]; o.x[2] = e.size[c]; o.info = 0;
+        }
+    }
+}
+
+// runs smem_lane with `n_lanes` emulated lanes (executed one after the other; lanes are independent)
+int emu_smem(const void *_x, int64_t n, const uint8_t *seq, const uint64_t *off, int self_match, int n_lanes,
+             int out_cap, fmg_intv_t **mem, uint64_t *mem_off) {
+    const EmuIndex *x = static_cast<const EmuIndex *>(_x);
+    int max_len = 1;
+    for (int64_t i = 0; i < n; ++i) if ((int)(off[i + 1] - off[i]) > max_len) max_len = (int)(off[i + 1] - off[i]);
+    const int cap = 2 * max_len + 2;
+    std::vector<uint4> F((size_t)n_lanes * cap * 2), W((size_t)n_lanes * cap * 2), out((size_t)n * out_cap * 2);
+    std::vector<uint32_t> cnt(n, 0);
+    unsigned long long next = 0;
+    SmemArgs A;
+    A.ix = x->view; A.seq = seq; A.off = off; A.n_reads = n; A.self_match = self_match;
+    A.F = F.data(); A.W = W.data(); A.cap = cap; A.out = out.data(); A.out_cap = out_cap;
+    A.rec_cnt = cnt.data(); A.next_read = &next;
+    // interleave the lanes' reads like concurrent lanes would: lane t takes reads t, t+n_lanes, ...
+    for (int t = 0; t < n_lanes; ++t) {
+        int64_t cur = t;
+        smem_lane(A, t, [&]() { int64_t r = cur; cur += n_lanes; return r; });
+    }
+    int overflow = 0;
+    mem_off[0] = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if ((int)cnt[i] > out_cap) overflow = 1;
+        mem_off[i + 1] = mem_off[i] + (cnt[i] > (uint32_t)out_cap ? (uint32_t)out_cap : cnt[i]);
+    }
+    *mem = (fmg_intv_t *)std::malloc((mem_off[n] ? mem_off[n] : 1) * sizeof(fmg_intv_t));
+    for (int64_t i = 0; i < n; ++i)
+        std::memcpy(*mem + mem_off[i], out.data() + (size_t)i * out_cap * 2, (mem_off[i + 1] - mem_off[i]) * 32);
+    return overflow;
+}
+
+} // extern "C"

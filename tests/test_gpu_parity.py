@@ -1,0 +1,140 @@
+"""GPU: the CUDA path (through the C-ABI of libfermi_b200.so) against the golden vectors generated
+from the unmodified reference and against the oracle on fresh seeded inputs.  Bit-exact everywhere
+(integer work): SA intervals, bi-intervals, SMEM records, BWT bytes."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from conftest import golden_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(case):
+    return np.load(os.path.join(H.GOLDEN_DIR, case + ".npz")), os.path.join(H.GOLDEN_DIR, case + ".fmd")
+
+
+@pytest.fixture(scope="module")
+def fb(product_lib):
+    import fermi_b200
+    return fermi_b200
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_golden_rank_extend_smem_search(fb, case):
+    g, fmd = _load(case)
+    idx = fb.FmdIndex(fb.Fmd.restore(fmd), 0)
+    ok, ol = fb.rld_rank2a(idx, g["k"], g["l"])
+    assert np.array_equal(ok, g["ok"]) and np.array_equal(ol, g["ol"])
+    assert np.array_equal(fb.fm6_extend(idx, g["ik"], g["is_back"]), g["ext"])
+    seq, off = H.reads_to_flat(g["q"])
+    for sm, rk, ok_ in ((0, "smem0", "moff0"), (1, "smem1", "moff1")):
+        rec, mo = fb.fm6_smem(idx, seq, off, sm)
+        assert np.array_equal(mo, g[ok_]) and np.array_equal(rec, g[rk])
+    b, e, s = fb.fm_backward_search(idx, seq, off)
+    assert np.array_equal(b, g["sa_beg"]) and np.array_equal(e, g["sa_end"]) and np.array_equal(s, g["sa_size"])
+    idx.close()
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_gpu_bwt_build_reproduces_reference_fmd(fb, case, tmp_path):
+    """fm_build on the GPU + host encoder == the reference's SA-IS build, byte for byte."""
+    g, fmd = _load(case)
+    out = str(tmp_path / "gpu.fmd")
+    fb.fm_build(g["text"], 0).dump(out)
+    assert open(out, "rb").read() == open(fmd, "rb").read()
+
+
+def test_bwt_build_edge_cases(fb):
+    rng = np.random.RandomState(4)
+    texts = [
+        np.array([0], np.uint8),
+        np.array([1, 0, 4, 0], np.uint8),
+        H.fmd_text([np.full(300, 1, np.uint8)] * 3),                       # long runs, identical sequences
+        H.fmd_text([rng.randint(1, 5, size=rng.randint(1, 400)).astype(np.uint8) for _ in range(50)]),  # ragged
+        H.fmd_text([np.tile(np.array([1, 2], np.uint8), 200)] * 2 + [np.tile(np.array([2, 1], np.uint8), 150)]),  # periodic
+    ]
+    for t in texts:
+        assert np.array_equal(fb.fm_build_bwt(t, 0), H.naive_bwt(t))
+
+
+def test_fresh_inputs_vs_oracle_100k_reads(fb, oracle, tmp_path):
+    """BASELINE config 1: build from 100k x 100 bp reads, SA intervals + SMEM records bit-exact."""
+    genome = fb.synth_genome(7, 1000000)
+    reads = fb.synth_reads(8, genome, 100000, 100, 0.0)
+    fmd = fb.fm_build(fb.fmd_text(reads), 0)
+    fn = str(tmp_path / "r.fmd")
+    fmd.dump(fn)
+    ho = oracle.load(fn)
+    assert np.array_equal(oracle.info(ho)["mcnt"], fmd.mcnt)
+    idx = fb.FmdIndex(fmd, 0)
+    q = np.concatenate([reads[:20000], fb.synth_reads(9, genome, 20000, 100, 0.01)])
+    seq, off = H.reads_to_flat(q)
+    b, e, s = fb.fm_backward_search(idx, seq, off)
+    ob, oe, os_ = oracle.backward_search(ho, seq, off)
+    assert np.array_equal(b, ob) and np.array_equal(e, oe) and np.array_equal(s, os_)
+    assert (s[:20000] > 0).all()
+    for sm in (0, 1):
+        rec, mo = fb.fm6_smem(idx, seq, off, sm)
+        orec, omo, _, _, _ = oracle.smem(ho, seq, off, sm, 8)
+        assert np.array_equal(mo, omo) and np.array_equal(rec, orec)
+    n = int(fmd.mcnt[0])
+    rng = np.random.RandomState(1)
+    k = rng.randint(0, n, size=200000).astype(np.uint64)
+    l = np.minimum(k + rng.randint(0, 3000, size=200000).astype(np.uint64), np.uint64(n - 1))
+    k[:100] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    ok, ol = fb.rld_rank2a(idx, k, l)
+    ook, ool = oracle.rank2a(ho, k, l)
+    assert np.array_equal(ok, ook) and np.array_equal(ol, ool)
+    oracle.destroy(ho)
+    idx.close()
+
+
+def test_ragged_empty_and_multibatch(fb, oracle):
+    """empty / 1-base / ragged reads, and the multi-batch host pipeline (tiny batches force many)."""
+    import ctypes as C
+    fmd_path = os.path.join(H.GOLDEN_DIR, "reads10x.fmd")
+    g = np.load(os.path.join(H.GOLDEN_DIR, "reads10x.npz"))
+    rng = np.random.RandomState(9)
+    reads = [g["q"][i % 300][: rng.randint(0, 101)] for i in range(3000)]
+    reads[0] = reads[0][:0]
+    reads[17] = g["q"][17][:1]
+    seq = np.concatenate(reads).astype(np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.uint64)
+    idx = fb.FmdIndex(fb.Fmd.restore(fmd_path), 0)
+    h = oracle.load(fmd_path)
+    for sm in (0, 1):
+        orec, omo, _, _, _ = oracle.smem(h, seq, off, sm, 4)
+        rec, mo = fb.fm6_smem(idx, seq, off, sm)
+        assert np.array_equal(mo, omo) and np.array_equal(rec, orec)
+        mem = np.zeros(len(orec) + 8, H.INTV)
+        mo2 = np.zeros(len(off), np.uint64)
+        n = fb.fm6_smem_raw(idx, len(off) - 1, seq.ctypes.data, off.ctypes.data, mem.ctypes.data, len(mem), mo2.ctypes.data,
+                            sm, batch_reads=257)
+        assert n == len(orec) and np.array_equal(mo2, omo) and np.array_equal(mem[:n], orec)
+    oracle.destroy(h)
+    idx.close()
+
+
+def test_record_slot_overflow_is_rerun_not_truncated(fb, oracle, tmp_path):
+    """a read with more SMEMs than the default 64 record slots: the session must grow and re-run."""
+    rng = np.random.RandomState(2)
+    # many short distinct sequences; one long query that stitches them together yields > 64 SMEMs
+    pieces = [rng.randint(1, 5, size=24).astype(np.uint8) for _ in range(120)]
+    text = H.fmd_text(pieces)
+    fmd = fb.fm_build(text, 0)
+    fn = str(tmp_path / "p.fmd")
+    fmd.dump(fn)
+    q = np.concatenate(pieces[:100]).astype(np.uint8)
+    seq = np.concatenate([q, pieces[3]])
+    off = np.array([0, len(q), len(q) + 24], np.uint64)
+    h = oracle.load(fn)
+    orec, omo, _, _, _ = oracle.smem(h, seq, off, 0, 1)
+    assert omo[1] > 64
+    idx = fb.FmdIndex(fmd, 0)
+    rec, mo = fb.fm6_smem(idx, seq, off, 0)
+    assert np.array_equal(mo, omo) and np.array_equal(rec, orec)
+    oracle.destroy(h)
+    idx.close()

@@ -1,0 +1,124 @@
+"""CPU: the product's host logic (.fmd reader/encoder, synthetic data, C-ABI surface) and the host
+compilation of its device-side core (occ-line rank, fm6_extend, SMEM lane state machine) against the
+golden vectors.  No GPU compute is called here."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers as H
+from conftest import golden_cases
+
+
+def _load(case):
+    return np.load(os.path.join(H.GOLDEN_DIR, case + ".npz")), os.path.join(H.GOLDEN_DIR, case + ".fmd")
+
+
+def test_library_exports_every_declared_symbol(product_lib):
+    hdr = open(os.path.join(H.ROOT, "include", "fermi_b200.h")).read()
+    declared = set(re.findall(r"\b(fmg_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(product_lib, name), name + " is declared in include/fermi_b200.h but not exported"
+
+
+def test_device_entry_points_fail_loudly_without_gpu(product_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import fermi_b200 as fb
+    f = fb.Fmd.restore(os.path.join(H.GOLDEN_DIR, "reads10x.fmd"))
+    with pytest.raises(RuntimeError):
+        fb.FmdIndex(f, 0)
+    with pytest.raises(RuntimeError):
+        fb.fm_build_bwt(np.array([1, 2, 0, 3, 4, 0], np.uint8))
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_fmd_reader_and_encoder_are_byte_identical(product_lib, case, tmp_path):
+    import fermi_b200 as fb
+    g, fmd = _load(case)
+    f = fb.Fmd.restore(fmd)
+    assert np.array_equal(f.mcnt, g["mcnt"]) and np.array_equal(f.cnt, g["cnt"])
+    assert (f.n_bytes, f.n_frames, f.ibits) == (int(g["n_bytes"]), int(g["n_frames"]), int(g["ibits"]))
+    bwt = f.decode_bwt()
+    assert np.array_equal(bwt, H.naive_bwt(g["text"]))
+    out = str(tmp_path / "o.fmd")
+    fb.Fmd.from_bwt(bwt).dump(out)
+    assert open(out, "rb").read() == open(fmd, "rb").read()
+    f.dump(out)
+    assert open(out, "rb").read() == open(fmd, "rb").read()
+
+
+def test_encoder_long_runs_and_32bit_headers(product_lib, oracle, tmp_path):
+    """runs >= 0x8000 symbols force the 7 x u32 block header (rld.c:119-124)."""
+    import fermi_b200 as fb
+    rng = np.random.RandomState(5)
+    parts = []
+    for _ in range(200):
+        parts.append(np.full(rng.choice([1, 2, 7, 300, 40000, 70000]), rng.randint(0, 6), np.uint8))
+    bwt = np.concatenate(parts)
+    a, b = str(tmp_path / "a.fmd"), str(tmp_path / "b.fmd")
+    fb.Fmd.from_bwt(bwt).dump(a)
+    h = oracle.from_bwt(bwt)
+    oracle.dump(h, b)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    assert np.array_equal(fb.Fmd.restore(a).decode_bwt(), bwt)
+    assert np.array_equal(oracle.decode_bwt(h), bwt)
+    R = H.reference()
+    if R is not None:      # the reference itself must read it and agree on ranks
+        hr = R.load(a)
+        k = rng.randint(0, len(bwt), size=3000).astype(np.uint64)
+        l = np.minimum(k + np.uint64(50000), np.uint64(len(bwt) - 1))
+        ra, oa = R.rank2a(hr, k, l), oracle.rank2a(h, k, l)
+        assert np.array_equal(ra[0], oa[0]) and np.array_equal(ra[1], oa[1])
+        R.destroy(hr)
+    oracle.destroy(h)
+
+
+def test_synthetic_data_matches_numpy_mirror(product_lib):
+    import fermi_b200 as fb
+    g = fb.synth_genome(7, 100003)
+    assert np.array_equal(g, H.synth_genome(100003, 7))
+    r = fb.synth_reads(11, g, 5000, 100, 0.02)
+    assert np.array_equal(r, H.synth_reads(g, 5000, 100, 0.02, 11))
+    r[3] = np.concatenate([r[3, :50], H.revcomp(r[3, :50])])      # even-length rc-palindrome
+    assert np.array_equal(fb.fmd_text(r), H.fmd_text(r))
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_device_core_on_host_matches_reference_vectors(emu, case):
+    g, fmd = _load(case)
+    x = emu.index(fmd)
+    ok, ol = emu.rank2a(x, g["k"], g["l"])
+    assert np.array_equal(ok, g["ok"]) and np.array_equal(ol, g["ol"])
+    assert np.array_equal(emu.extend(x, g["ik"], g["is_back"]), g["ext"])
+    seq, off = H.reads_to_flat(g["q"])
+    for sm, rk, ok_ in ((0, "smem0", "moff0"), (1, "smem1", "moff1")):
+        rec, mo, ov = emu.smem(x, seq, off, sm, n_lanes=5, out_cap=128)
+        assert ov == 0
+        assert np.array_equal(mo, g[ok_]) and np.array_equal(rec, g[rk])
+    # a slot capacity that is too small must be reported, never silently truncated
+    rec, mo, ov = emu.smem(x, seq, off, 0, n_lanes=3, out_cap=2)
+    assert ov == 1
+    emu.lib.emu_index_free(x)
+
+
+def test_device_core_ragged_and_empty_reads(emu, oracle):
+    fmd = os.path.join(H.GOLDEN_DIR, "reads10x.fmd")
+    g = np.load(os.path.join(H.GOLDEN_DIR, "reads10x.npz"))
+    rng = np.random.RandomState(9)
+    reads = [g["q"][i][: rng.randint(0, 101)] for i in range(200)]
+    reads[0] = reads[0][:0]
+    reads[17] = g["q"][17][:1]
+    seq = np.concatenate(reads).astype(np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.uint64)
+    x = emu.index(fmd)
+    h = oracle.load(fmd)
+    for sm in (0, 1):
+        rec, mo, ov = emu.smem(x, seq, off, sm)
+        orec, omo, _, _, _ = oracle.smem(h, seq, off, sm, 1)
+        assert ov == 0 and np.array_equal(mo, omo) and np.array_equal(rec, orec)
+    oracle.destroy(h)
+    emu.lib.emu_index_free(x)
