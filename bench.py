@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s through the SMEM path (fm6_smem, smem.c:397) on BASELINE.json config 2:
+10 M x 100 bp synthetic reads (1 % substitutions) against the FMD-index of a 100 Mbp i.i.d. genome cut
+into 10 kb records.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over the whole read set of a rank.
+  value        device-resident: reads and the index already in HBM, results left in HBM (kernels only)
+  e2e          through the C-ABI with pinned HOST buffers: H2D of the reads, kernels, D2H of the records
+  roofline     k_smem alone (CUDA events on its stream): algorithmic bytes (N_locate x 128 + L + 32 n_out
+               per read, SURVEY.md 8d, N_locate counted by an instrumented oracle run on a sample of the
+               same reads) / kernel time, against the measured HBM copy peak
+  cpu_baseline the reference's own fm6_smem (oracle/_ref, unmodified, all host threads) on a bounded
+               sample of the same reads and the same .fmd file
+N > 1: every rank holds the whole index and its own 10 M reads (weak scaling); no data-path collective,
+value = reads of all ranks / max-over-ranks device time.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GENOME_SEED, READ_SEED = 21, 22
+RECORD_LEN = 10000
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000)
+    ap.add_argument("--genome", type=int, default=100_000_000)
+    ap.add_argument("--read-len", type=int, default=100)
+    ap.add_argument("--err", type=float, default=0.01)
+    ap.add_argument("--batch-reads", type=int, default=2_000_000)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "fermi smem (fm6_smem): %d x %d bp reads, %.0f%% subst, vs FMD-index of a %d bp i.i.d. genome in 10 kb records" % (
+        a.reads, a.read_len, a.err * 100, a.genome)
+
+
+def index_path(a):
+    return os.path.join(tempfile.gettempdir(), "fermi_b200_bench_g%d_s%d.fmd" % (a.genome, GENOME_SEED))
+
+
+def genome_records(fb, a):
+    g = fb.synth_genome(GENOME_SEED, a.genome)
+    n_rec = a.genome // RECORD_LEN
+    return g, g[: n_rec * RECORD_LEN].reshape(n_rec, RECORD_LEN)
+
+
+def make_reads(fb, a, genome, rank, out=None):
+    return fb.synth_reads(READ_SEED + 1000 * rank, genome, a.reads, a.read_len, a.err, out=out)
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------- CPU side (checker libs)
+def cpu_lib():
+    """the compiled reference if it travelled with the repo (oracle/_ref), else the oracle port"""
+    import helpers as H
+    R = H.reference()
+    if R is not None:
+        return R, "reference"
+    return H.oracle(), "port"
+
+
+def cpu_smem_rate(fmd_file, reads, seconds, cores):
+    """fm6_smem of the reference (or port) with `cores` strided threads on a bounded sample of `reads`."""
+    import helpers as H
+    L, kind = cpu_lib()
+    h = L.load(fmd_file)
+    pilot = reads[: min(len(reads), 64 * cores)]
+    seq, off = H.reads_to_flat(pilot)
+    _, _, t, _, _ = L.smem(h, seq, off, 0, cores, want_records=False)
+    rate = len(pilot) / max(t, 1e-6)
+    n = int(min(len(reads), max(len(pilot), rate * seconds)))
+    seq, off = H.reads_to_flat(reads[:n])
+    _, mo, t, _, _ = L.smem(h, seq, off, 0, cores, want_records=False)
+    L.destroy(h)
+    return {"value": n / t, "unit": "reads/s", "cores": cores, "kind": kind,
+            "sample": "first %d reads of rank 0's read set, fm6_smem(self_match=0), %d strided pthreads, %.1f s wall" % (n, cores, t)}, int(mo[-1]), n
+
+
+def count_locates(fmd_file, reads, cores):
+    """N_locate / N_extend / n_out per read from the instrumented oracle port."""
+    import helpers as H
+    O = H.oracle()
+    h = O.load(fmd_file)
+    seq, off = H.reads_to_flat(reads)
+    _, mo, _, nloc, next_ = O.smem(h, seq, off, 0, cores, want_records=False)
+    O.destroy(h)
+    n = len(reads)
+    return nloc / n, next_ / n, int(mo[-1]) / n
+
+
+# ----------------------------------------------------------------------------------- reference arm
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import helpers as H
+    import fermi_b200 as fb
+    L, kind = cpu_lib()
+    cores = os.cpu_count() or 1
+    fn = index_path(a)
+    genome, recs = genome_records(fb, a)
+    if not os.path.exists(fn):
+        t0 = time.time()
+        if kind == "reference":
+            text = fb.fmd_text(recs)
+            h = L.build_text(text)                    # the reference's own SA-IS build (build.c:33)
+            L.dump(h, fn)
+            L.destroy(h)
+        else:                                          # no compiled reference on this box: set-up only, not timed
+            fb.fm_build(fb.fmd_text(recs), 0).dump(fn)
+        log("reference arm: index built in %.1f s (%s)" % (time.time() - t0, kind))
+    n_sample = min(a.reads, 12000 * cores)
+    reads = fb.synth_reads(READ_SEED, genome, n_sample, a.read_len, a.err)
+    seq, off = H.reads_to_flat(reads)
+    h = L.load(fn)
+    times = []
+    for it in range(a.warmup + a.steps):
+        _, _, t, _, _ = L.smem(h, seq, off, 0, cores, want_records=False)
+        if it >= a.warmup:
+            times.append(t)
+    L.destroy(h)
+    ms = 1e3 * sum(times) / len(times)
+    val = n_sample / (ms / 1e3)
+    sample = "each step = fm6_smem over the first %d reads of the read set with %d strided pthreads" % (n_sample, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "reads/sec through SMEM (fm6_smem)", "value": val, "unit": "reads/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "reads/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+# ----------------------------------------------------------------------------------- our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import fermi_b200 as fb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; fermi_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- set-up (untimed): genome, index file (rank 0 builds, everyone loads), reads
+    t0 = time.time()
+    genome, recs = genome_records(fb, a)
+    fn = index_path(a)
+    if rank == 0 and not os.path.exists(fn):
+        text = fb.fmd_text(recs)
+        t1 = time.time()
+        bwt = fb.fm_build_bwt(text, local)
+        t2 = time.time()
+        fmd = fb.Fmd.from_bwt(bwt)
+        fmd.dump(fn + ".tmp")
+        os.replace(fn + ".tmp", fn)
+        log("index: %d symbols, GPU BWT %.1f s, RLD encode + write %.1f s" % (len(text), t2 - t1, time.time() - t2))
+        del text, bwt, fmd
+    barrier()
+    fmd = fb.Fmd.restore(fn)
+    t1 = time.time()
+    idx = fb.FmdIndex(fmd, local)
+    log("rank %d: index upload %.1f s, %.1f MB occ lines; set-up so far %.1f s" % (rank, time.time() - t1, idx.nbytes / 1e6, time.time() - t0))
+
+    L = a.read_len
+    h_reads = torch.empty((a.reads, L), dtype=torch.uint8).pin_memory()
+    make_reads(fb, a, genome, rank, out=h_reads.numpy())
+    h_off = (torch.arange(a.reads + 1, dtype=torch.int64) * L).pin_memory()
+    d_reads = h_reads.to(dev, non_blocking=True)
+    d_off = h_off.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    B = min(a.batch_reads, a.reads)
+    sess = fb.SmemSession(idx, B, L)
+    stream = torch.cuda.current_stream().cuda_stream
+    batches = [(s, min(B, a.reads - s)) for s in range(0, a.reads, B)]
+    d_boff = [(d_off[s: s + n + 1] - s * L).contiguous() for s, n in batches]   # per-batch offsets, resident
+    torch.cuda.synchronize()
+
+    def device_step():
+        tot = 0
+        for (s, n), bo in zip(batches, d_boff):
+            sess.run(n, d_reads[s:].data_ptr(), bo.data_ptr(), 0, stream)
+        return tot
+
+    launches0 = fb.launch_count()
+    for _ in range(a.warmup):
+        device_step()
+    n_rec_last, _, _ = sess.result()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    sess.set_timing(True)
+    sess.kernel_ms()
+    launches1 = fb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        device_step()
+    e1.record()
+    barrier()
+    step_ms = e0.elapsed_time(e1) / a.steps
+    k_ms, k_n = sess.kernel_ms()
+    sess.set_timing(False)
+    launches_timed = fb.launch_count() - launches1
+    clocks = sampler.stop()
+
+    # ---- e2e: pinned host buffers through the C-ABI (H2D + kernels + D2H inside the timed region)
+    e2e = None
+    if not a.no_e2e:
+        rec_cap = int(a.reads * 16)
+        h_mem = torch.empty((rec_cap, 4), dtype=torch.int64).pin_memory()
+        h_moff = torch.empty(a.reads + 1, dtype=torch.int64).pin_memory()
+        sess.close()                                   # the host API owns its sessions
+        n_rec = 0
+        times = []
+        for it in range(max(1, min(a.warmup, 2)) + max(1, min(a.steps, 3))):
+            barrier()
+            t = time.perf_counter()
+            n_rec = fb.fm6_smem_raw(idx, a.reads, h_reads.data_ptr(), h_off.data_ptr(), h_mem.data_ptr(), rec_cap, h_moff.data_ptr(),
+                                    0, a.batch_reads)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t
+            if it >= max(1, min(a.warmup, 2)):
+                times.append(dt)
+        e2e_s = sum(times) / len(times)
+        e2e = {"seconds": e2e_s, "n_rec": n_rec, "h2d": a.reads * L + (a.reads + 1) * 8, "d2h": n_rec * 32 + (a.reads + 1) * 8}
+
+    # ---- reduce over ranks: max time, summed reads
+    t_dev = torch.tensor([step_ms, k_ms / max(1, a.steps), e2e["seconds"] if e2e else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    step_ms_max, k_ms_step_max, e2e_s_max = [float(x) for x in t_dev.tolist()]
+    total_reads = a.reads * world
+
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        sample_n = min(a.reads, 20000)
+        n_loc, n_ext, n_out = count_locates(fn, h_reads.numpy()[:sample_n], min(cores, 16))
+        bytes_per_read = n_loc * 128 + L + 32 * n_out
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        achieved = a.reads * bytes_per_read / (k_ms_step_max / 1e3) / 1e9
+        out = {
+            "metric": "reads/sec through SMEM (fm6_smem)", "value": total_reads / (step_ms_max / 1e3), "unit": "reads/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": step_ms_max, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {
+                "workload": workload_name(a), "reads_per_gpu": a.reads, "batch_reads": B, "index_symbols": int(fmd.mcnt[0]),
+                "index_sequences": int(fmd.mcnt[1]), "index_hbm_mb": round(idx.nbytes / 1e6, 1), "parallelism": "replicated index, reads sharded x%d" % world,
+                "l2": "each step streams %.2f GB of reads and %.2f GB of records (>> 126 MB L2); the %.0f MB index is re-read within a step by design"
+                      % (a.reads * L / 1e9, n_out * a.reads * 32 / 1e9, idx.nbytes / 1e6),
+                "records_per_read": round(n_out, 3), "n_locate_per_read": round(n_loc, 2), "n_extend_per_read": round(n_ext, 2),
+                "counter_sample": "instrumented oracle on the first %d reads" % sample_n},
+            "clocks": clocks,
+            "gpu_launches": int(launches_timed),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "k_smem", "kernel_ms_per_step": k_ms_step_max, "launches_per_step": k_n // max(1, a.steps),
+                         "algorithmic_bytes_per_read": bytes_per_read, "peak_source": peak_src,
+                         "frac_of_8TBs": achieved / 8000.0},
+        }
+        if e2e:
+            out["e2e"] = {"value": total_reads / e2e_s_max, "unit": "reads/s", "h2d_bytes_per_step": int(e2e["h2d"]),
+                          "d2h_bytes_per_step": int(e2e["d2h"]), "seconds_per_step": e2e_s_max,
+                          "api": "fmg_smem_batch_into (pinned host buffers, 3-stream batch pipeline)"}
+        if world == 1 and not a.no_cpu_baseline:
+            cb, _, _ = cpu_smem_rate(fn, h_reads.numpy(), a.cpu_seconds, cores)
+            out["cpu_baseline"] = cb
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -43,6 +43,8 @@ _PROTOS = {
     "fmg_smem_session_destroy": (None, [C.c_void_p]),
     "fmg_smem_session_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "fmg_smem_session_result": (C.c_int, [C.c_void_p, u64p, vpp, vpp]),
+    "fmg_smem_session_set_timing": (None, [C.c_void_p, C.c_int]),
+    "fmg_smem_session_kernel_ms": (C.c_double, [C.c_void_p, C.POINTER(C.c_int)]),
     "fmg_launch_count": (C.c_uint64, []),
     # construction + synthetic data
     "fmg_build_bwt": (C.c_int, [C.c_int, C.c_int64, u8p, u8p]),

@@ -176,6 +176,15 @@ class SmemSession:
         _check(lib().fmg_smem_session_result(self.h, C.byref(n), C.byref(mem), C.byref(off)), "smem session result")
         return n.value, mem.value, off.value
 
+    def set_timing(self, on=True):
+        lib().fmg_smem_session_set_timing(self.h, 1 if on else 0)
+
+    def kernel_ms(self):
+        """(summed k_smem milliseconds, number of launches) since the last call (CUDA events)."""
+        n = C.c_int()
+        ms = lib().fmg_smem_session_kernel_ms(self.h, C.byref(n))
+        return ms, n.value
+
     def close(self):
         if self.h:
             lib().fmg_smem_session_destroy(self.h)

@@ -343,6 +343,10 @@ struct fmg_smem_session_s {
     const uint64_t *last_off = nullptr;
     int last_self = 0;
     cudaStream_t last_stream = nullptr;
+    // optional CUDA-event timing of k_smem alone (bench.py's roofline figure)
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;               // pairs (start, stop), one per k_smem launch since the last query
+    std::vector<cudaEvent_t> ev_free;
 };
 
 static void session_free_slots(fmg_smem_session_t *s) {
@@ -395,6 +399,8 @@ void fmg_smem_session_destroy(fmg_smem_session_t *s) {
     session_free_slots(s);
     cudaFree(s->F); cudaFree(s->W); cudaFree(s->rec_cnt); cudaFree(s->mem_off); cudaFree(s->tile_sum); cudaFree(s->ctrl);
     cudaFreeHost(s->h_ctrl);
+    for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : s->ev_free) cudaEventDestroy(e);
     delete s;
 }
 
@@ -407,8 +413,20 @@ static int session_enqueue(fmg_smem_session_t *s, int64_t n, const uint8_t *d_se
     A.rec_cnt = s->rec_cnt; A.next_read = s->ctrl;
     const int64_t need_blocks = (n + SMEM_BLOCK - 1) / SMEM_BLOCK;
     const int grid = (int)std::min<int64_t>(s->grid, need_blocks);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (s->timing) {
+        for (cudaEvent_t *e : {&e0, &e1}) {
+            if (!s->ev_free.empty()) { *e = s->ev_free.back(); s->ev_free.pop_back(); }
+            else CUDA_TRY(cudaEventCreate(e), return -1);
+        }
+        CUDA_TRY(cudaEventRecord(e0, st), return -1);
+    }
     k_smem<<<grid, SMEM_BLOCK, 0, st>>>(A);
     LAUNCH_CHECK(return -1);
+    if (s->timing) {
+        CUDA_TRY(cudaEventRecord(e1, st), return -1);
+        s->ev.push_back(e0); s->ev.push_back(e1);
+    }
     const int64_t n_tiles = (n + 1 + kScanTile - 1) / kScanTile;
     k_compact_tile_sums<<<(unsigned)n_tiles, kScanBlock, 0, st>>>(s->rec_cnt, n, s->out_cap, s->tile_sum, s->ctrl + 1);
     LAUNCH_CHECK(return -1);
@@ -450,6 +468,25 @@ int fmg_smem_session_result(fmg_smem_session_t *s, uint64_t *n_records, const fm
     if (d_mem) *d_mem = reinterpret_cast<const fmg_intv_t *>(s->mem);
     if (d_mem_off) *d_mem_off = s->mem_off;
     return 0;
+}
+
+void fmg_smem_session_set_timing(fmg_smem_session_t *s, int on) { if (s) s->timing = on != 0; }
+
+// sum of the k_smem durations (CUDA events on the launching stream) since the last call; *n_launches = how many
+double fmg_smem_session_kernel_ms(fmg_smem_session_t *s, int *n_launches) {
+    double total = 0;
+    if (n_launches) *n_launches = 0;
+    if (!s) return 0;
+    for (size_t i = 0; i + 1 < s->ev.size(); i += 2) {
+        float ms = 0;
+        if (cudaEventSynchronize(s->ev[i + 1]) == cudaSuccess && cudaEventElapsedTime(&ms, s->ev[i], s->ev[i + 1]) == cudaSuccess) {
+            total += ms;
+            if (n_launches) ++*n_launches;
+        }
+        s->ev_free.push_back(s->ev[i]); s->ev_free.push_back(s->ev[i + 1]);
+    }
+    s->ev.clear();
+    return total;
 }
 
 // ------------------------------------------------------------------------------------ SMEM, host buffers

@@ -94,6 +94,10 @@ int fmg_smem_session_run(fmg_smem_session_t *s, int64_t n, const uint8_t *d_seq,
                          int self_match, void *stream);
 /* after the stream has been synchronised: device pointers to the compacted result of the last run */
 int fmg_smem_session_result(fmg_smem_session_t *s, uint64_t *n_records, const fmg_intv_t **d_mem, const uint64_t **d_mem_off);
+/* CUDA-event timing of the SMEM kernel alone, on the launching stream (bench.py's roofline figure):
+ * enable, run, then read the summed duration of the k_smem launches since the last query */
+void   fmg_smem_session_set_timing(fmg_smem_session_t *s, int on);
+double fmg_smem_session_kernel_ms(fmg_smem_session_t *s, int *n_launches);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t fmg_launch_count(void);
 
