@@ -205,8 +205,20 @@ struct SmemArgs {
     unsigned long long *next_read;
 };
 
-enum { PH_FETCH = 0, PH_FWD = 1, PH_FWD_TAIL = 2, PH_BWD = 3 };
+enum { PH_FETCH = 0, PH_BEGIN, PH_START_BWD, PH_FWD, PH_FWD_TAIL, PH_BWD, PH_DONE };
 
+FMG_HD bool warp_any(bool v) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(0xffffffffu, v);      // also the reconvergence point of the 32 lanes
+#else
+    return v;
+#endif
+}
+
+// Loop shape (per trip):  [divergent, short]  advance the lane's state machine to its next extension request
+//                         [warp vote]         leave when no lane has a request; reconverges the warp
+//                         [converged, long]   extend6: two line loads + popcounts for all requesting lanes
+//                         [divergent, short]  consume the result according to the lane's phase
 template <class FetchFn>
 FMG_HD void smem_lane(const SmemArgs &A, int64_t lane_slot, FetchFn fetch) {
     uint4 *F = A.F + (size_t)lane_slot * A.cap * 2;
@@ -219,111 +231,115 @@ FMG_HD void smem_lane(const SmemArgs &A, int64_t lane_slot, FetchFn fetch) {
     int len = 0, x = 0, i = 0, j = 0, nF = 0, nprev = 0, ncurr = 0, first_pass = 0, ret = 0;
     int call_base = 0, nmem = 0, last_start = 0;
     uint64_t last_x2 = 0;
-    Intv ik = {0, 0, 0, 0};
+    Intv ik = {0, 0, 0, 0};     // FWD: the interval being extended; BWD: the candidate p being extended
 
     for (;;) {
-        if (ph == PH_FETCH) {
-            for (;;) {
+        // ---- advance to the next extension request (no index access in here)
+        while (ph < PH_FWD) {
+            if (ph == PH_FETCH) {
                 r = fetch();
-                if (r >= A.n_reads) return;
+                if (r >= A.n_reads) { ph = PH_DONE; break; }
                 const uint64_t o = A.off[r];
                 len = (int)(A.off[r + 1] - o);
-                if (len > 0) { q = A.seq + o; break; }
-                A.rec_cnt[r] = 0;
-            }
-            out = A.out + (size_t)r * A.out_cap * 2;
-            nmem = 0;
-            x = 0;
-            ph = -1;                                    // start a forward sweep at x
-        }
-        if (ph < 0) {                                   // begin fm6_smem1_core at x (smem.c:19-21)
-            ik = base_intv(A.ix, ld_u8(q + x));
-            ik.info = (uint64_t)(x + 1);
-            i = x + 1; nF = 0;
-            ph = PH_FWD;
-            if (i == len) {                             // smem.c:35-36
-                st_intv(F + 2 * nF++, ik);
-                ph = sm ? PH_BWD : PH_FWD_TAIL;
-            }
-            if (ph == PH_BWD) goto start_bwd;
-        }
-        {
-            // ---- the one extension of this iteration
-            Intv p = ik;
-            const int back = (ph == PH_BWD);
-            if (back) p = ld_intv(first_pass ? F + 2 * (nF - 1 - j) : W + 2 * j);
-            Ext6 e;
-            extend6(A.ix, back ? p.x1 : p.x0, back ? p.x0 : p.x1, p.x2, e);
-            // x[0]/x[1] of ok[c]: far side is x[1] for a forward, x[0] for a backward extension
-#define FMG_OK(c, dst) do { const uint64_t nr_ = pick6(e.near, c), fr_ = pick6(e.far, c); \
-                            (dst).x0 = back ? fr_ : nr_; (dst).x1 = back ? nr_ : fr_; (dst).x2 = pick6(e.size, c); } while (0)
-            if (ph == PH_FWD) {                         // smem.c:22-34
-                const int c = comp6(ld_u8(q + i));
-                const uint64_t sc = pick6(e.size, c);
-                if (sc != ik.x2) {
-                    if (ik.x2 != e.size[0]) st_intv(F + 2 * nF++, ik);
-                    if (!sm && e.size[0]) {
-                        Intv s0; s0.x0 = e.near[0]; s0.x1 = e.far[0]; s0.x2 = e.size[0]; s0.info = (uint64_t)i;
-                        st_intv(F + 2 * nF++, s0);
-                    }
+                if (len <= 0) { A.rec_cnt[r] = 0; continue; }
+                q = A.seq + o;
+                out = A.out + (size_t)r * A.out_cap * 2;
+                nmem = 0; x = 0;
+                ph = PH_BEGIN;
+            } else if (ph == PH_BEGIN) {                // begin fm6_smem1_core at x (smem.c:19-21)
+                ik = base_intv(A.ix, ld_u8(q + x));
+                ik.info = (uint64_t)(x + 1);
+                i = x + 1; nF = 0;
+                ph = PH_FWD;
+                if (i == len) {                         // smem.c:35-36
+                    st_intv(F + 2 * nF++, ik);
+                    ph = sm ? PH_START_BWD : PH_FWD_TAIL;
                 }
-                const bool stop = sm ? sc < 2 : sc == 0;
-                if (!stop) {
-                    FMG_OK(c, ik); ik.info = (uint64_t)(i + 1);
-                    if (++i < len) continue;
-                    st_intv(F + 2 * nF++, ik);          // reached the end of the read (smem.c:35-36)
-                    if (!sm) { ph = PH_FWD_TAIL; continue; }
-                }
-            } else if (ph == PH_FWD_TAIL) {             // smem.c:37-43
-                if (e.size[0]) {
-                    Intv s0; s0.x0 = e.near[0]; s0.x1 = e.far[0]; s0.x2 = e.size[0]; s0.info = (uint64_t)len;
-                    st_intv(F + 2 * nF++, s0);
-                }
-            } else {                                    // backward sweep, smem.c:51-75
-                const int c = i < 0 ? 0 : (int)ld_u8(q + i);
-                const uint64_t sc = pick6(e.size, c);
-                const bool fl = e.size[0] != 0 && p.x1 < A.ix.n_seq;
-                const bool cont = sm ? sc > 1 : sc != 0;
-                if ((!cont || fl || i == -1) && (ncurr == 0 || fl) &&
-                    (fl || nmem == call_base || i + 1 < last_start)) {
-                    Intv m = p;
-                    m.info |= (uint64_t)(e.size[0] != 0) << 63 | (uint64_t)(i + 1) << 32;
-                    if (nmem < A.out_cap) st_intv(out + 2 * nmem, m);
-                    ++nmem; last_start = i + 1;
-                }
-                if (cont && (p.x1 < A.ix.n_seq || ncurr == 0 || sc != last_x2)) {
-                    Intv n; FMG_OK(c, n); n.info = p.info;
-                    st_intv(W + 2 * ncurr++, n);
-                    last_x2 = sc;
-                }
-                if (++j < nprev) continue;
-                if (ncurr != 0 && i != -1) {            // next backward position
-                    nprev = ncurr; ncurr = 0; j = 0; --i; first_pass = 0;
+            } else {                                    // PH_START_BWD: forward sweep finished (smem.c:45-50)
+                if (nF == 0) {                          // undefined in the reference: no SMEM here
+                    x = i < len ? i : len;
+                    if (x >= len) { A.rec_cnt[r] = (uint32_t)nmem; ph = PH_FETCH; } else ph = PH_BEGIN;
                     continue;
                 }
-                // ---- end of this fm6_smem1_core call: records were pushed by decreasing start (smem.c:76)
-                int lo = call_base, hi = (nmem < A.out_cap ? nmem : A.out_cap) - 1;
-                for (; lo < hi; ++lo, --hi) {
-                    const Intv a = ld_intv(out + 2 * lo), b = ld_intv(out + 2 * hi);
-                    st_intv(out + 2 * lo, b); st_intv(out + 2 * hi, a);
-                }
-                x = ret;
-                if (x >= len) { A.rec_cnt[r] = (uint32_t)nmem; ph = PH_FETCH; }
-                else ph = -1;
-                continue;
+                ik = ld_intv(F + 2 * (nF - 1));         // the longest match is the last push = first candidate
+                ret = (int)ik.info;
+                nprev = nF; first_pass = 1; i = x - 1; j = 0; ncurr = 0; call_base = nmem;
+                ph = PH_BWD;
             }
+        }
+        const bool active = ph != PH_DONE;
+        if (!warp_any(active)) return;
+        if (!active) continue;
+
+        // ---- the one extension of this trip (converged across the warp)
+        const int back = (ph == PH_BWD);
+        Ext6 e;
+        extend6(A.ix, back ? ik.x1 : ik.x0, back ? ik.x0 : ik.x1, ik.x2, e);
+
+        // ---- consume it
+        // x[0]/x[1] of ok[c]: the far side is x[1] for a forward, x[0] for a backward extension
+#define FMG_OK(c, dst) do { const uint64_t nr_ = pick6(e.near, c), fr_ = pick6(e.far, c); \
+                            (dst).x0 = back ? fr_ : nr_; (dst).x1 = back ? nr_ : fr_; (dst).x2 = pick6(e.size, c); } while (0)
+        if (ph == PH_FWD) {                             // smem.c:22-34
+            const int c = comp6(ld_u8(q + i));
+            const uint64_t sc = pick6(e.size, c);
+            if (sc != ik.x2) {
+                if (ik.x2 != e.size[0]) st_intv(F + 2 * nF++, ik);
+                if (!sm && e.size[0]) {
+                    Intv s0; s0.x0 = e.near[0]; s0.x1 = e.far[0]; s0.x2 = e.size[0]; s0.info = (uint64_t)i;
+                    st_intv(F + 2 * nF++, s0);
+                }
+            }
+            const bool stop = sm ? sc < 2 : sc == 0;
+            if (stop) ph = PH_START_BWD;
+            else {
+                FMG_OK(c, ik); ik.info = (uint64_t)(i + 1);
+                if (++i == len) {                       // reached the end of the read (smem.c:35-36)
+                    st_intv(F + 2 * nF++, ik);
+                    ph = sm ? PH_START_BWD : PH_FWD_TAIL;
+                }
+            }
+        } else if (ph == PH_FWD_TAIL) {                 // smem.c:37-43
+            if (e.size[0]) {
+                Intv s0; s0.x0 = e.near[0]; s0.x1 = e.far[0]; s0.x2 = e.size[0]; s0.info = (uint64_t)len;
+                st_intv(F + 2 * nF++, s0);
+            }
+            ph = PH_START_BWD;
+        } else {                                        // backward sweep, smem.c:51-75; ik is the candidate p
+            const int c = i < 0 ? 0 : (int)ld_u8(q + i);
+            const uint64_t sc = pick6(e.size, c);
+            const bool fl = e.size[0] != 0 && ik.x1 < A.ix.n_seq;
+            const bool cont = sm ? sc > 1 : sc != 0;
+            if ((!cont || fl || i == -1) && (ncurr == 0 || fl) &&
+                (fl || nmem == call_base || i + 1 < last_start)) {
+                Intv m = ik;
+                m.info |= (uint64_t)(e.size[0] != 0) << 63 | (uint64_t)(i + 1) << 32;
+                if (nmem < A.out_cap) st_intv(out + 2 * nmem, m);
+                ++nmem; last_start = i + 1;
+            }
+            if (cont && (ik.x1 < A.ix.n_seq || ncurr == 0 || sc != last_x2)) {
+                Intv n; FMG_OK(c, n); n.info = ik.info;
+                st_intv(W + 2 * ncurr++, n);
+                last_x2 = sc;
+            }
+            if (++j == nprev) {
+                if (ncurr != 0 && i != -1) {            // next backward position over the survivors
+                    nprev = ncurr; ncurr = 0; j = 0; --i; first_pass = 0;
+                } else {
+                    // end of this fm6_smem1_core call: records were pushed by decreasing start (smem.c:76)
+                    int lo = call_base, hi = (nmem < A.out_cap ? nmem : A.out_cap) - 1;
+                    for (; lo < hi; ++lo, --hi) {
+                        const Intv a = ld_intv(out + 2 * lo), b = ld_intv(out + 2 * hi);
+                        st_intv(out + 2 * lo, b); st_intv(out + 2 * hi, a);
+                    }
+                    x = ret;
+                    if (x >= len) { A.rec_cnt[r] = (uint32_t)nmem; ph = PH_FETCH; }
+                    else ph = PH_BEGIN;
+                }
+            }
+            if (ph == PH_BWD) ik = ld_intv(first_pass ? F + 2 * (nF - 1 - j) : W + 2 * j);   // next candidate
+        }
 #undef FMG_OK
-        }
-start_bwd:
-        // forward sweep finished: smem.c:45-50.  The longest match is the last push.
-        if (nF == 0) {                                  // undefined in the reference: no SMEM here
-            x = i < len ? i : len;
-            if (x >= len) { A.rec_cnt[r] = (uint32_t)nmem; ph = PH_FETCH; } else ph = -1;
-            continue;
-        }
-        ret = (int)ld_intv(F + 2 * (nF - 1)).info;
-        nprev = nF; first_pass = 1; i = x - 1; j = 0; ncurr = 0; call_base = nmem;
-        ph = PH_BWD;
     }
 }
 
