@@ -241,7 +241,7 @@ def run_ours(a):
     fmd = fb.Fmd.restore(fn)
     t1 = time.time()
     idx = fb.FmdIndex(fmd, local)
-    log("rank %d: index upload %.1f s, %.1f MB occ lines; set-up so far %.1f s" % (rank, time.time() - t1, idx.nbytes / 1e6, time.time() - t0))
+    log("rank %d: index upload %.1f s, %.1f MB occ blocks; set-up so far %.1f s" % (rank, time.time() - t1, idx.nbytes / 1e6, time.time() - t0))
 
     L = a.read_len
     h_reads = torch.empty((a.reads, L), dtype=torch.uint8).pin_memory()

@@ -1,23 +1,25 @@
-// Device-side core of libfermi_b200: the "occ line" rank, fm6_extend and the per-lane SMEM
+// Device-side core of libfermi_b200: the "occ block" rank, fm6_extend and the per-lane SMEM
 // state machine.  Everything here is a __host__ __device__ inline so that tests/emu can compile
 // the SAME source for the host and check it against the oracle where no GPU exists; the product
-// only ever instantiates these functions inside __global__ kernels (kernels.cu).
+// only ever instantiates these functions inside __global__ kernels (fmg_cuda.cu).
 //
-// Query layout in HBM ("occ lines", built by occ_build.cu from the .fmd image):
-//   one line = 128 B = 8 x uint4 covering 256 consecutive BWT symbols
-//     uint4 #0,#1 : u32 cnt[6] (+2 pad) = number of $,A,C,G,T,N in BWT[superblock_start, line*256+128)
-//                   i.e. cumulative counts at the MIDDLE of the line
-//     uint4 #2,#3 : bit plane 0 of symbols   0..127 | 128..255   (bit i of a plane = bit of symbol i)
-//     uint4 #4,#5 : bit plane 1
-//     uint4 #6,#7 : bit plane 2
-//   counts are relative to a 2^31-symbol superblock; `super` holds 8 x u64 absolute counts per
-//   superblock (NULL when the whole BWT has < 2^32-256 symbols, then the u32 counts are absolute).
-//   A rank touches exactly one line and popcounts at most 128 symbols on one side of the middle:
-//   rank(p) = mid -/+ popcount(symbols between p and the middle).  Replaces rld_locate_blk +
-//   rld_dec0 run decoding (rld.c:352-446): one 128-byte HBM line per rank instead of a frame row,
-//   ~7 block headers and a serial Elias-delta decode.
+// Query layout in HBM ("occ blocks", built from the .fmd image at upload):
+//   one block = 64 B = 16 x u32 covering 128 consecutive BWT symbols, read with two 256-bit loads
+//     w[0..3]   five 24-bit counts, byte-packed ($ A C G T; byte 15 spare): number of each symbol in
+//               BWT[superblock_start, 128*b + 64), i.e. cumulative counts at the MIDDLE of the block,
+//               relative to the 2^24-symbol superblock the block lies in
+//     w[4..7]   bit plane 0 of the 128 symbols (bit i of a plane = bit of symbol i)
+//     w[8..11]  bit plane 1
+//     w[12..15] bit plane 2          (positions past the end of the BWT hold symbol 7)
+//   cs[sb][c] (u64, 8 per superblock) = C[c] + number of c before the superblock, so that the SA
+//   coordinate C[c] + rank(c, p) is cs[sb][c] + rel[c].
+//   A rank touches exactly one 64-byte block and popcounts at most 64 symbols on one side of the
+//   middle: rel(p) = mid -/+ popcount(symbols between p and the middle); N is derived from the total.
+//   Replaces rld_locate_blk + rld_dec0 run decoding (rld.c:352-446): one 64-byte HBM access per rank
+//   instead of a frame row, ~7 block headers in distinct lines and a serial Elias-delta decode.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define FMG_HD __host__ __device__ __forceinline__
@@ -31,19 +33,20 @@ struct uint4 { uint32_t x, y, z, w; };
 
 namespace fmg {
 
-constexpr int kLineShift = 8;                 // 256 symbols per line
-constexpr int kSuperShift = 31;               // symbols per superblock
-constexpr uint64_t kLineU4 = 8;               // uint4 per line
+constexpr int kBlkShift = 7;                  // 128 symbols per occ block
+constexpr int kSuperShift = 24;               // symbols per superblock
+constexpr uint64_t kBlkWords = 16;            // u32 per block
 
 struct OccView {
-    const uint4 *lines;
-    const uint64_t *super;    // [n_super][8], or nullptr
+    const uint32_t *blocks;   // n_blocks x 16 u32, 64-byte aligned
+    const uint64_t *cs;       // [n_super][8]
     uint64_t n_sym;           // mcnt[0]
     uint64_t n_seq;           // mcnt[1]: number of sentinels = sequences (both strands)
     uint64_t C[8];            // C[c] = #symbols < c (rld cnt[], rld.c:233)
 };
 
 struct Intv { uint64_t x0, x1, x2, info; };   // fmintv_t (fermi.h:13-16)
+struct alignas(32) Vec8 { uint32_t v[8]; };
 
 FMG_HD uint32_t popc32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
@@ -53,11 +56,38 @@ FMG_HD uint32_t popc32(uint32_t v) {
 #endif
 }
 
-FMG_HD uint4 ld_line(const uint4 *p) {
+// 256-bit read-only load (LDG.E.256 on sm_100a)
+FMG_HD Vec8 ld256_nc(const void *p) {
+    Vec8 r;
 #if defined(__CUDA_ARCH__)
-    return __ldg(p);
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p));
 #else
-    return *p;
+    memcpy(&r, p, 32);
+#endif
+    return r;
+}
+
+// 256-bit load / store of read-write scratch
+FMG_HD Vec8 ld256(const void *p) {
+    Vec8 r;
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p) : "memory");
+#else
+    memcpy(&r, p, 32);
+#endif
+    return r;
+}
+
+FMG_HD void st256(void *p, const Vec8 &r) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]),
+                 "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7]) : "memory");
+#else
+    memcpy(p, &r, 32);
 #endif
 }
 
@@ -69,13 +99,25 @@ FMG_HD uint8_t ld_u8(const uint8_t *p) {
 #endif
 }
 
-// word w (0..3) of the 128-bit mask with the low `oo` bits set
-FMG_HD uint32_t low_mask_word(uint32_t oo, int w) {
-    const uint32_t lo = 32u * w;
-    return oo >= lo + 32u ? 0xffffffffu : (oo <= lo ? 0u : ((1u << (oo - lo)) - 1u));
+FMG_HD uint64_t ld_u64(const uint64_t *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
 }
 
-// number of positions where the 3-bit symbol (p2 p1 p0) equals SYM, among the bits of m
+struct Blk { Vec8 lo, hi; };       // lo = counts + plane 0, hi = planes 1 and 2
+
+FMG_HD Blk load_blk(const OccView &ix, uint64_t p) {
+    const uint32_t *b = ix.blocks + (p >> kBlkShift) * kBlkWords;
+    Blk r;
+    r.lo = ld256_nc(b);
+    r.hi = ld256_nc(b + 8);
+    return r;
+}
+
+// positions where the 3-bit symbol (p2 p1 p0) equals SYM; p2m / np2m are p2 / ~p2 already ANDed with the mask
 template <int SYM>
 FMG_HD uint32_t match32(uint32_t p0, uint32_t p1, uint32_t p2m, uint32_t np2m) {
     const uint32_t a = (SYM & 1) ? p0 : ~p0;
@@ -83,61 +125,63 @@ FMG_HD uint32_t match32(uint32_t p0, uint32_t p1, uint32_t p2m, uint32_t np2m) {
     return a & b & ((SYM & 4) ? p2m : np2m);
 }
 
-struct LineRegs { uint4 c0, c1, a, b, d; };
-
-FMG_HD LineRegs load_line(const OccView &ix, uint64_t p) {
-    const uint4 *L = ix.lines + (p >> kLineShift) * kLineU4;
-    const uint32_t half = (uint32_t)(p >> 7) & 1u;
-    LineRegs r;
-    r.c0 = ld_line(L);
-    r.c1 = ld_line(L + 1);
-    r.a = ld_line(L + 2 + half);
-    r.b = ld_line(L + 4 + half);
-    r.d = ld_line(L + 6 + half);
-    return r;
-}
-
-// cnt[c] = number of symbols c in BWT[0, p), for p in [0, n_sym]
-FMG_HD void rank_from_line(const OccView &ix, const LineRegs &r, uint64_t p, uint64_t cnt[6]) {
-    const uint32_t o = (uint32_t)p & 255u, half = o >> 7, oo = o & 127u;
-    const uint32_t flip = half ? 0u : 0xffffffffu;     // below the middle: count [oo,128) and subtract
-    const uint32_t m0 = low_mask_word(oo, 0) ^ flip, m1 = low_mask_word(oo, 1) ^ flip;
-    const uint32_t m2 = low_mask_word(oo, 2) ^ flip, m3 = low_mask_word(oo, 3) ^ flip;
-    const uint32_t q0 = r.d.x & m0, q1 = r.d.y & m1, q2 = r.d.z & m2, q3 = r.d.w & m3;
-    const uint32_t n0 = ~r.d.x & m0, n1 = ~r.d.y & m1, n2 = ~r.d.z & m2, n3 = ~r.d.w & m3;
+// rel[c] = number of symbols c in BWT[superblock_start(p), p), c = 0..5, for p in [0, n_sym]
+FMG_HD void rank_rel(const Blk &B, uint64_t p, uint32_t rel[6]) {
+    const uint32_t o = (uint32_t)p & 127u, half = o >> 6, oo = o & 63u;
+    // the 64-symbol half that holds p: words 2*half, 2*half+1 of each plane
+    const uint32_t a0 = half ? B.lo.v[6] : B.lo.v[4], a1 = half ? B.lo.v[7] : B.lo.v[5];
+    const uint32_t b0 = half ? B.hi.v[2] : B.hi.v[0], b1 = half ? B.hi.v[3] : B.hi.v[1];
+    const uint32_t d0 = half ? B.hi.v[6] : B.hi.v[4], d1 = half ? B.hi.v[7] : B.hi.v[5];
+    // upper half: count [64, 64+oo) and add; lower half: count [oo, 64) and subtract
+    const uint32_t lo0 = oo >= 32u ? 0xffffffffu : ((1u << oo) - 1u);
+    const uint32_t lo1 = oo <= 32u ? 0u : ((1u << (oo - 32u)) - 1u);
+    const uint32_t flip = half ? 0u : 0xffffffffu;
+    const uint32_t m0 = lo0 ^ flip, m1 = lo1 ^ flip;
+    const uint32_t q0 = d0 & m0, q1 = d1 & m1, n0 = ~d0 & m0, n1 = ~d1 & m1;
     uint32_t pc[5];
-#define FMG_PC(S) pc[S] = popc32(match32<S>(r.a.x, r.b.x, q0, n0)) + popc32(match32<S>(r.a.y, r.b.y, q1, n1)) + \
-                          popc32(match32<S>(r.a.z, r.b.z, q2, n2)) + popc32(match32<S>(r.a.w, r.b.w, q3, n3));
+#define FMG_PC(S) pc[S] = popc32(match32<S>(a0, b0, q0, n0)) + popc32(match32<S>(a1, b1, q1, n1));
     FMG_PC(0) FMG_PC(1) FMG_PC(2) FMG_PC(3) FMG_PC(4)
 #undef FMG_PC
-    const uint32_t base[5] = { r.c0.x, r.c0.y, r.c0.z, r.c0.w, r.c1.x };
-    uint64_t sum = 0;
-    const uint64_t *sb = ix.super ? ix.super + ((p >> kSuperShift) << 3) : nullptr;
+    // five byte-packed 24-bit counts in w[0..3]
+    const uint32_t w0 = B.lo.v[0], w1 = B.lo.v[1], w2 = B.lo.v[2], w3 = B.lo.v[3];
+    uint32_t base[5];
+    base[0] = w0 & 0xffffffu;
+    base[1] = (w0 >> 24) | ((w1 & 0xffffu) << 8);
+    base[2] = (w1 >> 16) | ((w2 & 0xffu) << 16);
+    base[3] = w2 >> 8;
+    base[4] = w3 & 0xffffffu;
+    uint32_t sum = 0;
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
-        const uint32_t rel = half ? base[c] + pc[c] : base[c] - pc[c];
-        cnt[c] = (sb ? sb[c] : 0ull) + rel;
-        sum += cnt[c];
+        rel[c] = half ? base[c] + pc[c] : base[c] - pc[c];
+        sum += rel[c];
     }
-    cnt[5] = p - sum;      // N: the six counts add up to p
+    rel[5] = ((uint32_t)p & ((1u << kSuperShift) - 1u)) - sum;     // N: the six counts add up to p - superblock_start
 }
 
 // All six extensions of one bi-interval: fm6_extend, exact.c:72-88 (A.5).
-// far side = x[!is_back]; size[c] = ok[c].x[2]; far[c] = ok[c].x[!is_back]; near[c] = ok[c].x[is_back]
-struct Ext6 { uint64_t size[6], far[6], near[6]; };
+//   size[c] = ok[c].x[2];  near[c] = ok[c].x[is_back];  ok[c].x[!is_back] = cs[sbk][c] + relk[c] (far_of)
+struct Ext6 { uint64_t size[6], near[6]; uint32_t relk[6]; uint64_t sbk; };
 
 FMG_HD void extend6(const OccView &ix, uint64_t x_near, uint64_t x_far, uint64_t size, Ext6 &e) {
     // rld_rank2a(x_far-1, x_far-1+size): counts in BWT[0,x_far) and BWT[0,x_far+size)  (k=-1 <=> p=0)
     const uint64_t pk = x_far, pl = x_far + size;
-    const LineRegs rk = load_line(ix, pk);
-    const LineRegs rl = load_line(ix, pl);
-    uint64_t tk[6], tl[6];
-    rank_from_line(ix, rk, pk, tk);
-    rank_from_line(ix, rl, pl, tl);
+    const bool same = (pk >> kBlkShift) == (pl >> kBlkShift);
+    const Blk bk = load_blk(ix, pk);
+    Blk bl = bk;
+    if (!same) bl = load_blk(ix, pl);              // small intervals: both ranks read the same 64 bytes
+    uint32_t rl[6];
+    rank_rel(bk, pk, e.relk);
+    rank_rel(bl, pl, rl);
+    // a position that is a multiple of 2^24 belongs to the superblock it starts (all its counts are 0 there)
+    const uint64_t sbk = pk >> kSuperShift, sbl = pl >> kSuperShift;
+    e.sbk = sbk;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-        e.size[c] = tl[c] - tk[c];
-        e.far[c] = ix.C[c] + tk[c];
+    for (int c = 0; c < 6; ++c) e.size[c] = (uint64_t)rl[c] - (uint64_t)e.relk[c];
+    if (sbk != sbl) {                               // rare: the interval straddles a superblock boundary
+        const uint64_t *ck = ix.cs + sbk * 8, *cl = ix.cs + sbl * 8;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) e.size[c] += ld_u64(cl + c) - ld_u64(ck + c);
     }
     e.near[0] = x_near;                       // cumulative in the order $,T,G,C,A,N (exact.c:81-86)
     e.near[4] = e.near[0] + e.size[0];
@@ -154,6 +198,16 @@ FMG_HD uint64_t pick6(const uint64_t v[6], int c) {
     return r;
 }
 
+FMG_HD uint32_t pick6(const uint32_t v[6], int c) {
+    uint32_t r = v[0];
+    r = c == 1 ? v[1] : r; r = c == 2 ? v[2] : r; r = c == 3 ? v[3] : r;
+    r = c == 4 ? v[4] : r; r = c == 5 ? v[5] : r;
+    return r;
+}
+
+// ok[c].x[!is_back] = C[c] + rank(c, x_far)
+FMG_HD uint64_t far_of(const OccView &ix, const Ext6 &e, int c) { return ld_u64(ix.cs + e.sbk * 8 + c) + pick6(e.relk, c); }
+
 FMG_HD int comp6(int c) { return (c >= 1 && c <= 4) ? 5 - c : c; }   // fm6_comp, fermi.h:52
 
 // fm6_set_intv, fermi.h:53
@@ -164,18 +218,18 @@ FMG_HD Intv base_intv(const OccView &ix, int c) {
 }
 
 FMG_HD Intv ld_intv(const uint4 *p) {
-    const uint4 a = p[0], b = p[1];
+    const Vec8 a = ld256(p);
     Intv k;
-    k.x0 = (uint64_t)a.y << 32 | a.x; k.x1 = (uint64_t)a.w << 32 | a.z;
-    k.x2 = (uint64_t)b.y << 32 | b.x; k.info = (uint64_t)b.w << 32 | b.z;
+    k.x0 = (uint64_t)a.v[1] << 32 | a.v[0]; k.x1 = (uint64_t)a.v[3] << 32 | a.v[2];
+    k.x2 = (uint64_t)a.v[5] << 32 | a.v[4]; k.info = (uint64_t)a.v[7] << 32 | a.v[6];
     return k;
 }
 
 FMG_HD void st_intv(uint4 *p, const Intv &k) {
-    uint4 a, b;
-    a.x = (uint32_t)k.x0; a.y = (uint32_t)(k.x0 >> 32); a.z = (uint32_t)k.x1; a.w = (uint32_t)(k.x1 >> 32);
-    b.x = (uint32_t)k.x2; b.y = (uint32_t)(k.x2 >> 32); b.z = (uint32_t)k.info; b.w = (uint32_t)(k.info >> 32);
-    p[0] = a; p[1] = b;
+    Vec8 a;
+    a.v[0] = (uint32_t)k.x0; a.v[1] = (uint32_t)(k.x0 >> 32); a.v[2] = (uint32_t)k.x1; a.v[3] = (uint32_t)(k.x1 >> 32);
+    a.v[4] = (uint32_t)k.x2; a.v[5] = (uint32_t)(k.x2 >> 32); a.v[6] = (uint32_t)k.info; a.v[7] = (uint32_t)(k.info >> 32);
+    st256(p, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -278,7 +332,7 @@ FMG_HD void smem_lane(const SmemArgs &A, int64_t lane_slot, FetchFn fetch) {
 
         // ---- consume it
         // x[0]/x[1] of ok[c]: the far side is x[1] for a forward, x[0] for a backward extension
-#define FMG_OK(c, dst) do { const uint64_t nr_ = pick6(e.near, c), fr_ = pick6(e.far, c); \
+#define FMG_OK(c, dst) do { const uint64_t nr_ = pick6(e.near, c), fr_ = far_of(A.ix, e, c); \
                             (dst).x0 = back ? fr_ : nr_; (dst).x1 = back ? nr_ : fr_; (dst).x2 = pick6(e.size, c); } while (0)
         if (ph == PH_FWD) {                             // smem.c:22-34
             const int c = comp6(ld_u8(q + i));
@@ -286,7 +340,7 @@ FMG_HD void smem_lane(const SmemArgs &A, int64_t lane_slot, FetchFn fetch) {
             if (sc != ik.x2) {
                 if (ik.x2 != e.size[0]) st_intv(F + 2 * nF++, ik);
                 if (!sm && e.size[0]) {
-                    Intv s0; s0.x0 = e.near[0]; s0.x1 = e.far[0]; s0.x2 = e.size[0]; s0.info = (uint64_t)i;
+                    Intv s0; s0.x0 = e.near[0]; s0.x1 = far_of(A.ix, e, 0); s0.x2 = e.size[0]; s0.info = (uint64_t)i;
                     st_intv(F + 2 * nF++, s0);
                 }
             }
@@ -301,7 +355,7 @@ FMG_HD void smem_lane(const SmemArgs &A, int64_t lane_slot, FetchFn fetch) {
             }
         } else if (ph == PH_FWD_TAIL) {                 // smem.c:37-43
             if (e.size[0]) {
-                Intv s0; s0.x0 = e.near[0]; s0.x1 = e.far[0]; s0.x2 = e.size[0]; s0.info = (uint64_t)len;
+                Intv s0; s0.x0 = e.near[0]; s0.x1 = far_of(A.ix, e, 0); s0.x2 = e.size[0]; s0.info = (uint64_t)len;
                 st_intv(F + 2 * nF++, s0);
             }
             ph = PH_START_BWD;

@@ -53,12 +53,16 @@ __global__ void __launch_bounds__(256) k_rank2a(OccView ix, int64_t n, const uin
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t pk = k[i] + 1, pl = l[i] + 1;          // k == (uint64_t)-1 -> counts of the empty prefix
-    const LineRegs rk = load_line(ix, pk), rl = load_line(ix, pl);
-    uint64_t a[6], b[6];
-    rank_from_line(ix, rk, pk, a);
-    rank_from_line(ix, rl, pl, b);
+    const Blk bk = load_blk(ix, pk), bl = load_blk(ix, pl);
+    uint32_t a[6], b[6];
+    rank_rel(bk, pk, a);
+    rank_rel(bl, pl, b);
+    const uint64_t *ck = ix.cs + (pk >> kSuperShift) * 8, *cl = ix.cs + (pl >> kSuperShift) * 8;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) ok[6 * i + c] = a[c], ol[6 * i + c] = b[c];
+    for (int c = 0; c < 6; ++c) {
+        ok[6 * i + c] = ck[c] - ix.C[c] + a[c];
+        ol[6 * i + c] = cl[c] - ix.C[c] + b[c];
+    }
 }
 
 __global__ void __launch_bounds__(256) k_extend(OccView ix, int64_t n, const uint4 *__restrict__ ik,
@@ -72,7 +76,8 @@ __global__ void __launch_bounds__(256) k_extend(OccView ix, int64_t n, const uin
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
         Intv o;
-        o.x0 = b ? e.far[c] : e.near[c]; o.x1 = b ? e.near[c] : e.far[c]; o.x2 = e.size[c]; o.info = 0;
+        const uint64_t fr = far_of(ix, e, c);
+        o.x0 = b ? fr : e.near[c]; o.x1 = b ? e.near[c] : fr; o.x2 = e.size[c]; o.info = 0;
         st_intv(ok6 + 2 * (6 * i + c), o);
     }
 }
@@ -92,12 +97,12 @@ __global__ void __launch_bounds__(256) k_backward_search(OccView ix, int64_t n, 
         for (i = len - 2; i >= 0; --i) {
             c = q[i];
             const uint64_t pk = k, pl = l + 1;             // rank11(k-1), rank11(l)
-            const LineRegs rk = load_line(ix, pk), rl = load_line(ix, pl);
-            uint64_t a[6], b[6];
-            rank_from_line(ix, rk, pk, a);
-            rank_from_line(ix, rl, pl, b);
-            k = ix.C[c] + pick6(a, c);
-            l = ix.C[c] + pick6(b, c) - 1;
+            const Blk bk = load_blk(ix, pk), bl = load_blk(ix, pl);
+            uint32_t a[6], b[6];
+            rank_rel(bk, pk, a);
+            rank_rel(bl, pl, b);
+            k = ix.cs[(pk >> kSuperShift) * 8 + c] + pick6(a, c);
+            l = ix.cs[(pl >> kSuperShift) * 8 + c] + pick6(b, c) - 1;
             if (k > l) break;
         }
         if (!(k > l)) beg = k, end = l, sz = l - k + 1;
@@ -233,12 +238,12 @@ fmg_index_t *fmg_index_upload(const fmg_fmd_t *e, int device) {
     std::memcpy(idx->cnt, img.cnt, sizeof(idx->cnt));
     if (occ_build_device(img, idx) != 0) { delete idx; return nullptr; }
     OccView &v = idx->view;
-    v.lines = idx->d_lines; v.super = idx->d_super;
+    v.blocks = idx->d_blocks; v.cs = idx->d_cs;
     v.n_sym = img.mcnt[0]; v.n_seq = img.mcnt[1];
     for (int c = 0; c < 8; ++c) v.C[c] = img.cnt[c];
     cudaDeviceGetAttribute(&idx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (fmg_verbose >= 3)
-        std::fprintf(stderr, "[M::%s] %llu symbols, %llu sequences -> %.1f MB of occ lines on device %d (%d SMs)\n", __func__,
+        std::fprintf(stderr, "[M::%s] %llu symbols, %llu sequences -> %.1f MB of occ blocks on device %d (%d SMs)\n", __func__,
                      (unsigned long long)v.n_sym, (unsigned long long)v.n_seq, idx->bytes / 1e6, device, idx->n_sm);
     return idx;
 }
@@ -246,8 +251,8 @@ fmg_index_t *fmg_index_upload(const fmg_fmd_t *e, int device) {
 void fmg_index_free(fmg_index_t *idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);
-    cudaFree(idx->d_lines);
-    cudaFree(idx->d_super);
+    cudaFree(idx->d_blocks);
+    cudaFree(idx->d_cs);
     delete idx;
 }
 

@@ -6,19 +6,19 @@
 
 // k_smem launch shape: 128-thread blocks, as many as the register budget allows per SM
 #define SMEM_BLOCK 128
-#define SMEM_MIN_BLOCKS 4
+#define SMEM_MIN_BLOCKS 5
 #define SMEM_DEFAULT_OUT_CAP 64
 
 struct fmg_fmd_s { fmg::FmdImage img; };
 
 struct fmg_index_s {
     int device = 0, n_sm = 0;
-    uint4 *d_lines = nullptr;
-    uint64_t *d_super = nullptr;
-    uint64_t n_lines = 0, bytes = 0;
+    uint32_t *d_blocks = nullptr;
+    uint64_t *d_cs = nullptr;
+    uint64_t n_blocks = 0, bytes = 0;
     uint64_t mcnt[8] = {0}, cnt[8] = {0};
     fmg::OccView view;
 };
 
-// occ_build.cu: build the occ lines of `img` in the HBM of the current device; fills d_lines/d_super/n_lines/bytes
+// occ_build.cu: build the occ blocks of `img` in the HBM of the current device; fills d_blocks/d_cs/n_blocks/bytes
 int occ_build_device(const fmg::FmdImage &img, fmg_index_s *idx);

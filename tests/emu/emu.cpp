@@ -25,8 +25,8 @@ extern "C" {
 void *emu_index_build(const fmg_fmd_t *e) {
     EmuIndex *x = new EmuIndex;
     x->occ = build_occ_host(e->img);
-    x->view.lines = reinterpret_cast<const uint4 *>(x->occ.lines.data());
-    x->view.super = x->occ.super.empty() ? nullptr : x->occ.super.data();
+    x->view.blocks = x->occ.blocks.data();
+    x->view.cs = x->occ.cs.data();
     x->view.n_sym = e->img.mcnt[0];
     x->view.n_seq = e->img.mcnt[1];
     for (int c = 0; c < 8; ++c) x->view.C[c] = e->img.cnt[c];
@@ -39,8 +39,13 @@ void emu_rank2a(const void *_x, int64_t n, const uint64_t *k, const uint64_t *l,
     const OccView &ix = static_cast<const EmuIndex *>(_x)->view;
     for (int64_t i = 0; i < n; ++i) {
         const uint64_t pk = k[i] + 1, pl = l[i] + 1;      // k == -1 -> p = 0
-        rank_from_line(ix, load_line(ix, pk), pk, ok + 6 * i);
-        rank_from_line(ix, load_line(ix, pl), pl, ol + 6 * i);
+        uint32_t rk[6], rl[6];
+        rank_rel(load_blk(ix, pk), pk, rk);
+        rank_rel(load_blk(ix, pl), pl, rl);
+        for (int c = 0; c < 6; ++c) {
+            ok[6 * i + c] = ix.cs[(pk >> kSuperShift) * 8 + c] - ix.C[c] + rk[c];
+            ol[6 * i + c] = ix.cs[(pl >> kSuperShift) * 8 + c] - ix.C[c] + rl[c];
+        }
     }
 }
 
@@ -52,7 +57,7 @@ void emu_extend(const void *_x, int64_t n, const fmg_intv_t *ik, const uint8_t *
         extend6(ix, ik[i].x[b], ik[i].x[!b], ik[i].x[2], e);
         for (int c = 0; c < 6; ++c) {
             fmg_intv_t &o = ok6[6 * i + c];
-            o.x[!b] = e.far[c]; o.x[b] = e.near[c]; o.x[2] = e.size[c]; o.info = 0;
+            o.x[!b] = far_of(ix, e, c); o.x[b] = e.near[c]; o.x[2] = e.size[c]; o.info = 0;
         }
     }
 }
