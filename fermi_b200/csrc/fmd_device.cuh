@@ -60,9 +60,9 @@ FMG_HD uint32_t popc32(uint32_t v) {
 FMG_HD Vec8 ld256_nc(const void *p) {
     Vec8 r;
 #if defined(__CUDA_ARCH__)
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
-                 : "l"(p));
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+        : "l"(p));
 #else
     memcpy(&r, p, 32);
 #endif
@@ -161,11 +161,16 @@ FMG_HD void rank_rel(const Blk &B, uint64_t p, uint32_t rel[6]) {
 
 // All six extensions of one bi-interval: fm6_extend, exact.c:72-88 (A.5).
 //   size[c] = ok[c].x[2];  near[c] = ok[c].x[is_back];  ok[c].x[!is_back] = cs[sbk][c] + relk[c] (far_of)
-struct Ext6 { uint64_t size[6], near[6]; uint32_t relk[6]; uint64_t sbk; };
+// U is the coordinate type: uint32_t when the whole BWT has < 2^32 symbols (half the registers, ALU
+// work and scratch bytes), uint64_t otherwise.
+template <typename U> struct IntvT { U x0, x1, x2, info; };
+template <typename U> struct Ext6T { U size[6], near[6]; uint32_t relk[6]; uint64_t sbk; };
+typedef Ext6T<uint64_t> Ext6;
 
-FMG_HD void extend6(const OccView &ix, uint64_t x_near, uint64_t x_far, uint64_t size, Ext6 &e) {
+template <typename U>
+FMG_HD void extend6(const OccView &ix, U x_near, U x_far, U size, Ext6T<U> &e) {
     // rld_rank2a(x_far-1, x_far-1+size): counts in BWT[0,x_far) and BWT[0,x_far+size)  (k=-1 <=> p=0)
-    const uint64_t pk = x_far, pl = x_far + size;
+    const uint64_t pk = x_far, pl = (uint64_t)x_far + size;
     const bool same = (pk >> kBlkShift) == (pl >> kBlkShift);
     const Blk bk = load_blk(ix, pk);
     Blk bl = bk;
@@ -177,11 +182,11 @@ FMG_HD void extend6(const OccView &ix, uint64_t x_near, uint64_t x_far, uint64_t
     const uint64_t sbk = pk >> kSuperShift, sbl = pl >> kSuperShift;
     e.sbk = sbk;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) e.size[c] = (uint64_t)rl[c] - (uint64_t)e.relk[c];
+    for (int c = 0; c < 6; ++c) e.size[c] = (U)rl[c] - (U)e.relk[c];
     if (sbk != sbl) {                               // rare: the interval straddles a superblock boundary
         const uint64_t *ck = ix.cs + sbk * 8, *cl = ix.cs + sbl * 8;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) e.size[c] += ld_u64(cl + c) - ld_u64(ck + c);
+        for (int c = 0; c < 6; ++c) e.size[c] += (U)(ld_u64(cl + c) - ld_u64(ck + c));
     }
     e.near[0] = x_near;                       // cumulative in the order $,T,G,C,A,N (exact.c:81-86)
     e.near[4] = e.near[0] + e.size[0];
@@ -191,32 +196,29 @@ FMG_HD void extend6(const OccView &ix, uint64_t x_near, uint64_t x_far, uint64_t
     e.near[5] = e.near[1] + e.size[1];
 }
 
-FMG_HD uint64_t pick6(const uint64_t v[6], int c) {
-    uint64_t r = v[0];
-    r = c == 1 ? v[1] : r; r = c == 2 ? v[2] : r; r = c == 3 ? v[3] : r;
-    r = c == 4 ? v[4] : r; r = c == 5 ? v[5] : r;
-    return r;
-}
-
-FMG_HD uint32_t pick6(const uint32_t v[6], int c) {
-    uint32_t r = v[0];
+template <typename T>
+FMG_HD T pick6(const T v[6], int c) {
+    T r = v[0];
     r = c == 1 ? v[1] : r; r = c == 2 ? v[2] : r; r = c == 3 ? v[3] : r;
     r = c == 4 ? v[4] : r; r = c == 5 ? v[5] : r;
     return r;
 }
 
 // ok[c].x[!is_back] = C[c] + rank(c, x_far)
-FMG_HD uint64_t far_of(const OccView &ix, const Ext6 &e, int c) { return ld_u64(ix.cs + e.sbk * 8 + c) + pick6(e.relk, c); }
+template <typename U>
+FMG_HD U far_of(const OccView &ix, const Ext6T<U> &e, int c) { return (U)(ld_u64(ix.cs + e.sbk * 8 + c) + pick6(e.relk, c)); }
 
 FMG_HD int comp6(int c) { return (c >= 1 && c <= 4) ? 5 - c : c; }   // fm6_comp, fermi.h:52
 
 // fm6_set_intv, fermi.h:53
-FMG_HD Intv base_intv(const OccView &ix, int c) {
-    Intv k;
-    k.x0 = ix.C[c]; k.x2 = ix.C[c + 1] - ix.C[c]; k.x1 = ix.C[comp6(c)]; k.info = 0;
+template <typename U>
+FMG_HD IntvT<U> base_intv(const OccView &ix, int c) {
+    IntvT<U> k;
+    k.x0 = (U)ix.C[c]; k.x2 = (U)(ix.C[c + 1] - ix.C[c]); k.x1 = (U)ix.C[comp6(c)]; k.info = 0;
     return k;
 }
 
+// 32-byte records (fmintv_t) in global memory
 FMG_HD Intv ld_intv(const uint4 *p) {
     const Vec8 a = ld256(p);
     Intv k;
@@ -230,6 +232,26 @@ FMG_HD void st_intv(uint4 *p, const Intv &k) {
     a.v[0] = (uint32_t)k.x0; a.v[1] = (uint32_t)(k.x0 >> 32); a.v[2] = (uint32_t)k.x1; a.v[3] = (uint32_t)(k.x1 >> 32);
     a.v[4] = (uint32_t)k.x2; a.v[5] = (uint32_t)(k.x2 >> 32); a.v[6] = (uint32_t)k.info; a.v[7] = (uint32_t)(k.info >> 32);
     st256(p, a);
+}
+
+// candidate entries of the per-lane scratch lists: 4 x U (32 bytes for u64, 16 bytes for u32 coordinates)
+FMG_HD IntvT<uint64_t> ld_cand(const IntvT<uint64_t> *p) {
+    const Intv k = ld_intv(reinterpret_cast<const uint4 *>(p));
+    IntvT<uint64_t> r; r.x0 = k.x0; r.x1 = k.x1; r.x2 = k.x2; r.info = k.info;
+    return r;
+}
+FMG_HD void st_cand(IntvT<uint64_t> *p, const IntvT<uint64_t> &k) {
+    Intv r; r.x0 = k.x0; r.x1 = k.x1; r.x2 = k.x2; r.info = k.info;
+    st_intv(reinterpret_cast<uint4 *>(p), r);
+}
+FMG_HD IntvT<uint32_t> ld_cand(const IntvT<uint32_t> *p) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(p);
+    IntvT<uint32_t> r; r.x0 = a.x; r.x1 = a.y; r.x2 = a.z; r.info = a.w;
+    return r;
+}
+FMG_HD void st_cand(IntvT<uint32_t> *p, const IntvT<uint32_t> &k) {
+    uint4 a; a.x = k.x0; a.y = k.x1; a.z = k.x2; a.w = k.info;
+    *reinterpret_cast<uint4 *>(p) = a;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -251,7 +273,7 @@ struct SmemArgs {
     const uint64_t *off;
     int64_t n_reads;
     int self_match;
-    uint4 *F, *W;
+    void *F, *W;              // per-lane candidate lists: cap entries of 4 x U each
     int cap;
     uint4 *out;
     int out_cap;
@@ -273,10 +295,11 @@ FMG_HD bool warp_any(bool v) {
 //                         [warp vote]         leave when no lane has a request; reconverges the warp
 //                         [converged, long]   extend6: two line loads + popcounts for all requesting lanes
 //                         [divergent, short]  consume the result according to the lane's phase
-template <class FetchFn>
+template <typename U, class FetchFn>
 FMG_HD void smem_lane(const SmemArgs &A, int64_t lane_slot, FetchFn fetch) {
-    uint4 *F = A.F + (size_t)lane_slot * A.cap * 2;
-    uint4 *W = A.W + (size_t)lane_slot * A.cap * 2;
+    typedef IntvT<U> Cand;
+    Cand *F = static_cast<Cand *>(A.F) + (size_t)lane_slot * A.cap;
+    Cand *W = static_cast<Cand *>(A.W) + (size_t)lane_slot * A.cap;
     const int sm = A.self_match;
     int ph = PH_FETCH;
     int64_t r = 0;
@@ -284,8 +307,8 @@ FMG_HD void smem_lane(const SmemArgs &A, int64_t lane_slot, FetchFn fetch) {
     uint4 *out = nullptr;
     int len = 0, x = 0, i = 0, j = 0, nF = 0, nprev = 0, ncurr = 0, first_pass = 0, ret = 0;
     int call_base = 0, nmem = 0, last_start = 0;
-    uint64_t last_x2 = 0;
-    Intv ik = {0, 0, 0, 0};     // FWD: the interval being extended; BWD: the candidate p being extended
+    U last_x2 = 0;
+    Cand ik = {0, 0, 0, 0};     // FWD: the interval being extended; BWD: the candidate p being extended
 
     for (;;) {
         // ---- advance to the next extension request (no index access in here)
@@ -301,12 +324,12 @@ FMG_HD void smem_lane(const SmemArgs &A, int64_t lane_slot, FetchFn fetch) {
                 nmem = 0; x = 0;
                 ph = PH_BEGIN;
             } else if (ph == PH_BEGIN) {                // begin fm6_smem1_core at x (smem.c:19-21)
-                ik = base_intv(A.ix, ld_u8(q + x));
-                ik.info = (uint64_t)(x + 1);
+                ik = base_intv<U>(A.ix, ld_u8(q + x));
+                ik.info = (U)(x + 1);
                 i = x + 1; nF = 0;
                 ph = PH_FWD;
                 if (i == len) {                         // smem.c:35-36
-                    st_intv(F + 2 * nF++, ik);
+                    st_cand(F + nF++, ik);
                     ph = sm ? PH_START_BWD : PH_FWD_TAIL;
                 }
             } else {                                    // PH_START_BWD: forward sweep finished (smem.c:45-50)
@@ -315,7 +338,7 @@ FMG_HD void smem_lane(const SmemArgs &A, int64_t lane_slot, FetchFn fetch) {
                     if (x >= len) { A.rec_cnt[r] = (uint32_t)nmem; ph = PH_FETCH; } else ph = PH_BEGIN;
                     continue;
                 }
-                ik = ld_intv(F + 2 * (nF - 1));         // the longest match is the last push = first candidate
+                ik = ld_cand(F + (nF - 1));         // the longest match is the last push = first candidate
                 ret = (int)ik.info;
                 nprev = nF; first_pass = 1; i = x - 1; j = 0; ncurr = 0; call_base = nmem;
                 ph = PH_BWD;
@@ -325,60 +348,68 @@ FMG_HD void smem_lane(const SmemArgs &A, int64_t lane_slot, FetchFn fetch) {
         if (!warp_any(active)) return;
         if (!active) continue;
 
-        // ---- the one extension of this trip (converged across the warp)
+        // ---- the one extension of this trip (converged across the warp).  The query base it will be
+        // consumed with and the next candidate of the backward pass are requested first, so that their
+        // latency overlaps the two block loads instead of following them.
         const int back = (ph == PH_BWD);
-        Ext6 e;
+        const int qc = (ph == PH_FWD_TAIL || i < 0) ? 0 : (int)ld_u8(q + i);
+        const bool have_nxt = back && j + 1 < nprev;       // entry j+1 of the list being read is final (writes go to <= j)
+        Cand nxt = ik;
+        if (have_nxt) nxt = ld_cand(first_pass ? F + (nF - 2 - j) : W + (j + 1));
+        Ext6T<U> e;
         extend6(A.ix, back ? ik.x1 : ik.x0, back ? ik.x0 : ik.x1, ik.x2, e);
 
         // ---- consume it
         // x[0]/x[1] of ok[c]: the far side is x[1] for a forward, x[0] for a backward extension
-#define FMG_OK(c, dst) do { const uint64_t nr_ = pick6(e.near, c), fr_ = far_of(A.ix, e, c); \
+#define FMG_OK(c, dst) do { const U nr_ = pick6(e.near, c), fr_ = far_of(A.ix, e, c); \
                             (dst).x0 = back ? fr_ : nr_; (dst).x1 = back ? nr_ : fr_; (dst).x2 = pick6(e.size, c); } while (0)
         if (ph == PH_FWD) {                             // smem.c:22-34
-            const int c = comp6(ld_u8(q + i));
-            const uint64_t sc = pick6(e.size, c);
+            const int c = comp6(qc);
+            const U sc = pick6(e.size, c);
             if (sc != ik.x2) {
-                if (ik.x2 != e.size[0]) st_intv(F + 2 * nF++, ik);
+                if (ik.x2 != e.size[0]) st_cand(F + nF++, ik);
                 if (!sm && e.size[0]) {
-                    Intv s0; s0.x0 = e.near[0]; s0.x1 = far_of(A.ix, e, 0); s0.x2 = e.size[0]; s0.info = (uint64_t)i;
-                    st_intv(F + 2 * nF++, s0);
+                    Cand s0; s0.x0 = e.near[0]; s0.x1 = far_of(A.ix, e, 0); s0.x2 = e.size[0]; s0.info = (U)i;
+                    st_cand(F + nF++, s0);
                 }
             }
             const bool stop = sm ? sc < 2 : sc == 0;
             if (stop) ph = PH_START_BWD;
             else {
-                FMG_OK(c, ik); ik.info = (uint64_t)(i + 1);
+                FMG_OK(c, ik); ik.info = (U)(i + 1);
                 if (++i == len) {                       // reached the end of the read (smem.c:35-36)
-                    st_intv(F + 2 * nF++, ik);
+                    st_cand(F + nF++, ik);
                     ph = sm ? PH_START_BWD : PH_FWD_TAIL;
                 }
             }
         } else if (ph == PH_FWD_TAIL) {                 // smem.c:37-43
             if (e.size[0]) {
-                Intv s0; s0.x0 = e.near[0]; s0.x1 = far_of(A.ix, e, 0); s0.x2 = e.size[0]; s0.info = (uint64_t)len;
-                st_intv(F + 2 * nF++, s0);
+                Cand s0; s0.x0 = e.near[0]; s0.x1 = far_of(A.ix, e, 0); s0.x2 = e.size[0]; s0.info = (U)len;
+                st_cand(F + nF++, s0);
             }
             ph = PH_START_BWD;
         } else {                                        // backward sweep, smem.c:51-75; ik is the candidate p
-            const int c = i < 0 ? 0 : (int)ld_u8(q + i);
-            const uint64_t sc = pick6(e.size, c);
+            const int c = qc;
+            const U sc = pick6(e.size, c);
             const bool fl = e.size[0] != 0 && ik.x1 < A.ix.n_seq;
             const bool cont = sm ? sc > 1 : sc != 0;
             if ((!cont || fl || i == -1) && (ncurr == 0 || fl) &&
                 (fl || nmem == call_base || i + 1 < last_start)) {
-                Intv m = ik;
-                m.info |= (uint64_t)(e.size[0] != 0) << 63 | (uint64_t)(i + 1) << 32;
+                Intv m; m.x0 = ik.x0; m.x1 = ik.x1; m.x2 = ik.x2;
+                m.info = (uint64_t)ik.info | (uint64_t)(e.size[0] != 0) << 63 | (uint64_t)(i + 1) << 32;
                 if (nmem < A.out_cap) st_intv(out + 2 * nmem, m);
                 ++nmem; last_start = i + 1;
             }
             if (cont && (ik.x1 < A.ix.n_seq || ncurr == 0 || sc != last_x2)) {
-                Intv n; FMG_OK(c, n); n.info = ik.info;
-                st_intv(W + 2 * ncurr++, n);
+                Cand n; FMG_OK(c, n); n.info = ik.info;
+                st_cand(W + ncurr++, n);
                 last_x2 = sc;
             }
-            if (++j == nprev) {
+            if (++j < nprev) ik = nxt;
+            else {
                 if (ncurr != 0 && i != -1) {            // next backward position over the survivors
                     nprev = ncurr; ncurr = 0; j = 0; --i; first_pass = 0;
+                    ik = ld_cand(W);
                 } else {
                     // end of this fm6_smem1_core call: records were pushed by decreasing start (smem.c:76)
                     int lo = call_base, hi = (nmem < A.out_cap ? nmem : A.out_cap) - 1;
@@ -391,7 +422,6 @@ FMG_HD void smem_lane(const SmemArgs &A, int64_t lane_slot, FetchFn fetch) {
                     else ph = PH_BEGIN;
                 }
             }
-            if (ph == PH_BWD) ik = ld_intv(first_pass ? F + 2 * (nF - 1 - j) : W + 2 * j);   // next candidate
         }
 #undef FMG_OK
     }

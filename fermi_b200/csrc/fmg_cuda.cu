@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) k_extend(OccView ix, int64_t n, const uin
     const Intv p = ld_intv(ik + 2 * i);
     const int b = is_back[i] != 0;
     Ext6 e;
-    extend6(ix, b ? p.x1 : p.x0, b ? p.x0 : p.x1, p.x2, e);
+    extend6<uint64_t>(ix, b ? p.x1 : p.x0, b ? p.x0 : p.x1, p.x2, e);
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
         Intv o;
@@ -110,9 +110,11 @@ __global__ void __launch_bounds__(256) k_backward_search(OccView ix, int64_t n, 
     sa_beg[r] = beg; sa_end[r] = end; size[r] = sz;
 }
 
-__global__ void __launch_bounds__(SMEM_BLOCK, SMEM_MIN_BLOCKS) k_smem(SmemArgs A) {
+// U = coordinate type: k_smem<uint32_t> for indexes of < 2^32 symbols, k_smem<uint64_t> beyond
+template <typename U>
+__global__ void __launch_bounds__(SMEM_BLOCK, sizeof(U) == 4 ? SMEM_MIN_BLOCKS_U32 : SMEM_MIN_BLOCKS_U64) k_smem(SmemArgs A) {
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    smem_lane(A, slot, [&]() -> int64_t { return (int64_t)atomicAdd(A.next_read, 1ull); });
+    smem_lane<U>(A, slot, [&]() -> int64_t { return (int64_t)atomicAdd(A.next_read, 1ull); });
 }
 
 // ---- compaction of the per-read record slots -------------------------------------------------
@@ -337,7 +339,9 @@ struct fmg_smem_session_s {
     int64_t max_reads = 0;
     int max_len = 0, cap = 0, out_cap = 0;
     int grid = 0, n_lanes = 0;
-    uint4 *F = nullptr, *W = nullptr, *slots = nullptr, *mem = nullptr;
+    void *F = nullptr, *W = nullptr;
+    uint4 *slots = nullptr, *mem = nullptr;
+    bool wide = true;                          // 64-bit coordinates (index of >= 2^32 symbols)
     uint32_t *rec_cnt = nullptr;
     uint64_t *mem_off = nullptr, *tile_sum = nullptr;
     unsigned long long *ctrl = nullptr;        // [0] next read, [1] overflow count, [2] total records
@@ -373,16 +377,18 @@ fmg_smem_session_t *fmg_smem_session_create(const fmg_index_t *idx, int64_t max_
     fmg_smem_session_t *s = new fmg_smem_session_s;
     s->idx = idx; s->max_reads = max_reads; s->max_len = max_len;
     s->cap = 2 * max_len + 2;
+    s->wide = idx->view.n_sym + 256 >= (1ull << 32) || std::getenv("FMG_FORCE_WIDE") != nullptr;
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_smem, SMEM_BLOCK, 0);
+    if (s->wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_smem<uint64_t>, SMEM_BLOCK, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_smem<uint32_t>, SMEM_BLOCK, 0);
     if (per_sm < 1) per_sm = 1;
     s->grid = idx->n_sm * per_sm;
     s->n_lanes = s->grid * SMEM_BLOCK;
     const int64_t n_tiles = (max_reads + 1 + kScanTile - 1) / kScanTile;
     bool ok = false;
     do {
-        CUDA_TRY(cudaMalloc(&s->F, (size_t)s->n_lanes * s->cap * 32), break);
-        CUDA_TRY(cudaMalloc(&s->W, (size_t)s->n_lanes * s->cap * 32), break);
+        CUDA_TRY(cudaMalloc(&s->F, (size_t)s->n_lanes * s->cap * (s->wide ? 32 : 16)), break);
+        CUDA_TRY(cudaMalloc(&s->W, (size_t)s->n_lanes * s->cap * (s->wide ? 32 : 16)), break);
         CUDA_TRY(cudaMalloc(&s->rec_cnt, (size_t)(max_reads + 1) * 4), break);
         CUDA_TRY(cudaMalloc(&s->mem_off, (size_t)(max_reads + 1) * 8), break);
         CUDA_TRY(cudaMalloc(&s->tile_sum, (size_t)n_tiles * 8), break);
@@ -393,8 +399,8 @@ fmg_smem_session_t *fmg_smem_session_create(const fmg_index_t *idx, int64_t max_
     } while (0);
     if (!ok) { fmg_smem_session_destroy(s); return nullptr; }
     if (fmg_verbose >= 4)
-        std::fprintf(stderr, "[M::%s] %d blocks x %d lanes (%d blocks/SM), %d candidate slots/lane, %d record slots/read\n",
-                     __func__, s->grid, SMEM_BLOCK, per_sm, s->cap, s->out_cap);
+        std::fprintf(stderr, "[M::%s] %d blocks x %d lanes (%d blocks/SM), %d-bit coordinates, %d candidate slots/lane, %d record slots/read\n",
+                     __func__, s->grid, SMEM_BLOCK, per_sm, s->wide ? 64 : 32, s->cap, s->out_cap);
     return s;
 }
 
@@ -426,7 +432,8 @@ static int session_enqueue(fmg_smem_session_t *s, int64_t n, const uint8_t *d_se
         }
         CUDA_TRY(cudaEventRecord(e0, st), return -1);
     }
-    k_smem<<<grid, SMEM_BLOCK, 0, st>>>(A);
+    if (s->wide) k_smem<uint64_t><<<grid, SMEM_BLOCK, 0, st>>>(A);
+    else k_smem<uint32_t><<<grid, SMEM_BLOCK, 0, st>>>(A);
     LAUNCH_CHECK(return -1);
     if (s->timing) {
         CUDA_TRY(cudaEventRecord(e1, st), return -1);

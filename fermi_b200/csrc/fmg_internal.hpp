@@ -6,7 +6,8 @@
 
 // k_smem launch shape: 128-thread blocks, as many as the register budget allows per SM
 #define SMEM_BLOCK 128
-#define SMEM_MIN_BLOCKS 5
+#define SMEM_MIN_BLOCKS_U32 6
+#define SMEM_MIN_BLOCKS_U64 5
 #define SMEM_DEFAULT_OUT_CAP 64
 
 struct fmg_fmd_s { fmg::FmdImage img; };

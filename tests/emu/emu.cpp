@@ -54,7 +54,7 @@ void emu_extend(const void *_x, int64_t n, const fmg_intv_t *ik, const uint8_t *
     for (int64_t i = 0; i < n; ++i) {
         const int b = is_back[i] != 0;
         Ext6 e;
-        extend6(ix, ik[i].x[b], ik[i].x[!b], ik[i].x[2], e);
+        extend6<uint64_t>(ix, ik[i].x[b], ik[i].x[!b], ik[i].x[2], e);
         for (int c = 0; c < 6; ++c) {
             fmg_intv_t &o = ok6[6 * i + c];
             o.x[!b] = far_of(ix, e, c); o.x[b] = e.near[c]; o.x[2] = e.size[c]; o.info = 0;
@@ -64,7 +64,7 @@ void emu_extend(const void *_x, int64_t n, const fmg_intv_t *ik, const uint8_t *
 
 // runs smem_lane with `n_lanes` emulated lanes (executed one after the other; lanes are independent)
 int emu_smem(const void *_x, int64_t n, const uint8_t *seq, const uint64_t *off, int self_match, int n_lanes,
-             int out_cap, fmg_intv_t **mem, uint64_t *mem_off) {
+             int out_cap, int wide, fmg_intv_t **mem, uint64_t *mem_off) {
     const EmuIndex *x = static_cast<const EmuIndex *>(_x);
     int max_len = 1;
     for (int64_t i = 0; i < n; ++i) if ((int)(off[i + 1] - off[i]) > max_len) max_len = (int)(off[i + 1] - off[i]);
@@ -79,7 +79,9 @@ int emu_smem(const void *_x, int64_t n, const uint8_t *seq, const uint64_t *off,
     // interleave the lanes' reads like concurrent lanes would: lane t takes reads t, t+n_lanes, ...
     for (int t = 0; t < n_lanes; ++t) {
         int64_t cur = t;
-        smem_lane(A, t, [&]() { int64_t r = cur; cur += n_lanes; return r; });
+        auto fetch = [&]() { int64_t r = cur; cur += n_lanes; return r; };
+        if (wide) smem_lane<uint64_t>(A, t, fetch);      // 64-bit coordinates (any index size)
+        else smem_lane<uint32_t>(A, t, fetch);           // 32-bit coordinates (BWT < 2^32 symbols)
     }
     int overflow = 0;
     mem_off[0] = 0;

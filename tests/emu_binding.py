@@ -27,7 +27,7 @@ class Emu:
         L.emu_index_free.argtypes = [C.c_void_p]
         L.emu_rank2a.argtypes = [C.c_void_p, C.c_int64, H.u64p, H.u64p, H.u64p, H.u64p]
         L.emu_extend.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, H.u8p, C.c_void_p]
-        L.emu_smem.argtypes = [C.c_void_p, C.c_int64, H.u8p, H.u64p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), H.u64p]
+        L.emu_smem.argtypes = [C.c_void_p, C.c_int64, H.u8p, H.u64p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), H.u64p]
         L.emu_smem.restype = C.c_int
         L.fmg_free.argtypes = [C.c_void_p]
 
@@ -53,12 +53,12 @@ class Emu:
         self.lib.emu_extend(x, len(ik), ik.ctypes.data, H._ptr(is_back, H.u8p), ok.ctypes.data)
         return ok
 
-    def smem(self, x, seq, off, self_match, n_lanes=7, out_cap=64):
+    def smem(self, x, seq, off, self_match, n_lanes=7, out_cap=64, wide=0):
         seq = np.ascontiguousarray(seq, np.uint8)
         off = np.ascontiguousarray(off, np.uint64)
         mo = np.zeros(len(off), np.uint64)
         mem = C.c_void_p()
-        ov = self.lib.emu_smem(x, len(off) - 1, H._ptr(seq, H.u8p), H._ptr(off, H.u64p), self_match, n_lanes, out_cap,
+        ov = self.lib.emu_smem(x, len(off) - 1, H._ptr(seq, H.u8p), H._ptr(off, H.u64p), self_match, n_lanes, out_cap, wide,
                                C.byref(mem), H._ptr(mo, H.u64p))
         tot = int(mo[-1])
         rec = np.frombuffer(C.string_at(mem.value, tot * 32), dtype=H.INTV).copy() if tot else np.zeros(0, H.INTV)

@@ -92,6 +92,19 @@ def test_fresh_inputs_vs_oracle_100k_reads(fb, oracle, tmp_path):
     idx.close()
 
 
+def test_64bit_coordinate_kernel_matches_too(fb, monkeypatch):
+    """indexes of >= 2^32 symbols use k_smem<uint64_t>; force it on a small index and compare with the vectors."""
+    monkeypatch.setenv("FMG_FORCE_WIDE", "1")
+    for case in golden_cases():
+        g, fmd = _load(case)
+        idx = fb.FmdIndex(fb.Fmd.restore(fmd), 0)
+        seq, off = H.reads_to_flat(g["q"])
+        for sm, rk, ok_ in ((0, "smem0", "moff0"), (1, "smem1", "moff1")):
+            rec, mo = fb.fm6_smem(idx, seq, off, sm)
+            assert np.array_equal(mo, g[ok_]) and np.array_equal(rec, g[rk])
+        idx.close()
+
+
 def test_ragged_empty_and_multibatch(fb, oracle):
     """empty / 1-base / ragged reads, and the multi-batch host pipeline (tiny batches force many)."""
     import ctypes as C

@@ -96,9 +96,10 @@ def test_device_core_on_host_matches_reference_vectors(emu, case):
     assert np.array_equal(emu.extend(x, g["ik"], g["is_back"]), g["ext"])
     seq, off = H.reads_to_flat(g["q"])
     for sm, rk, ok_ in ((0, "smem0", "moff0"), (1, "smem1", "moff1")):
-        rec, mo, ov = emu.smem(x, seq, off, sm, n_lanes=5, out_cap=128)
-        assert ov == 0
-        assert np.array_equal(mo, g[ok_]) and np.array_equal(rec, g[rk])
+        for wide in (0, 1):     # 32-bit and 64-bit coordinate instantiations of the lane
+            rec, mo, ov = emu.smem(x, seq, off, sm, n_lanes=5, out_cap=128, wide=wide)
+            assert ov == 0
+            assert np.array_equal(mo, g[ok_]) and np.array_equal(rec, g[rk])
     # a slot capacity that is too small must be reported, never silently truncated
     rec, mo, ov = emu.smem(x, seq, off, 0, n_lanes=3, out_cap=2)
     assert ov == 1
