@@ -328,6 +328,13 @@ def run_ours(a):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         achieved = a.reads * bytes_per_read / (k_ms_step_max / 1e3) / 1e9
+        traffic = None            # DRAM bytes per k_smem launch from the committed `ncu --set full` capture
+        try:
+            import glob
+            tr = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_smem_traffic.json")))[-1]))
+            traffic = tr["traffic_bytes_per_launch"] * (B / tr["reads_per_launch"])
+        except Exception:
+            pass
         out = {
             "metric": "reads/sec through SMEM (fm6_smem)", "value": total_reads / (step_ms_max / 1e3), "unit": "reads/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": step_ms_max, "higher_is_better": True,
@@ -341,9 +348,10 @@ def run_ours(a):
                 "counter_sample": "instrumented oracle on the first %d reads" % sample_n},
             "clocks": clocks,
             "gpu_launches": int(launches_timed),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_smem", "kernel_ms_per_step": k_ms_step_max, "launches_per_step": k_n // max(1, a.steps),
-                         "algorithmic_bytes_per_read": bytes_per_read, "peak_source": peak_src,
+                         "algorithmic_bytes_per_read": bytes_per_read, "algorithmic_bytes_per_launch": bytes_per_read * B,
+                         "peak_source": peak_src,
                          "frac_of_8TBs": achieved / 8000.0},
         }
         if e2e:
