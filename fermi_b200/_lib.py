@@ -46,6 +46,11 @@ _PROTOS = {
     "fmg_smem_session_set_timing": (None, [C.c_void_p, C.c_int]),
     "fmg_smem_session_kernel_ms": (C.c_double, [C.c_void_p, C.POINTER(C.c_int)]),
     "fmg_launch_count": (C.c_uint64, []),
+    # overlap / unitig
+    "fmg_overlap_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, u64p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, vpp, u64p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fmg_unitig_assemble": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, u64p, C.c_void_p, C.c_void_p, C.c_char_p, u64p]),
+    "fmg_unitig": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, u64p]),
     # construction + synthetic data
     "fmg_build_bwt": (C.c_int, [C.c_int, C.c_int64, u8p, u8p]),
     "fmg_synth_genome": (None, [C.c_uint64, C.c_int64, u8p]),

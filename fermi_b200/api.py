@@ -197,6 +197,46 @@ class SmemSession:
             pass
 
 
+def fm6_overlap(idx, min_match, ids=None, first=0, step=1, n=None, max_len=128):
+    """Per-sequence overlap records (fm_retrieve + fm6_is_contained + fm6_get_nei + check_left_simple,
+    unitig.c:77-204).  Returns dict(rec[n,10], nei INTV[], nei_off[n+1], seq[n,max_len], len[n], ext[n,max_len])."""
+    if ids is not None:
+        ids = np.ascontiguousarray(ids, np.uint64)
+        n = len(ids)
+    rec = np.zeros((n, 10), np.int64)
+    off = np.zeros(n + 1, np.uint64)
+    seq = np.zeros((n, max_len), np.uint8)
+    ext = np.zeros((n, max_len), np.uint8)
+    ln = np.zeros(n, np.int32)
+    nei = C.c_void_p()
+    rc = lib().fmg_overlap_batch(idx.h, int(min_match), n, _p(ids, u64p) if ids is not None else None, first, step, max_len,
+                                 rec.ctypes.data, C.byref(nei), _p(off, u64p), seq.ctypes.data, ln.ctypes.data, ext.ctypes.data)
+    _check(rc, "fm6_overlap")
+    tot = int(off[-1])
+    out = np.frombuffer(C.string_at(nei.value, tot * 32), dtype=INTV).copy() if tot else np.zeros(0, INTV)
+    lib().fmg_free(nei)
+    return dict(rec=rec, nei=out, nei_off=off, seq=seq, len=ln, ext=ext)
+
+
+def fm6_unitig_assemble(n_seq, min_match, o, out_path):
+    """The unitig walk (unitig.c:227-362) over the overlap records `o` of all n_seq sequences; writes MAG text."""
+    n = C.c_uint64()
+    nei = np.ascontiguousarray(o["nei"], INTV)
+    if len(nei) == 0:
+        nei = np.zeros(1, INTV)
+    _check(lib().fmg_unitig_assemble(n_seq, o["seq"].shape[1], int(min_match), o["rec"].ctypes.data, nei.ctypes.data,
+                                     _p(np.ascontiguousarray(o["nei_off"], np.uint64), u64p), o["seq"].ctypes.data, o["ext"].ctypes.data,
+                                     str(out_path).encode(), C.byref(n)), "fm6_unitig_assemble")
+    return n.value
+
+
+def fm6_unitig(idx, min_match, out_path, max_len=0):
+    """fm6_unitig (unitig.c:378) / `fermi unitig -l`: MAG records to out_path; returns the number of unitigs."""
+    n = C.c_uint64()
+    _check(lib().fmg_unitig(idx.h, int(min_match), int(max_len), str(out_path).encode(), C.byref(n)), "fm6_unitig")
+    return n.value
+
+
 def fm_build_bwt(text, device=0):
     """BWT of the FMD text on the GPU (replaces fm_bwtgen/ksa_bwt, build.c:5, ksa.c:231)."""
     text = np.ascontiguousarray(text, np.uint8)

@@ -1,0 +1,341 @@
+// Device-side core of the overlap path of `fermi unitig` (unitig.c:38-204):
+//   retrieve_lane   fm_retrieve (exact.c:59-70): LF walk that spells one indexed sequence
+//   overlap_lane    per sequence: fm6_is_contained (unitig.c:77-91) -> fm6_get_nei (unitig.c:93-179)
+//                   -> check_left_simple (unitig.c:186-204)
+// Everything the unitig walk (unitig_unidir / unitig1, unitig.c:227-317) asks the index is a pure function
+// of ONE read: its right neighbours, the consensus extension towards them and the simple left check of a
+// unique neighbour.  The GPU computes that record for every sequence of the index in parallel; the walk
+// itself then only chases these records (unitig_host.cpp).
+//
+// Control flow is written as the natural nested loops of the reference.  Lanes of a warp are on
+// different sequences and in different loops, so every extension goes through ext_sync(): a NOINLINE
+// function, i.e. one copy of the code that all call sites jump to, which starts with a full-warp vote.
+// The vote lines the 32 lanes up in time at the same program counter, so the expensive part (block
+// loads + popcounts) executes converged, whatever loop each lane came from.
+//
+// Same source compiles for the host (tests/emu) -- checker only, never linked by the product.
+#pragma once
+#include "fmd_device.cuh"
+
+#if defined(__CUDACC__)
+#define FMG_NOINLINE __device__ __noinline__
+#else
+#define FMG_NOINLINE
+#endif
+
+namespace fmg {
+
+struct OverlapArgs {
+    OccView ix;
+    int min_match;
+    int64_t n;                  // sequences in this batch
+    const uint8_t *seq;         // n x max_len nt6 bytes (retrieve_lane output)
+    const int32_t *len;         // n
+    int max_len;
+    // per-lane scratch
+    uint8_t *sbuf; int s_cap;   // growing consensus string (unitig.c:141)
+    void *A, *B; int cap;       // candidate interval lists (4 x U per entry)
+    int32_t *cat;               // category per candidate (unitig.c:105-151)
+    // per-sequence output
+    int64_t *rec;               // 10 per sequence, see OV_* below
+    uint4 *nei; int nei_cap;    // neighbour records (fmintv_t: x = interval of the neighbour, info = overlap length)
+    uint32_t *nei_cnt;
+    uint8_t *ext;               // n x max_len: bases appended to the read (s[len .. s_len))
+    unsigned long long *next;
+};
+
+// rec[] layout (the first nine match oracle/ref_harness.c:refh_overlap_batch)
+enum { OV_K = 0, OV_LEN, OV_CONTAINED, OV_X0, OV_X1, OV_X2, OV_RBEG, OV_NNEI, OV_SLEN, OV_LEFT, OV_NREC };
+// OV_CONTAINED: 0, -1 contained (unitig.c:86,89), -9 not longer than min_match (unitig.c:288), -100 scratch overflow
+// OV_LEFT: check_left_simple of the unique neighbour: 0 ok, -1 backward bifurcation, 1 not evaluated
+
+template <typename U>
+FMG_NOINLINE bool ext_sync(const OccView &ix, bool active, U x_near, U x_far, U size, Ext6T<U> *e) {
+#if defined(__CUDA_ARCH__)
+    const bool any = __any_sync(0xffffffffu, active);
+    if (active) extend6<U>(ix, x_near, x_far, size, *e);
+    return any;
+#else
+    if (active) extend6<U>(ix, x_near, x_far, size, *e);
+    return active;
+#endif
+}
+
+template <typename U> struct OvBits {     // packing of the candidate `info` word (unitig.c:132,150)
+    static constexpr int pos_bits = sizeof(U) == 8 ? 32 : 16;
+    static constexpr U pos_mask = (U)(((uint64_t)1 << pos_bits) - 1);
+    static constexpr U base_mask = (U)((uint64_t)0xf << pos_bits);
+    static constexpr int cat_shift = pos_bits + 4;
+    static constexpr int max_cat = sizeof(U) == 8 ? (1 << 27) : ((1 << 12) - 1);
+};
+
+template <typename U>
+struct OvLane {
+    typedef IntvT<U> Cand;
+    const OverlapArgs &A;
+    uint8_t *s;
+    Cand *P, *Q;
+    int32_t *cat;
+    int sl;           // current length of s
+    bool ovf;
+    Ext6T<U> e;
+    int e_back;
+
+    FMG_HD OvLane(const OverlapArgs &a, int64_t lane)
+        : A(a), s(a.sbuf + (size_t)lane * a.s_cap), P(static_cast<Cand *>(a.A) + (size_t)lane * a.cap),
+          Q(static_cast<Cand *>(a.B) + (size_t)lane * a.cap), cat(a.cat + (size_t)lane * a.cap), sl(0), ovf(false), e_back(0) {}
+
+    FMG_HD void extend(const Cand &k, int back) {
+        e_back = back;
+        ext_sync<U>(A.ix, true, back ? k.x1 : k.x0, back ? k.x0 : k.x1, k.x2, &e);
+    }
+    FMG_HD U size(int c) const { return pick6(e.size, c); }
+    FMG_HD Cand ok(int c) const {          // ok[c] of the last extension; info = 0
+        const U nr = pick6(e.near, c), fr = far_of(A.ix, e, c);
+        Cand r; r.x0 = e_back ? fr : nr; r.x1 = e_back ? nr : fr; r.x2 = pick6(e.size, c); r.info = 0;
+        return r;
+    }
+    // fm6_extend0 (exact.c:90-98): the sentinel extension only; NOTE x[!is_back] is the bare count tk[0]
+    FMG_HD Cand ok0_bare() const {
+        Cand r;
+        const U tk0 = e.relk[0] + (U)(ld_u64(A.ix.cs + e.sbk * 8) - A.ix.C[0]);
+        r.x0 = e_back ? tk0 : e.near[0]; r.x1 = e_back ? e.near[0] : tk0; r.x2 = e.size[0]; r.info = 0;
+        return r;
+    }
+    FMG_HD void push(Cand *list, int &n, const Cand &k) {
+        if (n < A.cap) st_cand(list + n, k); else ovf = true;
+        ++n;
+    }
+    static FMG_HD void reverse(Cand *list, int n, int cap) {
+        if (n > cap) n = cap;
+        for (int a = 0, b = n - 1; a < b; ++a, --b) {
+            const Cand x = ld_cand(list + a), y = ld_cand(list + b);
+            st_cand(list + a, y); st_cand(list + b, x);
+        }
+    }
+
+    // overlap_intv, unitig.c:38-64.  Returns the final interval; list = candidates, smallest interval first.
+    FMG_HD Cand overlap_intv(int len, const uint8_t *seq, int min, int j, int at5, Cand *list, int &n, int inc_sentinel) {
+        const int dir = at5 ? 1 : -1, end = at5 ? len : -1;
+        Cand ik = base_intv<U>(A.ix, seq[j]);
+        n = 0;
+        int depth = 1;
+        for (j += dir; j != end; j += dir, ++depth) {
+            const int c = at5 ? comp6(seq[j]) : seq[j];
+            extend(ik, !at5);
+            if (size(c) == 0) break;
+            if (depth >= min && e.size[0] != 0) {
+                if (inc_sentinel) { Cand t = ok(0); t.info = (U)(j - dir); push(list, n, t); }
+                else { ik.info = (U)(j - dir); push(list, n, ik); }
+            }
+            ik = ok(c);
+        }
+        reverse(list, n, A.cap);
+        return ik;
+    }
+
+    // the whole per-sequence record
+    FMG_HD void run(int64_t t) {
+        typedef OvBits<U> BT;
+        int64_t *rec = A.rec + t * OV_NREC;
+        const int L = A.len[t], min_match = A.min_match;
+        for (int k = 0; k < OV_NREC; ++k) rec[k] = 0;
+        rec[OV_LEN] = L; rec[OV_RBEG] = -1; rec[OV_LEFT] = 1;
+        A.nei_cnt[t] = 0;
+        if (L <= min_match) { rec[OV_CONTAINED] = -9; return; }       // unitig.c:288
+        if (L + 2 > A.s_cap) { rec[OV_CONTAINED] = -100; return; }
+        for (int k = 0; k < L; ++k) s[k] = A.seq[(size_t)t * A.max_len + k];
+        sl = L; ovf = false;
+
+        // ---- fm6_is_contained, unitig.c:77-91
+        int np = 0, nq = 0, ret = 0;
+        Cand ik = overlap_intv(L, s, min_match, L - 1, 0, P, np, 0);
+        extend(ik, 1);
+        if (ik.x2 != e.size[0]) ret = -1;               // left contained
+        ik = ok(0);
+        extend(ik, 0);
+        if (ik.x2 != e.size[0]) ret = -1;               // right contained
+        const Cand intv0 = ok(0);
+        rec[OV_CONTAINED] = ret; rec[OV_X0] = (int64_t)intv0.x0; rec[OV_X1] = (int64_t)intv0.x1; rec[OV_X2] = (int64_t)intv0.x2;
+        if (ret < 0 || np == 0) { if (ovf) rec[OV_CONTAINED] = -100; return; }
+
+        // ---- fm6_get_nei, unitig.c:93-179 (beg = 0; prev = P was filled by overlap_intv above)
+        const int ori_l = L;
+        int nnei = 0, is_forked = 0;
+        uint4 *nei = A.nei + (size_t)t * A.nei_cap * 2;
+        Cand nei0 = {0, 0, 0, 0};
+        Cand *prev = P, *curr = Q;
+        for (int j = 0; j < np && j < A.cap; ++j) cat[j] = 0;
+        while (np) {
+            nq = 0;
+            int first_base = 0;
+            const int npc = np < A.cap ? np : A.cap;
+            for (int j = 0; j < npc; ++j) {
+                if (cat[j] < 0) continue;
+                const Cand p = ld_cand(prev + j);
+                extend(p, 0);                                            // forward extension
+                const Ext6T<U> em = e;                                   // keep ok[1..4] across the sentinel probes
+                const U s0 = e.size[0];
+                if (s0 != 0 && ori_l != sl) {                            // some (partial) reads end here
+                    const Cand k0 = ok(0);
+                    extend(k0, 1);                                       // fm6_extend0(ok[0], back)
+                    if (e.size[0] != 0) {                                // bounded by sentinels on both sides: a full read
+                        if (s0 == p.x2 && p.x2 == e.size[0]) {           // not contained in a longer read
+                            const int cat0 = cat[j];
+                            Cand nb = ok0_bare();
+                            nb.info = (U)(ori_l - (int)(p.info & BT::pos_mask));
+                            for (int i = j; i < npc && cat[i] == cat0; ++i) cat[i] = -1;
+                            if (nnei < A.nei_cap) {
+                                Intv o; o.x0 = nb.x0; o.x1 = nb.x1; o.x2 = nb.x2; o.info = nb.info;
+                                st_intv(nei + 2 * nnei, o);
+                            } else ovf = true;
+                            if (nnei == 0) nei0 = nb;
+                            ++nnei;
+                            continue;
+                        }   // else: a read contained in another one (the reference only marks it `used`)
+                    }
+                }
+                if (cat[j] < 0) continue;
+                for (int c = 1; c < 5; ++c) {                            // collect extensible intervals
+                    const U sc = pick6(em.size, c);
+                    if (sc == 0) continue;
+                    Cand kc; { const U nr = pick6(em.near, c), fr = far_of(A.ix, em, c); kc.x0 = nr; kc.x1 = fr; kc.x2 = sc; kc.info = 0; }
+                    extend(kc, 1);                                       // fm6_extend0(ok[c], back)
+                    if (e.size[0] != 0) {                                // left end still bounded by a sentinel
+                        kc.info = (U)((p.info & ~BT::base_mask) | ((U)c << BT::pos_bits));
+                        if (nq == 0) first_base = c;
+                        push(curr, nq, kc);
+                    }
+                }
+            }
+            if (nq) {                                                    // update categories, unitig.c:137-153
+                const int nqc = nq < A.cap ? nq : A.cap;
+                if (sl + 2 <= A.s_cap) { s[sl++] = (uint8_t)comp6(first_base); } else ovf = true;
+                for (int a = 1; a < nqc; ++a) {                          // insertion sort by info (keys are unique)
+                    const Cand x = ld_cand(curr + a);
+                    int b = a - 1;
+                    while (b >= 0) {
+                        const Cand y = ld_cand(curr + b);
+                        if (y.info <= x.info) break;
+                        st_cand(curr + b + 1, y); --b;
+                    }
+                    st_cand(curr + b + 1, x);
+                }
+                U last = 0; int cat0 = 0;
+                for (int j = 0; j < nqc; ++j) {
+                    Cand x = ld_cand(curr + j);
+                    const U hi = (U)(x.info >> BT::pos_bits);
+                    if (j == 0 || hi != last) { last = hi; cat0 = j; }
+                    cat[j] = cat0;
+                    x.info = (U)((x.info & BT::pos_mask) | ((U)cat0 << BT::cat_shift));
+                    if (j == 0) x.info &= BT::pos_mask;
+                    st_cand(curr + j, x);
+                }
+                if (cat0 != 0) is_forked = 1;
+                if (cat0 > BT::max_cat) ovf = true;
+            }
+            Cand *tmp = curr; curr = prev; prev = tmp;
+            np = nq;
+        }
+        A.nei_cnt[t] = (uint32_t)nnei;
+        rec[OV_NNEI] = nnei;
+        if (nnei == 0) { rec[OV_SLEN] = sl; if (ovf) rec[OV_CONTAINED] = -100; return; }     // unitig.c:154 (returns -1, s keeps its growth)
+        const int rbeg = ori_l - (int)nei0.info;
+        if (nnei == 1 && is_forked) {             // contained reads forked the path: rebuild it along the one neighbour
+            Cand k0 = base_intv<U>(A.ix, 0);
+            for (int i = rbeg; i < ori_l; ++i) { extend(k0, 0); k0 = ok(comp6(s[i])); }
+            int i = ori_l;
+            for (; i < sl; ++i) {
+                int c0 = -1, hits = 0;
+                extend(k0, 0);
+                for (int c = 1; c < 5; ++c) {
+                    const Cand kc = ok(c);
+                    if (kc.x2 != 0 && kc.x0 <= nei0.x0 && kc.x0 + kc.x2 >= nei0.x0 + nei0.x2) ++hits, c0 = c;
+                }
+                if (hits == 0 && e.size[0] != 0) break;
+                if (hits != 1) { ovf = true; break; }                    // the reference asserts hits == 1 (unitig.c:171)
+                s[i] = (uint8_t)comp6(c0);
+                k0 = ok(c0);
+            }
+            sl = i;
+        }
+        if (nnei > 1) sl = ori_l;
+        rec[OV_RBEG] = rbeg; rec[OV_SLEN] = sl;
+        for (int k = ori_l; k < sl && k - ori_l < A.max_len; ++k) A.ext[(size_t)t * A.max_len + (k - ori_l)] = s[k];
+        if (sl - ori_l > A.max_len) ovf = true;
+
+        // ---- check_left_simple, unitig.c:186-204, for a unique neighbour (beg = 0)
+        if (nnei == 1 && !ovf) {
+            int left = 0;
+            overlap_intv(sl, s, min_match, rbeg, 1, P, np, 1);
+            prev = P; curr = Q;
+            for (int i = rbeg - 1; i >= 0 && left == 0; --i) {
+                nq = 0;
+                const int npc = np < A.cap ? np : A.cap;
+                for (int j = 0; j < npc; ++j) {
+                    const Cand p = ld_cand(prev + j);
+                    extend(p, 1);
+                    if ((U)(e.size[0] + size(s[i])) != p.x2) { left = -1; break; }   // potential backward bifurcation
+                    push(curr, nq, ok(s[i]));
+                }
+                Cand *tmp = curr; curr = prev; prev = tmp;
+                np = nq;
+            }
+            rec[OV_LEFT] = left;
+        }
+        if (ovf) rec[OV_CONTAINED] = -100;
+    }
+};
+
+template <typename U, class FetchFn>
+FMG_HD void overlap_lane(const OverlapArgs &A, int64_t lane, FetchFn fetch) {
+    OvLane<U> ln(A, lane);
+    for (;;) {
+        const int64_t t = fetch();
+        if (t >= A.n) break;
+        ln.run(t);
+    }
+    // out of work: keep answering the warp votes until every lane of the warp is done
+    while (ext_sync<U>(A.ix, false, 0, 0, 0, &ln.e)) {}
+}
+
+// ---------------------------------------------------------------------------------------------
+// fm_retrieve (exact.c:59-70): LF walk from sentinel rank x; one block load per base.
+// Writes the sequence in reading order to seq[t*max_len ..], its length to len[t] (clipped reads are
+// flagged by len[t] = -(true length)) and the returned k to ret[t].
+struct RetrieveArgs {
+    OccView ix;
+    int64_t n;
+    const uint64_t *ids;        // sentinel ranks, or nullptr for ids[t] = first + t*step
+    uint64_t first, step;
+    uint8_t *seq; int max_len;
+    int32_t *len;
+    int64_t *ret;
+};
+
+FMG_HD void retrieve_one(const RetrieveArgs &A, int64_t t) {
+    uint64_t k = A.ids ? A.ids[t] : A.first + (uint64_t)t * A.step;
+    uint8_t *out = A.seq + (size_t)t * A.max_len;
+    int n = 0;
+    for (;;) {
+        const Blk B = load_blk(A.ix, k);
+        uint32_t rel[6];
+        rank_rel(B, k, rel);                              // counts in [superblock_start, k)
+        const uint32_t w = ((uint32_t)k >> 5) & 3u, bit = (uint32_t)k & 31u;
+        const uint32_t p0 = w == 0 ? B.lo.v[4] : w == 1 ? B.lo.v[5] : w == 2 ? B.lo.v[6] : B.lo.v[7];
+        const uint32_t p1 = w == 0 ? B.hi.v[0] : w == 1 ? B.hi.v[1] : w == 2 ? B.hi.v[2] : B.hi.v[3];
+        const uint32_t p2 = w == 0 ? B.hi.v[4] : w == 1 ? B.hi.v[5] : w == 2 ? B.hi.v[6] : B.hi.v[7];
+        const int c = (int)((p0 >> bit & 1u) | (p1 >> bit & 1u) << 1 | (p2 >> bit & 1u) << 2);     // BWT[k]
+        // rank of c in BWT[0..k] is rel+1, so LF(k) = C[c] + rel (exact.c:66)
+        k = ld_u64(A.ix.cs + (k >> kSuperShift) * 8 + c) + pick6(rel, c);
+        if (c == 0 || c > 5) break;
+        if (n < A.max_len) out[n] = (uint8_t)c;
+        ++n;
+    }
+    A.ret[t] = (int64_t)k;
+    const int m = n < A.max_len ? n : A.max_len;
+    for (int a = 0, b = m - 1; a < b; ++a, --b) { const uint8_t x = out[a]; out[a] = out[b]; out[b] = x; }   // seq_reverse (unitig.c:285)
+    A.len[t] = n <= A.max_len ? n : -n;
+}
+
+} // namespace fmg

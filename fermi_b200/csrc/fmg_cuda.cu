@@ -206,6 +206,21 @@ __global__ void __launch_bounds__(kScanBlock) k_compact_gather(const uint32_t *_
     if (base <= n && n < base + kScanItems) mem_off[n] = o;     // the thread owning index n writes the end offset
 }
 
+int64_t fmg_compact_tiles(int64_t n) { return (n + 1 + kScanTile - 1) / kScanTile; }
+
+// slots[n][cap] (32-byte records, cnt[i] used) -> dense mem + mem_off[n+1]; ctrl[1] += overflowing rows, ctrl[2] = total
+int fmg_compact_slots(const uint32_t *cnt, int64_t n, int cap, const uint4 *slots, uint4 *mem, uint64_t *mem_off, uint64_t *tile_sum,
+                      unsigned long long *ctrl, cudaStream_t st) {
+    const int64_t n_tiles = fmg_compact_tiles(n);
+    k_compact_tile_sums<<<(unsigned)n_tiles, kScanBlock, 0, st>>>(cnt, n, cap, tile_sum, ctrl + 1);
+    LAUNCH_CHECK(return -1);
+    k_compact_scan_tiles<<<1, 1024, 0, st>>>(tile_sum, n_tiles, (uint64_t *)(ctrl + 2));
+    LAUNCH_CHECK(return -1);
+    k_compact_gather<<<(unsigned)n_tiles, kScanBlock, 0, st>>>(cnt, n, cap, tile_sum, slots, mem, mem_off);
+    LAUNCH_CHECK(return -1);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------ index
 
 static int use_device(int device, const char *who) {
@@ -439,13 +454,7 @@ static int session_enqueue(fmg_smem_session_t *s, int64_t n, const uint8_t *d_se
         CUDA_TRY(cudaEventRecord(e1, st), return -1);
         s->ev.push_back(e0); s->ev.push_back(e1);
     }
-    const int64_t n_tiles = (n + 1 + kScanTile - 1) / kScanTile;
-    k_compact_tile_sums<<<(unsigned)n_tiles, kScanBlock, 0, st>>>(s->rec_cnt, n, s->out_cap, s->tile_sum, s->ctrl + 1);
-    LAUNCH_CHECK(return -1);
-    k_compact_scan_tiles<<<1, 1024, 0, st>>>(s->tile_sum, n_tiles, (uint64_t *)(s->ctrl + 2));
-    LAUNCH_CHECK(return -1);
-    k_compact_gather<<<(unsigned)n_tiles, kScanBlock, 0, st>>>(s->rec_cnt, n, s->out_cap, s->tile_sum, s->slots, s->mem, s->mem_off);
-    LAUNCH_CHECK(return -1);
+    if (fmg_compact_slots(s->rec_cnt, n, s->out_cap, s->slots, s->mem, s->mem_off, s->tile_sum, s->ctrl, st)) return -1;
     CUDA_TRY(cudaMemcpyAsync(s->h_ctrl, s->ctrl, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), return -1);
     return 0;
 }

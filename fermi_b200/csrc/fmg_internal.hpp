@@ -9,6 +9,9 @@
 #define SMEM_MIN_BLOCKS_U32 6
 #define SMEM_MIN_BLOCKS_U64 5
 #define SMEM_DEFAULT_OUT_CAP 64
+// k_overlap launch shape
+#define OVLP_BLOCK 128
+#define OVLP_MIN_BLOCKS 4
 
 struct fmg_fmd_s { fmg::FmdImage img; };
 

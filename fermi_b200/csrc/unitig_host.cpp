@@ -1,0 +1,238 @@
+// `fermi unitig` on top of the GPU overlap records (host side of the path).
+//
+// The reference walks unitigs seed by seed and asks the FMD-index at every step (unitig.c:227-362).
+// Every such question is a pure function of one read -- its right neighbours, the consensus extension
+// and the simple left check (fmd_overlap.cuh) -- so here the index work is done once per sequence on
+// the GPU (fmg_overlap_batch) and the walk below only chases records.  It reproduces the single-thread
+// seed order of unitig_core (unitig.c:319-362) including the `used` / `bend` / `visited` bitmaps, so the
+// MAG records equal those of `fermi unitig -t1` (as a canonicalised set: SURVEY.md A.8).
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "fmd_overlap.cuh"
+#include "fmg_internal.hpp"
+#include "../../include/fermi_b200.h"
+
+using namespace fmg;
+
+namespace {
+
+struct Records {
+    uint64_t n_seq = 0;
+    int max_len = 0;
+    std::vector<int64_t> rec;        // n_seq x OV_NREC
+    std::vector<fmg_intv_t> nei;
+    std::vector<uint64_t> nei_off;   // n_seq + 1
+    std::vector<uint8_t> seq, ext;   // n_seq x max_len
+    // Records are indexed by BWT row (= sequence number in the text, the seed of unitig_core).  The ids the
+    // walk sees -- fm_retrieve's return value, intv0.x[], neighbour x[] -- are ranks of the sequence among all
+    // sequences in lexicographic order (LF of a sentinel counts the '$' above it), so neighbours are
+    // looked up through the inverse of rec[OV_K].
+    std::vector<uint64_t> row_of_rank;
+    const int64_t *r(uint64_t row) const { return &rec[row * OV_NREC]; }
+    uint64_t row(uint64_t rank) const { return row_of_rank[rank]; }
+    void index_ranks() {
+        row_of_rank.assign(n_seq, 0);
+        for (uint64_t t = 0; t < n_seq; ++t) row_of_rank[(uint64_t)rec[t * OV_NREC + OV_K]] = t;
+    }
+};
+
+struct Bits {
+    std::vector<uint64_t> w;
+    explicit Bits(uint64_t n) : w((n + 63) / 64, 0) {}
+    bool get(uint64_t i) const { return w[i >> 6] >> (i & 63) & 1; }
+    bool test_and_set(uint64_t i) { const uint64_t m = 1ull << (i & 63); const bool was = w[i >> 6] & m; w[i >> 6] |= m; return was; }
+    void set(uint64_t i) { w[i >> 6] |= 1ull << (i & 63); }
+    void set_intv(uint64_t x0, uint64_t x1, uint64_t x2) {           // set_bits, unitig.c:22-36
+        for (uint64_t k = 0; k < x2; ++k) set(x0 + k), set(x1 + k);
+    }
+};
+
+struct Nei { uint64_t x; uint64_t y; };
+
+struct Walker {
+    const Records &R;
+    int min_match;
+    Bits used, bend, visited;
+    std::string s, cov;
+    std::vector<Nei> last_nei;           // a->nei after unitig_unidir
+
+    Walker(const Records &r, int mm) : R(r), min_match(mm), used(r.n_seq), bend(r.n_seq), visited(r.n_seq) {}
+
+    // unitig_unidir, unitig.c:227-262.  `cur` = record row of the last read of s, which starts at s[beg].
+    int unidir(uint64_t cur, int beg, uint64_t k0, uint64_t *end, int *is_loop) {
+        int ori_l = (int)s.size(), n_reads = 0;
+        *is_loop = 0;
+        last_nei.clear();
+        for (;;) {
+            const int64_t *r = R.r(cur);
+            last_nei.clear();
+            if (r[OV_RBEG] < 0 || r[OV_NNEI] == 0) break;                 // try_right() < 0
+            const fmg_intv_t *nb = &R.nei[R.nei_off[cur]];
+            const int n_nei = (int)r[OV_NNEI];
+            for (int k = 0; k < n_nei; ++k) last_nei.push_back(Nei{nb[k].x[0], nb[k].info});
+            const int rbeg = beg + (int)r[OV_RBEG];
+            if (n_nei > 1) { bend.set(*end); break; }                      // forward bifurcation
+            const uint64_t k = nb[0].x[0];
+            if (k == *end) break;                                          // a loop like b>>c>>a><a
+            bool back_fork = bend.get(k);
+            if (!back_fork && r[OV_LEFT] != 0) {
+                // check_left (unitig.c:206-225): the simple test failed; confirm with the right neighbours of
+                // the reverse complement of the neighbour
+                const int64_t *rr = R.r(R.row(nb[0].x[1]));
+                back_fork = rr[OV_NNEI] > 1;
+            }
+            if (back_fork) { bend.set(k); break; }                         // backward bifurcation
+            if (k == k0) { *is_loop = 1; break; }                          // a loop like a>>b>>c>>a
+            if (nb[0].x[1] == *end) { last_nei.clear(); break; }           // a loop like b>>c>>a>>a; cut the last link
+            *end = nb[0].x[1];
+            used.set_intv(nb[0].x[0], nb[0].x[1], nb[0].x[2]);
+            ++n_reads;
+            // the consensus grows by the extension recorded for `cur` (unitig.c:141,253-257)
+            const int new_l = beg + (int)r[OV_SLEN];
+            const uint8_t *ext = &R.ext[cur * (uint64_t)R.max_len];
+            s.resize(new_l); cov.resize(new_l);
+            for (int i = ori_l; i < new_l; ++i) s[i] = (char)ext[i - ori_l], cov[i] = '"';
+            for (int i = rbeg; i < ori_l; ++i) if (cov[i] != '~') ++cov[i];
+            beg = rbeg; ori_l = new_l; cur = R.row(k);
+        }
+        s.resize(ori_l); cov.resize(ori_l);
+        return n_reads;
+    }
+
+    // unitig1, unitig.c:274-317
+    int unitig1(uint64_t seed, uint64_t end[2], std::vector<Nei> nei[2], int *n_reads) {
+        const int64_t *r = R.r(seed);
+        *n_reads = 0; nei[0].clear(); nei[1].clear();
+        const int seed_len = (int)r[OV_LEN];
+        if (seed_len <= min_match) return -1;                              // too short
+        const uint64_t k = (uint64_t)r[OV_K];
+        if (used.get(k)) return -2;
+        used.set_intv((uint64_t)r[OV_X0], (uint64_t)r[OV_X1], (uint64_t)r[OV_X2]);
+        if (r[OV_CONTAINED] < 0) return -3;
+        *n_reads = 1;
+        s.assign((const char *)&R.seq[seed * (uint64_t)R.max_len], seed_len);
+        cov.assign(seed_len, '"');
+        end[0] = (uint64_t)r[OV_X1]; end[1] = (uint64_t)r[OV_X0];
+        int is_loop = 0;
+        // (the reference skips this call when the read has no overlap candidate at all; the call is then a no-op)
+        *n_reads += unidir(seed, 0, (uint64_t)r[OV_X0], &end[0], &is_loop);
+        nei[0] = last_nei;
+        if (is_loop) {
+            nei[1].push_back(Nei{end[0], last_nei[0].y});
+            return 0;
+        }
+        // the other direction: reverse complement the consensus, reverse the coverage
+        std::reverse(s.begin(), s.end());
+        for (auto &c : s) c = (c >= 1 && c <= 4) ? 5 - c : c;
+        std::reverse(cov.begin(), cov.end());
+        *n_reads += unidir(R.row((uint64_t)r[OV_X1]), (int)s.size() - seed_len, (uint64_t)r[OV_X1], &end[1], &is_loop);
+        nei[1] = last_nei;
+        return 0;
+    }
+};
+
+void append_u64(std::string &o, uint64_t v) { char b[24]; o.append(b, std::snprintf(b, sizeof b, "%llu", (unsigned long long)v)); }
+void append_i64(std::string &o, int64_t v) { char b[24]; o.append(b, std::snprintf(b, sizeof b, "%lld", (long long)v)); }
+
+// mag_v_write, mag.c:149-174
+void write_mag(std::string &o, const uint64_t k[2], int nsr, const std::vector<Nei> nei[2], const std::string &seq, const std::string &cov) {
+    o += '@'; append_i64(o, (int64_t)k[0]); o += ':'; append_i64(o, (int64_t)k[1]); o += '\t'; append_i64(o, nsr);
+    for (int j = 0; j < 2; ++j) {
+        o += '\t';
+        for (const Nei &z : nei[j]) { append_i64(o, (int64_t)z.x); o += ','; append_i64(o, (int32_t)z.y); o += ';'; }
+        if (nei[j].empty()) o += '.';
+    }
+    o += '\n';
+    for (char c : seq) o += "ACGT"[(int)c - 1];
+    o += "\n+\n";
+    o += cov;
+    o += '\n';
+}
+
+} // namespace
+
+extern "C" {
+
+// The walk alone: MAG records from the per-sequence overlap records of ALL n_seq sequences of an index
+// (rec: n_seq x 10, nei/nei_off, seq/ext: n_seq x max_len; the layout fmg_overlap_batch produces).  Host code.
+int fmg_unitig_assemble(uint64_t n_seq, int max_len, int min_match, const int64_t *rec, const fmg_intv_t *nei,
+                        const uint64_t *nei_off, const uint8_t *seq, const uint8_t *ext, const char *out_path, uint64_t *n_unitigs) {
+    Records R;
+    R.n_seq = n_seq; R.max_len = max_len;
+    R.rec.assign(rec, rec + n_seq * OV_NREC);
+    R.nei_off.assign(nei_off, nei_off + n_seq + 1);
+    R.nei.assign(nei, nei + nei_off[n_seq]);
+    R.seq.assign(seq, seq + n_seq * (uint64_t)max_len);
+    R.ext.assign(ext, ext + n_seq * (uint64_t)max_len);
+    R.index_ranks();
+    FILE *fp = std::strcmp(out_path, "-") ? std::fopen(out_path, "wb") : stdout;
+    if (!fp) {
+        if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] cannot write '%s'\n", __func__, out_path);
+        return -1;
+    }
+    Walker W(R, min_match);
+    std::string out;
+    uint64_t end[2], count = 0;
+    std::vector<Nei> nb[2];
+    int n_reads;
+    // seeds = odd sentinel ranks in the order of unitig_core (unitig.c:333-334)
+    for (uint64_t j = 0; j <= n_seq >> 2; ++j)
+        for (uint64_t i = j << 2 | 1; i < (j << 2) + 4 && i < n_seq; i += 2) {
+            if (W.unitig1(i, end, nb, &n_reads) < 0) continue;
+            if (W.visited.test_and_set(end[0]) || W.visited.test_and_set(end[1])) continue;    // unitig.c:337-339 (short-circuit like the reference)
+            out.clear();
+            write_mag(out, end, n_reads, nb, W.s, W.cov);
+            std::fwrite(out.data(), 1, out.size(), fp);
+            ++count;
+        }
+    if (fp != stdout) std::fclose(fp); else std::fflush(fp);
+    if (n_unitigs) *n_unitigs = count;
+    return 0;
+}
+
+// fm6_unitig (unitig.c:378-407) + main_unitig (cmd.c:184-216): overlap records of every sequence on the GPU, then the
+// walk; MAG records go to `out_path` ("-" = stdout).  max_len = upper bound of the sequence length in the index
+// (0: estimate from the symbol counts, grown on demand).
+int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *out_path, uint64_t *n_unitigs) {
+    if (!idx) return -1;
+    const uint64_t n_seq = idx->mcnt[1];
+    if (n_unitigs) *n_unitigs = 0;
+    if (max_len <= 0) max_len = (int)((idx->mcnt[0] - n_seq + n_seq - 1) / (n_seq ? n_seq : 1)) + 8;
+    std::vector<int64_t> rec;
+    std::vector<fmg_intv_t> nei;
+    std::vector<uint64_t> nei_off;
+    std::vector<uint8_t> seq, ext;
+    for (;;) {
+        rec.assign(n_seq * OV_NREC, 0); nei_off.assign(n_seq + 1, 0);
+        seq.assign(n_seq * (uint64_t)max_len, 0); ext.assign(n_seq * (uint64_t)max_len, 0);
+        nei.clear();
+        const uint64_t batch = 1 << 21;
+        std::vector<int32_t> len;
+        std::vector<uint64_t> off;
+        int rc = 0;
+        for (uint64_t b = 0; b < n_seq && rc == 0; b += batch) {
+            const uint64_t m = std::min<uint64_t>(batch, n_seq - b);
+            fmg_intv_t *nb = nullptr;
+            len.assign(m, 0); off.assign(m + 1, 0);
+            rc = fmg_overlap_batch(idx, min_match, (int64_t)m, nullptr, b, 1, max_len, &rec[b * OV_NREC], &nb, off.data(),
+                                   &seq[b * (uint64_t)max_len], len.data(), &ext[b * (uint64_t)max_len]);
+            if (rc == 0) {
+                const uint64_t base = nei.size();
+                nei.insert(nei.end(), nb, nb + off[m]);
+                for (uint64_t i = 0; i <= m; ++i) nei_off[b + i] = base + off[i];
+            }
+            std::free(nb);
+        }
+        if (rc == 2) { max_len *= 2; continue; }            // a sequence was longer than assumed
+        if (rc != 0) return rc;
+        break;
+    }
+    return fmg_unitig_assemble(n_seq, max_len, min_match, rec.data(), nei.data(), nei_off.data(), seq.data(), ext.data(), out_path, n_unitigs);
+}
+
+} // extern "C"

@@ -101,6 +101,27 @@ double fmg_smem_session_kernel_ms(fmg_smem_session_t *s, int *n_launches);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t fmg_launch_count(void);
 
+/* ------------------------------------------------------------------ overlap / unitig (unitig.c)
+ * Per-sequence overlap record: everything unitig_unidir/unitig1 (unitig.c:227-317) ask the index about one
+ * read.  For sequence ids[t] (or first + t*step when ids == NULL):
+ *   rec[10*t + 0] value returned by fm_retrieve (exact.c:59)      rec[.. + 1] length
+ *   rec[.. + 2]  fm6_is_contained result (unitig.c:77): 0, -1 contained, -9 length <= min_match
+ *   rec[.. + 3..5] intv0.x[0..2]                                    rec[.. + 6] rbeg of fm6_get_nei (unitig.c:93), -1 = no neighbour
+ *   rec[.. + 7]  number of right neighbours                       rec[.. + 8] length of the grown consensus
+ *   rec[.. + 9]  check_left_simple (unitig.c:186) of a unique neighbour: 0 ok, -1 fork, 1 not evaluated
+ * nei (malloc'd, fmg_free) = neighbour intervals with info = overlap length, nei_off[n+1];
+ * seq / ext (n x max_len, may be NULL) = the sequence itself and the bases fm6_get_nei appended to it.
+ * Returns 0, or 2 when a sequence is longer than max_len. */
+int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const uint64_t *ids, uint64_t first, uint64_t step,
+                      int max_len, int64_t *rec, fmg_intv_t **nei, uint64_t *nei_off, uint8_t *seq, int32_t *len, uint8_t *ext);
+/* unitig walk over the records of ALL n_seq sequences (host code; this is what runs after the all-gather of
+ * per-GPU record shards): MAG text as written by mag_v_write (mag.c:149-174) to out_path ("-" = stdout) */
+int fmg_unitig_assemble(uint64_t n_seq, int max_len, int min_match, const int64_t *rec, const fmg_intv_t *nei,
+                        const uint64_t *nei_off, const uint8_t *seq, const uint8_t *ext, const char *out_path, uint64_t *n_unitigs);
+/* fm6_unitig (unitig.c:378-407) / `fermi unitig -l min_match`: records on the GPU, then the walk. The set of
+ * MAG records equals that of the reference after canonicalisation. max_len 0 = estimate. */
+int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *out_path, uint64_t *n_unitigs);
+
 /* ------------------------------------------------------------------ index construction
  * BWT of the FMD text  r0 $ rc(r0) $ r1 $ rc(r1) $ ...  (cmd.c:457-469) by prefix-doubling suffix
  * sorting on the GPU; replaces fm_build / ksa_bwt (build.c:33-50, ksa.c:231-242) for texts that fit

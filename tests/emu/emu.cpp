@@ -8,6 +8,7 @@
 #include <cstring>
 #include <vector>
 #include "../../fermi_b200/csrc/fmd_device.cuh"
+#include "../../fermi_b200/csrc/fmd_overlap.cuh"
 #include "../../fermi_b200/csrc/occ_layout.hpp"
 #include "../../include/fermi_b200.h"
 
@@ -93,6 +94,31 @@ int emu_smem(const void *_x, int64_t n, const uint8_t *seq, const uint64_t *off,
     for (int64_t i = 0; i < n; ++i)
         std::memcpy(*mem + mem_off[i], out.data() + (size_t)i * out_cap * 2, (mem_off[i + 1] - mem_off[i]) * 32);
     return overflow;
+}
+
+// retrieve + overlap record of the sequences ids[0..n) (both through the product's lane code)
+int emu_overlap(const void *_x, int min_match, int64_t n, const uint64_t *ids, int max_len, int cap, int nei_cap, int wide,
+                int64_t *rec, fmg_intv_t *nei, uint32_t *nei_cnt, uint8_t *seq, int32_t *len, uint8_t *ext) {
+    const EmuIndex *x = static_cast<const EmuIndex *>(_x);
+    std::vector<int64_t> ret(n);
+    RetrieveArgs R;
+    R.ix = x->view; R.n = n; R.ids = ids; R.first = 0; R.step = 1; R.seq = seq; R.max_len = max_len; R.len = len; R.ret = ret.data();
+    for (int64_t t = 0; t < n; ++t) retrieve_one(R, t);
+    const int n_lanes = 3, s_cap = 2 * max_len + 8;
+    std::vector<uint8_t> sbuf((size_t)n_lanes * s_cap);
+    std::vector<uint64_t> A((size_t)n_lanes * cap * 4), B((size_t)n_lanes * cap * 4);
+    std::vector<int32_t> cat((size_t)n_lanes * cap);
+    OverlapArgs O;
+    O.ix = x->view; O.min_match = min_match; O.n = n; O.seq = seq; O.len = len; O.max_len = max_len;
+    O.sbuf = sbuf.data(); O.s_cap = s_cap; O.A = A.data(); O.B = B.data(); O.cap = cap; O.cat = cat.data();
+    O.rec = rec; O.nei = reinterpret_cast<uint4 *>(nei); O.nei_cap = nei_cap; O.nei_cnt = nei_cnt; O.ext = ext; O.next = nullptr;
+    for (int t = 0; t < n_lanes; ++t) {
+        int64_t cur = t;
+        auto fetch = [&]() { int64_t r = cur; cur += n_lanes; return r; };
+        if (wide) overlap_lane<uint64_t>(O, t, fetch); else overlap_lane<uint32_t>(O, t, fetch);
+    }
+    for (int64_t t = 0; t < n; ++t) rec[t * OV_NREC + OV_K] = ret[t];
+    return 0;
 }
 
 } // extern "C"

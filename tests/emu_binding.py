@@ -13,7 +13,7 @@ OUT = os.path.join(ROOT, "build", "libemu.so")
 SRC = [os.path.join(ROOT, "tests", "emu", "emu.cpp"),
        os.path.join(ROOT, "fermi_b200", "csrc", "fmd_host.cpp"),
        os.path.join(ROOT, "fermi_b200", "csrc", "occ_build_host.cpp")]
-DEPS = SRC + [os.path.join(ROOT, "fermi_b200", "csrc", f) for f in ("fmd_device.cuh", "fmd_host.hpp", "occ_layout.hpp")]
+DEPS = SRC + [os.path.join(ROOT, "fermi_b200", "csrc", f) for f in ("fmd_device.cuh", "fmd_overlap.cuh", "fmd_host.hpp", "occ_layout.hpp")]
 
 
 class Emu:
@@ -30,6 +30,8 @@ class Emu:
         L.emu_smem.argtypes = [C.c_void_p, C.c_int64, H.u8p, H.u64p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), H.u64p]
         L.emu_smem.restype = C.c_int
         L.fmg_free.argtypes = [C.c_void_p]
+        L.emu_overlap.argtypes = [C.c_void_p, C.c_int, C.c_int64, H.u64p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  H.i64p, C.c_void_p, C.c_void_p, H.u8p, H.i32p, H.u8p]
 
     def index(self, fmd_path):
         f = self.lib.fmg_fmd_restore(fmd_path.encode())
@@ -64,6 +66,23 @@ class Emu:
         rec = np.frombuffer(C.string_at(mem.value, tot * 32), dtype=H.INTV).copy() if tot else np.zeros(0, H.INTV)
         self.lib.fmg_free(mem)
         return rec, mo, ov
+
+
+    def overlap(self, x, min_match, ids, max_len, cap=512, nei_cap=16, wide=0):
+        """returns (rec[n,10], nei INTV[], nei_off[n+1], seq[n,max_len], len[n], ext[n,max_len])"""
+        ids = np.ascontiguousarray(ids, np.uint64)
+        n = len(ids)
+        rec = np.zeros((n, 10), np.int64)
+        nei = np.zeros((n, nei_cap), H.INTV)
+        cnt = np.zeros(n, np.uint32)
+        seq = np.zeros((n, max_len), np.uint8)
+        ln = np.zeros(n, np.int32)
+        ext = np.zeros((n, max_len), np.uint8)
+        self.lib.emu_overlap(x, min_match, n, H._ptr(ids, H.u64p), max_len, cap, nei_cap, wide, H._ptr(rec, H.i64p),
+                             nei.ctypes.data, cnt.ctypes.data, H._ptr(seq, H.u8p), H._ptr(ln, H.i32p), H._ptr(ext, H.u8p))
+        off = np.concatenate([[0], np.cumsum(np.minimum(cnt, nei_cap))]).astype(np.uint64)
+        flat = np.concatenate([nei[i, :min(int(cnt[i]), nei_cap)] for i in range(n)]) if n else np.zeros(0, H.INTV)
+        return rec, flat, off, seq, ln, ext
 
 
 def load():

@@ -62,8 +62,11 @@ def case(name, genome_len, n_reads, L, err, seed, n_query, q_err, special=None, 
         text=text, k=k, l=l, ok=ok, ol=ol, ik=ik, is_back=is_back, ext=ext,
         q=q, smem0=smem0, moff0=moff0, smem1=smem1, moff1=moff1, sa_beg=sb, sa_end=se, sa_size=ss,
         ov_min=min(50, L // 2), ov_seeds=seeds, ov_rec=ov_rec, ov_nei=ov_nei, ov_off=ov_off)
+    mag = H.reference_unitig(fmd, min(50, L // 2), 1)            # fermi unitig -l.. -t1 (cmd.c:184)
+    with open(os.path.join(HERE, name + ".mag"), "w") as fh:
+        fh.write(mag)
     R.destroy(h)
-    print(name, "symbols", n, "fmd bytes", os.path.getsize(fmd), "smem", len(smem0), len(smem1))
+    print(name, "unitigs", len(H.parse_mag(mag)), "symbols", n, "fmd bytes", os.path.getsize(fmd), "smem", len(smem0), len(smem1))
 
 
 def with_dups_and_palindromes(reads):

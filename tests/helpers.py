@@ -324,3 +324,47 @@ def reference():
 def ref_fermi_binary():
     p = os.path.join(ORACLE_DIR, "_ref", "fermi")
     return p if os.path.exists(p) else None
+
+
+# ----------------------------------------------------------------------------- MAG records (mag.c:149-174)
+def parse_mag(text):
+    """MAG text -> list of (k0, k1, nsr, nei0, nei1, seq, cov); nei = tuple of (id, ovlp)."""
+    out = []
+    lines = text.split("\n")
+    i = 0
+    while i + 3 < len(lines):
+        if not lines[i].startswith("@"):
+            i += 1
+            continue
+        f = lines[i][1:].split("\t")
+        k0, k1 = (int(x) for x in f[0].split(":"))
+        nei = []
+        for col in f[2:4]:
+            nei.append(tuple(tuple(int(v) for v in e.split(",")) for e in col.split(";") if e and e != "."))
+        out.append((k0, k1, int(f[1]), nei[0], nei[1], lines[i + 1], lines[i + 3]))
+        i += 4
+    return out
+
+
+def _rc_str(s):
+    return s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+
+
+def canonical_mag(records):
+    """orientation-free, order-free form of a unitig set."""
+    canon = []
+    for k0, k1, nsr, n0, n1, seq, cov in records:
+        a = (k0, k1, nsr, tuple(sorted(n0)), tuple(sorted(n1)), seq, cov)
+        b = (k1, k0, nsr, tuple(sorted(n1)), tuple(sorted(n0)), _rc_str(seq), cov[::-1])
+        canon.append(min(a, b) if k0 == k1 else (a if k0 < k1 else b))
+    return sorted(canon)
+
+
+def reference_unitig(fmd_path, min_match, threads=1):
+    """MAG text of the compiled reference: fermi unitig -l <min_match> -t <threads> (cmd.c:184)."""
+    binary = ref_fermi_binary()
+    if binary is None:
+        return None
+    res = subprocess.run([binary, "unitig", "-l", str(min_match), "-t", str(threads), fmd_path], stdout=subprocess.PIPE,
+                         stderr=subprocess.DEVNULL, check=True)
+    return res.stdout.decode()

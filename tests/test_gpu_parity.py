@@ -151,3 +151,39 @@ def test_record_slot_overflow_is_rerun_not_truncated(fb, oracle, tmp_path):
     assert np.array_equal(mo, omo) and np.array_equal(rec, orec)
     oracle.destroy(h)
     idx.close()
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_overlap_records_and_unitigs_match_reference(fb, case, tmp_path):
+    """k_retrieve + k_overlap against the reference's fm_retrieve / fm6_is_contained / fm6_get_nei records, and the
+    unitig set of fmg_unitig against `fermi unitig -t1` (canonicalised MAG records)."""
+    g, fmd = _load(case)
+    idx = fb.FmdIndex(fb.Fmd.restore(fmd), 0)
+    max_len = int(g["ov_rec"][:, 1].max()) + 8
+    o = fb.fm6_overlap(idx, int(g["ov_min"]), ids=g["ov_seeds"], max_len=max_len)
+    assert np.array_equal(o["rec"][:, :9], g["ov_rec"])
+    assert np.array_equal(o["nei"], g["ov_nei"]) and np.array_equal(o["nei_off"], g["ov_off"])
+    out = str(tmp_path / "u.mag")
+    n = fb.fm6_unitig(idx, int(g["ov_min"]), out)
+    ours = H.parse_mag(open(out).read())
+    ref = H.parse_mag(open(os.path.join(H.GOLDEN_DIR, case + ".mag")).read())
+    assert n == len(ref) and H.canonical_mag(ours) == H.canonical_mag(ref)
+    idx.close()
+
+
+@pytest.mark.skipif(H.ref_fermi_binary() is None, reason="oracle/_ref/fermi did not travel with the repo")
+@pytest.mark.parametrize("err", [0.0, 0.01])
+def test_unitig_20k_reads_vs_reference_binary(fb, tmp_path, err):
+    """BASELINE config 3 in miniature: unitig -l50 over 20k x 100 bp reads (10x), set-equal to the reference."""
+    genome = fb.synth_genome(31, 200000)
+    reads = fb.synth_reads(32, genome, 20000, 100, err)
+    fmd = fb.fm_build(fb.fmd_text(reads), 0)
+    fn = str(tmp_path / "r.fmd")
+    fmd.dump(fn)
+    ref = H.parse_mag(H.reference_unitig(fn, 50, 4))
+    idx = fb.FmdIndex(fmd, 0)
+    out = str(tmp_path / "u.mag")
+    n = fb.fm6_unitig(idx, 50, out)
+    assert n == len(ref)
+    assert H.canonical_mag(H.parse_mag(open(out).read())) == H.canonical_mag(ref)
+    idx.close()
