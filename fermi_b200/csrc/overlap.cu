@@ -8,6 +8,7 @@
 #include <atomic>
 #include <vector>
 #include <algorithm>
+#include <chrono>
 #include "fmd_overlap.cuh"
 #include "fmg_internal.hpp"
 #include "../../include/fermi_b200.h"
@@ -73,6 +74,8 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
     OV_TRY(d_off.alloc((size_t)(n + 1) * 8)); OV_TRY(d_tiles.alloc((size_t)fmg_compact_tiles(n) * 8)); OV_TRY(d_ctrl.alloc(64));
     if (ids) { OV_TRY(d_ids.alloc((size_t)n * 8)); OV_TRY(cudaMemcpy(d_ids.p, ids, (size_t)n * 8, cudaMemcpyHostToDevice)); }
 
+    const auto t0 = std::chrono::steady_clock::now();
+    auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
     // ---- sequences
     RetrieveArgs R;
     R.ix = idx->view; R.n = n; R.ids = ids ? d_ids.as<uint64_t>() : nullptr; R.first = first; R.step = step;
@@ -82,6 +85,8 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
     OV_TRY(cudaGetLastError());
     std::vector<int32_t> h_len(n);
     OV_TRY(cudaMemcpy(h_len.data(), d_len.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    const double t_retrieve = since(t0);
+    const auto t1 = std::chrono::steady_clock::now();
     for (int64_t i = 0; i < n; ++i)
         if (h_len[i] < 0) {
             if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] a sequence of %d bases exceeds max_len=%d\n", __func__, -h_len[i], max_len);
@@ -97,7 +102,7 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
     const int64_t n_lanes = (int64_t)grid * OVLP_BLOCK;
     int cap = 4 * max_len, nei_cap = 8;
     const int s_cap = 2 * max_len + 8;
-    std::vector<int64_t> h_rec((size_t)n * OV_NREC);
+    int64_t *h_rec = rec;
     std::vector<uint32_t> h_cnt(n);
     for (int attempt = 0;; ++attempt) {
         const size_t esz = wide ? 32 : 16;
@@ -112,7 +117,9 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
         if (wide) k_overlap<uint64_t><<<grid, OVLP_BLOCK>>>(O); else k_overlap<uint32_t><<<grid, OVLP_BLOCK>>>(O);
         ++g_launches;
         OV_TRY(cudaGetLastError());
-        OV_TRY(cudaMemcpy(h_rec.data(), d_rec.p, (size_t)n * OV_NREC * 8, cudaMemcpyDeviceToHost));
+        OV_TRY(cudaDeviceSynchronize());
+        if (fmg_verbose >= 4) std::fprintf(stderr, "[M::%s] k_retrieve %.3f s, k_overlap (attempt %d) %.3f s for %lld sequences\n", __func__, t_retrieve, attempt, since(t1), (long long)n);
+        OV_TRY(cudaMemcpy(h_rec, d_rec.p, (size_t)n * OV_NREC * 8, cudaMemcpyDeviceToHost));
         OV_TRY(cudaMemcpy(h_cnt.data(), d_cnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
         bool list_ovf = false, nei_ovf = false;
         for (int64_t i = 0; i < n; ++i) {
@@ -132,7 +139,6 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
     std::vector<int64_t> h_ret(n);
     OV_TRY(cudaMemcpy(h_ret.data(), d_ret.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     for (int64_t i = 0; i < n; ++i) h_rec[i * OV_NREC + OV_K] = h_ret[i];
-    std::memcpy(rec, h_rec.data(), (size_t)n * OV_NREC * 8);
 
     // ---- neighbour slots -> dense array + offsets
     if (fmg_compact_slots(d_cnt.as<uint32_t>(), n, nei_cap, d_slots.as<uint4>(), d_mem.as<uint4>(), d_off.as<uint64_t>(),
@@ -144,6 +150,7 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
     if (seq) OV_TRY(cudaMemcpy(seq, d_seq.p, (size_t)n * max_len, cudaMemcpyDeviceToHost));
     if (len) std::memcpy(len, h_len.data(), (size_t)n * 4);
     if (ext) OV_TRY(cudaMemcpy(ext, d_ext.p, (size_t)n * max_len, cudaMemcpyDeviceToHost));
+    if (fmg_verbose >= 4) std::fprintf(stderr, "[M::%s] batch total %.3f s\n", __func__, since(t0));
     return 0;
 }
 

@@ -13,6 +13,10 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <chrono>
+#include <memory>
+#include <thread>
+#include <mutex>
 #include "fmd_overlap.cuh"
 #include "fmg_internal.hpp"
 #include "../../include/fermi_b200.h"
@@ -21,19 +25,19 @@ using namespace fmg;
 
 namespace {
 
-struct Records {
+struct Records {                     // non-owning views of the arrays fmg_overlap_batch fills
     uint64_t n_seq = 0;
     int max_len = 0;
-    std::vector<int64_t> rec;        // n_seq x OV_NREC
-    std::vector<fmg_intv_t> nei;
-    std::vector<uint64_t> nei_off;   // n_seq + 1
-    std::vector<uint8_t> seq, ext;   // n_seq x max_len
+    const int64_t *rec = nullptr;    // n_seq x OV_NREC
+    const fmg_intv_t *nei = nullptr;
+    const uint64_t *nei_off = nullptr;   // n_seq + 1
+    const uint8_t *seq = nullptr, *ext = nullptr;   // n_seq x max_len
     // Records are indexed by BWT row (= sequence number in the text, the seed of unitig_core).  The ids the
     // walk sees -- fm_retrieve's return value, intv0.x[], neighbour x[] -- are ranks of the sequence among all
     // sequences in lexicographic order (LF of a sentinel counts the '$' above it), so neighbours are
     // looked up through the inverse of rec[OV_K].
     std::vector<uint64_t> row_of_rank;
-    const int64_t *r(uint64_t row) const { return &rec[row * OV_NREC]; }
+    const int64_t *r(uint64_t row) const { return rec + row * OV_NREC; }
     uint64_t row(uint64_t rank) const { return row_of_rank[rank]; }
     void index_ranks() {
         row_of_rank.assign(n_seq, 0);
@@ -41,12 +45,12 @@ struct Records {
     }
 };
 
-struct Bits {
+struct Bits {                                   // shared by the walker threads like the reference's bitmaps (unitig.c:15-20)
     std::vector<uint64_t> w;
     explicit Bits(uint64_t n) : w((n + 63) / 64, 0) {}
-    bool get(uint64_t i) const { return w[i >> 6] >> (i & 63) & 1; }
-    bool test_and_set(uint64_t i) { const uint64_t m = 1ull << (i & 63); const bool was = w[i >> 6] & m; w[i >> 6] |= m; return was; }
-    void set(uint64_t i) { w[i >> 6] |= 1ull << (i & 63); }
+    bool get(uint64_t i) const { return __atomic_load_n(&w[i >> 6], __ATOMIC_RELAXED) >> (i & 63) & 1; }
+    bool test_and_set(uint64_t i) { const uint64_t m = 1ull << (i & 63); return __atomic_fetch_or(&w[i >> 6], m, __ATOMIC_RELAXED) & m; }
+    void set(uint64_t i) { __atomic_fetch_or(&w[i >> 6], 1ull << (i & 63), __ATOMIC_RELAXED); }
     void set_intv(uint64_t x0, uint64_t x1, uint64_t x2) {           // set_bits, unitig.c:22-36
         for (uint64_t k = 0; k < x2; ++k) set(x0 + k), set(x1 + k);
     }
@@ -57,11 +61,11 @@ struct Nei { uint64_t x; uint64_t y; };
 struct Walker {
     const Records &R;
     int min_match;
-    Bits used, bend, visited;
+    Bits &used, &bend, &visited;
     std::string s, cov;
     std::vector<Nei> last_nei;           // a->nei after unitig_unidir
 
-    Walker(const Records &r, int mm) : R(r), min_match(mm), used(r.n_seq), bend(r.n_seq), visited(r.n_seq) {}
+    Walker(const Records &r, int mm, Bits &u, Bits &b, Bits &v) : R(r), min_match(mm), used(u), bend(b), visited(v) {}
 
     // unitig_unidir, unitig.c:227-262.  `cur` = record row of the last read of s, which starts at s[beg].
     int unidir(uint64_t cur, int beg, uint64_t k0, uint64_t *end, int *is_loop) {
@@ -72,7 +76,7 @@ struct Walker {
             const int64_t *r = R.r(cur);
             last_nei.clear();
             if (r[OV_RBEG] < 0 || r[OV_NNEI] == 0) break;                 // try_right() < 0
-            const fmg_intv_t *nb = &R.nei[R.nei_off[cur]];
+            const fmg_intv_t *nb = R.nei + R.nei_off[cur];
             const int n_nei = (int)r[OV_NNEI];
             for (int k = 0; k < n_nei; ++k) last_nei.push_back(Nei{nb[k].x[0], nb[k].info});
             const int rbeg = beg + (int)r[OV_RBEG];
@@ -94,7 +98,7 @@ struct Walker {
             ++n_reads;
             // the consensus grows by the extension recorded for `cur` (unitig.c:141,253-257)
             const int new_l = beg + (int)r[OV_SLEN];
-            const uint8_t *ext = &R.ext[cur * (uint64_t)R.max_len];
+            const uint8_t *ext = R.ext + cur * (uint64_t)R.max_len;
             s.resize(new_l); cov.resize(new_l);
             for (int i = ori_l; i < new_l; ++i) s[i] = (char)ext[i - ori_l], cov[i] = '"';
             for (int i = rbeg; i < ori_l; ++i) if (cov[i] != '~') ++cov[i];
@@ -115,7 +119,7 @@ struct Walker {
         used.set_intv((uint64_t)r[OV_X0], (uint64_t)r[OV_X1], (uint64_t)r[OV_X2]);
         if (r[OV_CONTAINED] < 0) return -3;
         *n_reads = 1;
-        s.assign((const char *)&R.seq[seed * (uint64_t)R.max_len], seed_len);
+        s.assign((const char *)(R.seq + seed * (uint64_t)R.max_len), seed_len);
         cov.assign(seed_len, '"');
         end[0] = (uint64_t)r[OV_X1]; end[1] = (uint64_t)r[OV_X0];
         int is_loop = 0;
@@ -164,34 +168,60 @@ int fmg_unitig_assemble(uint64_t n_seq, int max_len, int min_match, const int64_
                         const uint64_t *nei_off, const uint8_t *seq, const uint8_t *ext, const char *out_path, uint64_t *n_unitigs) {
     Records R;
     R.n_seq = n_seq; R.max_len = max_len;
-    R.rec.assign(rec, rec + n_seq * OV_NREC);
-    R.nei_off.assign(nei_off, nei_off + n_seq + 1);
-    R.nei.assign(nei, nei + nei_off[n_seq]);
-    R.seq.assign(seq, seq + n_seq * (uint64_t)max_len);
-    R.ext.assign(ext, ext + n_seq * (uint64_t)max_len);
+    R.rec = rec; R.nei_off = nei_off; R.nei = nei; R.seq = seq; R.ext = ext;
     R.index_ranks();
     FILE *fp = std::strcmp(out_path, "-") ? std::fopen(out_path, "wb") : stdout;
     if (!fp) {
         if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] cannot write '%s'\n", __func__, out_path);
         return -1;
     }
-    Walker W(R, min_match);
-    std::string out;
-    uint64_t end[2], count = 0;
-    std::vector<Nei> nb[2];
-    int n_reads;
-    // seeds = odd sentinel ranks in the order of unitig_core (unitig.c:333-334)
-    for (uint64_t j = 0; j <= n_seq >> 2; ++j)
-        for (uint64_t i = j << 2 | 1; i < (j << 2) + 4 && i < n_seq; i += 2) {
-            if (W.unitig1(i, end, nb, &n_reads) < 0) continue;
-            if (W.visited.test_and_set(end[0]) || W.visited.test_and_set(end[1])) continue;    // unitig.c:337-339 (short-circuit like the reference)
-            out.clear();
-            write_mag(out, end, n_reads, nb, W.s, W.cov);
-            std::fwrite(out.data(), 1, out.size(), fp);
-            ++count;
-        }
+    const auto tw0 = std::chrono::steady_clock::now();
+    // Strided worker threads over the seeds, sharing the three bitmaps through atomics: the scheme of
+    // fm6_unitig (unitig.c:378-407).  One thread reproduces `fermi unitig -t1` record for record; with more
+    // threads the record order and orientation vary but the canonicalised set does not.
+    int n_threads = 1;
+    if (const char *e = std::getenv("FMG_THREADS")) n_threads = std::atoi(e);
+    else n_threads = (int)std::min<unsigned>(std::thread::hardware_concurrency(), 32u);
+    if (n_threads < 1 || n_seq < 64) n_threads = 1;
+    Bits used(n_seq), bend(n_seq), visited(n_seq);
+    std::vector<uint64_t> counts(n_threads, 0);
+    std::mutex out_lock;
+    auto work = [&](int tid) {
+        Walker W(R, min_match, used, bend, visited);
+        std::string out;
+        out.reserve(1 << 20);
+        uint64_t end[2];
+        std::vector<Nei> nb[2];
+        int n_reads;
+        // seeds = odd sentinel ranks in the order of unitig_core (unitig.c:333-334), start = tid, step = n_threads
+        for (uint64_t j = tid; j <= n_seq >> 2; j += n_threads)
+            for (uint64_t i = j << 2 | 1; i < (j << 2) + 4 && i < n_seq; i += 2) {
+                if (W.unitig1(i, end, nb, &n_reads) < 0) continue;
+                if (visited.test_and_set(end[0]) || visited.test_and_set(end[1])) continue;    // unitig.c:337-339 (short-circuit like the reference)
+                write_mag(out, end, n_reads, nb, W.s, W.cov);
+                ++counts[tid];
+                if (out.size() > (1 << 20)) {
+                    std::lock_guard<std::mutex> g(out_lock);
+                    std::fwrite(out.data(), 1, out.size(), fp);
+                    out.clear();
+                }
+            }
+        std::lock_guard<std::mutex> g(out_lock);
+        std::fwrite(out.data(), 1, out.size(), fp);
+    };
+    if (n_threads == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; ++t) th.emplace_back(work, t);
+        for (auto &t : th) t.join();
+    }
+    uint64_t count = 0;
+    for (uint64_t c : counts) count += c;
     if (fp != stdout) std::fclose(fp); else std::fflush(fp);
     if (n_unitigs) *n_unitigs = count;
+    if (fmg_verbose >= 4)
+        std::fprintf(stderr, "[M::%s] %llu unitigs from %llu sequences in %.3f s (%d threads)\n", __func__, (unsigned long long)count, (unsigned long long)n_seq,
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - tw0).count(), n_threads);
     return 0;
 }
 
@@ -202,25 +232,26 @@ int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *o
     if (!idx) return -1;
     const uint64_t n_seq = idx->mcnt[1];
     if (n_unitigs) *n_unitigs = 0;
+    const auto t0 = std::chrono::steady_clock::now();
     if (max_len <= 0) max_len = (int)((idx->mcnt[0] - n_seq + n_seq - 1) / (n_seq ? n_seq : 1)) + 8;
-    std::vector<int64_t> rec;
+    std::unique_ptr<int64_t[]> rec;
     std::vector<fmg_intv_t> nei;
-    std::vector<uint64_t> nei_off;
-    std::vector<uint8_t> seq, ext;
+    std::unique_ptr<uint64_t[]> nei_off;
+    std::unique_ptr<uint8_t[]> seq, ext;
     for (;;) {
-        rec.assign(n_seq * OV_NREC, 0); nei_off.assign(n_seq + 1, 0);
-        seq.assign(n_seq * (uint64_t)max_len, 0); ext.assign(n_seq * (uint64_t)max_len, 0);
+        rec.reset(new int64_t[n_seq * OV_NREC]); nei_off.reset(new uint64_t[n_seq + 1]);      // filled batch by batch, no zero fill
+        seq.reset(new uint8_t[n_seq * (uint64_t)max_len]); ext.reset(new uint8_t[n_seq * (uint64_t)max_len]);
         nei.clear();
+        nei_off[0] = 0;
         const uint64_t batch = 1 << 21;
-        std::vector<int32_t> len;
-        std::vector<uint64_t> off;
+        std::unique_ptr<int32_t[]> len(new int32_t[batch]);
+        std::unique_ptr<uint64_t[]> off(new uint64_t[batch + 1]);
         int rc = 0;
         for (uint64_t b = 0; b < n_seq && rc == 0; b += batch) {
             const uint64_t m = std::min<uint64_t>(batch, n_seq - b);
             fmg_intv_t *nb = nullptr;
-            len.assign(m, 0); off.assign(m + 1, 0);
-            rc = fmg_overlap_batch(idx, min_match, (int64_t)m, nullptr, b, 1, max_len, &rec[b * OV_NREC], &nb, off.data(),
-                                   &seq[b * (uint64_t)max_len], len.data(), &ext[b * (uint64_t)max_len]);
+            rc = fmg_overlap_batch(idx, min_match, (int64_t)m, nullptr, b, 1, max_len, &rec[b * OV_NREC], &nb, off.get(),
+                                   &seq[b * (uint64_t)max_len], len.get(), &ext[b * (uint64_t)max_len]);
             if (rc == 0) {
                 const uint64_t base = nei.size();
                 nei.insert(nei.end(), nb, nb + off[m]);
@@ -232,7 +263,13 @@ int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *o
         if (rc != 0) return rc;
         break;
     }
-    return fmg_unitig_assemble(n_seq, max_len, min_match, rec.data(), nei.data(), nei_off.data(), seq.data(), ext.data(), out_path, n_unitigs);
+    const auto t1 = std::chrono::steady_clock::now();
+    const int rc = fmg_unitig_assemble(n_seq, max_len, min_match, rec.get(), nei.data(), nei_off.get(), seq.get(), ext.get(), out_path, n_unitigs);
+    const auto t2 = std::chrono::steady_clock::now();
+    if (fmg_verbose >= 3)
+        std::fprintf(stderr, "[M::%s] %llu sequences: overlap records %.3f s (GPU, incl. copies), unitig walk + output %.3f s (host)\n", __func__,
+                     (unsigned long long)n_seq, std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count());
+    return rc;
 }
 
 } // extern "C"
