@@ -197,7 +197,12 @@ int fmg_unitig_assemble(uint64_t n_seq, int max_len, int min_match, const int64_
         for (uint64_t j = tid; j <= n_seq >> 2; j += n_threads)
             for (uint64_t i = j << 2 | 1; i < (j << 2) + 4 && i < n_seq; i += 2) {
                 if (W.unitig1(i, end, nb, &n_reads) < 0) continue;
-                if (visited.test_and_set(end[0]) || visited.test_and_set(end[1])) continue;    // unitig.c:337-339 (short-circuit like the reference)
+                // unitig.c:337-339: the first walk that claims both end ids emits the unitig.  One thread claims in the
+                // reference's order (k[0] then k[1], short-circuit).  With several threads the reference's order lets two
+                // walks of the same unitig in opposite orientations knock each other out (each claims its own k[0] first
+                // and then finds the other's); claiming the smaller id first makes exactly one of them win.
+                const int f = (n_threads > 1 && end[1] < end[0]) ? 1 : 0;
+                if (visited.test_and_set(end[f]) || visited.test_and_set(end[f ^ 1])) continue;
                 write_mag(out, end, n_reads, nb, W.s, W.cov);
                 ++counts[tid];
                 if (out.size() > (1 << 20)) {

@@ -1,0 +1,87 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): the index is replicated in every GPU's
+HBM and the units of work -- reads for SMEM, sequences for the unitig overlap records -- are sharded by
+contiguous ranges, the way the reference stripes its threads (unitig.c:394-404, smem.c:346-381).
+
+The only exchange on the path is the all-gather that reassembles the overlap records before the unitig
+walk; SMEM results stay with the rank that owns the reads.  torch.distributed is used for
+rendezvous and the collective only (NCCL over NVLink on GPUs, gloo in the CPU tests).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .api import INTV
+
+
+def shard_range(n, rank, world):
+    """contiguous [lo, hi) of n units for `rank`; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _device():
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def _allgather_rows(a, counts, group=None):
+    """all-gather of a 2-D array whose row count differs per rank (padded to the largest shard)."""
+    world = dist.get_world_size(group)
+    dev = _device()
+    width = a.shape[1]
+    pad = int(max(counts))
+    t = torch.zeros((pad, width), dtype=torch.from_numpy(a[:0]).dtype, device=dev)
+    if len(a):
+        t[: len(a)] = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t, group=group)
+    return np.concatenate([o[: int(c)].cpu().numpy() for o, c in zip(outs, counts)], axis=0)
+
+
+def allgather_overlap_records(local, group=None):
+    """Reassemble the per-sequence overlap records (fermi_b200.fm6_overlap) of all ranks, in rank order.
+    `local` holds this rank's shard: rec[m,10], nei INTV[], nei_off[m+1], seq[m,L], ext[m,L]."""
+    world = dist.get_world_size(group)
+    dev = _device()
+    m = len(local["rec"])
+    n_nei = len(local["nei"])
+    sizes = torch.tensor([m, n_nei], dtype=torch.int64, device=dev)
+    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)                    # (1) shard sizes
+    rows = [int(s[0]) for s in all_sizes]
+    neis = [int(s[1]) for s in all_sizes]
+    rec = _allgather_rows(local["rec"], rows, group)                   # (2) padded payloads
+    seq = _allgather_rows(local["seq"], rows, group)
+    ext = _allgather_rows(local["ext"], rows, group)
+    cnt = np.diff(local["nei_off"].astype(np.int64)).reshape(-1, 1)
+    cnt = _allgather_rows(cnt, rows, group).reshape(-1)
+    nei = _allgather_rows(np.ascontiguousarray(local["nei"]).view(np.int64).reshape(-1, 4), neis, group)
+    nei = np.ascontiguousarray(nei).view(INTV).reshape(-1)
+    nei_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint64)
+    return dict(rec=rec, nei=nei, nei_off=nei_off, seq=seq, ext=ext)
+
+
+def unitig_distributed(idx, min_match, out_path, max_len, overlap_fn=None, group=None):
+    """`fermi unitig` over all ranks: every rank computes the overlap records of its range of sequences on its
+    GPU, one all-gather reassembles them, rank 0 walks the unitigs and writes the MAG file.  Returns the
+    number of unitigs on rank 0 (None elsewhere)."""
+    from . import api
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n_seq = int(idx.mcnt[1])
+    lo, hi = shard_range(n_seq, rank, world)
+    fn = overlap_fn or (lambda first, n: api.fm6_overlap(idx, min_match, first=first, step=1, n=n, max_len=max_len))
+    local = fn(lo, hi - lo)
+    full = allgather_overlap_records(local, group)
+    if rank == 0:
+        return api.fm6_unitig_assemble(n_seq, min_match, full, out_path)
+    return None
+
+
+def allgather_counts(n_local, group=None):
+    """per-rank unit counts -> (counts, exclusive offsets): global numbering of sharded SMEM results."""
+    world = dist.get_world_size(group)
+    t = torch.tensor([n_local], dtype=torch.int64, device=_device())
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t, group=group)
+    counts = [int(o[0]) for o in outs]
+    return counts, [sum(counts[:i]) for i in range(world)]

@@ -65,3 +65,25 @@ def test_unitig_walk_fresh_inputs_vs_reference_binary(emu, product_lib, tmp_path
     fb.fm6_unitig_assemble(n_seq, 40, dict(rec=rec, nei=nei, nei_off=off, seq=seq, ext=ext), out)
     assert H.canonical_mag(H.parse_mag(open(out).read())) == H.canonical_mag(ref_t1)
     emu.lib.emu_index_free(x)
+
+
+def test_threaded_walk_gives_the_same_unitig_set(emu, product_lib, tmp_path, monkeypatch):
+    """many seeds per unitig (error-free 12x): 1 walker thread vs 7 must emit the same canonical set."""
+    import fermi_b200 as fb
+    g = fb.synth_genome(77, 40000)
+    reads = fb.synth_reads(78, g, 6000, 80, 0.0)
+    fmd = str(tmp_path / "f.fmd")
+    fb.Fmd.from_bwt(H.naive_bwt(fb.fmd_text(reads))).dump(fmd)
+    x = emu.index(fmd)
+    n_seq = 2 * len(reads)
+    rec, nei, off, seq, ln, ext = emu.overlap(x, 40, np.arange(n_seq, dtype=np.uint64), 88, nei_cap=32)
+    o = dict(rec=rec, nei=nei, nei_off=off, seq=seq, ext=ext)
+    sets = []
+    for threads in ("1", "7", "7", "7"):
+        monkeypatch.setenv("FMG_THREADS", threads)
+        out = str(tmp_path / ("u%s.mag" % threads))
+        fb.fm6_unitig_assemble(n_seq, 40, o, out)
+        sets.append(H.canonical_mag(H.parse_mag(open(out).read())))
+    assert len(sets[0]) > 10
+    assert all(s == sets[0] for s in sets[1:])
+    emu.lib.emu_index_free(x)

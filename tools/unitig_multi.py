@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""`fermi unitig` over N GPUs of one box (one rank per GPU, NCCL all-gather of the overlap records):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tools/unitig_multi.py --reads 1000000 [--check]
+Every rank holds the whole index; sequences are sharded by contiguous ranges (fermi_b200.parallel)."""
+import argparse, json, os, sys, tempfile, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch, torch.distributed as dist
+import fermi_b200 as fb
+from fermi_b200 import parallel
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--reads", type=int, default=1000000)
+ap.add_argument("--err", type=float, default=0.0)
+ap.add_argument("--check", action="store_true", help="compare with a single-GPU fm6_unitig on rank 0")
+a = ap.parse_args()
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+fn = os.path.join(tempfile.gettempdir(), "unitig_multi_%d.fmd" % a.reads)
+if rank == 0:
+    genome = fb.synth_genome(41, a.reads * 10)
+    reads = fb.synth_reads(42, genome, a.reads, 100, a.err)
+    fb.fm_build(fb.fmd_text(reads), local).dump(fn)
+dist.barrier()
+idx = fb.FmdIndex(fb.Fmd.restore(fn), local)
+out = os.path.join(tempfile.gettempdir(), "unitig_multi.mag")
+for it in range(2):
+    dist.barrier(); torch.cuda.synchronize(); t = time.time()
+    n = parallel.unitig_distributed(idx, 50, out, 108)
+    dist.barrier(); dt = time.time() - t
+if rank == 0:
+    res = {"n_gpus": world, "reads": a.reads, "unitigs": n, "seconds": dt, "reads_per_s": a.reads / dt}
+    if a.check:
+        import helpers as H
+        single = out + ".single"
+        fb.fm6_unitig(idx, 50, single)
+        res["set_equal_single_gpu"] = H.canonical_mag(H.parse_mag(open(out).read())) == H.canonical_mag(H.parse_mag(open(single).read()))
+    print(json.dumps(res))
+dist.barrier(); dist.destroy_process_group()
