@@ -53,6 +53,14 @@ _PROTOS = {
     "fmg_unitig": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, u64p]),
     # construction + synthetic data
     "fmg_build_bwt": (C.c_int, [C.c_int, C.c_int64, u8p, u8p]),
+    "fmg_bcr_init": (C.c_void_p, [C.c_int]),
+    "fmg_bcr_append": (C.c_int, [C.c_void_p, C.c_int, u8p]),
+    "fmg_bcr_append_batch": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, u8p]),
+    "fmg_bcr_build": (C.c_int, [C.c_void_p]),
+    "fmg_bcr_size": (C.c_int64, [C.c_void_p]),
+    "fmg_bcr_bwt": (C.c_int, [C.c_void_p, u8p]),
+    "fmg_bcr_rle": (C.c_int, [C.c_void_p, vpp, C.POINTER(C.c_int64)]),
+    "fmg_bcr_destroy": (None, [C.c_void_p]),
     "fmg_synth_genome": (None, [C.c_uint64, C.c_int64, u8p]),
     "fmg_synth_reads": (None, [C.c_uint64, C.c_int64, u8p, C.c_int64, C.c_int, C.c_double, u8p]),
     "fmg_fmd_text": (C.c_int64, [C.c_int64, C.c_int, u8p, u8p]),

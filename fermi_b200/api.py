@@ -250,6 +250,73 @@ def fm_build(text, device=0):
     return Fmd.from_bwt(fm_build_bwt(text, device))
 
 
+class Bcr:
+    """bcr_t (bcr.h:43-49): append sequences, build the BWT on the GPU, read it back."""
+
+    def __init__(self, device=0):
+        self.h = lib().fmg_bcr_init(device)
+
+    def append(self, seq):
+        seq = np.ascontiguousarray(seq, np.uint8)
+        _check(lib().fmg_bcr_append(self.h, len(seq), _p(seq, u8p)), "bcr_append")
+
+    def append_batch(self, seqs):
+        seqs = np.ascontiguousarray(seqs, np.uint8)
+        _check(lib().fmg_bcr_append_batch(self.h, seqs.shape[0], seqs.shape[1], _p(seqs, u8p)), "bcr_append")
+
+    def build(self):
+        _check(lib().fmg_bcr_build(self.h), "bcr_build")
+
+    def bwt(self):
+        n = lib().fmg_bcr_size(self.h)
+        out = np.zeros(n, np.uint8)
+        _check(lib().fmg_bcr_bwt(self.h, _p(out, u8p)), "bcr_bwt")
+        return out
+
+    def rle(self):
+        p = C.c_void_p()
+        n = C.c_int64()
+        _check(lib().fmg_bcr_rle(self.h, C.byref(p), C.byref(n)), "bcr_rle")
+        out = np.frombuffer(C.string_at(p.value, n.value), np.uint8).copy()
+        lib().fmg_free(p)
+        return out
+
+    def close(self):
+        if self.h:
+            lib().fmg_bcr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def fm_ropebwt(reads, device=0):
+    """`fermi ropebwt -a bcr` (ropebwt.c:47-158): every read, then its reverse complement (even-length
+    reverse-complement palindromes lose their last base first, ropebwt.c:25-29), through the GPU BCR. Returns the BWT."""
+    b = Bcr(device)
+    reads = np.ascontiguousarray(reads, np.uint8)
+    if reads.ndim == 2 and reads.shape[1] % 2 == 1:            # odd length: no palindromes, one batch of (read, revcomp) pairs
+        rc = 5 - reads[:, ::-1]
+        both = np.empty((2 * len(reads), reads.shape[1]), np.uint8)
+        both[0::2], both[1::2] = reads, rc
+        b.append_batch(both)
+    else:
+        for r in reads:
+            r = np.asarray(r, np.uint8)
+            l = len(r)
+            if l % 2 == 0 and l > 0 and np.all(r[: l // 2] + r[::-1][: l // 2] == 5):
+                r = r[:-1]
+            b.append(r)
+            b.append((5 - r[::-1]).astype(np.uint8))
+    b.build()
+    out = b.bwt()
+    b.close()
+    return out
+
+
 def launch_count():
     return int(lib().fmg_launch_count())
 

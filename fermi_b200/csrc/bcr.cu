@@ -1,0 +1,337 @@
+// BCR (Bauer-Cox-Rosone) BWT construction on the GPU: the builder behind `fermi ropebwt -a bcr`
+// (bcr.c:358-521, ropebwt.c:47-158), for collections of any total size that fits HBM (no 2^32 limit).
+//
+// Same cycle structure as the reference -- cycle `pos` inserts, for every sequence still active, the base
+// at distance `pos` from its end as the BWT symbol of the suffix that was completed in cycle pos-1, and the
+// sentinel when the sequence is exhausted (bcr.c:417-449) -- but laid out for a B200:
+//   * the partial BWT is ONE plain byte array in HBM (15 GB for 50 M x 150 bp; two buffers), not six
+//     run-length-encoded ropes: a cycle is a streaming merge of the old array with the sorted inserts;
+//   * the insert position of a suffix in the next cycle is the LF mapping C[a] + rank_a(B, F): ranks come
+//     from a per-tile symbol histogram (k_bcr_merge), an exclusive scan over the tiles and the in-tile
+//     prefix, all computed inside the merge pass -- no separate rank structure is maintained;
+//   * LF is monotone, so the order of the sequences in the next cycle is the STABLE partition of the current
+//     order by the inserted symbol: one 3-bit radix pass replaces the reference's per-bucket radix sort of
+//     64-bit positions (rs_sort, bcr.c:212-249,426).
+// The result is the BWT of  r0 $ r1 $ ...  with sentinels ordered by sequence number: byte-identical (after
+// RLD encoding) to what `fermi build` and `fermi ropebwt` + `recode` produce.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <atomic>
+#include <vector>
+#include "../../include/fermi_b200.h"
+
+extern std::atomic<uint64_t> g_launches;
+
+namespace {
+
+#define BCR_TRY(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t err__ = (call);                                                                     \
+        if (err__ != cudaSuccess) {                                                                     \
+            if (fmg_verbose >= 1)                                                                       \
+                std::fprintf(stderr, "[E::fmg_bcr_build] %s failed: %s\n", #call, cudaGetErrorString(err__)); \
+            return -1;                                                                                  \
+        }                                                                                               \
+    } while (0)
+
+constexpr int kTile = 2048;          // output symbols per block of the merge pass
+constexpr int kThreads = 256;        // 8 symbols per thread
+
+struct Vec4 { uint64_t v[4]; };      // occurrences of A,C,G,T
+struct Vec4Add { __host__ __device__ Vec4 operator()(const Vec4 &a, const Vec4 &b) const { Vec4 r; for (int i = 0; i < 4; ++i) r.v[i] = a.v[i] + b.v[i]; return r; } };
+struct Item { uint64_t f; uint32_t id; uint32_t pad; };      // (position of the suffix in the current BWT, sequence)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { cudaFree(p); }
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        cudaFree(p); p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+// symbol each active sequence inserts in cycle `pos`: its base at distance pos from the end, 0 when exhausted (bcr.c:430)
+__global__ void k_bcr_symbols(const Item *__restrict__ item, uint64_t n_act, const uint8_t *__restrict__ seq, const uint64_t *__restrict__ off,
+                              int pos, uint8_t *__restrict__ sym) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_act) return;
+    const uint32_t id = item[k].id;
+    const uint64_t b = off[id], e = off[id + 1];
+    sym[k] = (uint64_t)pos < e - b ? seq[e - 1 - pos] : 0;
+}
+
+__global__ void k_bcr_iota(Item *item, uint64_t n) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) { item[k].f = k; item[k].id = (uint32_t)k; item[k].pad = 0; }
+}
+
+__device__ __forceinline__ uint64_t lower_bound_f(const Item *item, uint64_t n, uint64_t q) {
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (item[mid].f < q) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// One tile of the new BWT: old symbols and inserts merged, the tile's A/C/G/T histogram, and for every insert
+// the number of equal symbols before it inside the tile.
+__global__ void __launch_bounds__(kThreads) k_bcr_merge(const uint8_t *__restrict__ old_bwt, uint64_t m_new, const Item *__restrict__ item,
+                                                        const uint8_t *__restrict__ sym, uint64_t n_act, uint8_t *__restrict__ new_bwt,
+                                                        Vec4 *__restrict__ tile_hist, uint32_t *__restrict__ rank_in_tile) {
+    __shared__ uint8_t s_sym[kTile], s_flag[kTile];
+    __shared__ uint64_t s_k[2];
+    __shared__ uint32_t s_warp_ins[kThreads / 32];
+    __shared__ uint64_t s_warp_cnt[kThreads / 32];
+    const uint64_t q0 = (uint64_t)blockIdx.x * kTile;
+    const int tid = threadIdx.x;
+    if (tid < 2) s_k[tid] = lower_bound_f(item, n_act, tid == 0 ? q0 : (q0 + kTile < m_new ? q0 + kTile : m_new));
+    for (int j = tid; j < kTile; j += kThreads) s_flag[j] = 0;
+    __syncthreads();
+    const uint64_t k_lo = s_k[0], k_hi = s_k[1];
+    for (uint64_t k = k_lo + tid; k < k_hi; k += kThreads) {
+        const int j = (int)(item[k].f - q0);
+        s_flag[j] = 1; s_sym[j] = sym[k];
+    }
+    __syncthreads();
+    // inserts before each thread's 8 positions
+    const int j0 = tid * 8;
+    uint32_t my_ins = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) my_ins += s_flag[j0 + t];
+    uint32_t incl = my_ins;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
+    if ((tid & 31) == 31) s_warp_ins[tid >> 5] = incl;
+    __syncthreads();
+    uint32_t ins_before = incl - my_ins;
+    for (int w = 0; w < (tid >> 5); ++w) ins_before += s_warp_ins[w];
+    // fill the old symbols
+    const uint64_t src0 = q0 - k_lo;            // old symbols before this tile
+    {
+        uint32_t ib = ins_before;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int j = j0 + t;
+            if (q0 + j < m_new) {
+                if (s_flag[j]) ++ib;
+                else s_sym[j] = old_bwt[src0 + (uint64_t)(j - ib)];
+            } else s_sym[j] = 7;
+        }
+    }
+    // packed A/C/G/T counts of the thread's 8 symbols (4 x 16 bit) and their block-wide exclusive prefix
+    uint64_t my_cnt = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { const uint32_t c = s_sym[j0 + t]; if (c >= 1 && c <= 4) my_cnt += 1ull << (16 * (c - 1)); }
+    uint64_t cincl = my_cnt;
+    for (int o = 1; o < 32; o <<= 1) { const uint64_t v = __shfl_up_sync(0xffffffffu, cincl, o); if ((tid & 31) >= o) cincl += v; }
+    if ((tid & 31) == 31) s_warp_cnt[tid >> 5] = cincl;
+    __syncthreads();
+    uint64_t cnt_before = cincl - my_cnt;
+    for (int w = 0; w < (tid >> 5); ++w) cnt_before += s_warp_cnt[w];
+    if (tid == kThreads - 1) {
+        const uint64_t tot = cnt_before + my_cnt;
+        Vec4 h;
+        for (int c = 0; c < 4; ++c) h.v[c] = (tot >> (16 * c)) & 0xffff;
+        tile_hist[blockIdx.x] = h;
+    }
+    // rank of every insert among equal symbols inside the tile
+    {
+        uint64_t run = cnt_before;
+        uint32_t ib = ins_before;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int j = j0 + t;
+            const uint32_t c = s_sym[j];
+            if (s_flag[j]) {
+                rank_in_tile[k_lo + ib] = (c >= 1 && c <= 4) ? (uint32_t)((run >> (16 * (c - 1))) & 0xffff) : 0u;
+                ++ib;
+            }
+            if (c >= 1 && c <= 4) run += 1ull << (16 * (c - 1));
+        }
+    }
+    // write the tile (8 bytes per thread)
+    if (q0 + j0 + 8 <= m_new) *reinterpret_cast<uint2 *>(new_bwt + q0 + j0) = *reinterpret_cast<const uint2 *>(s_sym + j0);
+    else for (int t = 0; t < 8; ++t) if (q0 + j0 + t < m_new) new_bwt[q0 + j0 + t] = s_sym[j0 + t];
+}
+
+// LF mapping of every insert: position of the extended suffix in the next cycle's BWT (bcr.c:442 + set_bwt bookkeeping)
+__global__ void k_bcr_lf(Item *__restrict__ item, const uint8_t *__restrict__ sym, const uint32_t *__restrict__ rank_in_tile,
+                         const Vec4 *__restrict__ tile_pref, const Vec4 *__restrict__ total, uint64_t n_act, uint64_t n_seq) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_act) return;
+    const uint32_t a = sym[k];
+    if (a < 1 || a > 4) return;                 // sequence finished: dropped by the partition
+    const uint64_t f = item[k].f;
+    uint64_t c = n_seq;                         // the sentinel bucket always holds one suffix per sequence
+    for (uint32_t b = 1; b < a; ++b) c += total->v[b - 1];
+    item[k].f = c + tile_pref[f / kTile].v[a - 1] + rank_in_tile[k];
+}
+
+__global__ void k_bcr_total(const Vec4 *tile_hist, const Vec4 *tile_pref, uint64_t n_tiles, Vec4 *total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        Vec4 t;
+        for (int c = 0; c < 4; ++c) t.v[c] = tile_pref[n_tiles - 1].v[c] + tile_hist[n_tiles - 1].v[c];
+        *total = t;
+    }
+}
+
+inline unsigned blocks_for(uint64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+} // namespace
+
+struct fmg_bcr_s {
+    int device = 0;
+    std::vector<uint8_t> seq;        // appended sequences, nt6 1..4
+    std::vector<uint64_t> off{0};
+    int max_len = 0;
+    std::vector<uint8_t> bwt;        // result (host), one nt6 byte per symbol
+    bool built = false;
+};
+
+static int bcr_build_device(fmg_bcr_s *b) {
+    const uint64_t n_seq = b->off.size() - 1;
+    const uint64_t total = b->seq.size() + n_seq;
+    if (n_seq == 0) { b->built = true; return 0; }
+    if (n_seq >= 0xffffffffull) { if (fmg_verbose >= 1) std::fprintf(stderr, "[E::fmg_bcr_build] more than 2^32-1 sequences\n"); return -1; }
+    DevBuf d_seq, d_off, d_bwt[2], d_item[2], d_sym[2], d_rank, d_hist, d_pref, d_total, d_tmp;
+    BCR_TRY(d_seq.reserve(b->seq.size())); BCR_TRY(d_off.reserve((n_seq + 1) * 8));
+    BCR_TRY(cudaMemcpy(d_seq.p, b->seq.data(), b->seq.size(), cudaMemcpyHostToDevice));
+    BCR_TRY(cudaMemcpy(d_off.p, b->off.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice));
+    BCR_TRY(d_bwt[0].reserve(total + 8)); BCR_TRY(d_bwt[1].reserve(total + 8));
+    BCR_TRY(d_item[0].reserve(n_seq * sizeof(Item))); BCR_TRY(d_item[1].reserve(n_seq * sizeof(Item)));
+    BCR_TRY(d_sym[0].reserve(n_seq)); BCR_TRY(d_sym[1].reserve(n_seq)); BCR_TRY(d_rank.reserve(n_seq * 4));
+    const uint64_t max_tiles = (total + kTile - 1) / kTile;
+    BCR_TRY(d_hist.reserve(max_tiles * sizeof(Vec4))); BCR_TRY(d_pref.reserve(max_tiles * sizeof(Vec4))); BCR_TRY(d_total.reserve(sizeof(Vec4)));
+    size_t tmp_scan = 0, tmp_sort = 0;
+    {
+        Vec4 zero{};
+        BCR_TRY(cub::DeviceScan::ExclusiveScan(nullptr, tmp_scan, d_hist.as<Vec4>(), d_pref.as<Vec4>(), Vec4Add(), zero, (int64_t)max_tiles));
+        cub::DoubleBuffer<uint8_t> dk(d_sym[0].as<uint8_t>(), d_sym[1].as<uint8_t>());
+        cub::DoubleBuffer<Item> dv(d_item[0].as<Item>(), d_item[1].as<Item>());
+        BCR_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, dk, dv, (int64_t)n_seq, 0, 3));
+    }
+    BCR_TRY(d_tmp.reserve(tmp_scan > tmp_sort ? tmp_scan : tmp_sort));
+
+    cub::DoubleBuffer<uint8_t> syms(d_sym[0].as<uint8_t>(), d_sym[1].as<uint8_t>());
+    cub::DoubleBuffer<Item> items(d_item[0].as<Item>(), d_item[1].as<Item>());
+    k_bcr_iota<<<blocks_for(n_seq, 256), 256>>>(items.Current(), n_seq); ++g_launches;
+    uint64_t n_act = n_seq, m = 0;
+    int cur = 0;
+    Vec4 h_total{}, h_prev{};
+    for (int pos = 0; n_act > 0; ++pos) {
+        const uint64_t m_new = m + n_act, n_tiles = (m_new + kTile - 1) / kTile;
+        k_bcr_symbols<<<blocks_for(n_act, 256), 256>>>(items.Current(), n_act, d_seq.as<uint8_t>(), d_off.as<uint64_t>(), pos, syms.Current()); ++g_launches;
+        k_bcr_merge<<<(unsigned)n_tiles, kThreads>>>(d_bwt[cur].as<uint8_t>(), m_new, items.Current(), syms.Current(), n_act, d_bwt[cur ^ 1].as<uint8_t>(),
+                                                     d_hist.as<Vec4>(), d_rank.as<uint32_t>()); ++g_launches;
+        size_t need = d_tmp.cap;
+        Vec4 zero{};
+        BCR_TRY(cub::DeviceScan::ExclusiveScan(d_tmp.p, need, d_hist.as<Vec4>(), d_pref.as<Vec4>(), Vec4Add(), zero, (int64_t)n_tiles));
+        k_bcr_total<<<1, 32>>>(d_hist.as<Vec4>(), d_pref.as<Vec4>(), n_tiles, d_total.as<Vec4>()); ++g_launches;
+        k_bcr_lf<<<blocks_for(n_act, 256), 256>>>(items.Current(), syms.Current(), d_rank.as<uint32_t>(), d_pref.as<Vec4>(), d_total.as<Vec4>(), n_act, n_seq); ++g_launches;
+        // next order = stable partition by the inserted symbol; finished sequences (symbol 0) sort first and are dropped
+        need = d_tmp.cap;
+        BCR_TRY(cub::DeviceRadixSort::SortPairs(d_tmp.p, need, syms, items, (int64_t)n_act, 0, 3));
+        BCR_TRY(cudaMemcpy(&h_total, d_total.p, sizeof(Vec4), cudaMemcpyDeviceToHost));
+        // sequences that inserted their sentinel in this cycle: all inserts that were not A/C/G/T
+        uint64_t bases_now = 0, bases_prev = 0;
+        for (int c = 0; c < 4; ++c) bases_now += h_total.v[c], bases_prev += h_prev.v[c];
+        const uint64_t finished = n_act - (bases_now - bases_prev);
+        h_prev = h_total;
+        // drop them: the sorted arrays start with the `finished` zero-symbol entries
+        if (finished) {
+            BCR_TRY(cudaMemcpyAsync(items.Alternate(), items.Current() + finished, (n_act - finished) * sizeof(Item), cudaMemcpyDeviceToDevice));
+            items.selector ^= 1;
+        }
+        n_act -= finished;
+        m = m_new;
+        cur ^= 1;
+        if (fmg_verbose >= 4) std::fprintf(stderr, "[M::fmg_bcr_build] cycle %d: %llu symbols, %llu sequences still active\n", pos, (unsigned long long)m, (unsigned long long)n_act);
+    }
+    BCR_TRY(cudaGetLastError());
+    b->bwt.resize(m);
+    BCR_TRY(cudaMemcpy(b->bwt.data(), d_bwt[cur].p, m, cudaMemcpyDeviceToHost));
+    b->built = true;
+    return 0;
+}
+
+extern "C" {
+
+fmg_bcr_t *fmg_bcr_init(int device) {
+    fmg_bcr_s *b = new fmg_bcr_s;
+    b->device = device;
+    return b;
+}
+
+void fmg_bcr_destroy(fmg_bcr_t *b) { delete b; }
+
+int fmg_bcr_append(fmg_bcr_t *b, int len, const uint8_t *seq) {
+    if (!b || len < 1) return -1;
+    for (int i = 0; i < len; ++i)
+        if (seq[i] < 1 || seq[i] > 4) {
+            if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] only A/C/G/T (nt6 1..4) are supported, like bcr_append (ropebwt.c:98,118)\n", __func__);
+            return -1;
+        }
+    b->seq.insert(b->seq.end(), seq, seq + len);
+    b->off.push_back(b->seq.size());
+    if (len > b->max_len) b->max_len = len;
+    return 0;
+}
+
+int fmg_bcr_append_batch(fmg_bcr_t *b, int64_t n, int len, const uint8_t *seqs) {
+    if (!b || len < 1 || n < 0) return -1;
+    const size_t base = b->seq.size();
+    b->seq.insert(b->seq.end(), seqs, seqs + (size_t)n * len);
+    for (size_t i = base; i < b->seq.size(); ++i)
+        if (b->seq[i] < 1 || b->seq[i] > 4) {
+            if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] only A/C/G/T (nt6 1..4) are supported\n", __func__);
+            b->seq.resize(base);
+            return -1;
+        }
+    for (int64_t i = 1; i <= n; ++i) b->off.push_back(base + (size_t)i * len);
+    if (len > b->max_len) b->max_len = len;
+    return 0;
+}
+
+int fmg_bcr_build(fmg_bcr_t *b) {
+    if (!b) return -1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] no CUDA device available; libfermi_b200 has no CPU path\n", __func__);
+        return -1;
+    }
+    if (cudaSetDevice(b->device) != cudaSuccess) return -1;
+    return bcr_build_device(b);
+}
+
+int64_t fmg_bcr_size(const fmg_bcr_t *b) { return b && b->built ? (int64_t)b->bwt.size() : -1; }
+
+int fmg_bcr_bwt(const fmg_bcr_t *b, uint8_t *bwt) {
+    if (!b || !b->built) return -1;
+    std::memcpy(bwt, b->bwt.data(), b->bwt.size());
+    return 0;
+}
+
+// the byte run-length stream of bcr_itr_next / `fermi ropebwt -b` (ropebwt.c:127-144): bytes len<<3|sym, len <= 31
+int fmg_bcr_rle(const fmg_bcr_t *b, uint8_t **rle, int64_t *n) {
+    if (!b || !b->built) return -1;
+    std::vector<uint8_t> out;
+    const std::vector<uint8_t> &w = b->bwt;
+    for (size_t i = 0; i < w.size();) {
+        size_t j = i;
+        while (j < w.size() && w[j] == w[i] && j - i < 31) ++j;
+        out.push_back((uint8_t)((j - i) << 3 | w[i]));
+        i = j;
+    }
+    *rle = (uint8_t *)std::malloc(out.size() ? out.size() : 1);
+    std::memcpy(*rle, out.data(), out.size());
+    *n = (int64_t)out.size();
+    return 0;
+}
+
+} // extern "C"

@@ -128,6 +128,20 @@ int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *o
  * one GPU.  `text` = nt6 bytes with 0 sentinels (n < 2^32); `bwt` receives n symbols. */
 int fmg_build_bwt(int device, int64_t n, const uint8_t *text, uint8_t *bwt);
 
+/* BCR construction (bcr.h:43-49: bcr_init / bcr_append / bcr_build / bcr_itr_next / bcr_destroy), for collections of
+ * any total size that fits HBM.  Sequences are nt6 codes 1..4 (no N, like bcr_append, ropebwt.c:98); they are
+ * indexed in the order appended, so `fermi ropebwt` semantics = append the read, then its reverse complement
+ * (ropebwt.c:22-45).  The BWT equals the one of fmg_build_bwt / fermi build on the same text. */
+typedef struct fmg_bcr_s fmg_bcr_t;
+fmg_bcr_t *fmg_bcr_init(int device);                                    /* bcr_init, bcr.c:330 */
+int        fmg_bcr_append(fmg_bcr_t *b, int len, const uint8_t *seq);   /* bcr_append, bcr.c:358 */
+int        fmg_bcr_append_batch(fmg_bcr_t *b, int64_t n, int len, const uint8_t *seqs);  /* n equal-length sequences */
+int        fmg_bcr_build(fmg_bcr_t *b);                                 /* bcr_build, bcr.c:462 (all cycles on the GPU) */
+int64_t    fmg_bcr_size(const fmg_bcr_t *b);                            /* symbols in the BWT, -1 before the build */
+int        fmg_bcr_bwt(const fmg_bcr_t *b, uint8_t *bwt);               /* one nt6 byte per symbol */
+int        fmg_bcr_rle(const fmg_bcr_t *b, uint8_t **rle, int64_t *n);  /* bcr_itr_next stream: bytes len<<3|sym (ropebwt.c:127-144) */
+void       fmg_bcr_destroy(fmg_bcr_t *b);                               /* bcr_destroy, bcr.c:342 */
+
 /* ------------------------------------------------------------------ synthetic data
  * Deterministic, seed-addressed generators shared by the GPU run, the CPU baseline and the tests. */
 void fmg_synth_genome(uint64_t seed, int64_t n, uint8_t *nt6);

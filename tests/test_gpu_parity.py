@@ -187,3 +187,33 @@ def test_unitig_20k_reads_vs_reference_binary(fb, tmp_path, err):
     assert n == len(ref)
     assert H.canonical_mag(H.parse_mag(open(out).read())) == H.canonical_mag(ref)
     idx.close()
+
+
+def test_bcr_bwt_equals_suffix_sort_and_reference(fb, tmp_path):
+    """GPU BCR (fmg_bcr_*) == naive BWT on small/ragged inputs, == the GPU suffix-sort builder on 40k reads, and the
+    RLD-encoded result is byte-identical to the golden .fmd the reference built with SA-IS."""
+    rng = np.random.RandomState(3)
+    # ragged lengths, duplicates, a 1-base sequence
+    seqs = [rng.randint(1, 5, size=rng.randint(1, 60)).astype(np.uint8) for _ in range(300)]
+    seqs[5] = seqs[3].copy()
+    seqs[9] = np.array([2], np.uint8)
+    b = fb.Bcr(0)
+    for s_ in seqs:
+        b.append(s_)
+    b.build()
+    text = np.concatenate([np.concatenate([s_, [0]]) for s_ in seqs]).astype(np.uint8)
+    assert np.array_equal(b.bwt(), H.naive_bwt(text))
+    # byte-RLE stream decodes to the same BWT (ropebwt.c:127-144 / rld.c:295-309)
+    rle = b.rle()
+    assert np.array_equal(fb.Fmd.from_rle6(rle).decode_bwt(), b.bwt())
+    b.close()
+    # golden: reads10x.fmd was built by the reference from r0 $ rc(r0) $ ...
+    g, fmd = _load("reads10x")
+    reads = g["text"][g["text"] != 0].reshape(-1, 100)[0::2]
+    out = str(tmp_path / "bcr.fmd")
+    fb.Fmd.from_bwt(fb.fm_ropebwt(reads, 0)).dump(out)
+    assert open(out, "rb").read() == open(fmd, "rb").read()
+    # 40k x 101 bp
+    genome = fb.synth_genome(51, 400000)
+    reads = fb.synth_reads(52, genome, 40000, 101, 0.005)
+    assert np.array_equal(fb.fm_ropebwt(reads, 0), fb.fm_build_bwt(fb.fmd_text(reads), 0))
