@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfermi_b200.so")
 
-SOURCES = ["fmg_cuda.cu", "overlap.cu", "occ_build.cu", "build_bwt.cu", "bcr.cu", "fmd_host.cpp", "occ_build_host.cpp", "unitig_host.cpp", "synth.cpp"]
+SOURCES = ["fmg_cuda.cu", "overlap.cu", "occ_build.cu", "build_bwt.cu", "bcr.cu", "ec.cu", "fmd_host.cpp", "occ_build_host.cpp", "unitig_host.cpp", "synth.cpp"]
 HEADERS = ["fmd_device.cuh", "fmd_overlap.cuh", "fmd_host.hpp", "occ_layout.hpp", "fmg_internal.hpp", "../../include/fermi_b200.h"]
 
 NVCC_FLAGS = [

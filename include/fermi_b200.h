@@ -122,6 +122,15 @@ int fmg_unitig_assemble(uint64_t n_seq, int max_len, int min_match, const int64_
  * MAG records equals that of the reference after canonicalisation. max_len 0 = estimate. */
 int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *out_path, uint64_t *n_unitigs);
 
+/* ------------------------------------------------------------------ `fermi correct`: k-mer collection
+ * fm6_traverse (exact.c:141-171) + ec_collect (correct.c:35-87) for all 4^SUF_LEN suffixes, as a breadth-first
+ * frontier expansion on the GPU.  w < 0 selects the k-mer length like fm6_ec_correct (correct.c:313-318).
+ * triples (malloc'd, fmg_free), sorted: suffix << 40 | key << 8 | val  -- exactly the (key, val) pairs ec_collect
+ * stores in solid[suffix] (correct.c:71-75); cnt[0], cnt[1] as in correct.c:59,66.  The host fills khash from them
+ * and runs ec_fix (correct.c:121-300) unchanged. */
+int fmg_ec_collect(const fmg_index_t *idx, int w, int min_occ, uint64_t **triples, uint64_t *n_triples, int64_t cnt[2]);
+int fmg_ec_kmer_length(uint64_t n_symbols);
+
 /* ------------------------------------------------------------------ index construction
  * BWT of the FMD text  r0 $ rc(r0) $ r1 $ rc(r1) $ ...  (cmd.c:457-469) by prefix-doubling suffix
  * sorting on the GPU; replaces fm_build / ksa_bwt (build.c:33-50, ksa.c:231-242) for texts that fit

@@ -12,6 +12,7 @@
 #include <assert.h>
 #include <pthread.h>
 #include <sys/time.h>
+#include <math.h>
 #include "fmd_oracle.h"
 
 #define FO_CHUNK_WORDS (1ull << 23)     /* rld.h:9-10 */
@@ -898,4 +899,66 @@ int fo_overlap_batch(const fo_index_t *e, int min_match, int64_t n, const uint64
 	if (n_locate) *n_locate = tl_n_locate;
 	free(s.s); free(a[0].a); free(a[1].a); free(nei.a); free(cat.a);
 	return 0;
+}
+
+/*******************
+ * k-mer collection *
+ *******************/
+
+static int cmp_u64(const void *a, const void *b)
+{
+	uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;
+	return x < y ? -1 : x > y;
+}
+
+/* One recursive walk of the backward-extension trie.  Above depth suf_len every non-empty child is followed
+ * (fm6_traverse, exact.c:158-164); below it only children with >= min_occ occurrences (correct.c:77-82); at depth w
+ * the node is summarised (correct.c:56-75).  `path` packs the prepended bases, 2 bits each, first base lowest. */
+typedef struct { uint64_t *a; uint64_t n, m; int64_t cnt[2]; int w, suf_len; uint64_t min_occ; } eccol_t;
+
+static void ec_walk(const fo_index_t *e, eccol_t *z, const fo_intv_t *ik, int depth, uint64_t path)
+{
+	fo_intv_t ok[6];
+	int c;
+	fo_extend(e, ik, ok, 1);
+	if (depth == z->w) {
+		uint64_t max = 0, rest, key, suffix;
+		int max_c = 6;
+		double r;
+		for (c = 1; c <= 4; ++c) if (ok[c].x[2] > max) max = ok[c].x[2], max_c = c;
+		if (max < z->min_occ) return;
+		++z->cnt[0];
+		rest = ik->x[2] - max - ok[0].x[2] - ok[5].x[2];
+		r = rest == 0 ? (double)max : (double)max / rest;
+		if (r > 31.) r = 31.;
+		if (rest <= 7 && r >= z->min_occ) ++z->cnt[1];
+		suffix = path & ((1ull << (2 * z->suf_len)) - 1);
+		key = (path >> (2 * z->suf_len)) << 2 | (uint64_t)(max_c - 1);
+		if (z->n == z->m) { z->m = z->m ? z->m << 1 : 1024; z->a = (uint64_t*)realloc(z->a, z->m * 8); }
+		z->a[z->n++] = suffix << 40 | (key & 0xffffffffull) << 8 | ((uint64_t)(int)(r + .499) << 3 | (rest < 7 ? rest : 7));
+		return;
+	}
+	for (c = 1; c <= 4; ++c) {
+		uint64_t thr = depth < z->suf_len ? 1 : z->min_occ;
+		if (ok[c].x[2] >= thr) ec_walk(e, z, &ok[c], depth + 1, path | (uint64_t)(c - 1) << (2 * depth));
+	}
+}
+
+int fo_ec_collect(const fo_index_t *e, int w, int min_occ, uint64_t **triples, uint64_t *n_triples, int64_t cnt[2])
+{
+	eccol_t z;
+	int c;
+	memset(&z, 0, sizeof(z));
+	if (w < 0) { w = (int)(log((double)e->mcnt[0]) / log(4) + 8.499); if (w >= 27) w = 27; }
+	z.w = w; z.suf_len = w > 15 ? w - 15 : 1; z.min_occ = min_occ;
+	for (c = 1; c <= 4; ++c) {          /* depth 1: the single-base intervals (exact.c:153-156) */
+		fo_intv_t ik;
+		set_intv(e, c, &ik);
+		if (ik.x[2]) ec_walk(e, &z, &ik, 1, (uint64_t)(c - 1));
+	}
+	qsort(z.a, z.n, 8, cmp_u64);
+	*triples = z.a ? z.a : (uint64_t*)malloc(8);
+	*n_triples = z.n;
+	cnt[0] = z.cnt[0]; cnt[1] = z.cnt[1];
+	return w;
 }

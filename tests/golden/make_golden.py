@@ -56,11 +56,14 @@ def case(name, genome_len, n_reads, L, err, seed, n_query, q_err, special=None, 
     sb, se, ss = R.backward_search(h, seq, off)
     seeds = np.arange(1, min(int(info["mcnt"][1]), 2 * 600), 2).astype(np.uint64)
     ov_rec, ov_nei, ov_off, _ = R.overlap(h, min(50, L // 2), seeds)
+    ec_a, ec_a_cnt, ec_a_w = R.ec_collect(h, -1, 3)            # ec_collect over all suffixes (correct.c:35-87)
+    ec_b, ec_b_cnt, ec_b_w = R.ec_collect(h, 12, 2)
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"),
         mcnt=info["mcnt"], cnt=info["cnt"], n_bytes=info["n_bytes"], n_frames=info["n_frames"], ibits=info["ibits"],
         text=text, k=k, l=l, ok=ok, ol=ol, ik=ik, is_back=is_back, ext=ext,
         q=q, smem0=smem0, moff0=moff0, smem1=smem1, moff1=moff1, sa_beg=sb, sa_end=se, sa_size=ss,
+        ec_a=ec_a, ec_a_cnt=np.array(ec_a_cnt), ec_a_w=ec_a_w, ec_b=ec_b, ec_b_cnt=np.array(ec_b_cnt), ec_b_w=ec_b_w,
         ov_min=min(50, L // 2), ov_seeds=seeds, ov_rec=ov_rec, ov_nei=ov_nei, ov_off=ov_off)
     mag = H.reference_unitig(fmd, min(50, L // 2), 1)            # fermi unitig -l.. -t1 (cmd.c:184)
     with open(os.path.join(HERE, name + ".mag"), "w") as fh:

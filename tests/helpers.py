@@ -183,6 +183,19 @@ class _Lib:
             L.refh_build_text.restype = C.c_void_p
             L.refh_build_text.argtypes = [C.c_int64, u8p]
 
+    def ec_collect(self, h, w, min_occ):
+        """(triples u64[] sorted, (cnt0, cnt1), w)"""
+        f = getattr(self.lib, self.p + "ec_collect")
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), u64p, i64p]
+        f.restype = C.c_int
+        p = C.c_void_p()
+        n = C.c_uint64()
+        cnt = np.zeros(2, np.int64)
+        w = f(h, w, min_occ, C.byref(p), C.byref(n), _ptr(cnt, i64p))
+        out = np.frombuffer(C.string_at(p.value, n.value * 8), np.uint64).copy() if n.value else np.zeros(0, np.uint64)
+        self._free(p)
+        return out, (int(cnt[0]), int(cnt[1])), w
+
     # --- index lifecycle
     def load(self, fn):
         h = self._load(fn.encode())

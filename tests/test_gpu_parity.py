@@ -217,3 +217,32 @@ def test_bcr_bwt_equals_suffix_sort_and_reference(fb, tmp_path):
     genome = fb.synth_genome(51, 400000)
     reads = fb.synth_reads(52, genome, 40000, 101, 0.005)
     assert np.array_equal(fb.fm_ropebwt(reads, 0), fb.fm_build_bwt(fb.fmd_text(reads), 0))
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_ec_collect_matches_reference(fb, case, monkeypatch):
+    """fm6_traverse + ec_collect (correct.c:35-87) as a frontier expansion: identical (suffix, key, val) triples and counters."""
+    g, fmd = _load(case)
+    idx = fb.FmdIndex(fb.Fmd.restore(fmd), 0)
+    for w, mo, k in ((-1, 3, "ec_a"), (12, 2, "ec_b")):
+        tri, cnt = fb.fm6_ec_collect(idx, w, mo)
+        assert np.array_equal(tri, g[k]) and list(cnt) == list(g[k + "_cnt"])
+    monkeypatch.setenv("FMG_FORCE_WIDE", "1")
+    tri, cnt = fb.fm6_ec_collect(idx, -1, 3)
+    assert np.array_equal(tri, g["ec_a"])
+    idx.close()
+
+
+def test_ec_collect_100k_reads_vs_oracle(fb, oracle, tmp_path):
+    genome = fb.synth_genome(71, 500000)
+    reads = fb.synth_reads(72, genome, 50000, 100, 0.01)
+    fmd = fb.fm_build(fb.fmd_text(reads), 0)
+    fn = str(tmp_path / "r.fmd")
+    fmd.dump(fn)
+    idx = fb.FmdIndex(fmd, 0)
+    ho = oracle.load(fn)
+    tri, cnt = fb.fm6_ec_collect(idx, -1, 3)
+    otri, ocnt, _ = oracle.ec_collect(ho, -1, 3)
+    assert len(tri) > 100000 and np.array_equal(tri, otri) and tuple(cnt) == tuple(ocnt)
+    oracle.destroy(ho)
+    idx.close()

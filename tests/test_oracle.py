@@ -63,6 +63,9 @@ def test_queries_match_reference_vectors(oracle, case):
         assert nloc >= next_ > 0
     b, e, s = oracle.backward_search(h, seq, off)
     assert np.array_equal(b, g["sa_beg"]) and np.array_equal(e, g["sa_end"]) and np.array_equal(s, g["sa_size"])
+    for w, mo, k in ((-1, 3, "ec_a"), (12, 2, "ec_b")):
+        tri, cnt, ww = oracle.ec_collect(h, w, mo)
+        assert ww == int(g[k + "_w"]) and np.array_equal(tri, g[k]) and list(cnt) == list(g[k + "_cnt"])
     rec, nei, noff, _ = oracle.overlap(h, int(g["ov_min"]), g["ov_seeds"])
     assert np.array_equal(rec, g["ov_rec"]) and np.array_equal(nei, g["ov_nei"]) and np.array_equal(noff, g["ov_off"])
     oracle.destroy(h)

@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Secondary measurement: BCR BWT build (BASELINE config 4, scaled by --reads) on one GPU next to
+`fermi ropebwt -a bcr -bt` (4 threads fixed, bcr.c:336) of the compiled reference on a sample.
+    python tools/bench_bcr.py --reads 5000000 --len 150 --ref-reads 500000
+"""
+import argparse, json, os, subprocess, sys, tempfile, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import fermi_b200 as fb
+import helpers as H
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--reads", type=int, default=5000000)
+ap.add_argument("--len", type=int, default=150)
+ap.add_argument("--cov", type=float, default=30.0)
+ap.add_argument("--ref-reads", type=int, default=500000)
+ap.add_argument("--check", action="store_true")
+a = ap.parse_args()
+L = a.len | 1 if False else a.len
+genome = fb.synth_genome(61, int(a.reads * L / a.cov))
+reads = fb.synth_reads(62, genome, a.reads, L, 0.0)
+rc = (5 - reads[:, ::-1]).astype(np.uint8)
+both = np.empty((2 * a.reads, L), np.uint8); both[0::2] = reads; both[1::2] = rc       # r, rc(r), ... (ropebwt.c:30-44); no palindromes at random
+res = {"reads": a.reads, "len": L, "symbols": int(2 * a.reads * (L + 1))}
+for it in range(2):
+    b = fb.Bcr(0)
+    t = time.time(); b.append_batch(both); t_app = time.time() - t
+    t = time.time(); b.build(); t_build = time.time() - t
+    if it == 1:
+        res.update({"append_s": t_app, "build_s": t_build, "symbols_per_s": res["symbols"] / t_build, "reads_per_s": a.reads / t_build})
+        if a.check:
+            res["equals_suffix_sort"] = bool(np.array_equal(b.bwt(), fb.fm_build_bwt(fb.fmd_text(reads), 0)))
+    b.close()
+if a.ref_reads and H.ref_fermi_binary():
+    fa = os.path.join(tempfile.gettempdir(), "bench_bcr.fa")
+    with open(fa, "w") as fh:
+        tab = np.array(list("$ACGTN"))
+        for i in range(a.ref_reads):
+            fh.write(">%d\n%s\n" % (i, "".join(tab[reads[i]])))
+    for flag, key in (("-bNt", "ref_4thr"), ("-bN", "ref_1thr")):
+        t = time.time()
+        subprocess.run([H.ref_fermi_binary(), "ropebwt", "-a", "bcr", flag, fa], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        dt = time.time() - t
+        res[key + "_s"] = dt; res[key + "_reads"] = a.ref_reads; res[key + "_symbols_per_s"] = 2 * a.ref_reads * (L + 1) / dt
+print(json.dumps(res))
