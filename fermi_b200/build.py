@@ -15,7 +15,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfermi_b200.so")
 
 SOURCES = ["fmg_cuda.cu", "overlap.cu", "occ_build.cu", "build_bwt.cu", "bcr.cu", "ec.cu", "fmd_host.cpp", "occ_build_host.cpp", "unitig_host.cpp", "synth.cpp"]
-HEADERS = ["fmd_device.cuh", "fmd_overlap.cuh", "fmd_host.hpp", "occ_layout.hpp", "fmg_internal.hpp", "../../include/fermi_b200.h"]
+HEADERS = ["cli_main.cpp", "fmd_device.cuh", "fmd_overlap.cuh", "fmd_host.hpp", "occ_layout.hpp", "fmg_internal.hpp", "../../include/fermi_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -50,6 +50,16 @@ def build_library(force=False, verbose=False):
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed, see " + log)
+    # the command-line front end (fermi's command surface), host code linked against the library
+    cli = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-o", os.path.join(HERE, "bin", "fermi-b200"),
+           os.path.join(CSRC, "cli_main.cpp"), "-L" + LIBDIR, "-lfermi_b200", "-Wl,-rpath,$ORIGIN/../lib", "-lz"]
+    os.makedirs(os.path.join(HERE, "bin"), exist_ok=True)
+    res = subprocess.run(cli, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(log, "a") as fh:
+        fh.write(" ".join(cli) + "\n" + res.stdout)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("building the fermi-b200 front end failed, see " + log)
     return LIB
 
 

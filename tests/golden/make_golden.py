@@ -68,6 +68,16 @@ def case(name, genome_len, n_reads, L, err, seed, n_query, q_err, special=None, 
     mag = H.reference_unitig(fmd, min(50, L // 2), 1)            # fermi unitig -l.. -t1 (cmd.c:184)
     with open(os.path.join(HERE, name + ".mag"), "w") as fh:
         fh.write(mag)
+    # the text `fermi exact` prints for the queries (cmd.c:316-328): the CLI parity fixture
+    import subprocess
+    fa = os.path.join(HERE, name + ".query.fa")
+    tab = np.array(list("$ACGTN"))
+    with open(fa, "w") as fh:
+        for i, r in enumerate(q):
+            fh.write(">q%d\n%s\n" % (i, "".join(tab[r])))
+    txt = subprocess.run([H.ref_fermi_binary(), "exact", fmd, fa], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+    with open(os.path.join(HERE, name + ".exact.txt"), "wb") as fh:
+        fh.write(txt)
     R.destroy(h)
     print(name, "unitigs", len(H.parse_mag(mag)), "symbols", n, "fmd bytes", os.path.getsize(fmd), "smem", len(smem0), len(smem1))
 

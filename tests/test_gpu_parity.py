@@ -246,3 +246,31 @@ def test_ec_collect_100k_reads_vs_oracle(fb, oracle, tmp_path):
     assert len(tri) > 100000 and np.array_equal(tri, otri) and tuple(cnt) == tuple(ocnt)
     oracle.destroy(ho)
     idx.close()
+
+
+def test_command_line_front_end(fb, tmp_path):
+    """fermi-b200 exact / unitig / build / ropebwt+recode against the text the reference's commands print."""
+    import subprocess
+    exe = os.path.join(H.ROOT, "fermi_b200", "bin", "fermi-b200")
+    case = "reads10x"
+    g, fmd = _load(case)
+    run = lambda *a: subprocess.run([exe] + list(a), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+    # exact: byte-identical to `fermi exact` (cmd.c:292-333)
+    assert run("exact", fmd, os.path.join(H.GOLDEN_DIR, case + ".query.fa")) == open(os.path.join(H.GOLDEN_DIR, case + ".exact.txt"), "rb").read()
+    # unitig: same canonical MAG set as `fermi unitig -l50`
+    ours = H.parse_mag(run("unitig", "-l", str(int(g["ov_min"])), fmd).decode())
+    ref = H.parse_mag(open(os.path.join(H.GOLDEN_DIR, case + ".mag")).read())
+    assert H.canonical_mag(ours) == H.canonical_mag(ref)
+    # build and ropebwt -b | recode from FASTA: the reference's .fmd, byte for byte
+    reads = g["text"][g["text"] != 0].reshape(-1, 100)[0::2]
+    fa = str(tmp_path / "r.fa")
+    tab = np.array(list("$ACGTN"))
+    with open(fa, "w") as fh:
+        for i, r in enumerate(reads):
+            fh.write(">r%d\n%s\n" % (i, "".join(tab[r])))
+    a, b, rle = str(tmp_path / "a.fmd"), str(tmp_path / "b.fmd"), str(tmp_path / "b.rle")
+    run("build", "-fo", a, fa)
+    run("ropebwt", "-a", "bcr", "-bN", "-o", rle, fa)
+    run("recode", rle, b)
+    want = open(fmd, "rb").read()
+    assert open(a, "rb").read() == want and open(b, "rb").read() == want
