@@ -30,6 +30,7 @@ _PROTOS = {
     "fmg_index_free": (None, [C.c_void_p]),
     "fmg_index_bytes": (C.c_uint64, [C.c_void_p]),
     "fmg_index_device": (C.c_int, [C.c_void_p]),
+    "fmg_index_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, u64p, u64p]),
     # batched queries
     "fmg_rank2a_batch": (C.c_int, [C.c_void_p, C.c_int64, u64p, u64p, u64p, u64p]),
     "fmg_extend_batch": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, u8p, C.c_void_p]),

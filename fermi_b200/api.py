@@ -84,6 +84,15 @@ class FmdIndex:
     def nbytes(self):
         return int(lib().fmg_index_bytes(self.h))
 
+    def export(self):
+        """(blocks u32[n_blocks,16], cs u64[n_super,8]): the occ-block layout as it sits in HBM."""
+        nb, ns = C.c_uint64(), C.c_uint64()
+        _check(lib().fmg_index_export(self.h, None, None, C.byref(nb), C.byref(ns)), "index export")
+        blocks = np.zeros((nb.value, 16), np.uint32)
+        cs = np.zeros((ns.value, 8), np.uint64)
+        _check(lib().fmg_index_export(self.h, blocks.ctypes.data, cs.ctypes.data, None, None), "index export")
+        return blocks, cs
+
     def close(self):
         if self.h:
             lib().fmg_index_free(self.h)

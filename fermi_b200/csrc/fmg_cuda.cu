@@ -15,6 +15,7 @@
 #include <atomic>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 #include "fmd_device.cuh"
 #include "occ_layout.hpp"
 #include "fmg_internal.hpp"
@@ -268,6 +269,7 @@ fmg_index_t *fmg_index_upload(const fmg_fmd_t *e, int device) {
 void fmg_index_free(fmg_index_t *idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);
+    fmg_pipe_destroy(idx->pipe);
     cudaFree(idx->d_blocks);
     cudaFree(idx->d_cs);
     delete idx;
@@ -542,6 +544,59 @@ struct BatchBuf {
     uint64_t rec_base = 0, n_rec = 0;
 };
 
+} // extern "C"
+
+// Streams, events, device input buffers and the two sessions of the host-buffer pipeline.  They are kept with the
+// index between calls (allocating ~10 GB of slots per call costs more than a batch of kernels).
+struct fmg_pipe_s {
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    BatchBuf buf[2];
+    int64_t batch_reads = 0;
+    int max_len = 0;
+    uint64_t max_bytes = 0;
+};
+
+void fmg_pipe_destroy(fmg_pipe_s *p) {
+    if (!p) return;
+    for (int k = 0; k < 2; ++k) {
+        if (p->buf[k].sess) fmg_smem_session_destroy(p->buf[k].sess);
+        cudaFree(p->buf[k].d_seq); cudaFree(p->buf[k].d_off);
+        if (p->buf[k].h2d_done) cudaEventDestroy(p->buf[k].h2d_done);
+        if (p->buf[k].run_done) cudaEventDestroy(p->buf[k].run_done);
+        if (p->buf[k].d2h_done) cudaEventDestroy(p->buf[k].d2h_done);
+    }
+    if (p->s_in) cudaStreamDestroy(p->s_in);
+    if (p->s_run) cudaStreamDestroy(p->s_run);
+    if (p->s_out) cudaStreamDestroy(p->s_out);
+    delete p;
+}
+
+static fmg_pipe_s *pipe_create(const fmg_index_t *idx, int64_t batch_reads, int max_len, uint64_t max_bytes) {
+    fmg_pipe_s *p = new fmg_pipe_s;
+    p->batch_reads = batch_reads; p->max_len = max_len; p->max_bytes = max_bytes;
+    bool ok = false;
+    do {
+        CUDA_TRY(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking), break);
+        CUDA_TRY(cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking), break);
+        CUDA_TRY(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking), break);
+        int k = 0;
+        for (; k < 2; ++k) {
+            CUDA_TRY(cudaMalloc(&p->buf[k].d_seq, max_bytes), break);
+            CUDA_TRY(cudaMalloc(&p->buf[k].d_off, (size_t)(batch_reads + 1) * 8), break);
+            CUDA_TRY(cudaEventCreateWithFlags(&p->buf[k].h2d_done, cudaEventDisableTiming), break);
+            CUDA_TRY(cudaEventCreateWithFlags(&p->buf[k].run_done, cudaEventDisableTiming), break);
+            CUDA_TRY(cudaEventCreateWithFlags(&p->buf[k].d2h_done, cudaEventDisableTiming), break);
+            p->buf[k].sess = fmg_smem_session_create(idx, batch_reads, max_len);
+            if (!p->buf[k].sess) break;
+        }
+        ok = k == 2;
+    } while (0);
+    if (!ok) { fmg_pipe_destroy(p); return nullptr; }
+    return p;
+}
+
+extern "C" {
+
 __global__ void k_rebase_offsets(uint64_t *off, int64_t n, uint64_t sub) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) off[i] -= sub;
@@ -563,29 +618,21 @@ int fmg_smem_batch_into(const fmg_index_t *idx, int64_t n, const uint8_t *seq, c
     }
     for (int64_t i = 0; i < n; ++i) max_len = std::max<int>(max_len, (int)(off[i + 1] - off[i]));
 
-    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
-    BatchBuf buf[2];
+    // one pipeline per index, rebuilt only when a call needs larger batches or longer reads
+    std::lock_guard<std::mutex> guard(idx->pipe_lock);
+    if (idx->pipe && (idx->pipe->batch_reads < batch_reads || idx->pipe->max_len < max_len || idx->pipe->max_bytes < max_bytes)) {
+        fmg_pipe_destroy(idx->pipe);
+        idx->pipe = nullptr;
+    }
+    if (!idx->pipe) idx->pipe = pipe_create(idx, batch_reads, max_len, max_bytes);
+    if (!idx->pipe) return -1;
+    fmg_pipe_s &P = *idx->pipe;
+    cudaStream_t s_in = P.s_in, s_run = P.s_run, s_out = P.s_out;
+    BatchBuf *buf = P.buf;
     int rc = -1;
     uint64_t total = 0;
     bool short_cap = false;
     do {
-        CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking), break);
-        CUDA_TRY(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking), break);
-        CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking), break);
-        bool ok = true;
-        for (int k = 0; k < 2 && ok; ++k) {
-            ok = false;
-            CUDA_TRY(cudaMalloc(&buf[k].d_seq, max_bytes), break);
-            CUDA_TRY(cudaMalloc(&buf[k].d_off, (size_t)(batch_reads + 1) * 8), break);
-            CUDA_TRY(cudaEventCreateWithFlags(&buf[k].h2d_done, cudaEventDisableTiming), break);
-            CUDA_TRY(cudaEventCreateWithFlags(&buf[k].run_done, cudaEventDisableTiming), break);
-            CUDA_TRY(cudaEventCreateWithFlags(&buf[k].d2h_done, cudaEventDisableTiming), break);
-            buf[k].sess = fmg_smem_session_create(idx, batch_reads, max_len);
-            if (!buf[k].sess) break;
-            ok = true;
-        }
-        if (!ok) break;
-
         const int64_t n_batches = (n + batch_reads - 1) / batch_reads;
         auto issue = [&](int64_t b) -> int {          // H2D + kernels of batch b
             BatchBuf &B = buf[b & 1];
@@ -635,16 +682,6 @@ int fmg_smem_batch_into(const fmg_index_t *idx, int64_t n, const uint8_t *seq, c
         if (n_records) *n_records = total;
         rc = short_cap ? 1 : 0;
     } while (0);
-    for (int k = 0; k < 2; ++k) {
-        if (buf[k].sess) fmg_smem_session_destroy(buf[k].sess);
-        cudaFree(buf[k].d_seq); cudaFree(buf[k].d_off);
-        if (buf[k].h2d_done) cudaEventDestroy(buf[k].h2d_done);
-        if (buf[k].run_done) cudaEventDestroy(buf[k].run_done);
-        if (buf[k].d2h_done) cudaEventDestroy(buf[k].d2h_done);
-    }
-    if (s_in) cudaStreamDestroy(s_in);
-    if (s_run) cudaStreamDestroy(s_run);
-    if (s_out) cudaStreamDestroy(s_out);
     return rc;
 }
 

@@ -1,6 +1,7 @@
 // Internal definitions shared by the translation units of libfermi_b200.
 #pragma once
 #include <cstdint>
+#include <mutex>
 #include "fmd_host.hpp"
 #include "fmd_device.cuh"
 
@@ -15,6 +16,9 @@
 
 struct fmg_fmd_s { fmg::FmdImage img; };
 
+struct fmg_pipe_s;
+void fmg_pipe_destroy(fmg_pipe_s *p);
+
 struct fmg_index_s {
     int device = 0, n_sm = 0;
     uint32_t *d_blocks = nullptr;
@@ -22,6 +26,9 @@ struct fmg_index_s {
     uint64_t n_blocks = 0, bytes = 0;
     uint64_t mcnt[8] = {0}, cnt[8] = {0};
     fmg::OccView view;
+    // lazily created host-buffer SMEM pipeline (fmg_cuda.cu), reused between calls
+    mutable fmg_pipe_s *pipe = nullptr;
+    mutable std::mutex pipe_lock;
 };
 
 // occ_build.cu: build the occ blocks of `img` in the HBM of the current device; fills d_blocks/d_cs/n_blocks/bytes

@@ -57,6 +57,8 @@ fmg_index_t *fmg_index_upload(const fmg_fmd_t *e, int device);
 void         fmg_index_free(fmg_index_t *idx);
 uint64_t     fmg_index_bytes(const fmg_index_t *idx);         /* HBM bytes of the query layout */
 int          fmg_index_device(const fmg_index_t *idx);
+/* copy the query layout back to the host: blocks = n_blocks x 16 u32, cs = n_super x 8 u64 (either may be NULL to query sizes) */
+int          fmg_index_export(const fmg_index_t *idx, uint32_t *blocks, uint64_t *cs, uint64_t *n_blocks, uint64_t *n_super);
 
 /* ------------------------------------------------------------------ batched queries, HOST buffers
  * (host->device and device->host copies happen inside the call) */

@@ -274,3 +274,18 @@ def test_command_line_front_end(fb, tmp_path):
     run("recode", rle, b)
     want = open(fmd, "rb").read()
     assert open(a, "rb").read() == want and open(b, "rb").read() == want
+
+
+def test_gpu_transcode_equals_host_builder(fb, monkeypatch, tmp_path):
+    """.fmd -> occ blocks on the GPU (RLD run decode per block) == the host transcoder, byte for byte;
+    includes 32-bit block headers and very long runs."""
+    rng = np.random.RandomState(5)
+    parts = [np.full(rng.choice([1, 2, 7, 300, 40000, 70000]), rng.randint(0, 6), np.uint8) for _ in range(200)]
+    long_runs = str(tmp_path / "long.fmd")
+    fb.Fmd.from_bwt(np.concatenate(parts)).dump(long_runs)
+    for fn in [os.path.join(H.GOLDEN_DIR, c + ".fmd") for c in golden_cases()] + [long_runs]:
+        monkeypatch.delenv("FMG_HOST_OCC_BUILD", raising=False)
+        dev = fb.FmdIndex(fb.Fmd.restore(fn), 0).export()
+        monkeypatch.setenv("FMG_HOST_OCC_BUILD", "1")
+        host = fb.FmdIndex(fb.Fmd.restore(fn), 0).export()
+        assert np.array_equal(dev[0], host[0]) and np.array_equal(dev[1], host[1])
