@@ -46,6 +46,7 @@ _PROTOS = {
     "fmg_smem_session_result": (C.c_int, [C.c_void_p, u64p, vpp, vpp]),
     "fmg_smem_session_set_timing": (None, [C.c_void_p, C.c_int]),
     "fmg_smem_session_kernel_ms": (C.c_double, [C.c_void_p, C.POINTER(C.c_int)]),
+    "fmg_release_cache": (None, []),
     "fmg_launch_count": (C.c_uint64, []),
     # overlap / unitig
     "fmg_overlap_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, u64p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, vpp, u64p,

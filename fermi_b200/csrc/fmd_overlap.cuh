@@ -49,16 +49,31 @@ enum { OV_K = 0, OV_LEN, OV_CONTAINED, OV_X0, OV_X1, OV_X2, OV_RBEG, OV_NNEI, OV
 // OV_CONTAINED: 0, -1 contained (unitig.c:86,89), -9 not longer than min_match (unitig.c:288), -100 scratch overflow
 // OV_LEFT: check_left_simple of the unique neighbour: 0 ok, -1 backward bifurcation, 1 not evaluated
 
+// All six result intervals of fm6_extend (exact.c:72-88), info = 0.  Computed inside ext_sync, i.e. while the warp is
+// converged, so that the (divergent) callers only index the array.
+template <typename U> struct Ok6 { IntvT<U> v[6]; };
+
 template <typename U>
-FMG_NOINLINE bool ext_sync(const OccView &ix, bool active, U x_near, U x_far, U size, Ext6T<U> *e) {
+FMG_NOINLINE bool ext_sync(const OccView &ix, bool active, U x0, U x1, U x2, int back, Ok6<U> *out) {
 #if defined(__CUDA_ARCH__)
     const bool any = __any_sync(0xffffffffu, active);
-    if (active) extend6<U>(ix, x_near, x_far, size, *e);
-    return any;
 #else
-    if (active) extend6<U>(ix, x_near, x_far, size, *e);
-    return active;
+    const bool any = active;
 #endif
+    if (active) {
+        Ext6T<U> e;
+        extend6<U>(ix, back ? x1 : x0, back ? x0 : x1, x2, e);
+        const uint64_t *row = ix.cs + e.sbk * 8;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const U fr = (U)(ld_u64(row + c) + e.relk[c]);
+            out->v[c].x0 = back ? fr : e.near[c];
+            out->v[c].x1 = back ? e.near[c] : fr;
+            out->v[c].x2 = e.size[c];
+            out->v[c].info = 0;
+        }
+    }
+    return any;
 }
 
 template <typename U> struct OvBits {     // packing of the candidate `info` word (unitig.c:132,150)
@@ -78,30 +93,15 @@ struct OvLane {
     int32_t *cat;
     int sl;           // current length of s
     bool ovf;
-    Ext6T<U> e;
-    int e_back;
+    Ok6<U> r;         // ok[0..5] of the last extension
 
     FMG_HD OvLane(const OverlapArgs &a, int64_t lane)
         : A(a), s(a.sbuf + (size_t)lane * a.s_cap), P(static_cast<Cand *>(a.A) + (size_t)lane * a.cap),
-          Q(static_cast<Cand *>(a.B) + (size_t)lane * a.cap), cat(a.cat + (size_t)lane * a.cap), sl(0), ovf(false), e_back(0) {}
+          Q(static_cast<Cand *>(a.B) + (size_t)lane * a.cap), cat(a.cat + (size_t)lane * a.cap), sl(0), ovf(false) {}
 
-    FMG_HD void extend(const Cand &k, int back) {
-        e_back = back;
-        ext_sync<U>(A.ix, true, back ? k.x1 : k.x0, back ? k.x0 : k.x1, k.x2, &e);
-    }
-    FMG_HD U size(int c) const { return pick6(e.size, c); }
-    FMG_HD Cand ok(int c) const {          // ok[c] of the last extension; info = 0
-        const U nr = pick6(e.near, c), fr = far_of(A.ix, e, c);
-        Cand r; r.x0 = e_back ? fr : nr; r.x1 = e_back ? nr : fr; r.x2 = pick6(e.size, c); r.info = 0;
-        return r;
-    }
-    // fm6_extend0 (exact.c:90-98): the sentinel extension only; NOTE x[!is_back] is the bare count tk[0]
-    FMG_HD Cand ok0_bare() const {
-        Cand r;
-        const U tk0 = e.relk[0] + (U)(ld_u64(A.ix.cs + e.sbk * 8) - A.ix.C[0]);
-        r.x0 = e_back ? tk0 : e.near[0]; r.x1 = e_back ? e.near[0] : tk0; r.x2 = e.size[0]; r.info = 0;
-        return r;
-    }
+    FMG_HD void extend(const Cand &k, int back) { ext_sync<U>(A.ix, true, k.x0, k.x1, k.x2, back, &r); }
+    FMG_HD U size(int c) const { return r.v[c].x2; }
+    FMG_HD Cand ok(int c) const { return r.v[c]; }
     FMG_HD void push(Cand *list, int &n, const Cand &k) {
         if (n < A.cap) st_cand(list + n, k); else ovf = true;
         ++n;
@@ -124,7 +124,7 @@ struct OvLane {
             const int c = at5 ? comp6(seq[j]) : seq[j];
             extend(ik, !at5);
             if (size(c) == 0) break;
-            if (depth >= min && e.size[0] != 0) {
+            if (depth >= min && size(0) != 0) {
                 if (inc_sentinel) { Cand t = ok(0); t.info = (U)(j - dir); push(list, n, t); }
                 else { ik.info = (U)(j - dir); push(list, n, ik); }
             }
@@ -151,10 +151,10 @@ struct OvLane {
         int np = 0, nq = 0, ret = 0;
         Cand ik = overlap_intv(L, s, min_match, L - 1, 0, P, np, 0);
         extend(ik, 1);
-        if (ik.x2 != e.size[0]) ret = -1;               // left contained
+        if (ik.x2 != size(0)) ret = -1;                 // left contained
         ik = ok(0);
         extend(ik, 0);
-        if (ik.x2 != e.size[0]) ret = -1;               // right contained
+        if (ik.x2 != size(0)) ret = -1;                 // right contained
         const Cand intv0 = ok(0);
         rec[OV_CONTAINED] = ret; rec[OV_X0] = (int64_t)intv0.x0; rec[OV_X1] = (int64_t)intv0.x1; rec[OV_X2] = (int64_t)intv0.x2;
         if (ret < 0 || np == 0) { if (ovf) rec[OV_CONTAINED] = -100; return; }
@@ -174,15 +174,15 @@ struct OvLane {
                 if (cat[j] < 0) continue;
                 const Cand p = ld_cand(prev + j);
                 extend(p, 0);                                            // forward extension
-                const Ext6T<U> em = e;                                   // keep ok[1..4] across the sentinel probes
-                const U s0 = e.size[0];
+                const Ok6<U> em = r;                                     // keep ok[1..4] across the sentinel probes
+                const U s0 = size(0);
                 if (s0 != 0 && ori_l != sl) {                            // some (partial) reads end here
                     const Cand k0 = ok(0);
                     extend(k0, 1);                                       // fm6_extend0(ok[0], back)
-                    if (e.size[0] != 0) {                                // bounded by sentinels on both sides: a full read
-                        if (s0 == p.x2 && p.x2 == e.size[0]) {           // not contained in a longer read
+                    if (size(0) != 0) {                                  // bounded by sentinels on both sides: a full read
+                        if (s0 == p.x2 && p.x2 == size(0)) {             // not contained in a longer read
                             const int cat0 = cat[j];
-                            Cand nb = ok0_bare();
+                            Cand nb = ok(0);                             // fm6_extend0's ok0 (x[0] = tk[0]; cnt[0] is 0)
                             nb.info = (U)(ori_l - (int)(p.info & BT::pos_mask));
                             for (int i = j; i < npc && cat[i] == cat0; ++i) cat[i] = -1;
                             if (nnei < A.nei_cap) {
@@ -197,11 +197,10 @@ struct OvLane {
                 }
                 if (cat[j] < 0) continue;
                 for (int c = 1; c < 5; ++c) {                            // collect extensible intervals
-                    const U sc = pick6(em.size, c);
-                    if (sc == 0) continue;
-                    Cand kc; { const U nr = pick6(em.near, c), fr = far_of(A.ix, em, c); kc.x0 = nr; kc.x1 = fr; kc.x2 = sc; kc.info = 0; }
+                    Cand kc = em.v[c];
+                    if (kc.x2 == 0) continue;
                     extend(kc, 1);                                       // fm6_extend0(ok[c], back)
-                    if (e.size[0] != 0) {                                // left end still bounded by a sentinel
+                    if (size(0) != 0) {                                  // left end still bounded by a sentinel
                         kc.info = (U)((p.info & ~BT::base_mask) | ((U)c << BT::pos_bits));
                         if (nq == 0) first_base = c;
                         push(curr, nq, kc);
@@ -252,7 +251,7 @@ struct OvLane {
                     const Cand kc = ok(c);
                     if (kc.x2 != 0 && kc.x0 <= nei0.x0 && kc.x0 + kc.x2 >= nei0.x0 + nei0.x2) ++hits, c0 = c;
                 }
-                if (hits == 0 && e.size[0] != 0) break;
+                if (hits == 0 && size(0) != 0) break;
                 if (hits != 1) { ovf = true; break; }                    // the reference asserts hits == 1 (unitig.c:171)
                 s[i] = (uint8_t)comp6(c0);
                 k0 = ok(c0);
@@ -275,7 +274,7 @@ struct OvLane {
                 for (int j = 0; j < npc; ++j) {
                     const Cand p = ld_cand(prev + j);
                     extend(p, 1);
-                    if ((U)(e.size[0] + size(s[i])) != p.x2) { left = -1; break; }   // potential backward bifurcation
+                    if ((U)(size(0) + size(s[i])) != p.x2) { left = -1; break; }     // potential backward bifurcation
                     push(curr, nq, ok(s[i]));
                 }
                 Cand *tmp = curr; curr = prev; prev = tmp;
@@ -296,7 +295,7 @@ FMG_HD void overlap_lane(const OverlapArgs &A, int64_t lane, FetchFn fetch) {
         ln.run(t);
     }
     // out of work: keep answering the warp votes until every lane of the warp is done
-    while (ext_sync<U>(A.ix, false, 0, 0, 0, &ln.e)) {}
+    while (ext_sync<U>(A.ix, false, 0, 0, 0, 0, &ln.r)) {}
 }
 
 // ---------------------------------------------------------------------------------------------

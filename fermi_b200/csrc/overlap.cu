@@ -9,6 +9,7 @@
 #include <vector>
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include "fmd_overlap.cuh"
 #include "fmg_internal.hpp"
 #include "../../include/fermi_b200.h"
@@ -44,13 +45,47 @@ int fmg_compact_slots(const uint32_t *cnt, int64_t n, int cap, const uint4 *slot
 int64_t fmg_compact_tiles(int64_t n);
 
 namespace {
+// Device scratch is recycled between calls: a unitig run issues one call per 2 M sequences and each needs ~3 GB of
+// lists and slots; cudaMalloc/cudaFree of those costs more than the kernels.  Blocks return to a small pool and are
+// handed out again when they fit (released by fmg_release_cache or at process exit).
+struct Pool {
+    struct Blk { void *p; size_t cap; int dev; };
+    std::vector<Blk> free_list;
+    std::mutex lock;
+    cudaError_t get(size_t bytes, int dev, void **out, size_t *cap) {
+        {
+            std::lock_guard<std::mutex> g(lock);
+            for (size_t i = 0; i < free_list.size(); ++i)
+                if (free_list[i].dev == dev && free_list[i].cap >= bytes && free_list[i].cap <= 2 * bytes + (1 << 20)) {
+                    *out = free_list[i].p; *cap = free_list[i].cap;
+                    free_list.erase(free_list.begin() + i);
+                    return cudaSuccess;
+                }
+        }
+        *cap = bytes;
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e != cudaSuccess) { release(); cudaGetLastError(); e = cudaMalloc(out, bytes); }
+        return e;
+    }
+    void put(void *p, size_t cap, int dev) { std::lock_guard<std::mutex> g(lock); free_list.push_back(Blk{p, cap, dev}); }
+    void release() { std::lock_guard<std::mutex> g(lock); for (auto &b : free_list) cudaFree(b.p); free_list.clear(); }
+} g_pool;
+
 struct Dev {
     void *p = nullptr;
-    ~Dev() { cudaFree(p); }
-    cudaError_t alloc(size_t b) { cudaFree(p); p = nullptr; return cudaMalloc(&p, b ? b : 1); }
+    size_t cap = 0;
+    int dev = 0;
+    ~Dev() { if (p) g_pool.put(p, cap, dev); }
+    cudaError_t alloc(size_t b) {
+        if (p) { g_pool.put(p, cap, dev); p = nullptr; }
+        cudaGetDevice(&dev);
+        return g_pool.get(b ? b : 1, dev, &p, &cap);
+    }
     template <class T> T *as() const { return static_cast<T *>(p); }
 };
 }
+
+extern "C" void fmg_release_cache(void) { g_pool.release(); }
 
 extern "C" {
 

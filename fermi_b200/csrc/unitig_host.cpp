@@ -246,6 +246,18 @@ int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *o
     for (;;) {
         rec.reset(new int64_t[n_seq * OV_NREC]); nei_off.reset(new uint64_t[n_seq + 1]);      // filled batch by batch, no zero fill
         seq.reset(new uint8_t[n_seq * (uint64_t)max_len]); ext.reset(new uint8_t[n_seq * (uint64_t)max_len]);
+        {   // fault the pages in with all cores before the device-to-host copies land in them
+            struct Span { uint8_t *p; uint64_t n; } spans[3] = {{(uint8_t *)rec.get(), n_seq * OV_NREC * 8}, {seq.get(), n_seq * (uint64_t)max_len},
+                                                               {ext.get(), n_seq * (uint64_t)max_len}};
+            const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nt; ++t)
+                th.emplace_back([&, t]() {
+                    for (auto &sp : spans)
+                        for (uint64_t o = (uint64_t)t * 4096; o < sp.n; o += (uint64_t)nt * 4096) sp.p[o] = 0;
+                });
+            for (auto &x : th) x.join();
+        }
         nei.clear();
         nei_off[0] = 0;
         const uint64_t batch = 1 << 21;

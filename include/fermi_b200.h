@@ -100,6 +100,8 @@ int fmg_smem_session_result(fmg_smem_session_t *s, uint64_t *n_records, const fm
  * enable, run, then read the summed duration of the k_smem launches since the last query */
 void   fmg_smem_session_set_timing(fmg_smem_session_t *s, int on);
 double fmg_smem_session_kernel_ms(fmg_smem_session_t *s, int *n_launches);
+/* return the device scratch the library keeps between calls (overlap batches) to the driver */
+void fmg_release_cache(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t fmg_launch_count(void);
 

@@ -289,3 +289,57 @@ def test_gpu_transcode_equals_host_builder(fb, monkeypatch, tmp_path):
         monkeypatch.setenv("FMG_HOST_OCC_BUILD", "1")
         host = fb.FmdIndex(fb.Fmd.restore(fn), 0).export()
         assert np.array_equal(dev[0], host[0]) and np.array_equal(dev[1], host[1])
+
+
+def test_full_size_smem_properties(fb, oracle, tmp_path):
+    """BASELINE config 2 at full size (10 M x 100 bp reads, 100 Mbp genome index): the oracle cannot run all of it in
+    seconds, so: exact equality on 20 k sampled reads, structural invariants on all ~86 M records, an independent
+    re-derivation of 200 k records by backward search (a different kernel), and run-to-run identity."""
+    import hashlib
+    G, N, L = 100_000_000, 10_000_000, 100
+    genome = fb.synth_genome(21, G)
+    fmd = fb.fm_build(fb.fmd_text(genome[: G // 10000 * 10000].reshape(-1, 10000)), 0)
+    fn = str(tmp_path / "g.fmd")
+    fmd.dump(fn)
+    idx = fb.FmdIndex(fmd, 0)
+    reads = fb.synth_reads(22, genome, N, L, 0.01)
+    seq, off = H.reads_to_flat(reads)
+    cap = N * 16
+    mem = np.zeros(cap, H.INTV)
+    mo = np.zeros(N + 1, np.uint64)
+    digests = []
+    for _ in range(2):
+        n = fb.fm6_smem_raw(idx, N, seq.ctypes.data, off.ctypes.data, mem.ctypes.data, cap, mo.ctypes.data, 0, 2_000_000)
+        digests.append((n, hashlib.sha1(mem[:n].tobytes()).hexdigest(), hashlib.sha1(mo.tobytes()).hexdigest()))
+    assert digests[0] == digests[1]
+    rec = mem[:n]
+    # (1) sampled reads, bit-exact vs the oracle
+    ho = oracle.load(fn)
+    for lo in (0, N - 10000, 4_999_000):
+        sl = slice(lo, lo + 10000)
+        orec, omo, _, _, _ = oracle.smem(ho, reads[sl].reshape(-1), (np.arange(10001, dtype=np.uint64) * np.uint64(L)), 0, 8)
+        a, b = int(mo[lo]), int(mo[lo + 10000])
+        assert np.array_equal(mo[lo: lo + 10001] - mo[lo], omo) and np.array_equal(rec[a:b], orec)
+    oracle.destroy(ho)
+    # (2) invariants over everything
+    cnt = np.diff(mo.astype(np.int64))
+    assert mo[0] == 0 and int(mo[-1]) == n and cnt.min() >= 1
+    start = (rec["info"] >> np.uint64(32)) & np.uint64(0x3FFFFFFF)
+    end = rec["info"] & np.uint64(0x3FFFFFFF)
+    assert (start < end).all() and (end <= L).all() and (rec["x2"] >= 1).all()
+    n_sym = np.uint64(fmd.mcnt[0])
+    assert (rec["x0"] + rec["x2"] <= n_sym).all() and (rec["x1"] + rec["x2"] <= n_sym).all()
+    # (3) 200 k records re-derived with fm_backward_search on the matched substring (exact.c:7): for a match that is not
+    # closed by a sentinel on the right, [x0, x0+x2-1] is the SA interval of the substring (SURVEY.md row E5)
+    rng = np.random.RandomState(1)
+    pick = rng.randint(0, n, size=200000)
+    pick = pick[rec["x1"][pick] >= np.uint64(fmd.mcnt[1])]
+    owner = np.searchsorted(mo, pick, side="right") - 1
+    s_, e_ = start[pick].astype(np.int64), end[pick].astype(np.int64)
+    lens = e_ - s_
+    sub_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    idxs = np.repeat(owner * L + s_, lens) + (np.arange(int(sub_off[-1])) - np.repeat(sub_off[:-1].astype(np.int64), lens))
+    sub = seq[idxs]
+    b, e, sz = fb.fm_backward_search(idx, sub, sub_off)
+    assert np.array_equal(b, rec["x0"][pick]) and np.array_equal(sz, rec["x2"][pick])
+    idx.close()
