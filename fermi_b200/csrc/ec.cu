@@ -8,6 +8,7 @@
 // the packed (suffix, key, val) triple that ec_collect puts into solid[suffix] (correct.c:56-75); the host
 // fills the hash tables from them (the correction itself, ec_fix*, is host code and out of scope).
 #include <cuda_runtime.h>
+#include <cub/cub.cuh>
 #include <cstdio>
 #include <cstdint>
 #include <cstdlib>
@@ -157,8 +158,15 @@ int ec_collect_impl(const fmg_index_s *idx, int w, int suf_len, uint64_t min_occ
         *n_triples = h_ctr[0];
         cnt[0] = (int64_t)h_ctr[1]; cnt[1] = (int64_t)h_ctr[2];
         *triples = (uint64_t *)std::malloc((h_ctr[0] ? h_ctr[0] : 1) * 8);
-        EC_TRY(cudaMemcpy(*triples, d_tri, h_ctr[0] * 8, cudaMemcpyDeviceToHost));
-        std::sort(*triples, *triples + h_ctr[0]);                     // canonical order: by suffix, then key
+        if (h_ctr[0]) {                                               // canonical order: by suffix, then key (radix sort on the device)
+            uint64_t *d_sorted = nullptr; void *d_tmp = nullptr; size_t need = 0;
+            EC_TRY(cudaMalloc(&d_sorted, h_ctr[0] * 8));
+            EC_TRY(cub::DeviceRadixSort::SortKeys(nullptr, need, d_tri, d_sorted, (int64_t)h_ctr[0]));
+            EC_TRY(cudaMalloc(&d_tmp, need));
+            EC_TRY(cub::DeviceRadixSort::SortKeys(d_tmp, need, d_tri, d_sorted, (int64_t)h_ctr[0]));
+            EC_TRY(cudaMemcpy(*triples, d_sorted, h_ctr[0] * 8, cudaMemcpyDeviceToHost));
+            cudaFree(d_sorted); cudaFree(d_tmp);
+        }
     } else *triples = (uint64_t *)std::malloc(8);
     cudaFree(d_tri); cudaFree(d_ctr);
     return 0;
