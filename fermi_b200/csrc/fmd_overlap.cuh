@@ -49,6 +49,40 @@ enum { OV_K = 0, OV_LEN, OV_CONTAINED, OV_X0, OV_X1, OV_X2, OV_RBEG, OV_NNEI, OV
 // OV_CONTAINED: 0, -1 contained (unitig.c:86,89), -9 not longer than min_match (unitig.c:288), -100 scratch overflow
 // OV_LEFT: check_left_simple of the unique neighbour: 0 ok, -1 backward bifurcation, 1 not evaluated
 
+// ---------------------------------------------------------------------------------------------
+// Packed record the unitig walk chases: one 64-byte line per sequence, indexed by the RANK of the sequence
+// (the id the walk sees: fm_retrieve's return value, intv0.x[], neighbour x[]), so that one step of
+// unitig_unidir (unitig.c:227-262) costs one cache miss for the record and one for the appended bases.
+// The overlap length of a unique neighbour is len - rbeg (unitig.c:118,155), so it is not stored.
+struct alignas(64) OvPack {
+    uint64_t x0, x1;          // intv0.x[0], intv0.x[1]                              (OV_X0, OV_X1)
+    uint64_t nx0, nx1;        // nnei == 1: x[0], x[1] of the neighbour;  nnei > 1: nx0 = first entry in the spill array
+    uint64_t ext_first;       // nnei == 1: offset of the slen - len appended bases in the ext array
+    uint32_t x2, nx2;         // intv0.x[2]; x[2] of the unique neighbour
+    uint32_t len, slen;       // OV_LEN, OV_SLEN
+    int32_t  rbeg;            // OV_RBEG (-1: no neighbour)
+    uint16_t nnei;            // OV_NNEI
+    int8_t   contained, left; // OV_CONTAINED (0, -1, -9), OV_LEFT (0, -1, 1)
+};
+static_assert(sizeof(OvPack) == 64, "OvPack must be one 64-byte line");
+
+// number of appended bases the walk will read for this record (only a unique neighbour extends the consensus)
+FMG_HD uint32_t ov_ext_len(const int64_t *rec) {
+    return (rec[OV_NNEI] == 1 && rec[OV_SLEN] > rec[OV_LEN]) ? (uint32_t)(rec[OV_SLEN] - rec[OV_LEN]) : 0u;
+}
+
+// rec[] (OV_*) + first neighbour / spill index + ext offset -> OvPack; returns false when a field does not fit
+FMG_HD bool ov_pack(const int64_t *rec, uint64_t nx0, uint64_t nx1, uint64_t nx2, uint64_t ext_first, OvPack *o) {
+    o->x0 = (uint64_t)rec[OV_X0]; o->x1 = (uint64_t)rec[OV_X1];
+    o->nx0 = nx0; o->nx1 = nx1; o->ext_first = ext_first;
+    o->x2 = (uint32_t)rec[OV_X2]; o->nx2 = (uint32_t)nx2;
+    o->len = (uint32_t)rec[OV_LEN]; o->slen = (uint32_t)rec[OV_SLEN];
+    o->rbeg = (int32_t)rec[OV_RBEG];
+    o->nnei = (uint16_t)rec[OV_NNEI];
+    o->contained = (int8_t)rec[OV_CONTAINED]; o->left = (int8_t)rec[OV_LEFT];
+    return (uint64_t)rec[OV_X2] < (1ull << 32) && nx2 < (1ull << 32) && rec[OV_NNEI] < 65536 && rec[OV_LEN] < (1ll << 31) && rec[OV_SLEN] < (1ll << 31);
+}
+
 // All six result intervals of fm6_extend (exact.c:72-88), info = 0.  Computed inside ext_sync, i.e. while the warp is
 // converged, so that the (divergent) callers only index the array.
 template <typename U> struct Ok6 { IntvT<U> v[6]; };

@@ -270,6 +270,7 @@ void fmg_index_free(fmg_index_t *idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);
     fmg_pipe_destroy(idx->pipe);
+    fmg_ovcache_destroy(idx->ovc);
     cudaFree(idx->d_blocks);
     cudaFree(idx->d_cs);
     delete idx;

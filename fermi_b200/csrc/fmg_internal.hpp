@@ -18,6 +18,8 @@ struct fmg_fmd_s { fmg::FmdImage img; };
 
 struct fmg_pipe_s;
 void fmg_pipe_destroy(fmg_pipe_s *p);
+struct fmg_ovcache_s;
+void fmg_ovcache_destroy(fmg_ovcache_s *p);
 
 struct fmg_index_s {
     int device = 0, n_sm = 0;
@@ -29,6 +31,8 @@ struct fmg_index_s {
     // lazily created host-buffer SMEM pipeline (fmg_cuda.cu), reused between calls
     mutable fmg_pipe_s *pipe = nullptr;
     mutable std::mutex pipe_lock;
+    // pinned host arrays of the last whole-index overlap pass (overlap.cu: fmg_overlap_all), reused between calls
+    mutable fmg_ovcache_s *ovc = nullptr;
 };
 
 // occ_build.cu: build the occ blocks of `img` in the HBM of the current device; fills d_blocks/d_cs/n_blocks/bytes

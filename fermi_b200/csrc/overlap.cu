@@ -11,6 +11,7 @@
 #include <chrono>
 #include <mutex>
 #include "fmd_overlap.cuh"
+#include "ov_records.hpp"
 #include "fmg_internal.hpp"
 #include "../../include/fermi_b200.h"
 
@@ -37,6 +38,86 @@ template <typename U>
 __global__ void __launch_bounds__(OVLP_BLOCK, OVLP_MIN_BLOCKS) k_overlap(OverlapArgs A) {
     const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     overlap_lane<U>(A, lane, [&]() -> int64_t { return (int64_t)atomicAdd(A.next, 1ull); });
+}
+
+// ---- whole-index pass (fmg_overlap_all): per-batch records -> rank-indexed packed records + compact ext / spill arrays
+enum { OVC_NEXT = 0, OVC_EXT, OVC_SPILL, OVC_FLAGS, OVC_MAXLEN, OVC_N };
+enum { OVF_LIST = 1, OVF_NEI = 2, OVF_EXT = 4, OVF_SPILL = 8, OVF_FIELD = 16, OVF_RANK = 32 };
+
+struct PackArgs {
+    int64_t n;                          // sequences (BWT rows) of this batch
+    const int64_t *rec;                 // n x OV_NREC
+    const int64_t *ret;                 // n: fm_retrieve's return value = rank of the sequence
+    const int32_t *len;                 // n: < 0 flags a sequence longer than max_len
+    const uint32_t *nei_cnt;
+    const uint4 *nei_slots; int nei_cap;
+    const uint8_t *ext; int max_len;
+    OvPack *pack; uint64_t n_seq;
+    uint8_t *ext_out; uint64_t ext_cap;
+    uint4 *spill_out; uint64_t spill_cap;
+    unsigned long long *ctrl;
+};
+
+// Space in the ext / spill arrays is handed out by one atomicAdd per warp (warp-inclusive scan of the needs); the
+// order of the entries therefore varies from run to run, the records address them through ext_first / nx0.
+__global__ void __launch_bounds__(256) k_ov_pack(PackArgs A) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < A.n;
+    const int64_t *rec = A.rec + (live ? t : 0) * OV_NREC;
+    uint32_t flags = 0, el = 0, sp = 0, cnt = 0;
+    if (live) {
+        cnt = A.nei_cnt[t];
+        if (rec[OV_CONTAINED] == -100) flags |= OVF_LIST;
+        if (cnt > (uint32_t)A.nei_cap) flags |= OVF_NEI;
+        if (A.len[t] < 0) atomicMax(A.ctrl + OVC_MAXLEN, (unsigned long long)(-(int64_t)A.len[t]));
+        if (!flags) { el = ov_ext_len(rec); sp = cnt > 1 ? cnt : 0; }
+    }
+    uint32_t ie = el, is = sp;
+    const int lane = threadIdx.x & 31;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, ie, o), b = __shfl_up_sync(0xffffffffu, is, o);
+        if (lane >= o) ie += a, is += b;
+    }
+    unsigned long long be = 0, bs = 0;
+    if (lane == 31) {
+        if (ie) be = atomicAdd(A.ctrl + OVC_EXT, (unsigned long long)ie);
+        if (is) bs = atomicAdd(A.ctrl + OVC_SPILL, (unsigned long long)is);
+    }
+    be = __shfl_sync(0xffffffffu, be, 31) + ie - el;
+    bs = __shfl_sync(0xffffffffu, bs, 31) + is - sp;
+    if (live && !flags) {
+        const uint64_t k = (uint64_t)A.ret[t];
+        if (k >= A.n_seq) flags |= OVF_RANK;
+        if (be + el > A.ext_cap) flags |= OVF_EXT;
+        if (bs + sp > A.spill_cap) flags |= OVF_SPILL;
+        if (!flags) {
+            const uint8_t *e = A.ext + (size_t)t * A.max_len;
+            for (uint32_t i = 0; i < el; ++i) A.ext_out[be + i] = e[i];
+            const uint4 *nb = A.nei_slots + (size_t)t * A.nei_cap * 2;
+            uint64_t nx0 = 0, nx1 = 0, nx2 = 0;
+            if (cnt == 1) {
+                const Intv v = ld_intv(nb);
+                nx0 = v.x0; nx1 = v.x1; nx2 = v.x2;
+            } else if (cnt > 1) {
+                nx0 = bs;
+                for (uint32_t i = 0; i < 2 * cnt; ++i) A.spill_out[2 * bs + i] = nb[i];
+            }
+            OvPack o;
+            if (!ov_pack(rec, nx0, nx1, nx2, be, &o)) flags |= OVF_FIELD;
+            uint4 *dst = reinterpret_cast<uint4 *>(A.pack + k);
+            const uint4 *src = reinterpret_cast<const uint4 *>(&o);
+            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+        }
+    }
+    if (flags) atomicOr(A.ctrl + OVC_FLAGS, (unsigned long long)flags);
+}
+
+// the sequences of the odd rows (the seeds of unitig_core, unitig.c:333-334) of a batch whose first row is even
+__global__ void __launch_bounds__(256) k_seq_odd(const uint8_t *__restrict__ seq, int max_len, int64_t n_odd, uint8_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_odd * max_len) return;
+    const int64_t row = i / max_len, col = i - row * max_len;
+    out[i] = seq[(2 * row + 1) * max_len + col];
 }
 
 // the record compaction kernels of the SMEM path (fmg_cuda.cu) are reused for the neighbour slots
@@ -86,6 +167,171 @@ struct Dev {
 }
 
 extern "C" void fmg_release_cache(void) { g_pool.release(); }
+
+// Pinned host arrays of the whole-index pass.  Page-locking gigabytes costs more than the pass itself, so the arrays
+// stay with the index handle and are reused (grown on demand) by the next fmg_unitig on it.
+struct fmg_ovcache_s {
+    struct Pin {
+        void *p = nullptr;
+        size_t cap = 0;
+        cudaError_t need(size_t bytes) {
+            if (bytes <= cap) return cudaSuccess;
+            if (p) cudaFreeHost(p);
+            p = nullptr; cap = 0;
+            const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+            if (e == cudaSuccess) cap = bytes;
+            return e;
+        }
+        ~Pin() { if (p) cudaFreeHost(p); }
+    } pack, rank, seq, ext, spill, ctrl;
+};
+void fmg_ovcache_destroy(fmg_ovcache_s *p) { delete p; }
+
+// Overlap records of EVERY sequence of the index (fm_retrieve + fm6_is_contained + fm6_get_nei + check_left_simple per
+// BWT row, unitig.c:77-204) for the unitig walk.  Rows are processed in batches queued back to back on one stream with
+// no host synchronisation in between: k_retrieve -> k_overlap -> k_ov_pack scatter the batch into device-resident,
+// rank-indexed 64-byte records plus compact ext / spill arrays; the seed sequences of batch b travel to pinned host
+// memory on a second stream while batch b+1 computes.  Overflow of any scratch or output capacity is flagged on the
+// device and answered by ONE re-run of the whole pass with larger capacities.
+int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *out) {
+    if (!idx || !out) return -1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] no CUDA device available; libfermi_b200 has no CPU path\n", __func__);
+        return -1;
+    }
+    OV_TRY(cudaSetDevice(idx->device));
+    const uint64_t n_seq = idx->mcnt[1];
+    if (max_len <= 0) max_len = (int)((idx->mcnt[0] - n_seq + n_seq - 1) / (n_seq ? n_seq : 1)) + 8;
+    if (!idx->ovc) idx->ovc = new fmg_ovcache_s;
+    fmg_ovcache_s &H = *idx->ovc;
+    const bool wide = idx->view.n_sym + 256 >= (1ull << 32) || std::getenv("FMG_FORCE_WIDE") != nullptr;
+    int per_sm = 0;
+    if (wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_overlap<uint64_t>, OVLP_BLOCK, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_overlap<uint32_t>, OVLP_BLOCK, 0);
+    if (per_sm < 1) per_sm = 1;
+    const int64_t batch = 1 << 21;                           // even, so that the odd rows of a batch are its local odd rows
+    const int64_t nb_max = (int64_t)std::min<uint64_t>(batch, n_seq ? n_seq : 1);
+    const int grid = (int)std::min<int64_t>((int64_t)idx->n_sm * per_sm, (nb_max + OVLP_BLOCK - 1) / OVLP_BLOCK);
+    const int64_t n_lanes = (int64_t)grid * OVLP_BLOCK;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
+
+    cudaStream_t s_run = nullptr, s_copy = nullptr;
+    cudaEvent_t run_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
+    struct Guard {
+        cudaStream_t &a, &b; cudaEvent_t *e, *f;
+        ~Guard() { for (int k = 0; k < 2; ++k) { if (e[k]) cudaEventDestroy(e[k]); if (f[k]) cudaEventDestroy(f[k]); }
+                   if (a) cudaStreamDestroy(a); if (b) cudaStreamDestroy(b); }
+    } guard{s_run, s_copy, run_done, copy_done};
+    OV_TRY(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking));
+    OV_TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        OV_TRY(cudaEventCreateWithFlags(&run_done[k], cudaEventDisableTiming));
+        OV_TRY(cudaEventCreateWithFlags(&copy_done[k], cudaEventDisableTiming));
+    }
+
+    int cap = 4 * max_len, nei_cap = 8;
+    uint64_t ext_cap = std::max<uint64_t>(n_seq * 24, 1 << 20), spill_cap = std::max<uint64_t>(n_seq, 1 << 16);
+    OV_TRY(H.ctrl.need(OVC_N * 8));
+    unsigned long long *h_ctrl = static_cast<unsigned long long *>(H.ctrl.p);
+    Dev d_pack, d_ret, d_extout, d_spill, d_ctrl, d_seq, d_len, d_rec, d_ext, d_cnt, d_slots, d_sbuf, d_A, d_B, d_cat, d_odd[2];
+    for (int attempt = 0;; ++attempt) {
+        const int s_cap = 2 * max_len + 8;
+        const size_t esz = wide ? 32 : 16;
+        const uint64_t n_odd_all = n_seq / 2;
+        OV_TRY(d_pack.alloc(n_seq * sizeof(OvPack))); OV_TRY(d_ret.alloc(n_seq * 8));
+        OV_TRY(d_extout.alloc(ext_cap)); OV_TRY(d_spill.alloc(spill_cap * 32)); OV_TRY(d_ctrl.alloc(OVC_N * 8));
+        OV_TRY(d_seq.alloc((size_t)nb_max * max_len)); OV_TRY(d_len.alloc((size_t)nb_max * 4)); OV_TRY(d_rec.alloc((size_t)nb_max * OV_NREC * 8));
+        OV_TRY(d_ext.alloc((size_t)nb_max * max_len)); OV_TRY(d_cnt.alloc((size_t)(nb_max + 1) * 4)); OV_TRY(d_slots.alloc((size_t)nb_max * nei_cap * 32));
+        OV_TRY(d_sbuf.alloc((size_t)n_lanes * s_cap)); OV_TRY(d_A.alloc((size_t)n_lanes * cap * esz)); OV_TRY(d_B.alloc((size_t)n_lanes * cap * esz));
+        OV_TRY(d_cat.alloc((size_t)n_lanes * cap * 4));
+        for (int k = 0; k < 2; ++k) OV_TRY(d_odd[k].alloc((size_t)(nb_max / 2 + 1) * max_len));
+        OV_TRY(H.seq.need(std::max<uint64_t>(n_odd_all, 1) * (uint64_t)max_len));
+        OV_TRY(cudaMemsetAsync(d_ctrl.p, 0, OVC_N * 8, s_run));
+        // records of sequences that overflow are not written: keep the array defined
+        OV_TRY(cudaMemsetAsync(d_pack.p, 0, n_seq * sizeof(OvPack), s_run));
+        int64_t b = 0;
+        for (uint64_t row0 = 0; row0 < n_seq; row0 += batch, ++b) {
+            const int64_t m = (int64_t)std::min<uint64_t>(batch, n_seq - row0);
+            RetrieveArgs R;
+            R.ix = idx->view; R.n = m; R.ids = nullptr; R.first = row0; R.step = 1;
+            R.seq = d_seq.as<uint8_t>(); R.max_len = max_len; R.len = d_len.as<int32_t>(); R.ret = d_ret.as<int64_t>() + row0;
+            k_retrieve<<<(unsigned)((m + 255) / 256), 256, 0, s_run>>>(R);
+            ++g_launches;
+            OV_TRY(cudaGetLastError());
+            OV_TRY(cudaMemsetAsync(d_ctrl.p, 0, 8, s_run));                   // OVC_NEXT: the work counter of k_overlap
+            OverlapArgs O;
+            O.ix = idx->view; O.min_match = min_match; O.n = m; O.seq = d_seq.as<uint8_t>(); O.len = d_len.as<int32_t>(); O.max_len = max_len;
+            O.sbuf = d_sbuf.as<uint8_t>(); O.s_cap = s_cap; O.A = d_A.p; O.B = d_B.p; O.cap = cap; O.cat = d_cat.as<int32_t>();
+            O.rec = d_rec.as<int64_t>(); O.nei = d_slots.as<uint4>(); O.nei_cap = nei_cap; O.nei_cnt = d_cnt.as<uint32_t>();
+            O.ext = d_ext.as<uint8_t>(); O.next = d_ctrl.as<unsigned long long>() + OVC_NEXT;
+            const int g = (int)std::min<int64_t>(grid, (m + OVLP_BLOCK - 1) / OVLP_BLOCK);
+            if (wide) k_overlap<uint64_t><<<g, OVLP_BLOCK, 0, s_run>>>(O); else k_overlap<uint32_t><<<g, OVLP_BLOCK, 0, s_run>>>(O);
+            ++g_launches;
+            OV_TRY(cudaGetLastError());
+            PackArgs P;
+            P.n = m; P.rec = d_rec.as<int64_t>(); P.ret = d_ret.as<int64_t>() + row0; P.len = d_len.as<int32_t>(); P.nei_cnt = d_cnt.as<uint32_t>();
+            P.nei_slots = d_slots.as<uint4>(); P.nei_cap = nei_cap; P.ext = d_ext.as<uint8_t>(); P.max_len = max_len;
+            P.pack = d_pack.as<OvPack>(); P.n_seq = n_seq; P.ext_out = d_extout.as<uint8_t>(); P.ext_cap = ext_cap;
+            P.spill_out = d_spill.as<uint4>(); P.spill_cap = spill_cap; P.ctrl = d_ctrl.as<unsigned long long>();
+            k_ov_pack<<<(unsigned)((m + 255) / 256), 256, 0, s_run>>>(P);
+            ++g_launches;
+            OV_TRY(cudaGetLastError());
+            const int64_t n_odd = m / 2;
+            if (n_odd) {
+                OV_TRY(cudaStreamWaitEvent(s_run, copy_done[b & 1], 0));     // the staging buffer of batch b-2 has left the device
+                k_seq_odd<<<(unsigned)((n_odd * max_len + 255) / 256), 256, 0, s_run>>>(d_seq.as<uint8_t>(), max_len, n_odd, d_odd[b & 1].as<uint8_t>());
+                ++g_launches;
+                OV_TRY(cudaGetLastError());
+                OV_TRY(cudaEventRecord(run_done[b & 1], s_run));
+                OV_TRY(cudaStreamWaitEvent(s_copy, run_done[b & 1], 0));
+                OV_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(H.seq.p) + (row0 / 2) * (uint64_t)max_len, d_odd[b & 1].p, (size_t)n_odd * max_len,
+                                       cudaMemcpyDeviceToHost, s_copy));
+                OV_TRY(cudaEventRecord(copy_done[b & 1], s_copy));
+            }
+        }
+        OV_TRY(cudaMemcpyAsync(h_ctrl, d_ctrl.p, OVC_N * 8, cudaMemcpyDeviceToHost, s_run));
+        OV_TRY(cudaStreamSynchronize(s_run));
+        const unsigned long long flags = h_ctrl[OVC_FLAGS], too_long = h_ctrl[OVC_MAXLEN];
+        if (fmg_verbose >= 4)
+            std::fprintf(stderr, "[M::%s] attempt %d: %lld batches, %.3f s; ext %llu B, spill %llu, flags %llx, longest clipped %llu\n", __func__, attempt,
+                         (long long)b, since(t0), h_ctrl[OVC_EXT], h_ctrl[OVC_SPILL], flags, too_long);
+        if (!flags && !too_long) break;
+        OV_TRY(cudaStreamSynchronize(s_copy));
+        if (attempt == 6 || (flags & (OVF_FIELD | OVF_RANK))) {
+            if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] cannot represent the overlap records (flags %llx, cap=%d, nei_cap=%d)\n", __func__, flags, cap, nei_cap);
+            return -1;
+        }
+        if (too_long) { max_len = (int)too_long + 8; cap = std::max(cap, 4 * max_len); }
+        if (flags & OVF_LIST) cap *= 4;
+        if (flags & (OVF_LIST | OVF_NEI)) nei_cap *= 4;
+        // the totals keep counting past the capacity, so they are the true need unless other sequences were skipped
+        if (flags & OVF_EXT) ext_cap = std::max<uint64_t>(2 * ext_cap, h_ctrl[OVC_EXT] + (h_ctrl[OVC_EXT] >> 3));
+        if (flags & OVF_SPILL) spill_cap = std::max<uint64_t>(2 * spill_cap, h_ctrl[OVC_SPILL] + (h_ctrl[OVC_SPILL] >> 3));
+        if (fmg_verbose >= 3)
+            std::fprintf(stderr, "[M::%s] capacity exceeded (flags %llx); re-running with max_len=%d, %d candidate / %d neighbour slots, %llu ext bytes, %llu spill entries\n",
+                         __func__, flags, max_len, cap, nei_cap, (unsigned long long)ext_cap, (unsigned long long)spill_cap);
+    }
+    const uint64_t ext_total = h_ctrl[OVC_EXT], spill_total = h_ctrl[OVC_SPILL];
+    OV_TRY(H.pack.need(std::max<uint64_t>(n_seq, 1) * sizeof(OvPack))); OV_TRY(H.rank.need(std::max<uint64_t>(n_seq, 1) * 8));
+    OV_TRY(H.ext.need(std::max<uint64_t>(ext_total, 1))); OV_TRY(H.spill.need(std::max<uint64_t>(spill_total, 1) * 32));
+    if (n_seq) {
+        OV_TRY(cudaMemcpyAsync(H.pack.p, d_pack.p, n_seq * sizeof(OvPack), cudaMemcpyDeviceToHost, s_run));
+        OV_TRY(cudaMemcpyAsync(H.rank.p, d_ret.p, n_seq * 8, cudaMemcpyDeviceToHost, s_run));
+    }
+    if (ext_total) OV_TRY(cudaMemcpyAsync(H.ext.p, d_extout.p, ext_total, cudaMemcpyDeviceToHost, s_run));
+    if (spill_total) OV_TRY(cudaMemcpyAsync(H.spill.p, d_spill.p, spill_total * 32, cudaMemcpyDeviceToHost, s_run));
+    OV_TRY(cudaStreamSynchronize(s_run));
+    OV_TRY(cudaStreamSynchronize(s_copy));
+    out->n_seq = n_seq; out->max_len = max_len;
+    out->pack = static_cast<const OvPack *>(H.pack.p); out->rank_of_row = static_cast<const uint64_t *>(H.rank.p);
+    out->seq = static_cast<const uint8_t *>(H.seq.p); out->seq_stride = (uint64_t)max_len; out->seq_odd_only = 1;
+    out->ext = static_cast<const uint8_t *>(H.ext.p); out->spill = static_cast<const fmg_intv_t *>(H.spill.p);
+    out->ext_total = ext_total; out->spill_total = spill_total;
+    if (fmg_verbose >= 4) std::fprintf(stderr, "[M::%s] %llu sequences, records on the host after %.3f s\n", __func__, (unsigned long long)n_seq, since(t0));
+    return 0;
+}
 
 extern "C" {
 

@@ -18,6 +18,7 @@
 #include <thread>
 #include <mutex>
 #include "fmd_overlap.cuh"
+#include "ov_records.hpp"
 #include "fmg_internal.hpp"
 #include "../../include/fermi_b200.h"
 
@@ -25,32 +26,15 @@ using namespace fmg;
 
 namespace {
 
-struct Records {                     // non-owning views of the arrays fmg_overlap_batch fills
-    uint64_t n_seq = 0;
-    int max_len = 0;
-    const int64_t *rec = nullptr;    // n_seq x OV_NREC
-    const fmg_intv_t *nei = nullptr;
-    const uint64_t *nei_off = nullptr;   // n_seq + 1
-    const uint8_t *seq = nullptr, *ext = nullptr;   // n_seq x max_len
-    // Records are indexed by BWT row (= sequence number in the text, the seed of unitig_core).  The ids the
-    // walk sees -- fm_retrieve's return value, intv0.x[], neighbour x[] -- are ranks of the sequence among all
-    // sequences in lexicographic order (LF of a sentinel counts the '$' above it), so neighbours are
-    // looked up through the inverse of rec[OV_K].
-    std::vector<uint64_t> row_of_rank;
-    const int64_t *r(uint64_t row) const { return rec + row * OV_NREC; }
-    uint64_t row(uint64_t rank) const { return row_of_rank[rank]; }
-    void index_ranks() {
-        row_of_rank.assign(n_seq, 0);
-        for (uint64_t t = 0; t < n_seq; ++t) row_of_rank[(uint64_t)rec[t * OV_NREC + OV_K]] = t;
-    }
-};
-
 struct Bits {                                   // shared by the walker threads like the reference's bitmaps (unitig.c:15-20)
     std::vector<uint64_t> w;
     explicit Bits(uint64_t n) : w((n + 63) / 64, 0) {}
     bool get(uint64_t i) const { return __atomic_load_n(&w[i >> 6], __ATOMIC_RELAXED) >> (i & 63) & 1; }
     bool test_and_set(uint64_t i) { const uint64_t m = 1ull << (i & 63); return __atomic_fetch_or(&w[i >> 6], m, __ATOMIC_RELAXED) & m; }
-    void set(uint64_t i) { __atomic_fetch_or(&w[i >> 6], 1ull << (i & 63), __ATOMIC_RELAXED); }
+    void set(uint64_t i) {
+        const uint64_t m = 1ull << (i & 63);
+        if (!(__atomic_load_n(&w[i >> 6], __ATOMIC_RELAXED) & m)) __atomic_fetch_or(&w[i >> 6], m, __ATOMIC_RELAXED);
+    }
     void set_intv(uint64_t x0, uint64_t x1, uint64_t x2) {           // set_bits, unitig.c:22-36
         for (uint64_t k = 0; k < x2; ++k) set(x0 + k), set(x1 + k);
     }
@@ -58,51 +42,56 @@ struct Bits {                                   // shared by the walker threads 
 
 struct Nei { uint64_t x; uint64_t y; };
 
+// Records are indexed by the rank of the sequence among all sequences (LF of a sentinel counts the '$' above it):
+// the ids the walk sees -- fm_retrieve's return value, intv0.x[], neighbour x[] -- address OvHost::pack directly.
+// Only the seeds are BWT rows; they go through rank_of_row once.
 struct Walker {
-    const Records &R;
+    const OvHost &R;
     int min_match;
     Bits &used, &bend, &visited;
     std::string s, cov;
     std::vector<Nei> last_nei;           // a->nei after unitig_unidir
 
-    Walker(const Records &r, int mm, Bits &u, Bits &b, Bits &v) : R(r), min_match(mm), used(u), bend(b), visited(v) {}
+    Walker(const OvHost &r, int mm, Bits &u, Bits &b, Bits &v) : R(r), min_match(mm), used(u), bend(b), visited(v) {}
 
-    // unitig_unidir, unitig.c:227-262.  `cur` = record row of the last read of s, which starts at s[beg].
+    // unitig_unidir, unitig.c:227-262.  `cur` = rank of the last read of s, which starts at s[beg].
     int unidir(uint64_t cur, int beg, uint64_t k0, uint64_t *end, int *is_loop) {
         int ori_l = (int)s.size(), n_reads = 0;
         *is_loop = 0;
         last_nei.clear();
         for (;;) {
-            const int64_t *r = R.r(cur);
+            const OvPack &p = R.pack[cur];
             last_nei.clear();
-            if (r[OV_RBEG] < 0 || r[OV_NNEI] == 0) break;                 // try_right() < 0
-            const fmg_intv_t *nb = R.nei + R.nei_off[cur];
-            const int n_nei = (int)r[OV_NNEI];
-            for (int k = 0; k < n_nei; ++k) last_nei.push_back(Nei{nb[k].x[0], nb[k].info});
-            const int rbeg = beg + (int)r[OV_RBEG];
-            if (n_nei > 1) { bend.set(*end); break; }                      // forward bifurcation
-            const uint64_t k = nb[0].x[0];
+            if (p.rbeg < 0 || p.nnei == 0) break;                          // try_right() < 0
+            if (p.nnei > 1) {                                              // forward bifurcation
+                const fmg_intv_t *nb = R.spill + p.nx0;
+                for (int k = 0; k < (int)p.nnei; ++k) last_nei.push_back(Nei{nb[k].x[0], nb[k].info});
+                bend.set(*end);
+                break;
+            }
+            const uint64_t k = p.nx0;
+            last_nei.push_back(Nei{k, (uint64_t)((int64_t)p.len - p.rbeg)});
+            const int rbeg = beg + p.rbeg;
             if (k == *end) break;                                          // a loop like b>>c>>a><a
             bool back_fork = bend.get(k);
-            if (!back_fork && r[OV_LEFT] != 0) {
+            if (!back_fork && p.left != 0)
                 // check_left (unitig.c:206-225): the simple test failed; confirm with the right neighbours of
                 // the reverse complement of the neighbour
-                const int64_t *rr = R.r(R.row(nb[0].x[1]));
-                back_fork = rr[OV_NNEI] > 1;
-            }
+                back_fork = R.pack[p.nx1].nnei > 1;
             if (back_fork) { bend.set(k); break; }                         // backward bifurcation
             if (k == k0) { *is_loop = 1; break; }                          // a loop like a>>b>>c>>a
-            if (nb[0].x[1] == *end) { last_nei.clear(); break; }           // a loop like b>>c>>a>>a; cut the last link
-            *end = nb[0].x[1];
-            used.set_intv(nb[0].x[0], nb[0].x[1], nb[0].x[2]);
+            if (p.nx1 == *end) { last_nei.clear(); break; }                // a loop like b>>c>>a>>a; cut the last link
+            *end = p.nx1;
+            __builtin_prefetch(&R.pack[k]);
+            used.set_intv(p.nx0, p.nx1, p.nx2);
             ++n_reads;
             // the consensus grows by the extension recorded for `cur` (unitig.c:141,253-257)
-            const int new_l = beg + (int)r[OV_SLEN];
-            const uint8_t *ext = R.ext + cur * (uint64_t)R.max_len;
+            const int new_l = beg + (int)p.slen;
+            const uint8_t *ext = R.ext + p.ext_first;
             s.resize(new_l); cov.resize(new_l);
             for (int i = ori_l; i < new_l; ++i) s[i] = (char)ext[i - ori_l], cov[i] = '"';
-            for (int i = rbeg; i < ori_l; ++i) if (cov[i] != '~') ++cov[i];
-            beg = rbeg; ori_l = new_l; cur = R.row(k);
+            for (int i = rbeg; i < ori_l; ++i) cov[i] += cov[i] != '~';
+            beg = rbeg; ori_l = new_l; cur = k;
         }
         s.resize(ori_l); cov.resize(ori_l);
         return n_reads;
@@ -110,21 +99,24 @@ struct Walker {
 
     // unitig1, unitig.c:274-317
     int unitig1(uint64_t seed, uint64_t end[2], std::vector<Nei> nei[2], int *n_reads) {
-        const int64_t *r = R.r(seed);
+        const uint64_t k = R.rank_of_row[seed];
         *n_reads = 0; nei[0].clear(); nei[1].clear();
-        const int seed_len = (int)r[OV_LEN];
+        if (used.get(k)) {                                                 // -2, unless the read is too short (-1); both skip the seed
+            return -2;
+        }
+        const OvPack &p = R.pack[k];
+        const int seed_len = (int)p.len;
         if (seed_len <= min_match) return -1;                              // too short
-        const uint64_t k = (uint64_t)r[OV_K];
-        if (used.get(k)) return -2;
-        used.set_intv((uint64_t)r[OV_X0], (uint64_t)r[OV_X1], (uint64_t)r[OV_X2]);
-        if (r[OV_CONTAINED] < 0) return -3;
+        used.set_intv(p.x0, p.x1, p.x2);
+        if (p.contained < 0) return -3;
         *n_reads = 1;
-        s.assign((const char *)(R.seq + seed * (uint64_t)R.max_len), seed_len);
+        const uint8_t *sq = R.seq + (R.seq_odd_only ? seed >> 1 : seed) * R.seq_stride;
+        s.assign((const char *)sq, seed_len);
         cov.assign(seed_len, '"');
-        end[0] = (uint64_t)r[OV_X1]; end[1] = (uint64_t)r[OV_X0];
+        end[0] = p.x1; end[1] = p.x0;
         int is_loop = 0;
         // (the reference skips this call when the read has no overlap candidate at all; the call is then a no-op)
-        *n_reads += unidir(seed, 0, (uint64_t)r[OV_X0], &end[0], &is_loop);
+        *n_reads += unidir(k, 0, p.x0, &end[0], &is_loop);
         nei[0] = last_nei;
         if (is_loop) {
             nei[1].push_back(Nei{end[0], last_nei[0].y});
@@ -134,13 +126,13 @@ struct Walker {
         std::reverse(s.begin(), s.end());
         for (auto &c : s) c = (c >= 1 && c <= 4) ? 5 - c : c;
         std::reverse(cov.begin(), cov.end());
-        *n_reads += unidir(R.row((uint64_t)r[OV_X1]), (int)s.size() - seed_len, (uint64_t)r[OV_X1], &end[1], &is_loop);
+        *n_reads += unidir(p.x1, (int)s.size() - seed_len, p.x1, &end[1], &is_loop);
         nei[1] = last_nei;
         return 0;
     }
 };
 
-void append_u64(std::string &o, uint64_t v) { char b[24]; o.append(b, std::snprintf(b, sizeof b, "%llu", (unsigned long long)v)); }
+
 void append_i64(std::string &o, int64_t v) { char b[24]; o.append(b, std::snprintf(b, sizeof b, "%lld", (long long)v)); }
 
 // mag_v_write, mag.c:149-174
@@ -160,25 +152,18 @@ void write_mag(std::string &o, const uint64_t k[2], int nsr, const std::vector<N
 
 } // namespace
 
-extern "C" {
-
-// The walk alone: MAG records from the per-sequence overlap records of ALL n_seq sequences of an index
-// (rec: n_seq x 10, nei/nei_off, seq/ext: n_seq x max_len; the layout fmg_overlap_batch produces).  Host code.
-int fmg_unitig_assemble(uint64_t n_seq, int max_len, int min_match, const int64_t *rec, const fmg_intv_t *nei,
-                        const uint64_t *nei_off, const uint8_t *seq, const uint8_t *ext, const char *out_path, uint64_t *n_unitigs) {
-    Records R;
-    R.n_seq = n_seq; R.max_len = max_len;
-    R.rec = rec; R.nei_off = nei_off; R.nei = nei; R.seq = seq; R.ext = ext;
-    R.index_ranks();
+// The walk alone (host code): MAG records from the packed overlap records of ALL sequences of an index.
+// Strided worker threads over the seeds, sharing the three bitmaps through atomics: the scheme of fm6_unitig
+// (unitig.c:378-407).  One thread reproduces `fermi unitig -t1` record for record; with more threads the record
+// order and orientation vary but the canonicalised set does not.
+int fmg_unitig_walk(const OvHost &R, int min_match, const char *out_path, uint64_t *n_unitigs) {
+    const uint64_t n_seq = R.n_seq;
     FILE *fp = std::strcmp(out_path, "-") ? std::fopen(out_path, "wb") : stdout;
     if (!fp) {
         if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] cannot write '%s'\n", __func__, out_path);
         return -1;
     }
     const auto tw0 = std::chrono::steady_clock::now();
-    // Strided worker threads over the seeds, sharing the three bitmaps through atomics: the scheme of
-    // fm6_unitig (unitig.c:378-407).  One thread reproduces `fermi unitig -t1` record for record; with more
-    // threads the record order and orientation vary but the canonicalised set does not.
     int n_threads = 1;
     if (const char *e = std::getenv("FMG_THREADS")) n_threads = std::atoi(e);
     else n_threads = (int)std::min<unsigned>(std::thread::hardware_concurrency(), 32u);
@@ -230,62 +215,58 @@ int fmg_unitig_assemble(uint64_t n_seq, int max_len, int min_match, const int64_
     return 0;
 }
 
+extern "C" {
+
+// The walk over records that arrive as separate arrays (rec: n_seq x 10, nei/nei_off, seq/ext: n_seq x max_len; the layout
+// fmg_overlap_batch produces, e.g. after the all-gather of per-GPU shards): packs them by rank, then walks.  Host code.
+int fmg_unitig_assemble(uint64_t n_seq, int max_len, int min_match, const int64_t *rec, const fmg_intv_t *nei,
+                        const uint64_t *nei_off, const uint8_t *seq, const uint8_t *ext, const char *out_path, uint64_t *n_unitigs) {
+    std::unique_ptr<OvPack[]> pack(new OvPack[n_seq ? n_seq : 1]);
+    std::vector<uint64_t> rank_of_row(n_seq);
+    std::vector<uint8_t> xt;
+    std::vector<fmg_intv_t> spill;
+    for (uint64_t t = 0; t < n_seq; ++t) {
+        const int64_t *r = rec + t * OV_NREC;
+        const uint64_t k = (uint64_t)r[OV_K];
+        if (k >= n_seq) {
+            if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] record %llu has rank %llu >= %llu sequences\n", __func__, (unsigned long long)t, (unsigned long long)k, (unsigned long long)n_seq);
+            return -1;
+        }
+        rank_of_row[t] = k;
+        const fmg_intv_t *nb = nei + nei_off[t];
+        uint64_t nx0 = 0, nx1 = 0, nx2 = 0;
+        if (r[OV_NNEI] == 1) nx0 = nb[0].x[0], nx1 = nb[0].x[1], nx2 = nb[0].x[2];
+        else if (r[OV_NNEI] > 1) { nx0 = spill.size(); spill.insert(spill.end(), nb, nb + r[OV_NNEI]); }
+        const uint32_t el = ov_ext_len(r);
+        if (!ov_pack(r, nx0, nx1, nx2, xt.size(), &pack[k])) {
+            if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] record %llu does not fit the packed layout\n", __func__, (unsigned long long)t);
+            return -1;
+        }
+        xt.insert(xt.end(), ext + t * (uint64_t)max_len, ext + t * (uint64_t)max_len + el);
+    }
+    OvHost R;
+    R.n_seq = n_seq; R.max_len = max_len; R.pack = pack.get(); R.rank_of_row = rank_of_row.data();
+    R.seq = seq; R.seq_stride = (uint64_t)max_len; R.seq_odd_only = 0;
+    R.ext = xt.data(); R.spill = spill.data(); R.ext_total = xt.size(); R.spill_total = spill.size();
+    return fmg_unitig_walk(R, min_match, out_path, n_unitigs);
+}
+
 // fm6_unitig (unitig.c:378-407) + main_unitig (cmd.c:184-216): overlap records of every sequence on the GPU, then the
 // walk; MAG records go to `out_path` ("-" = stdout).  max_len = upper bound of the sequence length in the index
 // (0: estimate from the symbol counts, grown on demand).
 int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *out_path, uint64_t *n_unitigs) {
     if (!idx) return -1;
-    const uint64_t n_seq = idx->mcnt[1];
     if (n_unitigs) *n_unitigs = 0;
     const auto t0 = std::chrono::steady_clock::now();
-    if (max_len <= 0) max_len = (int)((idx->mcnt[0] - n_seq + n_seq - 1) / (n_seq ? n_seq : 1)) + 8;
-    std::unique_ptr<int64_t[]> rec;
-    std::vector<fmg_intv_t> nei;
-    std::unique_ptr<uint64_t[]> nei_off;
-    std::unique_ptr<uint8_t[]> seq, ext;
-    for (;;) {
-        rec.reset(new int64_t[n_seq * OV_NREC]); nei_off.reset(new uint64_t[n_seq + 1]);      // filled batch by batch, no zero fill
-        seq.reset(new uint8_t[n_seq * (uint64_t)max_len]); ext.reset(new uint8_t[n_seq * (uint64_t)max_len]);
-        {   // fault the pages in with all cores before the device-to-host copies land in them
-            struct Span { uint8_t *p; uint64_t n; } spans[3] = {{(uint8_t *)rec.get(), n_seq * OV_NREC * 8}, {seq.get(), n_seq * (uint64_t)max_len},
-                                                               {ext.get(), n_seq * (uint64_t)max_len}};
-            const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
-            std::vector<std::thread> th;
-            for (unsigned t = 0; t < nt; ++t)
-                th.emplace_back([&, t]() {
-                    for (auto &sp : spans)
-                        for (uint64_t o = (uint64_t)t * 4096; o < sp.n; o += (uint64_t)nt * 4096) sp.p[o] = 0;
-                });
-            for (auto &x : th) x.join();
-        }
-        nei.clear();
-        nei_off[0] = 0;
-        const uint64_t batch = 1 << 21;
-        std::unique_ptr<int32_t[]> len(new int32_t[batch]);
-        std::unique_ptr<uint64_t[]> off(new uint64_t[batch + 1]);
-        int rc = 0;
-        for (uint64_t b = 0; b < n_seq && rc == 0; b += batch) {
-            const uint64_t m = std::min<uint64_t>(batch, n_seq - b);
-            fmg_intv_t *nb = nullptr;
-            rc = fmg_overlap_batch(idx, min_match, (int64_t)m, nullptr, b, 1, max_len, &rec[b * OV_NREC], &nb, off.get(),
-                                   &seq[b * (uint64_t)max_len], len.get(), &ext[b * (uint64_t)max_len]);
-            if (rc == 0) {
-                const uint64_t base = nei.size();
-                nei.insert(nei.end(), nb, nb + off[m]);
-                for (uint64_t i = 0; i <= m; ++i) nei_off[b + i] = base + off[i];
-            }
-            std::free(nb);
-        }
-        if (rc == 2) { max_len *= 2; continue; }            // a sequence was longer than assumed
-        if (rc != 0) return rc;
-        break;
-    }
+    OvHost R;
+    const int rc0 = fmg_overlap_all(idx, min_match, max_len, &R);
+    if (rc0 != 0) return rc0;
     const auto t1 = std::chrono::steady_clock::now();
-    const int rc = fmg_unitig_assemble(n_seq, max_len, min_match, rec.get(), nei.data(), nei_off.get(), seq.get(), ext.get(), out_path, n_unitigs);
+    const int rc = fmg_unitig_walk(R, min_match, out_path, n_unitigs);
     const auto t2 = std::chrono::steady_clock::now();
     if (fmg_verbose >= 3)
         std::fprintf(stderr, "[M::%s] %llu sequences: overlap records %.3f s (GPU, incl. copies), unitig walk + output %.3f s (host)\n", __func__,
-                     (unsigned long long)n_seq, std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count());
+                     (unsigned long long)R.n_seq, std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count());
     return rc;
 }
 
