@@ -1,17 +1,17 @@
 // Device-side core of the overlap path of `fermi unitig` (unitig.c:38-204):
-//   retrieve_lane   fm_retrieve (exact.c:59-70): LF walk that spells one indexed sequence
-//   overlap_lane    per sequence: fm6_is_contained (unitig.c:77-91) -> fm6_get_nei (unitig.c:93-179)
-//                   -> check_left_simple (unitig.c:186-204)
+//   retrieve_one    fm_retrieve (exact.c:59-70): LF walk that spells one indexed sequence
+//   OvLane          per sequence: fm6_is_contained (unitig.c:77-91) -> fm6_get_nei (unitig.c:93-179)
+//                   -> check_left_simple (unitig.c:186-204), in four phases (see OvLane)
 // Everything the unitig walk (unitig_unidir / unitig1, unitig.c:227-317) asks the index is a pure function
 // of ONE read: its right neighbours, the consensus extension towards them and the simple left check of a
 // unique neighbour.  The GPU computes that record for every sequence of the index in parallel; the walk
 // itself then only chases these records (unitig_host.cpp).
 //
-// Control flow is written as the natural nested loops of the reference.  Lanes of a warp are on
-// different sequences and in different loops, so every extension goes through ext_sync(): a NOINLINE
-// function, i.e. one copy of the code that all call sites jump to, which starts with a full-warp vote.
-// The vote lines the 32 lanes up in time at the same program counter, so the expensive part (block
-// loads + popcounts) executes converged, whatever loop each lane came from.
+// Control flow is written as the natural nested loops of the reference.  In the list-chasing phases the
+// lanes of a warp are on different sequences and in different loops, so every extension goes through
+// ext_sync(): a NOINLINE function, i.e. one copy of the code that all call sites jump to, which starts with
+// a full-warp vote.  The vote lines the 32 lanes up in time at the same program counter, so the expensive
+// part (block loads + popcounts) executes converged, whatever loop each lane came from.
 //
 // Same source compiles for the host (tests/emu) -- checker only, never linked by the product.
 #pragma once
@@ -29,18 +29,20 @@ struct OverlapArgs {
     OccView ix;
     int min_match;
     int64_t n;                  // sequences in this batch
-    const uint8_t *seq;         // n x max_len nt6 bytes (retrieve_lane output)
+    const uint8_t *seq;         // n x max_len nt6 bytes (retrieve_one output)
     const int32_t *len;         // n
     int max_len;
-    // per-lane scratch
-    uint8_t *sbuf; int s_cap;   // growing consensus string (unitig.c:141)
+    // per-sequence scratch handed from phase to phase
+    void *P0; int pcap;         // candidate list of overlap_intv (unitig.c:38-64): n x pcap entries of 4 x U
+    int32_t *np0;               // n: entries in P0 for the next phase; -1 = the next phase has nothing to do
+    // per-lane scratch of the two list-chasing phases
     void *A, *B; int cap;       // candidate interval lists (4 x U per entry)
     int32_t *cat;               // category per candidate (unitig.c:105-151)
     // per-sequence output
     int64_t *rec;               // 10 per sequence, see OV_* below
     uint4 *nei; int nei_cap;    // neighbour records (fmintv_t: x = interval of the neighbour, info = overlap length)
     uint32_t *nei_cnt;
-    uint8_t *ext;               // n x max_len: bases appended to the read (s[len .. s_len))
+    uint8_t *ext;               // n x max_len: bases fm6_get_nei appends to the read (s[len .. s_len), unitig.c:141)
     unsigned long long *next;
 };
 
@@ -87,7 +89,8 @@ FMG_HD bool ov_pack(const int64_t *rec, uint64_t nx0, uint64_t nx1, uint64_t nx2
 // converged, so that the (divergent) callers only index the array.
 template <typename U> struct Ok6 { IntvT<U> v[6]; };
 
-template <typename U>
+// TAG gives every kernel its own copy of the function (ptxas 12.9 crashes on a noinline function shared by two entries)
+template <typename U, int TAG>
 FMG_NOINLINE bool ext_sync(const OccView &ix, bool active, U x0, U x1, U x2, int back, Ok6<U> *out) {
 #if defined(__CUDA_ARCH__)
     const bool any = __any_sync(0xffffffffu, active);
@@ -118,72 +121,98 @@ template <typename U> struct OvBits {     // packing of the candidate `info` wor
     static constexpr int max_cat = sizeof(U) == 8 ? (1 << 27) : ((1 << 12) - 1);
 };
 
-template <typename U>
+// the consensus string of fm6_get_nei: the read itself followed by the appended bases
+struct SeqView {
+    const uint8_t *a; int la; const uint8_t *b;
+    FMG_HD int at(int i) const { return i < la ? a[i] : b[i - la]; }
+};
+
+// The per-sequence record is computed in FOUR phases, each its own kernel over the batch, handing the
+// candidate list of overlap_intv from one to the next through P0 / np0:
+//   1 phase_contained  fm6_is_contained (unitig.c:77-91): a chain of len+1 extensions, no lists read    [SYNC = false]
+//   2 phase_nei        fm6_get_nei (unitig.c:93-179): breadth-first over the candidate list             [SYNC = true]
+//   3 phase_left1      overlap_intv of check_left_simple (unitig.c:186-190): a chain of extensions      [SYNC = false]
+//   4 phase_left2      the candidate loop of check_left_simple (unitig.c:191-203)                       [SYNC = true]
+// Phases 1 and 3 are the same straight loop for every lane of a warp (equal-length reads: exactly the same trip
+// count), so they run converged without help and with few registers.  Phases 2 and 4 have data-dependent nested
+// loops; there every extension goes through ext_sync (warp vote + one shared copy of the code).  Splitting them
+// keeps the lanes of a warp in the same phase: one fused kernel had lanes in all four at once, and every distinct
+// path between two votes costs the warp its own serialized round trips to the scratch lists.
+template <typename U, bool SYNC, int TAG>
 struct OvLane {
     typedef IntvT<U> Cand;
+    typedef OvBits<U> BT;
     const OverlapArgs &A;
-    uint8_t *s;
-    Cand *P, *Q;
+    Cand *P, *Q;      // lane lists (phases 2 and 4)
     int32_t *cat;
-    int sl;           // current length of s
     bool ovf;
-    Ok6<U> r;         // ok[0..5] of the last extension
+    Ok6<U> r;         // SYNC: ok[0..5] of the last extension
+    Ext6T<U> e;       // !SYNC: the same, before the far coordinates are formed
+    int eback;
 
     FMG_HD OvLane(const OverlapArgs &a, int64_t lane)
-        : A(a), s(a.sbuf + (size_t)lane * a.s_cap), P(static_cast<Cand *>(a.A) + (size_t)lane * a.cap),
-          Q(static_cast<Cand *>(a.B) + (size_t)lane * a.cap), cat(a.cat + (size_t)lane * a.cap), sl(0), ovf(false) {}
+        : A(a), P(static_cast<Cand *>(a.A) + (size_t)lane * a.cap), Q(static_cast<Cand *>(a.B) + (size_t)lane * a.cap),
+          cat(a.cat + (size_t)lane * a.cap), ovf(false), eback(0) {}
 
-    FMG_HD void extend(const Cand &k, int back) { ext_sync<U>(A.ix, true, k.x0, k.x1, k.x2, back, &r); }
-    FMG_HD U size(int c) const { return r.v[c].x2; }
-    FMG_HD Cand ok(int c) const { return r.v[c]; }
-    FMG_HD void push(Cand *list, int &n, const Cand &k) {
-        if (n < A.cap) st_cand(list + n, k); else ovf = true;
+    FMG_HD void extend(const Cand &k, int back) {
+        if (SYNC) ext_sync<U, TAG>(A.ix, true, k.x0, k.x1, k.x2, back, &r);
+        else { extend6<U>(A.ix, back ? k.x1 : k.x0, back ? k.x0 : k.x1, k.x2, e); eback = back; }
+    }
+    FMG_HD U size(int c) const { return SYNC ? r.v[c].x2 : pick6(e.size, c); }
+    FMG_HD Cand ok(int c) const {
+        if (SYNC) return r.v[c];
+        Cand o;
+        const U nr = pick6(e.near, c), fr = far_of(A.ix, e, c);
+        o.x0 = eback ? fr : nr; o.x1 = eback ? nr : fr; o.x2 = pick6(e.size, c); o.info = 0;
+        return o;
+    }
+    FMG_HD void push(Cand *list, int lcap, int &n, const Cand &k) {
+        if (n < lcap) st_cand(list + n, k); else ovf = true;
         ++n;
     }
-    static FMG_HD void reverse(Cand *list, int n, int cap) {
-        if (n > cap) n = cap;
+    static FMG_HD void reverse(Cand *list, int n, int lcap) {
+        if (n > lcap) n = lcap;
         for (int a = 0, b = n - 1; a < b; ++a, --b) {
             const Cand x = ld_cand(list + a), y = ld_cand(list + b);
             st_cand(list + a, y); st_cand(list + b, x);
         }
     }
+    FMG_HD Cand *list0(int64_t t) const { return static_cast<Cand *>(A.P0) + (size_t)t * A.pcap; }
 
     // overlap_intv, unitig.c:38-64.  Returns the final interval; list = candidates, smallest interval first.
-    FMG_HD Cand overlap_intv(int len, const uint8_t *seq, int min, int j, int at5, Cand *list, int &n, int inc_sentinel) {
+    FMG_HD Cand overlap_intv(int len, const SeqView &sv, int min, int j, int at5, Cand *list, int lcap, int &n, int inc_sentinel) {
         const int dir = at5 ? 1 : -1, end = at5 ? len : -1;
-        Cand ik = base_intv<U>(A.ix, seq[j]);
+        Cand ik = base_intv<U>(A.ix, sv.at(j));
         n = 0;
         int depth = 1;
         for (j += dir; j != end; j += dir, ++depth) {
-            const int c = at5 ? comp6(seq[j]) : seq[j];
+            const int b = sv.at(j);
+            const int c = at5 ? comp6(b) : b;
             extend(ik, !at5);
             if (size(c) == 0) break;
             if (depth >= min && size(0) != 0) {
-                if (inc_sentinel) { Cand t = ok(0); t.info = (U)(j - dir); push(list, n, t); }
-                else { ik.info = (U)(j - dir); push(list, n, ik); }
+                if (inc_sentinel) { Cand t = ok(0); t.info = (U)(j - dir); push(list, lcap, n, t); }
+                else { ik.info = (U)(j - dir); push(list, lcap, n, ik); }
             }
             ik = ok(c);
         }
-        reverse(list, n, A.cap);
+        reverse(list, n, lcap);
         return ik;
     }
 
-    // the whole per-sequence record
-    FMG_HD void run(int64_t t) {
-        typedef OvBits<U> BT;
+    // ---- phase 1: fm6_is_contained, unitig.c:77-91
+    FMG_HD void phase_contained(int64_t t) {
         int64_t *rec = A.rec + t * OV_NREC;
         const int L = A.len[t], min_match = A.min_match;
         for (int k = 0; k < OV_NREC; ++k) rec[k] = 0;
         rec[OV_LEN] = L; rec[OV_RBEG] = -1; rec[OV_LEFT] = 1;
         A.nei_cnt[t] = 0;
+        A.np0[t] = -1;
         if (L <= min_match) { rec[OV_CONTAINED] = -9; return; }       // unitig.c:288
-        if (L + 2 > A.s_cap) { rec[OV_CONTAINED] = -100; return; }
-        for (int k = 0; k < L; ++k) s[k] = A.seq[(size_t)t * A.max_len + k];
-        sl = L; ovf = false;
-
-        // ---- fm6_is_contained, unitig.c:77-91
-        int np = 0, nq = 0, ret = 0;
-        Cand ik = overlap_intv(L, s, min_match, L - 1, 0, P, np, 0);
+        ovf = false;
+        int np = 0, ret = 0;
+        const SeqView sv = {A.seq + (size_t)t * A.max_len, L, nullptr};
+        Cand ik = overlap_intv(L, sv, min_match, L - 1, 0, list0(t), A.pcap, np, 0);
         extend(ik, 1);
         if (ik.x2 != size(0)) ret = -1;                 // left contained
         ik = ok(0);
@@ -191,19 +220,32 @@ struct OvLane {
         if (ik.x2 != size(0)) ret = -1;                 // right contained
         const Cand intv0 = ok(0);
         rec[OV_CONTAINED] = ret; rec[OV_X0] = (int64_t)intv0.x0; rec[OV_X1] = (int64_t)intv0.x1; rec[OV_X2] = (int64_t)intv0.x2;
-        if (ret < 0 || np == 0) { if (ovf) rec[OV_CONTAINED] = -100; return; }
+        if (ovf) { rec[OV_CONTAINED] = -100; return; }
+        if (ret < 0 || np == 0) return;
+        A.np0[t] = np;
+    }
 
-        // ---- fm6_get_nei, unitig.c:93-179 (beg = 0; prev = P was filled by overlap_intv above)
-        const int ori_l = L;
+    // ---- phase 2: fm6_get_nei, unitig.c:93-179 (beg = 0; the first `prev` list was filled by phase 1)
+    FMG_HD void phase_nei(int64_t t) {
+        int np = A.np0[t];
+        if (np <= 0) return;
+        A.np0[t] = -1;
+        int64_t *rec = A.rec + t * OV_NREC;
+        const int ori_l = A.len[t];
+        const uint8_t *sq = A.seq + (size_t)t * A.max_len;
+        uint8_t *xt = A.ext + (size_t)t * A.max_len;
+        int sl = ori_l, nq = 0;
+        ovf = false;
         int nnei = 0, is_forked = 0;
         uint4 *nei = A.nei + (size_t)t * A.nei_cap * 2;
         Cand nei0 = {0, 0, 0, 0};
-        Cand *prev = P, *curr = Q;
+        Cand *prev = list0(t), *curr = P;
+        int pcap = A.pcap;                                               // capacity of `prev`; `curr` always holds A.cap
         for (int j = 0; j < np && j < A.cap; ++j) cat[j] = 0;
         while (np) {
             nq = 0;
             int first_base = 0;
-            const int npc = np < A.cap ? np : A.cap;
+            const int npc = np < pcap ? np : pcap;
             for (int j = 0; j < npc; ++j) {
                 if (cat[j] < 0) continue;
                 const Cand p = ld_cand(prev + j);
@@ -237,13 +279,13 @@ struct OvLane {
                     if (size(0) != 0) {                                  // left end still bounded by a sentinel
                         kc.info = (U)((p.info & ~BT::base_mask) | ((U)c << BT::pos_bits));
                         if (nq == 0) first_base = c;
-                        push(curr, nq, kc);
+                        push(curr, A.cap, nq, kc);
                     }
                 }
             }
             if (nq) {                                                    // update categories, unitig.c:137-153
                 const int nqc = nq < A.cap ? nq : A.cap;
-                if (sl + 2 <= A.s_cap) { s[sl++] = (uint8_t)comp6(first_base); } else ovf = true;
+                if (sl - ori_l < A.max_len) { xt[sl - ori_l] = (uint8_t)comp6(first_base); ++sl; } else ovf = true;
                 for (int a = 1; a < nqc; ++a) {                          // insertion sort by info (keys are unique)
                     const Cand x = ld_cand(curr + a);
                     int b = a - 1;
@@ -267,7 +309,8 @@ struct OvLane {
                 if (cat0 != 0) is_forked = 1;
                 if (cat0 > BT::max_cat) ovf = true;
             }
-            Cand *tmp = curr; curr = prev; prev = tmp;
+            prev = curr; curr = curr == P ? Q : P;
+            pcap = A.cap;
             np = nq;
         }
         A.nei_cnt[t] = (uint32_t)nnei;
@@ -276,7 +319,7 @@ struct OvLane {
         const int rbeg = ori_l - (int)nei0.info;
         if (nnei == 1 && is_forked) {             // contained reads forked the path: rebuild it along the one neighbour
             Cand k0 = base_intv<U>(A.ix, 0);
-            for (int i = rbeg; i < ori_l; ++i) { extend(k0, 0); k0 = ok(comp6(s[i])); }
+            for (int i = rbeg; i < ori_l; ++i) { extend(k0, 0); k0 = ok(comp6(sq[i])); }
             int i = ori_l;
             for (; i < sl; ++i) {
                 int c0 = -1, hits = 0;
@@ -287,49 +330,74 @@ struct OvLane {
                 }
                 if (hits == 0 && size(0) != 0) break;
                 if (hits != 1) { ovf = true; break; }                    // the reference asserts hits == 1 (unitig.c:171)
-                s[i] = (uint8_t)comp6(c0);
+                xt[i - ori_l] = (uint8_t)comp6(c0);
                 k0 = ok(c0);
             }
             sl = i;
         }
         if (nnei > 1) sl = ori_l;
         rec[OV_RBEG] = rbeg; rec[OV_SLEN] = sl;
-        for (int k = ori_l; k < sl && k - ori_l < A.max_len; ++k) A.ext[(size_t)t * A.max_len + (k - ori_l)] = s[k];
-        if (sl - ori_l > A.max_len) ovf = true;
+        if (ovf) rec[OV_CONTAINED] = -100;
+    }
 
-        // ---- check_left_simple, unitig.c:186-204, for a unique neighbour (beg = 0)
-        if (nnei == 1 && !ovf) {
-            int left = 0;
-            overlap_intv(sl, s, min_match, rbeg, 1, P, np, 1);
-            prev = P; curr = Q;
-            for (int i = rbeg - 1; i >= 0 && left == 0; --i) {
-                nq = 0;
-                const int npc = np < A.cap ? np : A.cap;
-                for (int j = 0; j < npc; ++j) {
-                    const Cand p = ld_cand(prev + j);
-                    extend(p, 1);
-                    if ((U)(size(0) + size(s[i])) != p.x2) { left = -1; break; }     // potential backward bifurcation
-                    push(curr, nq, ok(s[i]));
-                }
-                Cand *tmp = curr; curr = prev; prev = tmp;
-                np = nq;
+    // ---- phase 3: the overlap_intv call of check_left_simple, unitig.c:186-190, for a unique neighbour (beg = 0)
+    FMG_HD void phase_left1(int64_t t) {
+        int64_t *rec = A.rec + t * OV_NREC;
+        if (rec[OV_NNEI] != 1 || rec[OV_CONTAINED] != 0) return;
+        const int L = A.len[t], sl = (int)rec[OV_SLEN], rbeg = (int)rec[OV_RBEG];
+        const SeqView sv = {A.seq + (size_t)t * A.max_len, L, A.ext + (size_t)t * A.max_len};
+        ovf = false;
+        int np = 0;
+        overlap_intv(sl, sv, A.min_match, rbeg, 1, list0(t), A.pcap, np, 1);
+        if (ovf) { rec[OV_CONTAINED] = -100; return; }
+        A.np0[t] = np;
+    }
+
+    // ---- phase 4: the candidate loop of check_left_simple, unitig.c:191-203
+    FMG_HD void phase_left2(int64_t t) {
+        int np = A.np0[t];
+        if (np < 0) return;
+        int64_t *rec = A.rec + t * OV_NREC;
+        const uint8_t *sq = A.seq + (size_t)t * A.max_len;
+        const int rbeg = (int)rec[OV_RBEG];
+        ovf = false;
+        int left = 0, pcap = A.pcap;
+        Cand *prev = list0(t), *curr = P;
+        for (int i = rbeg - 1; i >= 0 && left == 0; --i) {
+            int nq = 0;
+            const int npc = np < pcap ? np : pcap, c = sq[i];
+            for (int j = 0; j < npc; ++j) {
+                const Cand p = ld_cand(prev + j);
+                extend(p, 1);
+                if ((U)(size(0) + size(c)) != p.x2) { left = -1; break; }       // potential backward bifurcation
+                push(curr, A.cap, nq, ok(c));
             }
-            rec[OV_LEFT] = left;
+            prev = curr; curr = curr == P ? Q : P;
+            pcap = A.cap;
+            np = nq;
         }
+        rec[OV_LEFT] = left;
         if (ovf) rec[OV_CONTAINED] = -100;
     }
 };
 
-template <typename U, class FetchFn>
-FMG_HD void overlap_lane(const OverlapArgs &A, int64_t lane, FetchFn fetch) {
-    OvLane<U> ln(A, lane);
+// list-chasing phases: persistent lanes; a lane that runs out of work keeps answering the warp votes
+template <typename U, int PHASE, class FetchFn>
+FMG_HD void overlap_lane_sync(const OverlapArgs &A, int64_t lane, FetchFn fetch) {
+    OvLane<U, true, PHASE> ln(A, lane);
     for (;;) {
         const int64_t t = fetch();
         if (t >= A.n) break;
-        ln.run(t);
+        if (PHASE == 2) ln.phase_nei(t); else ln.phase_left2(t);
     }
-    // out of work: keep answering the warp votes until every lane of the warp is done
-    while (ext_sync<U>(A.ix, false, 0, 0, 0, 0, &ln.r)) {}
+    while (ext_sync<U, PHASE>(A.ix, false, 0, 0, 0, 0, &ln.r)) {}
+}
+
+// chain phases: one sequence per thread
+template <typename U, int PHASE>
+FMG_HD void overlap_chain(const OverlapArgs &A, int64_t t) {
+    OvLane<U, false, PHASE> ln(A, 0);
+    if (PHASE == 1) ln.phase_contained(t); else ln.phase_left1(t);
 }
 
 // ---------------------------------------------------------------------------------------------

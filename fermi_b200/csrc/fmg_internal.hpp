@@ -10,9 +10,10 @@
 #define SMEM_MIN_BLOCKS_U32 6
 #define SMEM_MIN_BLOCKS_U64 5
 #define SMEM_DEFAULT_OUT_CAP 64
-// k_overlap launch shape
+// overlap kernels: list-chasing phases (persistent lanes) and chain phases (one sequence per thread)
 #define OVLP_BLOCK 128
 #define OVLP_MIN_BLOCKS 4
+#define OVCH_BLOCK 128
 
 struct fmg_fmd_s { fmg::FmdImage img; };
 

@@ -1,6 +1,8 @@
 // Overlap path of `fermi unitig` on the GPU: kernels + C-ABI (see fmd_overlap.cuh for the algorithm).
 //   k_retrieve     fm_retrieve (exact.c:59-70), one sequence per thread
-//   k_overlap<U>   fm6_is_contained + fm6_get_nei + check_left_simple (unitig.c:77-204), persistent lanes
+//   k_ov_chain<U,1|3>  fm6_is_contained / the overlap_intv of check_left_simple (unitig.c:77-91,186-190), one sequence per thread
+//   k_ov_lists<U,2|4>  fm6_get_nei / the candidate loop of check_left_simple (unitig.c:93-179,191-203), persistent lanes
+//   k_ov_pack          batch records -> rank-indexed 64-byte records + compact ext / spill arrays (whole-index pass)
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -34,14 +36,22 @@ __global__ void __launch_bounds__(256) k_retrieve(RetrieveArgs A) {
     if (t < A.n) retrieve_one(A, t);
 }
 
-template <typename U>
-__global__ void __launch_bounds__(OVLP_BLOCK, OVLP_MIN_BLOCKS) k_overlap(OverlapArgs A) {
+// phases 1 and 3: one sequence per thread, a straight chain of extensions (converged for equal-length reads)
+template <typename U, int PHASE>
+__global__ void __launch_bounds__(OVCH_BLOCK) k_ov_chain(OverlapArgs A) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < A.n) overlap_chain<U, PHASE>(A, t);
+}
+
+// phases 2 and 4: persistent lanes, sequences handed out by atomicAdd, every extension behind a warp vote
+template <typename U, int PHASE>
+__global__ void __launch_bounds__(OVLP_BLOCK, OVLP_MIN_BLOCKS) k_ov_lists(OverlapArgs A) {
     const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    overlap_lane<U>(A, lane, [&]() -> int64_t { return (int64_t)atomicAdd(A.next, 1ull); });
+    overlap_lane_sync<U, PHASE>(A, lane, [&]() -> int64_t { return (int64_t)atomicAdd(A.next, 1ull); });
 }
 
 // ---- whole-index pass (fmg_overlap_all): per-batch records -> rank-indexed packed records + compact ext / spill arrays
-enum { OVC_NEXT = 0, OVC_EXT, OVC_SPILL, OVC_FLAGS, OVC_MAXLEN, OVC_N };
+enum { OVC_NEXT = 0, OVC_NEXT2, OVC_EXT, OVC_SPILL, OVC_FLAGS, OVC_MAXLEN, OVC_N };
 enum { OVF_LIST = 1, OVF_NEI = 2, OVF_EXT = 4, OVF_SPILL = 8, OVF_FIELD = 16, OVF_RANK = 32 };
 
 struct PackArgs {
@@ -125,6 +135,40 @@ int fmg_compact_slots(const uint32_t *cnt, int64_t n, int cap, const uint4 *slot
                       unsigned long long *ctrl, cudaStream_t st);
 int64_t fmg_compact_tiles(int64_t n);
 
+// the four phases of the overlap record over one batch, back to back on `st`; ctrl2 = two work counters (zeroed here)
+template <typename U>
+static cudaError_t launch_phases(OverlapArgs O, int grid, unsigned long long *ctrl2, cudaStream_t st, cudaEvent_t *ev = nullptr) {
+    cudaError_t e = cudaMemsetAsync(ctrl2, 0, 16, st);
+    if (e != cudaSuccess) return e;
+    const unsigned gch = (unsigned)((O.n + OVCH_BLOCK - 1) / OVCH_BLOCK);
+    const int g = (int)std::min<int64_t>(grid, (O.n + OVLP_BLOCK - 1) / OVLP_BLOCK);
+    if (ev) cudaEventRecord(ev[0], st);
+    k_ov_chain<U, 1><<<gch, OVCH_BLOCK, 0, st>>>(O);
+    if (ev) cudaEventRecord(ev[1], st);
+    O.next = ctrl2;
+    k_ov_lists<U, 2><<<g, OVLP_BLOCK, 0, st>>>(O);
+    if (ev) cudaEventRecord(ev[2], st);
+    k_ov_chain<U, 3><<<gch, OVCH_BLOCK, 0, st>>>(O);
+    if (ev) cudaEventRecord(ev[3], st);
+    O.next = ctrl2 + 1;
+    k_ov_lists<U, 4><<<g, OVLP_BLOCK, 0, st>>>(O);
+    if (ev) cudaEventRecord(ev[4], st);
+    g_launches += 4;
+    return cudaGetLastError();
+}
+
+static int lists_blocks_per_sm(bool wide) {
+    int a = 0, b = 0;
+    if (wide) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_ov_lists<uint64_t, 2>, OVLP_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_ov_lists<uint64_t, 4>, OVLP_BLOCK, 0);
+    } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_ov_lists<uint32_t, 2>, OVLP_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_ov_lists<uint32_t, 4>, OVLP_BLOCK, 0);
+    }
+    return std::max(1, std::max(a, b));       // lane scratch is sized for the larger grid
+}
+
 namespace {
 // Device scratch is recycled between calls: a unitig run issues one call per 2 M sequences and each needs ~3 GB of
 // lists and slots; cudaMalloc/cudaFree of those costs more than the kernels.  Blocks return to a small pool and are
@@ -189,7 +233,7 @@ void fmg_ovcache_destroy(fmg_ovcache_s *p) { delete p; }
 
 // Overlap records of EVERY sequence of the index (fm_retrieve + fm6_is_contained + fm6_get_nei + check_left_simple per
 // BWT row, unitig.c:77-204) for the unitig walk.  Rows are processed in batches queued back to back on one stream with
-// no host synchronisation in between: k_retrieve -> k_overlap -> k_ov_pack scatter the batch into device-resident,
+// no host synchronisation in between: k_retrieve -> four overlap phases -> k_ov_pack scatter the batch into device-resident,
 // rank-indexed 64-byte records plus compact ext / spill arrays; the seed sequences of batch b travel to pinned host
 // memory on a second stream while batch b+1 computes.  Overflow of any scratch or output capacity is flagged on the
 // device and answered by ONE re-run of the whole pass with larger capacities.
@@ -206,10 +250,7 @@ int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *
     if (!idx->ovc) idx->ovc = new fmg_ovcache_s;
     fmg_ovcache_s &H = *idx->ovc;
     const bool wide = idx->view.n_sym + 256 >= (1ull << 32) || std::getenv("FMG_FORCE_WIDE") != nullptr;
-    int per_sm = 0;
-    if (wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_overlap<uint64_t>, OVLP_BLOCK, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_overlap<uint32_t>, OVLP_BLOCK, 0);
-    if (per_sm < 1) per_sm = 1;
+    const int per_sm = lists_blocks_per_sm(wide);
     const int64_t batch = 1 << 21;                           // even, so that the odd rows of a batch are its local odd rows
     const int64_t nb_max = (int64_t)std::min<uint64_t>(batch, n_seq ? n_seq : 1);
     const int grid = (int)std::min<int64_t>((int64_t)idx->n_sm * per_sm, (nb_max + OVLP_BLOCK - 1) / OVLP_BLOCK);
@@ -231,20 +272,22 @@ int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *
         OV_TRY(cudaEventCreateWithFlags(&copy_done[k], cudaEventDisableTiming));
     }
 
-    int cap = 4 * max_len, nei_cap = 8;
+    int cap = 4 * max_len, nei_cap = 8, pcap_mul = 1;
+    cudaEvent_t phase_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t ext_cap = std::max<uint64_t>(n_seq * 24, 1 << 20), spill_cap = std::max<uint64_t>(n_seq, 1 << 16);
     OV_TRY(H.ctrl.need(OVC_N * 8));
     unsigned long long *h_ctrl = static_cast<unsigned long long *>(H.ctrl.p);
-    Dev d_pack, d_ret, d_extout, d_spill, d_ctrl, d_seq, d_len, d_rec, d_ext, d_cnt, d_slots, d_sbuf, d_A, d_B, d_cat, d_odd[2];
+    Dev d_pack, d_ret, d_extout, d_spill, d_ctrl, d_seq, d_len, d_rec, d_ext, d_cnt, d_slots, d_P0, d_np0, d_A, d_B, d_cat, d_odd[2];
     for (int attempt = 0;; ++attempt) {
-        const int s_cap = 2 * max_len + 8;
+        const int pcap = std::max(8, max_len - min_match + 8) * pcap_mul;
         const size_t esz = wide ? 32 : 16;
         const uint64_t n_odd_all = n_seq / 2;
         OV_TRY(d_pack.alloc(n_seq * sizeof(OvPack))); OV_TRY(d_ret.alloc(n_seq * 8));
         OV_TRY(d_extout.alloc(ext_cap)); OV_TRY(d_spill.alloc(spill_cap * 32)); OV_TRY(d_ctrl.alloc(OVC_N * 8));
         OV_TRY(d_seq.alloc((size_t)nb_max * max_len)); OV_TRY(d_len.alloc((size_t)nb_max * 4)); OV_TRY(d_rec.alloc((size_t)nb_max * OV_NREC * 8));
         OV_TRY(d_ext.alloc((size_t)nb_max * max_len)); OV_TRY(d_cnt.alloc((size_t)(nb_max + 1) * 4)); OV_TRY(d_slots.alloc((size_t)nb_max * nei_cap * 32));
-        OV_TRY(d_sbuf.alloc((size_t)n_lanes * s_cap)); OV_TRY(d_A.alloc((size_t)n_lanes * cap * esz)); OV_TRY(d_B.alloc((size_t)n_lanes * cap * esz));
+        OV_TRY(d_P0.alloc((size_t)nb_max * pcap * esz)); OV_TRY(d_np0.alloc((size_t)nb_max * 4));
+        OV_TRY(d_A.alloc((size_t)n_lanes * cap * esz)); OV_TRY(d_B.alloc((size_t)n_lanes * cap * esz));
         OV_TRY(d_cat.alloc((size_t)n_lanes * cap * 4));
         for (int k = 0; k < 2; ++k) OV_TRY(d_odd[k].alloc((size_t)(nb_max / 2 + 1) * max_len));
         OV_TRY(H.seq.need(std::max<uint64_t>(n_odd_all, 1) * (uint64_t)max_len));
@@ -260,16 +303,15 @@ int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *
             k_retrieve<<<(unsigned)((m + 255) / 256), 256, 0, s_run>>>(R);
             ++g_launches;
             OV_TRY(cudaGetLastError());
-            OV_TRY(cudaMemsetAsync(d_ctrl.p, 0, 8, s_run));                   // OVC_NEXT: the work counter of k_overlap
             OverlapArgs O;
             O.ix = idx->view; O.min_match = min_match; O.n = m; O.seq = d_seq.as<uint8_t>(); O.len = d_len.as<int32_t>(); O.max_len = max_len;
-            O.sbuf = d_sbuf.as<uint8_t>(); O.s_cap = s_cap; O.A = d_A.p; O.B = d_B.p; O.cap = cap; O.cat = d_cat.as<int32_t>();
+            O.P0 = d_P0.p; O.pcap = pcap; O.np0 = d_np0.as<int32_t>(); O.A = d_A.p; O.B = d_B.p; O.cap = cap; O.cat = d_cat.as<int32_t>();
             O.rec = d_rec.as<int64_t>(); O.nei = d_slots.as<uint4>(); O.nei_cap = nei_cap; O.nei_cnt = d_cnt.as<uint32_t>();
-            O.ext = d_ext.as<uint8_t>(); O.next = d_ctrl.as<unsigned long long>() + OVC_NEXT;
-            const int g = (int)std::min<int64_t>(grid, (m + OVLP_BLOCK - 1) / OVLP_BLOCK);
-            if (wide) k_overlap<uint64_t><<<g, OVLP_BLOCK, 0, s_run>>>(O); else k_overlap<uint32_t><<<g, OVLP_BLOCK, 0, s_run>>>(O);
-            ++g_launches;
-            OV_TRY(cudaGetLastError());
+            O.ext = d_ext.as<uint8_t>(); O.next = nullptr;
+            unsigned long long *c2 = d_ctrl.as<unsigned long long>() + OVC_NEXT;       // OVC_NEXT, OVC_NEXT2: the work counters
+            cudaEvent_t *ev = (fmg_verbose >= 4 && b == 0 && attempt == 0) ? phase_ev : nullptr;
+            if (ev) for (int k = 0; k < 5; ++k) OV_TRY(cudaEventCreate(&ev[k]));
+            OV_TRY(wide ? launch_phases<uint64_t>(O, grid, c2, s_run, ev) : launch_phases<uint32_t>(O, grid, c2, s_run, ev));
             PackArgs P;
             P.n = m; P.rec = d_rec.as<int64_t>(); P.ret = d_ret.as<int64_t>() + row0; P.len = d_len.as<int32_t>(); P.nei_cnt = d_cnt.as<uint32_t>();
             P.nei_slots = d_slots.as<uint4>(); P.nei_cap = nei_cap; P.ext = d_ext.as<uint8_t>(); P.max_len = max_len;
@@ -294,6 +336,12 @@ int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *
         OV_TRY(cudaMemcpyAsync(h_ctrl, d_ctrl.p, OVC_N * 8, cudaMemcpyDeviceToHost, s_run));
         OV_TRY(cudaStreamSynchronize(s_run));
         const unsigned long long flags = h_ctrl[OVC_FLAGS], too_long = h_ctrl[OVC_MAXLEN];
+        if (phase_ev[0]) {
+            float ms[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms[k], phase_ev[k], phase_ev[k + 1]);
+            std::fprintf(stderr, "[M::%s] first batch: contained %.2f ms, neighbours %.2f ms, left chain %.2f ms, left lists %.2f ms\n", __func__, ms[0], ms[1], ms[2], ms[3]);
+            for (int k = 0; k < 5; ++k) { cudaEventDestroy(phase_ev[k]); phase_ev[k] = nullptr; }
+        }
         if (fmg_verbose >= 4)
             std::fprintf(stderr, "[M::%s] attempt %d: %lld batches, %.3f s; ext %llu B, spill %llu, flags %llx, longest clipped %llu\n", __func__, attempt,
                          (long long)b, since(t0), h_ctrl[OVC_EXT], h_ctrl[OVC_SPILL], flags, too_long);
@@ -304,7 +352,7 @@ int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *
             return -1;
         }
         if (too_long) { max_len = (int)too_long + 8; cap = std::max(cap, 4 * max_len); }
-        if (flags & OVF_LIST) cap *= 4;
+        if (flags & OVF_LIST) cap *= 4, pcap_mul *= 4;
         if (flags & (OVF_LIST | OVF_NEI)) nei_cap *= 4;
         // the totals keep counting past the capacity, so they are the true need unless other sequences were skipped
         if (flags & OVF_EXT) ext_cap = std::max<uint64_t>(2 * ext_cap, h_ctrl[OVC_EXT] + (h_ctrl[OVC_EXT] >> 3));
@@ -349,7 +397,7 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
     if (n == 0) { *nei = (fmg_intv_t *)std::malloc(32); return 0; }
     const bool wide = idx->view.n_sym + 256 >= (1ull << 32) || std::getenv("FMG_FORCE_WIDE") != nullptr;
 
-    Dev d_ids, d_seq, d_len, d_ret, d_rec, d_ext, d_cnt, d_slots, d_mem, d_off, d_tiles, d_ctrl, d_sbuf, d_A, d_B, d_cat;
+    Dev d_ids, d_seq, d_len, d_ret, d_rec, d_ext, d_cnt, d_slots, d_mem, d_off, d_tiles, d_ctrl, d_A, d_B, d_cat;
     OV_TRY(d_seq.alloc((size_t)n * max_len)); OV_TRY(d_len.alloc((size_t)n * 4)); OV_TRY(d_ret.alloc((size_t)n * 8));
     OV_TRY(d_rec.alloc((size_t)n * OV_NREC * 8)); OV_TRY(d_ext.alloc((size_t)n * max_len)); OV_TRY(d_cnt.alloc((size_t)(n + 1) * 4));
     OV_TRY(d_off.alloc((size_t)(n + 1) * 8)); OV_TRY(d_tiles.alloc((size_t)fmg_compact_tiles(n) * 8)); OV_TRY(d_ctrl.alloc(64));
@@ -375,31 +423,26 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
         }
 
     // ---- overlap records; scratch capacities grow until nothing overflows
-    int per_sm = 0;
-    if (wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_overlap<uint64_t>, OVLP_BLOCK, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_overlap<uint32_t>, OVLP_BLOCK, 0);
-    if (per_sm < 1) per_sm = 1;
+    const int per_sm = lists_blocks_per_sm(wide);
     const int grid = (int)std::min<int64_t>((int64_t)idx->n_sm * per_sm, (n + OVLP_BLOCK - 1) / OVLP_BLOCK);
     const int64_t n_lanes = (int64_t)grid * OVLP_BLOCK;
-    int cap = 4 * max_len, nei_cap = 8;
-    const int s_cap = 2 * max_len + 8;
+    int cap = 4 * max_len, nei_cap = 8, pcap = std::max(8, max_len - min_match + 8);
     int64_t *h_rec = rec;
     std::vector<uint32_t> h_cnt(n);
+    Dev d_P0, d_np0;
+    OV_TRY(d_np0.alloc((size_t)n * 4));
     for (int attempt = 0;; ++attempt) {
         const size_t esz = wide ? 32 : 16;
-        OV_TRY(d_sbuf.alloc((size_t)n_lanes * s_cap)); OV_TRY(d_A.alloc((size_t)n_lanes * cap * esz)); OV_TRY(d_B.alloc((size_t)n_lanes * cap * esz));
+        OV_TRY(d_P0.alloc((size_t)n * pcap * esz)); OV_TRY(d_A.alloc((size_t)n_lanes * cap * esz)); OV_TRY(d_B.alloc((size_t)n_lanes * cap * esz));
         OV_TRY(d_cat.alloc((size_t)n_lanes * cap * 4)); OV_TRY(d_slots.alloc((size_t)n * nei_cap * 32)); OV_TRY(d_mem.alloc((size_t)n * nei_cap * 32));
-        OV_TRY(cudaMemset(d_ctrl.p, 0, 64));
         OverlapArgs O;
         O.ix = idx->view; O.min_match = min_match; O.n = n; O.seq = d_seq.as<uint8_t>(); O.len = d_len.as<int32_t>(); O.max_len = max_len;
-        O.sbuf = d_sbuf.as<uint8_t>(); O.s_cap = s_cap; O.A = d_A.p; O.B = d_B.p; O.cap = cap; O.cat = d_cat.as<int32_t>();
+        O.P0 = d_P0.p; O.pcap = pcap; O.np0 = d_np0.as<int32_t>(); O.A = d_A.p; O.B = d_B.p; O.cap = cap; O.cat = d_cat.as<int32_t>();
         O.rec = d_rec.as<int64_t>(); O.nei = d_slots.as<uint4>(); O.nei_cap = nei_cap; O.nei_cnt = d_cnt.as<uint32_t>();
-        O.ext = d_ext.as<uint8_t>(); O.next = d_ctrl.as<unsigned long long>();
-        if (wide) k_overlap<uint64_t><<<grid, OVLP_BLOCK>>>(O); else k_overlap<uint32_t><<<grid, OVLP_BLOCK>>>(O);
-        ++g_launches;
-        OV_TRY(cudaGetLastError());
+        O.ext = d_ext.as<uint8_t>(); O.next = nullptr;
+        OV_TRY(wide ? launch_phases<uint64_t>(O, grid, d_ctrl.as<unsigned long long>(), nullptr) : launch_phases<uint32_t>(O, grid, d_ctrl.as<unsigned long long>(), nullptr));
         OV_TRY(cudaDeviceSynchronize());
-        if (fmg_verbose >= 4) std::fprintf(stderr, "[M::%s] k_retrieve %.3f s, k_overlap (attempt %d) %.3f s for %lld sequences\n", __func__, t_retrieve, attempt, since(t1), (long long)n);
+        if (fmg_verbose >= 4) std::fprintf(stderr, "[M::%s] k_retrieve %.3f s, overlap phases (attempt %d) %.3f s for %lld sequences\n", __func__, t_retrieve, attempt, since(t1), (long long)n);
         OV_TRY(cudaMemcpy(h_rec, d_rec.p, (size_t)n * OV_NREC * 8, cudaMemcpyDeviceToHost));
         OV_TRY(cudaMemcpy(h_cnt.data(), d_cnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
         bool list_ovf = false, nei_ovf = false;
@@ -412,7 +455,7 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
             if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] scratch overflow persists (cap=%d, nei_cap=%d)\n", __func__, cap, nei_cap);
             return -1;
         }
-        if (list_ovf) cap *= 4;
+        if (list_ovf) cap *= 4, pcap *= 4;
         if (nei_ovf || list_ovf) nei_cap *= 4;
         if (fmg_verbose >= 3) std::fprintf(stderr, "[M::%s] scratch overflow; re-running with %d candidate / %d neighbour slots\n", __func__, cap, nei_cap);
     }

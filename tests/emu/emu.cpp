@@ -104,19 +104,26 @@ int emu_overlap(const void *_x, int min_match, int64_t n, const uint64_t *ids, i
     RetrieveArgs R;
     R.ix = x->view; R.n = n; R.ids = ids; R.first = 0; R.step = 1; R.seq = seq; R.max_len = max_len; R.len = len; R.ret = ret.data();
     for (int64_t t = 0; t < n; ++t) retrieve_one(R, t);
-    const int n_lanes = 3, s_cap = 2 * max_len + 8;
-    std::vector<uint8_t> sbuf((size_t)n_lanes * s_cap);
-    std::vector<uint64_t> A((size_t)n_lanes * cap * 4), B((size_t)n_lanes * cap * 4);
-    std::vector<int32_t> cat((size_t)n_lanes * cap);
+    // the four phases in the order the product launches them (overlap.cu: launch_phases), over the whole batch
+    const int n_lanes = 3, pcap = (max_len - min_match + 8 > 8 ? max_len - min_match + 8 : 8);
+    std::vector<uint64_t> P0((size_t)n * pcap * 4), A((size_t)n_lanes * cap * 4), B((size_t)n_lanes * cap * 4);
+    std::vector<int32_t> cat((size_t)n_lanes * cap), np0(n);
     OverlapArgs O;
     O.ix = x->view; O.min_match = min_match; O.n = n; O.seq = seq; O.len = len; O.max_len = max_len;
-    O.sbuf = sbuf.data(); O.s_cap = s_cap; O.A = A.data(); O.B = B.data(); O.cap = cap; O.cat = cat.data();
+    O.P0 = P0.data(); O.pcap = pcap; O.np0 = np0.data(); O.A = A.data(); O.B = B.data(); O.cap = cap; O.cat = cat.data();
     O.rec = rec; O.nei = reinterpret_cast<uint4 *>(nei); O.nei_cap = nei_cap; O.nei_cnt = nei_cnt; O.ext = ext; O.next = nullptr;
-    for (int t = 0; t < n_lanes; ++t) {
-        int64_t cur = t;
-        auto fetch = [&]() { int64_t r = cur; cur += n_lanes; return r; };
-        if (wide) overlap_lane<uint64_t>(O, t, fetch); else overlap_lane<uint32_t>(O, t, fetch);
-    }
+    auto lists = [&](int phase) {
+        for (int t = 0; t < n_lanes; ++t) {
+            int64_t cur = t;
+            auto fetch = [&]() { int64_t r = cur; cur += n_lanes; return r; };
+            if (wide) { if (phase == 2) overlap_lane_sync<uint64_t, 2>(O, t, fetch); else overlap_lane_sync<uint64_t, 4>(O, t, fetch); }
+            else { if (phase == 2) overlap_lane_sync<uint32_t, 2>(O, t, fetch); else overlap_lane_sync<uint32_t, 4>(O, t, fetch); }
+        }
+    };
+    for (int64_t t = 0; t < n; ++t) { if (wide) overlap_chain<uint64_t, 1>(O, t); else overlap_chain<uint32_t, 1>(O, t); }
+    lists(2);
+    for (int64_t t = 0; t < n; ++t) { if (wide) overlap_chain<uint64_t, 3>(O, t); else overlap_chain<uint32_t, 3>(O, t); }
+    lists(4);
     for (int64_t t = 0; t < n; ++t) rec[t * OV_NREC + OV_K] = ret[t];
     return 0;
 }
