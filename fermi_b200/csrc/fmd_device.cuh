@@ -167,14 +167,9 @@ template <typename U> struct IntvT { U x0, x1, x2, info; };
 template <typename U> struct Ext6T { U size[6], near[6]; uint32_t relk[6]; uint64_t sbk; };
 typedef Ext6T<uint64_t> Ext6;
 
+// the arithmetic of extend6 on blocks that are already in registers: bk holds position pk = x_far, bl holds pl = x_far + size
 template <typename U>
-FMG_HD void extend6(const OccView &ix, U x_near, U x_far, U size, Ext6T<U> &e) {
-    // rld_rank2a(x_far-1, x_far-1+size): counts in BWT[0,x_far) and BWT[0,x_far+size)  (k=-1 <=> p=0)
-    const uint64_t pk = x_far, pl = (uint64_t)x_far + size;
-    const bool same = (pk >> kBlkShift) == (pl >> kBlkShift);
-    const Blk bk = load_blk(ix, pk);
-    Blk bl = bk;
-    if (!same) bl = load_blk(ix, pl);              // small intervals: both ranks read the same 64 bytes
+FMG_HD void extend6_with(const OccView &ix, U x_near, uint64_t pk, uint64_t pl, const Blk &bk, const Blk &bl, Ext6T<U> &e) {
     uint32_t rl[6];
     rank_rel(bk, pk, e.relk);
     rank_rel(bl, pl, rl);
@@ -194,6 +189,26 @@ FMG_HD void extend6(const OccView &ix, U x_near, U x_far, U size, Ext6T<U> &e) {
     e.near[2] = e.near[3] + e.size[3];
     e.near[1] = e.near[2] + e.size[2];
     e.near[5] = e.near[1] + e.size[1];
+}
+
+template <typename U>
+FMG_HD void extend6(const OccView &ix, U x_near, U x_far, U size, Ext6T<U> &e) {
+    // rld_rank2a(x_far-1, x_far-1+size): counts in BWT[0,x_far) and BWT[0,x_far+size)  (k=-1 <=> p=0)
+    const uint64_t pk = x_far, pl = (uint64_t)x_far + size;
+    const bool same = (pk >> kBlkShift) == (pl >> kBlkShift);
+    const Blk bk = load_blk(ix, pk);
+    Blk bl = bk;
+    if (!same) bl = load_blk(ix, pl);              // small intervals: both ranks read the same 64 bytes
+    extend6_with<U>(ix, x_near, pk, pl, bk, bl, e);
+}
+
+// BWT[k] from the block that holds position k
+FMG_HD int blk_symbol(const Blk &B, uint64_t k) {
+    const uint32_t w = ((uint32_t)k >> 5) & 3u, bit = (uint32_t)k & 31u;
+    const uint32_t p0 = w == 0 ? B.lo.v[4] : w == 1 ? B.lo.v[5] : w == 2 ? B.lo.v[6] : B.lo.v[7];
+    const uint32_t p1 = w == 0 ? B.hi.v[0] : w == 1 ? B.hi.v[1] : w == 2 ? B.hi.v[2] : B.hi.v[3];
+    const uint32_t p2 = w == 0 ? B.hi.v[4] : w == 1 ? B.hi.v[5] : w == 2 ? B.hi.v[6] : B.hi.v[7];
+    return (int)((p0 >> bit & 1u) | (p1 >> bit & 1u) << 1 | (p2 >> bit & 1u) << 2);
 }
 
 template <typename T>

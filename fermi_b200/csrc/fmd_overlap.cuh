@@ -29,15 +29,19 @@ struct OverlapArgs {
     OccView ix;
     int min_match;
     int64_t n;                  // sequences in this batch
-    const uint8_t *seq;         // n x max_len nt6 bytes (retrieve_one output)
-    const int32_t *len;         // n
+    // phase 1 spells the sequences itself (fm_retrieve, exact.c:59-70, fused with the backward search of fm6_is_contained)
+    const uint64_t *ids;        // BWT rows (sentinel ranks) of the batch, or nullptr for row t = first + t * step
+    uint64_t first, step;
+    uint8_t *seq;               // n x max_len nt6 bytes, reading order
+    int32_t *len;               // n; a sequence longer than max_len is flagged by len = -(true length)
+    int64_t *ret;               // n: the value fm_retrieve returns = rank of the sequence among all sequences
     int max_len;
     // per-sequence scratch handed from phase to phase
     void *P0; int pcap;         // candidate list of overlap_intv (unitig.c:38-64): n x pcap entries of 4 x U
     int32_t *np0;               // n: entries in P0 for the next phase; -1 = the next phase has nothing to do
     // per-lane scratch of the two list-chasing phases
     void *A, *B; int cap;       // candidate interval lists (4 x U per entry)
-    int32_t *cat;               // category per candidate (unitig.c:105-151)
+    int32_t *cat;               // category per candidate (unitig.c:105-151): 2 x cap per lane (previous / current level)
     // per-sequence output
     int64_t *rec;               // 10 per sequence, see OV_* below
     uint4 *nei; int nei_cap;    // neighbour records (fmintv_t: x = interval of the neighbour, info = overlap length)
@@ -146,14 +150,15 @@ struct OvLane {
     Cand *P, *Q;      // lane lists (phases 2 and 4)
     int32_t *cat;
     bool ovf;
-    Ok6<U> r;         // SYNC: ok[0..5] of the last extension
+    Ok6<U> r, em;     // SYNC: ok[0..5] of the last extension; em = those of the last forward extension of phase 2
     Ext6T<U> e;       // !SYNC: the same, before the far coordinates are formed
     int eback;
 
     FMG_HD OvLane(const OverlapArgs &a, int64_t lane)
         : A(a), P(static_cast<Cand *>(a.A) + (size_t)lane * a.cap), Q(static_cast<Cand *>(a.B) + (size_t)lane * a.cap),
-          cat(a.cat + (size_t)lane * a.cap), ovf(false), eback(0) {}
+          cat(a.cat + (size_t)lane * a.cap * 2), ovf(false), eback(0) {}
 
+    FMG_HD void ext_to(const Cand &k, int back, Ok6<U> *dst) { ext_sync<U, TAG>(A.ix, true, k.x0, k.x1, k.x2, back, dst); }
     FMG_HD void extend(const Cand &k, int back) {
         if (SYNC) ext_sync<U, TAG>(A.ix, true, k.x0, k.x1, k.x2, back, &r);
         else { extend6<U>(A.ix, back ? k.x1 : k.x0, back ? k.x0 : k.x1, k.x2, e); eback = back; }
@@ -200,25 +205,80 @@ struct OvLane {
         return ik;
     }
 
-    // ---- phase 1: fm6_is_contained, unitig.c:77-91
+    // ---- phase 1: fm_retrieve (exact.c:59-70) + fm6_is_contained (unitig.c:77-91) in ONE chain.
+    // fm_retrieve spells the sequence from its last base to its first by LF steps from BWT row k; fm6_is_contained
+    // extends the bi-interval of the growing suffix backward by exactly those bases (overlap_intv, unitig.c:38-64,
+    // at5 = 0).  Row k always lies inside that interval [x0, x0+x2), so for the small intervals of most steps the block
+    // that yields BWT[k] and LF(k) is the block the extension reads anyway: one 64-byte access per base for both.
+    // The read length is only known at the end, so candidates are pushed with the suffix length in `info` and get the
+    // start position (unitig.c:55) when the list is reversed.
     FMG_HD void phase_contained(int64_t t) {
         int64_t *rec = A.rec + t * OV_NREC;
-        const int L = A.len[t], min_match = A.min_match;
-        for (int k = 0; k < OV_NREC; ++k) rec[k] = 0;
+        const int min_match = A.min_match;
+        uint8_t *out = A.seq + (size_t)t * A.max_len;
+        Cand *list = list0(t);
+        ovf = false;
+        uint64_t k = A.ids ? A.ids[t] : A.first + (uint64_t)t * A.step;
+        int n = 0, np = 0, ret = 0;
+        Cand ik = {0, 0, 0, 0}, intv0 = {0, 0, 0, 0};
+        for (;;) {
+            // blocks: the two ends of the interval (from the second base on) and the one holding row k
+            const uint64_t pk = ik.x0, pl = (uint64_t)ik.x0 + ik.x2;
+            Blk bk, bl, bq;
+            if (n > 0) {
+                bk = load_blk(A.ix, pk);
+                bl = bk;
+                if ((pk >> kBlkShift) != (pl >> kBlkShift)) bl = load_blk(A.ix, pl);
+                const uint64_t qb = k >> kBlkShift;
+                if (qb == (pk >> kBlkShift)) bq = bk;
+                else if (qb == (pl >> kBlkShift)) bq = bl;
+                else bq = load_blk(A.ix, k);
+            } else bq = load_blk(A.ix, k);
+            uint32_t rel[6];
+            rank_rel(bq, k, rel);                             // counts in [superblock_start, k)
+            const int c = blk_symbol(bq, k);                  // BWT[k]
+            // rank of c in BWT[0..k] is rel+1, so LF(k) = C[c] + rel (exact.c:66)
+            k = ld_u64(A.ix.cs + (k >> kSuperShift) * 8 + c) + pick6(rel, c);
+            const bool last = c == 0 || c > 5;
+            if (n > 0) {
+                extend6_with<U>(A.ix, ik.x1, pk, pl, bk, bl, e);      // backward extension of the suffix read so far
+                eback = 1;
+                if (last) {                                   // fm6_is_contained after overlap_intv: extend(ik, 1)
+                    if (ik.x2 != size(0)) ret = -1;           // left contained
+                    intv0 = ok(0);
+                    break;
+                }
+                if (n >= min_match && size(0) != 0) { ik.info = (U)n; push(list, A.pcap, np, ik); }
+                ik = ok(c);
+            } else {
+                if (last) break;                              // an empty sequence
+                ik = base_intv<U>(A.ix, c);
+            }
+            if (n < A.max_len) out[n] = (uint8_t)c;
+            ++n;
+        }
+        A.ret[t] = (int64_t)k;
+        const int L = n <= A.max_len ? n : -n;
+        A.len[t] = L;
+        for (int a = 0, b = (n < A.max_len ? n : A.max_len) - 1; a < b; ++a, --b) { const uint8_t x = out[a]; out[a] = out[b]; out[b] = x; }   // seq_reverse (unitig.c:285)
+        for (int q = 0; q < OV_NREC; ++q) rec[q] = 0;
         rec[OV_LEN] = L; rec[OV_RBEG] = -1; rec[OV_LEFT] = 1;
         A.nei_cnt[t] = 0;
         A.np0[t] = -1;
-        if (L <= min_match) { rec[OV_CONTAINED] = -9; return; }       // unitig.c:288
-        ovf = false;
-        int np = 0, ret = 0;
-        const SeqView sv = {A.seq + (size_t)t * A.max_len, L, nullptr};
-        Cand ik = overlap_intv(L, sv, min_match, L - 1, 0, list0(t), A.pcap, np, 0);
-        extend(ik, 1);
-        if (ik.x2 != size(0)) ret = -1;                 // left contained
-        ik = ok(0);
-        extend(ik, 0);
-        if (ik.x2 != size(0)) ret = -1;                 // right contained
-        const Cand intv0 = ok(0);
+        if (L <= min_match) { rec[OV_CONTAINED] = -9; return; }       // unitig.c:288 (also: clipped sequences, re-run by the host)
+        // candidates: smallest interval first, info = start of the suffix in the read
+        {
+            const int m = np < A.pcap ? np : A.pcap;
+            for (int a = 0, b = m - 1; a <= b; ++a, --b) {
+                Cand x = ld_cand(list + a), y = ld_cand(list + b);
+                x.info = (U)(L - (int)x.info); y.info = (U)(L - (int)y.info);
+                st_cand(list + a, y);
+                if (a != b) st_cand(list + b, x);
+            }
+        }
+        extend(intv0, 0);
+        if (intv0.x2 != size(0)) ret = -1;              // right contained
+        intv0 = ok(0);
         rec[OV_CONTAINED] = ret; rec[OV_X0] = (int64_t)intv0.x0; rec[OV_X1] = (int64_t)intv0.x1; rec[OV_X2] = (int64_t)intv0.x2;
         if (ovf) { rec[OV_CONTAINED] = -100; return; }
         if (ret < 0 || np == 0) return;
@@ -226,6 +286,10 @@ struct OvLane {
     }
 
     // ---- phase 2: fm6_get_nei, unitig.c:93-179 (beg = 0; the first `prev` list was filled by phase 1)
+    // List entries keep the RAW sort key of unitig.c:132 in `info` (category of the parent | base | position); the category
+    // an entry gets at the end of its level (unitig.c:142-151) lives in a parallel array and is merged in when the entry
+    // is read.  Children arrive almost always in key order already (one category, one base), so the category is computed
+    // while pushing and the sort + renumbering pass of the reference only runs for a level whose pushes were out of order.
     FMG_HD void phase_nei(int64_t t) {
         int np = A.np0[t];
         if (np <= 0) return;
@@ -240,76 +304,91 @@ struct OvLane {
         uint4 *nei = A.nei + (size_t)t * A.nei_cap * 2;
         Cand nei0 = {0, 0, 0, 0};
         Cand *prev = list0(t), *curr = P;
+        int32_t *pcat = cat, *ccat = cat + A.cap;                        // categories of `prev` / `curr`
         int pcap = A.pcap;                                               // capacity of `prev`; `curr` always holds A.cap
-        for (int j = 0; j < np && j < A.cap; ++j) cat[j] = 0;
+        for (int j = 0; j < np && j < A.cap; ++j) pcat[j] = 0;
         while (np) {
             nq = 0;
-            int first_base = 0;
+            int first_base = 0, cat_run = 0;
+            bool sorted = true;
+            U last_key = 0, last_hi = 0;
             const int npc = np < pcap ? np : pcap;
+            Cand p = ld_cand(prev);
+            int cj = pcat[0];
             for (int j = 0; j < npc; ++j) {
-                if (cat[j] < 0) continue;
-                const Cand p = ld_cand(prev + j);
-                extend(p, 0);                                            // forward extension
-                const Ok6<U> em = r;                                     // keep ok[1..4] across the sentinel probes
-                const U s0 = size(0);
-                if (s0 != 0 && ori_l != sl) {                            // some (partial) reads end here
-                    const Cand k0 = ok(0);
-                    extend(k0, 1);                                       // fm6_extend0(ok[0], back)
-                    if (size(0) != 0) {                                  // bounded by sentinels on both sides: a full read
-                        if (s0 == p.x2 && p.x2 == size(0)) {             // not contained in a longer read
-                            const int cat0 = cat[j];
-                            Cand nb = ok(0);                             // fm6_extend0's ok0 (x[0] = tk[0]; cnt[0] is 0)
-                            nb.info = (U)(ori_l - (int)(p.info & BT::pos_mask));
-                            for (int i = j; i < npc && cat[i] == cat0; ++i) cat[i] = -1;
-                            if (nnei < A.nei_cap) {
-                                Intv o; o.x0 = nb.x0; o.x1 = nb.x1; o.x2 = nb.x2; o.info = nb.info;
-                                st_intv(nei + 2 * nnei, o);
-                            } else ovf = true;
-                            if (nnei == 0) nei0 = nb;
-                            ++nnei;
-                            continue;
-                        }   // else: a read contained in another one (the reference only marks it `used`)
+                // the next candidate is requested before this one is extended: its latency hides behind the extension
+                const bool more = j + 1 < npc;
+                Cand pn = p;
+                int cn = -1;
+                if (more) { pn = ld_cand(prev + j + 1); cn = pcat[j + 1]; }
+                do {
+                    if (cj < 0) break;
+                    p.info = (U)((p.info & BT::pos_mask) | ((U)cj << BT::cat_shift));
+                    ext_to(p, 0, &em);                                   // forward extension; ok[1..4] stay in `em` across the probes
+                    const U s0 = em.v[0].x2;
+                    if (s0 != 0 && ori_l != sl) {                        // some (partial) reads end here
+                        extend(em.v[0], 1);                              // fm6_extend0(ok[0], back)
+                        if (size(0) != 0) {                              // bounded by sentinels on both sides: a full read
+                            if (s0 == p.x2 && p.x2 == size(0)) {         // not contained in a longer read
+                                Cand nb = ok(0);                         // fm6_extend0's ok0 (x[0] = tk[0]; cnt[0] is 0)
+                                nb.info = (U)(ori_l - (int)(p.info & BT::pos_mask));
+                                for (int i = j; i < npc && pcat[i] == cj; ++i) pcat[i] = -1;
+                                if (more) cn = pcat[j + 1];              // the request above may predate the masking
+                                if (nnei < A.nei_cap) {
+                                    Intv o; o.x0 = nb.x0; o.x1 = nb.x1; o.x2 = nb.x2; o.info = nb.info;
+                                    st_intv(nei + 2 * nnei, o);
+                                } else ovf = true;
+                                if (nnei == 0) nei0 = nb;
+                                ++nnei;
+                                break;
+                            }   // else: a read contained in another one (the reference only marks it `used`)
+                        }
                     }
-                }
-                if (cat[j] < 0) continue;
-                for (int c = 1; c < 5; ++c) {                            // collect extensible intervals
-                    Cand kc = em.v[c];
-                    if (kc.x2 == 0) continue;
-                    extend(kc, 1);                                       // fm6_extend0(ok[c], back)
-                    if (size(0) != 0) {                                  // left end still bounded by a sentinel
-                        kc.info = (U)((p.info & ~BT::base_mask) | ((U)c << BT::pos_bits));
-                        if (nq == 0) first_base = c;
-                        push(curr, A.cap, nq, kc);
+                    for (int c = 1; c < 5; ++c) {                        // collect extensible intervals
+                        Cand kc = em.v[c];
+                        if (kc.x2 == 0) continue;
+                        extend(kc, 1);                                   // fm6_extend0(ok[c], back)
+                        if (size(0) != 0) {                              // left end still bounded by a sentinel
+                            kc.info = (U)((p.info & ~BT::base_mask) | ((U)c << BT::pos_bits));
+                            const U hi = (U)(kc.info >> BT::pos_bits);
+                            if (nq == 0) first_base = c;
+                            else if (kc.info < last_key) sorted = false;
+                            if (nq == 0 || hi != last_hi) { last_hi = hi; cat_run = nq; }
+                            last_key = kc.info;
+                            if (nq < A.cap) ccat[nq] = cat_run;
+                            push(curr, A.cap, nq, kc);
+                        }
                     }
-                }
+                } while (0);
+                p = pn; cj = cn;
             }
             if (nq) {                                                    // update categories, unitig.c:137-153
                 const int nqc = nq < A.cap ? nq : A.cap;
                 if (sl - ori_l < A.max_len) { xt[sl - ori_l] = (uint8_t)comp6(first_base); ++sl; } else ovf = true;
-                for (int a = 1; a < nqc; ++a) {                          // insertion sort by info (keys are unique)
-                    const Cand x = ld_cand(curr + a);
-                    int b = a - 1;
-                    while (b >= 0) {
-                        const Cand y = ld_cand(curr + b);
-                        if (y.info <= x.info) break;
-                        st_cand(curr + b + 1, y); --b;
+                if (!sorted) {
+                    for (int a = 1; a < nqc; ++a) {                      // insertion sort by info (keys are unique)
+                        const Cand x = ld_cand(curr + a);
+                        int b = a - 1;
+                        while (b >= 0) {
+                            const Cand y = ld_cand(curr + b);
+                            if (y.info <= x.info) break;
+                            st_cand(curr + b + 1, y); --b;
+                        }
+                        st_cand(curr + b + 1, x);
                     }
-                    st_cand(curr + b + 1, x);
+                    U last = 0;
+                    cat_run = 0;
+                    for (int j = 0; j < nqc; ++j) {
+                        const U hi = (U)(ld_cand(curr + j).info >> BT::pos_bits);
+                        if (j == 0 || hi != last) { last = hi; cat_run = j; }
+                        ccat[j] = cat_run;
+                    }
                 }
-                U last = 0; int cat0 = 0;
-                for (int j = 0; j < nqc; ++j) {
-                    Cand x = ld_cand(curr + j);
-                    const U hi = (U)(x.info >> BT::pos_bits);
-                    if (j == 0 || hi != last) { last = hi; cat0 = j; }
-                    cat[j] = cat0;
-                    x.info = (U)((x.info & BT::pos_mask) | ((U)cat0 << BT::cat_shift));
-                    if (j == 0) x.info &= BT::pos_mask;
-                    st_cand(curr + j, x);
-                }
-                if (cat0 != 0) is_forked = 1;
-                if (cat0 > BT::max_cat) ovf = true;
+                if (cat_run != 0) is_forked = 1;
+                if (cat_run > BT::max_cat) ovf = true;
             }
             prev = curr; curr = curr == P ? Q : P;
+            int32_t *tc = pcat; pcat = ccat; ccat = tc;
             pcap = A.cap;
             np = nq;
         }

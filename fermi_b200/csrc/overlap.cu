@@ -1,6 +1,5 @@
 // Overlap path of `fermi unitig` on the GPU: kernels + C-ABI (see fmd_overlap.cuh for the algorithm).
-//   k_retrieve     fm_retrieve (exact.c:59-70), one sequence per thread
-//   k_ov_chain<U,1|3>  fm6_is_contained / the overlap_intv of check_left_simple (unitig.c:77-91,186-190), one sequence per thread
+//   k_ov_chain<U,1|3>  fm_retrieve (exact.c:59-70) fused with fm6_is_contained / the overlap_intv of check_left_simple (unitig.c:77-91,186-190), one sequence per thread
 //   k_ov_lists<U,2|4>  fm6_get_nei / the candidate loop of check_left_simple (unitig.c:93-179,191-203), persistent lanes
 //   k_ov_pack          batch records -> rank-indexed 64-byte records + compact ext / spill arrays (whole-index pass)
 #include <cuda_runtime.h>
@@ -30,11 +29,6 @@ extern std::atomic<uint64_t> g_launches;
             return -1;                                                                                \
         }                                                                                             \
     } while (0)
-
-__global__ void __launch_bounds__(256) k_retrieve(RetrieveArgs A) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < A.n) retrieve_one(A, t);
-}
 
 // phases 1 and 3: one sequence per thread, a straight chain of extensions (converged for equal-length reads)
 template <typename U, int PHASE>
@@ -233,7 +227,7 @@ void fmg_ovcache_destroy(fmg_ovcache_s *p) { delete p; }
 
 // Overlap records of EVERY sequence of the index (fm_retrieve + fm6_is_contained + fm6_get_nei + check_left_simple per
 // BWT row, unitig.c:77-204) for the unitig walk.  Rows are processed in batches queued back to back on one stream with
-// no host synchronisation in between: k_retrieve -> four overlap phases -> k_ov_pack scatter the batch into device-resident,
+// no host synchronisation in between: the four overlap phases -> k_ov_pack scatter the batch into device-resident,
 // rank-indexed 64-byte records plus compact ext / spill arrays; the seed sequences of batch b travel to pinned host
 // memory on a second stream while batch b+1 computes.  Overflow of any scratch or output capacity is flagged on the
 // device and answered by ONE re-run of the whole pass with larger capacities.
@@ -273,7 +267,8 @@ int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *
     }
 
     int cap = 4 * max_len, nei_cap = 8, pcap_mul = 1;
-    cudaEvent_t phase_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // fmg_verbose >= 4: 8 events per batch = [start | (unused) | retrieve + contained | neighbours | left chain | left lists | pack | seed rows]
+    std::vector<cudaEvent_t> phase_ev;
     uint64_t ext_cap = std::max<uint64_t>(n_seq * 24, 1 << 20), spill_cap = std::max<uint64_t>(n_seq, 1 << 16);
     OV_TRY(H.ctrl.need(OVC_N * 8));
     unsigned long long *h_ctrl = static_cast<unsigned long long *>(H.ctrl.p);
@@ -288,7 +283,7 @@ int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *
         OV_TRY(d_ext.alloc((size_t)nb_max * max_len)); OV_TRY(d_cnt.alloc((size_t)(nb_max + 1) * 4)); OV_TRY(d_slots.alloc((size_t)nb_max * nei_cap * 32));
         OV_TRY(d_P0.alloc((size_t)nb_max * pcap * esz)); OV_TRY(d_np0.alloc((size_t)nb_max * 4));
         OV_TRY(d_A.alloc((size_t)n_lanes * cap * esz)); OV_TRY(d_B.alloc((size_t)n_lanes * cap * esz));
-        OV_TRY(d_cat.alloc((size_t)n_lanes * cap * 4));
+        OV_TRY(d_cat.alloc((size_t)n_lanes * cap * 8));
         for (int k = 0; k < 2; ++k) OV_TRY(d_odd[k].alloc((size_t)(nb_max / 2 + 1) * max_len));
         OV_TRY(H.seq.need(std::max<uint64_t>(n_odd_all, 1) * (uint64_t)max_len));
         OV_TRY(cudaMemsetAsync(d_ctrl.p, 0, OVC_N * 8, s_run));
@@ -297,21 +292,22 @@ int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *
         int64_t b = 0;
         for (uint64_t row0 = 0; row0 < n_seq; row0 += batch, ++b) {
             const int64_t m = (int64_t)std::min<uint64_t>(batch, n_seq - row0);
-            RetrieveArgs R;
-            R.ix = idx->view; R.n = m; R.ids = nullptr; R.first = row0; R.step = 1;
-            R.seq = d_seq.as<uint8_t>(); R.max_len = max_len; R.len = d_len.as<int32_t>(); R.ret = d_ret.as<int64_t>() + row0;
-            k_retrieve<<<(unsigned)((m + 255) / 256), 256, 0, s_run>>>(R);
-            ++g_launches;
-            OV_TRY(cudaGetLastError());
+            cudaEvent_t *ev = nullptr;
+            if (fmg_verbose >= 4) {
+                const size_t e0 = phase_ev.size();
+                phase_ev.resize(e0 + 8, nullptr);
+                for (int k = 0; k < 8; ++k) OV_TRY(cudaEventCreate(&phase_ev[e0 + k]));
+                ev = &phase_ev[e0];
+                OV_TRY(cudaEventRecord(ev[0], s_run));
+            }
             OverlapArgs O;
             O.ix = idx->view; O.min_match = min_match; O.n = m; O.seq = d_seq.as<uint8_t>(); O.len = d_len.as<int32_t>(); O.max_len = max_len;
+            O.ids = nullptr; O.first = row0; O.step = 1; O.ret = d_ret.as<int64_t>() + row0;
             O.P0 = d_P0.p; O.pcap = pcap; O.np0 = d_np0.as<int32_t>(); O.A = d_A.p; O.B = d_B.p; O.cap = cap; O.cat = d_cat.as<int32_t>();
             O.rec = d_rec.as<int64_t>(); O.nei = d_slots.as<uint4>(); O.nei_cap = nei_cap; O.nei_cnt = d_cnt.as<uint32_t>();
             O.ext = d_ext.as<uint8_t>(); O.next = nullptr;
             unsigned long long *c2 = d_ctrl.as<unsigned long long>() + OVC_NEXT;       // OVC_NEXT, OVC_NEXT2: the work counters
-            cudaEvent_t *ev = (fmg_verbose >= 4 && b == 0 && attempt == 0) ? phase_ev : nullptr;
-            if (ev) for (int k = 0; k < 5; ++k) OV_TRY(cudaEventCreate(&ev[k]));
-            OV_TRY(wide ? launch_phases<uint64_t>(O, grid, c2, s_run, ev) : launch_phases<uint32_t>(O, grid, c2, s_run, ev));
+            OV_TRY(wide ? launch_phases<uint64_t>(O, grid, c2, s_run, ev ? ev + 1 : nullptr) : launch_phases<uint32_t>(O, grid, c2, s_run, ev ? ev + 1 : nullptr));
             PackArgs P;
             P.n = m; P.rec = d_rec.as<int64_t>(); P.ret = d_ret.as<int64_t>() + row0; P.len = d_len.as<int32_t>(); P.nei_cnt = d_cnt.as<uint32_t>();
             P.nei_slots = d_slots.as<uint4>(); P.nei_cap = nei_cap; P.ext = d_ext.as<uint8_t>(); P.max_len = max_len;
@@ -320,6 +316,7 @@ int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *
             k_ov_pack<<<(unsigned)((m + 255) / 256), 256, 0, s_run>>>(P);
             ++g_launches;
             OV_TRY(cudaGetLastError());
+            if (ev) OV_TRY(cudaEventRecord(ev[6], s_run));
             const int64_t n_odd = m / 2;
             if (n_odd) {
                 OV_TRY(cudaStreamWaitEvent(s_run, copy_done[b & 1], 0));     // the staging buffer of batch b-2 has left the device
@@ -332,15 +329,23 @@ int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *
                                        cudaMemcpyDeviceToHost, s_copy));
                 OV_TRY(cudaEventRecord(copy_done[b & 1], s_copy));
             }
+            if (ev) OV_TRY(cudaEventRecord(ev[7], s_run));
         }
         OV_TRY(cudaMemcpyAsync(h_ctrl, d_ctrl.p, OVC_N * 8, cudaMemcpyDeviceToHost, s_run));
         OV_TRY(cudaStreamSynchronize(s_run));
         const unsigned long long flags = h_ctrl[OVC_FLAGS], too_long = h_ctrl[OVC_MAXLEN];
-        if (phase_ev[0]) {
-            float ms[4] = {0, 0, 0, 0};
-            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms[k], phase_ev[k], phase_ev[k + 1]);
-            std::fprintf(stderr, "[M::%s] first batch: contained %.2f ms, neighbours %.2f ms, left chain %.2f ms, left lists %.2f ms\n", __func__, ms[0], ms[1], ms[2], ms[3]);
-            for (int k = 0; k < 5; ++k) { cudaEventDestroy(phase_ev[k]); phase_ev[k] = nullptr; }
+        if (!phase_ev.empty()) {
+            double tot[7] = {0, 0, 0, 0, 0, 0, 0};
+            for (size_t e0 = 0; e0 + 8 <= phase_ev.size(); e0 += 8)
+                for (int k = 0; k < 7; ++k) {
+                    float ms = 0;
+                    cudaEventElapsedTime(&ms, phase_ev[e0 + k], phase_ev[e0 + k + 1]);
+                    tot[k] += ms;
+                }
+            std::fprintf(stderr, "[M::%s] kernels over %zu batches (ms): memset %.1f, retrieve + contained %.1f, neighbours %.1f, left chain %.1f, left lists %.1f, pack %.1f, seed rows (+ wait for the copy engine) %.1f\n",
+                         __func__, phase_ev.size() / 8, tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], tot[6]);
+            for (cudaEvent_t e : phase_ev) cudaEventDestroy(e);
+            phase_ev.clear();
         }
         if (fmg_verbose >= 4)
             std::fprintf(stderr, "[M::%s] attempt %d: %lld batches, %.3f s; ext %llu B, spill %llu, flags %llx, longest clipped %llu\n", __func__, attempt,
@@ -405,23 +410,7 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
 
     const auto t0 = std::chrono::steady_clock::now();
     auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
-    // ---- sequences
-    RetrieveArgs R;
-    R.ix = idx->view; R.n = n; R.ids = ids ? d_ids.as<uint64_t>() : nullptr; R.first = first; R.step = step;
-    R.seq = d_seq.as<uint8_t>(); R.max_len = max_len; R.len = d_len.as<int32_t>(); R.ret = d_ret.as<int64_t>();
-    k_retrieve<<<(unsigned)((n + 255) / 256), 256>>>(R);
-    ++g_launches;
-    OV_TRY(cudaGetLastError());
-    std::vector<int32_t> h_len(n);
-    OV_TRY(cudaMemcpy(h_len.data(), d_len.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
-    const double t_retrieve = since(t0);
     const auto t1 = std::chrono::steady_clock::now();
-    for (int64_t i = 0; i < n; ++i)
-        if (h_len[i] < 0) {
-            if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] a sequence of %d bases exceeds max_len=%d\n", __func__, -h_len[i], max_len);
-            return 2;
-        }
-
     // ---- overlap records; scratch capacities grow until nothing overflows
     const int per_sm = lists_blocks_per_sm(wide);
     const int grid = (int)std::min<int64_t>((int64_t)idx->n_sm * per_sm, (n + OVLP_BLOCK - 1) / OVLP_BLOCK);
@@ -430,19 +419,27 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
     int64_t *h_rec = rec;
     std::vector<uint32_t> h_cnt(n);
     Dev d_P0, d_np0;
+    std::vector<int32_t> h_len(n);
     OV_TRY(d_np0.alloc((size_t)n * 4));
     for (int attempt = 0;; ++attempt) {
         const size_t esz = wide ? 32 : 16;
         OV_TRY(d_P0.alloc((size_t)n * pcap * esz)); OV_TRY(d_A.alloc((size_t)n_lanes * cap * esz)); OV_TRY(d_B.alloc((size_t)n_lanes * cap * esz));
-        OV_TRY(d_cat.alloc((size_t)n_lanes * cap * 4)); OV_TRY(d_slots.alloc((size_t)n * nei_cap * 32)); OV_TRY(d_mem.alloc((size_t)n * nei_cap * 32));
+        OV_TRY(d_cat.alloc((size_t)n_lanes * cap * 8)); OV_TRY(d_slots.alloc((size_t)n * nei_cap * 32)); OV_TRY(d_mem.alloc((size_t)n * nei_cap * 32));
         OverlapArgs O;
         O.ix = idx->view; O.min_match = min_match; O.n = n; O.seq = d_seq.as<uint8_t>(); O.len = d_len.as<int32_t>(); O.max_len = max_len;
+        O.ids = ids ? d_ids.as<uint64_t>() : nullptr; O.first = first; O.step = step; O.ret = d_ret.as<int64_t>();
         O.P0 = d_P0.p; O.pcap = pcap; O.np0 = d_np0.as<int32_t>(); O.A = d_A.p; O.B = d_B.p; O.cap = cap; O.cat = d_cat.as<int32_t>();
         O.rec = d_rec.as<int64_t>(); O.nei = d_slots.as<uint4>(); O.nei_cap = nei_cap; O.nei_cnt = d_cnt.as<uint32_t>();
         O.ext = d_ext.as<uint8_t>(); O.next = nullptr;
         OV_TRY(wide ? launch_phases<uint64_t>(O, grid, d_ctrl.as<unsigned long long>(), nullptr) : launch_phases<uint32_t>(O, grid, d_ctrl.as<unsigned long long>(), nullptr));
         OV_TRY(cudaDeviceSynchronize());
-        if (fmg_verbose >= 4) std::fprintf(stderr, "[M::%s] k_retrieve %.3f s, overlap phases (attempt %d) %.3f s for %lld sequences\n", __func__, t_retrieve, attempt, since(t1), (long long)n);
+        if (fmg_verbose >= 4) std::fprintf(stderr, "[M::%s] overlap phases (attempt %d) %.3f s for %lld sequences\n", __func__, attempt, since(t1), (long long)n);
+        OV_TRY(cudaMemcpy(h_len.data(), d_len.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < n; ++i)
+            if (h_len[i] < 0) {
+                if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] a sequence of %d bases exceeds max_len=%d\n", __func__, -h_len[i], max_len);
+                return 2;
+            }
         OV_TRY(cudaMemcpy(h_rec, d_rec.p, (size_t)n * OV_NREC * 8, cudaMemcpyDeviceToHost));
         OV_TRY(cudaMemcpy(h_cnt.data(), d_cnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
         bool list_ovf = false, nei_ovf = false;

@@ -101,15 +101,13 @@ int emu_overlap(const void *_x, int min_match, int64_t n, const uint64_t *ids, i
                 int64_t *rec, fmg_intv_t *nei, uint32_t *nei_cnt, uint8_t *seq, int32_t *len, uint8_t *ext) {
     const EmuIndex *x = static_cast<const EmuIndex *>(_x);
     std::vector<int64_t> ret(n);
-    RetrieveArgs R;
-    R.ix = x->view; R.n = n; R.ids = ids; R.first = 0; R.step = 1; R.seq = seq; R.max_len = max_len; R.len = len; R.ret = ret.data();
-    for (int64_t t = 0; t < n; ++t) retrieve_one(R, t);
     // the four phases in the order the product launches them (overlap.cu: launch_phases), over the whole batch
     const int n_lanes = 3, pcap = (max_len - min_match + 8 > 8 ? max_len - min_match + 8 : 8);
     std::vector<uint64_t> P0((size_t)n * pcap * 4), A((size_t)n_lanes * cap * 4), B((size_t)n_lanes * cap * 4);
-    std::vector<int32_t> cat((size_t)n_lanes * cap), np0(n);
+    std::vector<int32_t> cat((size_t)n_lanes * cap * 2), np0(n);
     OverlapArgs O;
     O.ix = x->view; O.min_match = min_match; O.n = n; O.seq = seq; O.len = len; O.max_len = max_len;
+    O.ids = ids; O.first = 0; O.step = 1; O.ret = ret.data();
     O.P0 = P0.data(); O.pcap = pcap; O.np0 = np0.data(); O.A = A.data(); O.B = B.data(); O.cap = cap; O.cat = cat.data();
     O.rec = rec; O.nei = reinterpret_cast<uint4 *>(nei); O.nei_cap = nei_cap; O.nei_cnt = nei_cnt; O.ext = ext; O.next = nullptr;
     auto lists = [&](int phase) {

@@ -1,5 +1,7 @@
 #!/bin/bash
+# one full ncu capture of each list-chasing overlap phase (k_ov_lists<.,2> and <.,4>) and each chain phase, on the 1 M read index
 mkdir -p gpurun_out
-ncu --set full --clock-control none --import-source on -k regex:k_overlap -s 1 -c 1 -o gpurun_out/prof_overlap -f python tools/bench_unitig.py --reads 500000 --err 0.0 --no-ref > gpurun_out/prof_overlap.log 2>&1
-ncu -i gpurun_out/prof_overlap.ncu-rep --page raw --csv > gpurun_out/prof_overlap_raw.csv 2>/dev/null
+READS=${READS:-1000000}
+ncu --set full --clock-control none --import-source on -k regex:k_ov_ -s 4 -c 4 -o gpurun_out/prof_overlap -f python tools/bench_unitig.py --reads $READS --err 0.0 --no-ref > gpurun_out/prof_overlap.log 2>&1
 tail -2 gpurun_out/prof_overlap.log
+ls -la gpurun_out/prof_overlap.ncu-rep
