@@ -13,6 +13,7 @@
 #include <mutex>
 #include "fmd_overlap.cuh"
 #include "ov_records.hpp"
+#include "dev_pool.hpp"
 #include "fmg_internal.hpp"
 #include "../../include/fermi_b200.h"
 
@@ -163,66 +164,10 @@ static int lists_blocks_per_sm(bool wide) {
     return std::max(1, std::max(a, b));       // lane scratch is sized for the larger grid
 }
 
-namespace {
-// Device scratch is recycled between calls: a unitig run issues one call per 2 M sequences and each needs ~3 GB of
-// lists and slots; cudaMalloc/cudaFree of those costs more than the kernels.  Blocks return to a small pool and are
-// handed out again when they fit (released by fmg_release_cache or at process exit).
-struct Pool {
-    struct Blk { void *p; size_t cap; int dev; };
-    std::vector<Blk> free_list;
-    std::mutex lock;
-    cudaError_t get(size_t bytes, int dev, void **out, size_t *cap) {
-        {
-            std::lock_guard<std::mutex> g(lock);
-            for (size_t i = 0; i < free_list.size(); ++i)
-                if (free_list[i].dev == dev && free_list[i].cap >= bytes && free_list[i].cap <= 2 * bytes + (1 << 20)) {
-                    *out = free_list[i].p; *cap = free_list[i].cap;
-                    free_list.erase(free_list.begin() + i);
-                    return cudaSuccess;
-                }
-        }
-        *cap = bytes;
-        cudaError_t e = cudaMalloc(out, bytes);
-        if (e != cudaSuccess) { release(); cudaGetLastError(); e = cudaMalloc(out, bytes); }
-        return e;
-    }
-    void put(void *p, size_t cap, int dev) { std::lock_guard<std::mutex> g(lock); free_list.push_back(Blk{p, cap, dev}); }
-    void release() { std::lock_guard<std::mutex> g(lock); for (auto &b : free_list) cudaFree(b.p); free_list.clear(); }
-} g_pool;
-
-struct Dev {
-    void *p = nullptr;
-    size_t cap = 0;
-    int dev = 0;
-    ~Dev() { if (p) g_pool.put(p, cap, dev); }
-    cudaError_t alloc(size_t b) {
-        if (p) { g_pool.put(p, cap, dev); p = nullptr; }
-        cudaGetDevice(&dev);
-        return g_pool.get(b ? b : 1, dev, &p, &cap);
-    }
-    template <class T> T *as() const { return static_cast<T *>(p); }
-};
-}
+namespace fmg { Pool g_pool; }
 
 extern "C" void fmg_release_cache(void) { g_pool.release(); }
 
-// Pinned host arrays of the whole-index pass.  Page-locking gigabytes costs more than the pass itself, so the arrays
-// stay with the index handle and are reused (grown on demand) by the next fmg_unitig on it.
-struct fmg_ovcache_s {
-    struct Pin {
-        void *p = nullptr;
-        size_t cap = 0;
-        cudaError_t need(size_t bytes) {
-            if (bytes <= cap) return cudaSuccess;
-            if (p) cudaFreeHost(p);
-            p = nullptr; cap = 0;
-            const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
-            if (e == cudaSuccess) cap = bytes;
-            return e;
-        }
-        ~Pin() { if (p) cudaFreeHost(p); }
-    } pack, rank, seq, ext, spill, ctrl;
-};
 void fmg_ovcache_destroy(fmg_ovcache_s *p) { delete p; }
 
 // Overlap records of EVERY sequence of the index (fm_retrieve + fm6_is_contained + fm6_get_nei + check_left_simple per
@@ -232,7 +177,11 @@ void fmg_ovcache_destroy(fmg_ovcache_s *p) { delete p; }
 // memory on a second stream while batch b+1 computes.  Overflow of any scratch or output capacity is flagged on the
 // device and answered by ONE re-run of the whole pass with larger capacities.
 int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *out) {
-    if (!idx || !out) return -1;
+    return out ? fmg_overlap_pass(idx, min_match, max_len, nullptr, out) : -1;
+}
+
+int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevice *dev_out, OvHost *out) {
+    if (!idx || (!out && !dev_out)) return -1;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] no CUDA device available; libfermi_b200 has no CPU path\n", __func__);
@@ -285,7 +234,7 @@ int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *
         OV_TRY(d_A.alloc((size_t)n_lanes * cap * esz)); OV_TRY(d_B.alloc((size_t)n_lanes * cap * esz));
         OV_TRY(d_cat.alloc((size_t)n_lanes * cap * 8));
         for (int k = 0; k < 2; ++k) OV_TRY(d_odd[k].alloc((size_t)(nb_max / 2 + 1) * max_len));
-        OV_TRY(H.seq.need(std::max<uint64_t>(n_odd_all, 1) * (uint64_t)max_len));
+        if (out) OV_TRY(H.seq.need(std::max<uint64_t>(n_odd_all, 1) * (uint64_t)max_len));
         OV_TRY(cudaMemsetAsync(d_ctrl.p, 0, OVC_N * 8, s_run));
         // records of sequences that overflow are not written: keep the array defined
         OV_TRY(cudaMemsetAsync(d_pack.p, 0, n_seq * sizeof(OvPack), s_run));
@@ -317,7 +266,7 @@ int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *
             ++g_launches;
             OV_TRY(cudaGetLastError());
             if (ev) OV_TRY(cudaEventRecord(ev[6], s_run));
-            const int64_t n_odd = m / 2;
+            const int64_t n_odd = out ? m / 2 : 0;             // the seed sequences only travel for the host walk
             if (n_odd) {
                 OV_TRY(cudaStreamWaitEvent(s_run, copy_done[b & 1], 0));     // the staging buffer of batch b-2 has left the device
                 k_seq_odd<<<(unsigned)((n_odd * max_len + 255) / 256), 256, 0, s_run>>>(d_seq.as<uint8_t>(), max_len, n_odd, d_odd[b & 1].as<uint8_t>());
@@ -367,22 +316,28 @@ int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *
                          __func__, flags, max_len, cap, nei_cap, (unsigned long long)ext_cap, (unsigned long long)spill_cap);
     }
     const uint64_t ext_total = h_ctrl[OVC_EXT], spill_total = h_ctrl[OVC_SPILL];
-    OV_TRY(H.pack.need(std::max<uint64_t>(n_seq, 1) * sizeof(OvPack))); OV_TRY(H.rank.need(std::max<uint64_t>(n_seq, 1) * 8));
-    OV_TRY(H.ext.need(std::max<uint64_t>(ext_total, 1))); OV_TRY(H.spill.need(std::max<uint64_t>(spill_total, 1) * 32));
-    if (n_seq) {
-        OV_TRY(cudaMemcpyAsync(H.pack.p, d_pack.p, n_seq * sizeof(OvPack), cudaMemcpyDeviceToHost, s_run));
-        OV_TRY(cudaMemcpyAsync(H.rank.p, d_ret.p, n_seq * 8, cudaMemcpyDeviceToHost, s_run));
+    if (out) {
+        OV_TRY(H.pack.need(std::max<uint64_t>(n_seq, 1) * sizeof(OvPack))); OV_TRY(H.rank.need(std::max<uint64_t>(n_seq, 1) * 8));
+        OV_TRY(H.ext.need(std::max<uint64_t>(ext_total, 1))); OV_TRY(H.spill.need(std::max<uint64_t>(spill_total, 1) * 32));
+        if (n_seq) {
+            OV_TRY(cudaMemcpyAsync(H.pack.p, d_pack.p, n_seq * sizeof(OvPack), cudaMemcpyDeviceToHost, s_run));
+            OV_TRY(cudaMemcpyAsync(H.rank.p, d_ret.p, n_seq * 8, cudaMemcpyDeviceToHost, s_run));
+        }
+        if (ext_total) OV_TRY(cudaMemcpyAsync(H.ext.p, d_extout.p, ext_total, cudaMemcpyDeviceToHost, s_run));
+        if (spill_total) OV_TRY(cudaMemcpyAsync(H.spill.p, d_spill.p, spill_total * 32, cudaMemcpyDeviceToHost, s_run));
+        OV_TRY(cudaStreamSynchronize(s_run));
+        OV_TRY(cudaStreamSynchronize(s_copy));
+        out->n_seq = n_seq; out->max_len = max_len;
+        out->pack = static_cast<const OvPack *>(H.pack.p); out->rank_of_row = static_cast<const uint64_t *>(H.rank.p);
+        out->seq = static_cast<const uint8_t *>(H.seq.p); out->seq_stride = (uint64_t)max_len; out->seq_odd_only = 1;
+        out->ext = static_cast<const uint8_t *>(H.ext.p); out->spill = static_cast<const fmg_intv_t *>(H.spill.p);
+        out->ext_total = ext_total; out->spill_total = spill_total;
     }
-    if (ext_total) OV_TRY(cudaMemcpyAsync(H.ext.p, d_extout.p, ext_total, cudaMemcpyDeviceToHost, s_run));
-    if (spill_total) OV_TRY(cudaMemcpyAsync(H.spill.p, d_spill.p, spill_total * 32, cudaMemcpyDeviceToHost, s_run));
-    OV_TRY(cudaStreamSynchronize(s_run));
-    OV_TRY(cudaStreamSynchronize(s_copy));
-    out->n_seq = n_seq; out->max_len = max_len;
-    out->pack = static_cast<const OvPack *>(H.pack.p); out->rank_of_row = static_cast<const uint64_t *>(H.rank.p);
-    out->seq = static_cast<const uint8_t *>(H.seq.p); out->seq_stride = (uint64_t)max_len; out->seq_odd_only = 1;
-    out->ext = static_cast<const uint8_t *>(H.ext.p); out->spill = static_cast<const fmg_intv_t *>(H.spill.p);
-    out->ext_total = ext_total; out->spill_total = spill_total;
-    if (fmg_verbose >= 4) std::fprintf(stderr, "[M::%s] %llu sequences, records on the host after %.3f s\n", __func__, (unsigned long long)n_seq, since(t0));
+    if (dev_out) {
+        dev_out->pack.swap(d_pack); dev_out->rank.swap(d_ret); dev_out->ext.swap(d_extout); dev_out->spill.swap(d_spill);
+        dev_out->n_seq = n_seq; dev_out->ext_total = ext_total; dev_out->spill_total = spill_total; dev_out->max_len = max_len;
+    }
+    if (fmg_verbose >= 4) std::fprintf(stderr, "[M::%s] %llu sequences, records %s after %.3f s\n", __func__, (unsigned long long)n_seq, out ? "on the host" : "in HBM", since(t0));
     return 0;
 }
 

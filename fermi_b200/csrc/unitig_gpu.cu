@@ -1,0 +1,476 @@
+// Unitig construction on the GPU from the device-resident overlap records (replaces the seed-by-seed walk of
+// unitig_core / unitig1 / unitig_unidir, unitig.c:227-362, for regular link graphs).
+//
+// The walk of the reference advances from a read to its neighbour when (unitig.c:236-251): the read has exactly one
+// right neighbour k, k is not the read's own reverse complement, k has no other left neighbour (check_left), and k is
+// not the read itself.  Every one of these tests is a function of the packed records (OvPack), so the links
+// succ(v) = k form a static graph over the sequence ranks.  It contains every unitig twice -- v1 > v2 > ... > vm and
+// rc(vm) > ... > rc(v1) -- and the reference emits whichever orientation its first unused seed happens to walk.
+// Here:   k_links        succ(v) for every primary, non-contained sequence
+//         k_pred         pred = inverse of succ (must be injective) and the check that rc(k) links back to rc(v)
+//         k_jump         pointer jumping along pred: head, number of reads and base offset of every read in its chain
+//         k_tails/k_select  one orientation per chain (head <= rc(tail)), sizes for the output scans
+//         k_emit_*       consensus = head sequence (LF walk, exact.c:59-70) + appended bases of every link (unitig.c:141),
+//                        coverage = 33 + min(93, reads covering the base) via a difference array + scan (unitig.c:253-257),
+//                        end ids and end neighbour lists exactly as unitig1 leaves them (unitig.c:300-316)
+// A link graph with a cycle, a one-sided link or a shared successor has no order-free answer (the reference resolves it
+// by seed order): the function then reports 1 and fmg_unitig runs the host walk, which reproduces that order.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fcntl.h>
+#include <unistd.h>
+#include <atomic>
+#include <chrono>
+#include <string>
+#include <thread>
+#include <vector>
+#include <algorithm>
+#include "fmd_overlap.cuh"
+#include "ov_records.hpp"
+#include "dev_pool.hpp"
+#include "fmg_internal.hpp"
+#include "../../include/fermi_b200.h"
+
+using namespace fmg;
+
+extern std::atomic<uint64_t> g_launches;
+
+#define UG_TRY(call)                                                                                  \
+    do {                                                                                              \
+        cudaError_t err__ = (call);                                                                   \
+        if (err__ != cudaSuccess) {                                                                   \
+            if (fmg_verbose >= 1)                                                                     \
+                std::fprintf(stderr, "[E::%s] %s failed: %s\n", __func__, #call, cudaGetErrorString(err__)); \
+            return -1;                                                                                \
+        }                                                                                             \
+    } while (0)
+
+namespace {
+
+constexpr uint32_t kNone = 0xffffffffu;
+enum { UGF_NONINJ = 1, UGF_ASYM = 2, UGF_NOTNODE = 4, UGF_CHANGED = 8 };
+
+struct UMeta {                  // one unitig, as mag_v_write prints it (mag.c:149-174)
+    uint64_t k0, k1;            // end ids
+    uint64_t seq_off;           // first base in useq / ucov
+    uint64_t nei_off;           // first neighbour entry: n0 entries of end 0, then n1 of end 1
+    uint32_t len, nsr, n0, n1;
+};
+struct UNei { uint64_t x; int64_t ovlp; };
+
+struct G {
+    const OvPack *pack;
+    const uint4 *spill;         // fmg_intv_t entries
+    const uint8_t *ext;
+    const int64_t *rank_of_row;
+    uint64_t n;
+    int min_match;
+    uint32_t *succ, *pred, *row_of_rank, *tail_of;
+    uint32_t *flags;
+    unsigned long long *counts;     // [0] nodes, [1] nodes reachable from a head (they differ when the graph has a cycle)
+};
+
+__device__ __forceinline__ bool is_node(const OvPack &p, uint64_t v, int min_match) {
+    return p.x0 == v && p.contained == 0 && (int)p.len > min_match;
+}
+
+// does the walk step from the read with record p to its unique neighbour?  (unitig.c:236-251 without the `bend` cache)
+__device__ __forceinline__ bool links(const G &g, const OvPack &p) {
+    if (p.rbeg < 0 || p.nnei != 1) return false;
+    if (p.nx0 == p.x1) return false;                                   // the neighbour is the read's own reverse complement
+    if (p.left != 0 && g.pack[p.nx1].nnei > 1) return false;           // check_left: backward bifurcation
+    if (p.nx1 == p.x1) return false;                                   // the neighbour is the read itself
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_links(G g) {
+    const uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = v0 < g.n;
+    const uint64_t v = in ? v0 : 0;
+    if (in) g.row_of_rank[(uint64_t)g.rank_of_row[v]] = (uint32_t)v;   // v is a BWT row here; the array maps rank -> row
+    const OvPack p = g.pack[v];
+    uint32_t s = kNone;
+    const bool node = in && is_node(p, v, g.min_match);
+    if (node && links(g, p)) s = (uint32_t)p.nx0;
+    if (in) g.succ[v] = s;
+    const int c = __syncthreads_count(node);
+    if (threadIdx.x == 0 && c) atomicAdd(g.counts, (unsigned long long)c);
+}
+
+__global__ void __launch_bounds__(256) k_pred(G g) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= g.n) return;
+    const uint32_t k = g.succ[v];
+    if (k == kNone) return;
+    uint32_t f = 0;
+    if (atomicCAS(&g.pred[k], kNone, (uint32_t)v) != kNone) f |= UGF_NONINJ;
+    const OvPack pk = g.pack[k];
+    if (!is_node(pk, k, g.min_match)) f |= UGF_NOTNODE;
+    else if (g.succ[pk.x1] != (uint32_t)g.pack[v].x1) f |= UGF_ASYM;  // rc(k) must link back to rc(v)
+    if (f) atomicOr(g.flags, f);
+}
+
+// pointer jumping along pred: ptr -> head, dn = reads before this one in the chain, db = start of the read in the consensus
+__global__ void __launch_bounds__(256) k_jump_init(G g, uint32_t *ptr, uint32_t *dn, uint64_t *db) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= g.n) return;
+    const uint32_t p = g.pred[v];
+    ptr[v] = p == kNone ? (uint32_t)v : p;
+    dn[v] = p == kNone ? 0u : 1u;
+    db[v] = p == kNone ? 0ull : (uint64_t)g.pack[p].rbeg;
+}
+
+__global__ void __launch_bounds__(256) k_jump(uint64_t n, const uint32_t *__restrict__ ptr, const uint32_t *__restrict__ dn, const uint64_t *__restrict__ db,
+                                             uint32_t *__restrict__ ptr2, uint32_t *__restrict__ dn2, uint64_t *__restrict__ db2, uint32_t *flags) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const uint32_t p = ptr[v], q = ptr[p];
+    ptr2[v] = q;
+    dn2[v] = dn[v] + (p != v ? dn[p] : 0u);
+    db2[v] = db[v] + (p != v ? db[p] : 0ull);
+    if (q != p) atomicOr(flags, (uint32_t)UGF_CHANGED);
+}
+
+__global__ void __launch_bounds__(256) k_tails(G g, const uint32_t *__restrict__ head) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= g.n) return;
+    if (g.succ[v] == kNone && is_node(g.pack[v], v, g.min_match)) g.tail_of[head[v]] = (uint32_t)v;
+}
+
+// neighbour list the walk holds when it stops at u (a->nei after unitig_unidir, unitig.c:233-250); out may be nullptr
+__device__ __forceinline__ uint32_t stop_nei(const G &g, uint64_t u, UNei *out) {
+    const OvPack p = g.pack[u];
+    if (p.rbeg < 0 || p.nnei == 0) return 0;
+    if (p.nnei > 1) {
+        if (out)
+            for (uint32_t i = 0; i < p.nnei; ++i) {
+                const Intv v = ld_intv(g.spill + 2 * (p.nx0 + i));
+                out[i].x = v.x0; out[i].ovlp = (int64_t)(int32_t)v.info;
+            }
+        return p.nnei;
+    }
+    // one neighbour the walk did not step to; the link "b>>c>>a>>a" is cut, the others are reported (unitig.c:246)
+    const bool self_rc = p.nx0 == p.x1, back_fork = p.left != 0 && g.pack[p.nx1].nnei > 1;
+    if (!self_rc && !back_fork && p.nx1 == p.x1) return 0;
+    if (out) { out[0].x = p.nx0; out[0].ovlp = (int64_t)p.len - p.rbeg; }
+    return 1;
+}
+
+// one orientation per chain: the head h emits when h <= rc(tail)
+__global__ void __launch_bounds__(256) k_select(G g, const uint32_t *__restrict__ dn, const uint64_t *__restrict__ db,
+                                               uint64_t *e_cnt, uint64_t *e_len, uint64_t *e_nei) {
+    const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= g.n) return;
+    uint64_t c = 0, l = 0, m = 0;
+    const OvPack ph = g.pack[h];
+    if (g.pred[h] == kNone && is_node(ph, h, g.min_match)) {
+        const uint32_t t = g.tail_of[h];
+        const OvPack pt = g.pack[t];
+        atomicAdd(g.counts + 1, (unsigned long long)dn[t] + 1);
+        if (h <= pt.x1) {
+            c = 1;
+            l = db[t] + pt.len;
+            m = stop_nei(g, ph.x1, nullptr) + stop_nei(g, t, nullptr);
+        }
+    }
+    e_cnt[h] = c; e_len[h] = l; e_nei[h] = m;
+}
+
+__global__ void __launch_bounds__(256) k_emit_meta(G g, const uint32_t *__restrict__ dn, const uint64_t *__restrict__ db, const uint64_t *__restrict__ e_cnt,
+                                                  const uint64_t *__restrict__ u_idx, const uint64_t *__restrict__ u_off, const uint64_t *__restrict__ n_off,
+                                                  UMeta *meta, UNei *nei) {
+    const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= g.n || e_cnt[h] == 0) return;
+    const OvPack ph = g.pack[h];
+    const uint32_t t = g.tail_of[h];
+    const OvPack pt = g.pack[t];
+    UMeta m;
+    // the consensus reads v1 -> vm: the record is "@v1:rc(vm)" with the neighbours of rc(v1), then those of vm
+    m.k0 = h; m.k1 = pt.x1;
+    m.seq_off = u_off[h]; m.nei_off = n_off[h];
+    m.len = (uint32_t)(db[t] + pt.len); m.nsr = dn[t] + 1;
+    m.n0 = stop_nei(g, ph.x1, nei + m.nei_off);
+    m.n1 = stop_nei(g, t, nei + m.nei_off + m.n0);
+    meta[u_idx[h]] = m;
+}
+
+// every read of an emitted chain: +1 / -1 of the coverage difference array, the bases it appends, and for the head its own
+// sequence spelled by LF steps from its BWT row (fm_retrieve, exact.c:59-70: last base first)
+__global__ void __launch_bounds__(256) k_emit_nodes(G g, OccView ix, const uint32_t *__restrict__ head, const uint64_t *__restrict__ db, const uint64_t *__restrict__ e_cnt,
+                                                   const uint64_t *__restrict__ u_off, uint8_t *useq, int32_t *diff) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= g.n) return;
+    const OvPack p = g.pack[v];
+    if (!is_node(p, v, g.min_match)) return;
+    const uint32_t h = head[v];
+    if (e_cnt[h] == 0) return;
+    const uint64_t base = u_off[h] + db[v];
+    atomicAdd(diff + base, 1);
+    atomicAdd(diff + base + p.len, -1);
+    if (g.succ[v] != kNone) {
+        const uint8_t *e = g.ext + p.ext_first;
+        for (uint32_t i = p.len; i < p.slen; ++i) useq[base + i] = e[i - p.len];
+    }
+    if (h == v) {
+        uint64_t k = g.row_of_rank[v];
+        for (uint32_t n = 0; n < p.len; ++n) {
+            const Blk B = load_blk(ix, k);
+            uint32_t rel[6];
+            rank_rel(B, k, rel);
+            const int c = blk_symbol(B, k);
+            k = ld_u64(ix.cs + (k >> kSuperShift) * 8 + c) + pick6(rel, c);
+            useq[base + p.len - 1 - n] = (uint8_t)c;
+        }
+    }
+}
+
+// depth -> coverage character (unitig.c:253-257: '"' for the first read, +1 per further read, saturating at '~'); bases -> letters
+__global__ void __launch_bounds__(256) k_emit_text(uint64_t total, const int32_t *__restrict__ depth, uint8_t *useq, uint8_t *ucov) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int d = depth[i];
+    ucov[i] = (uint8_t)(33 + (d < 93 ? d : 93));
+    const uint8_t c = useq[i];
+    useq[i] = c == 1 ? 'A' : c == 2 ? 'C' : c == 3 ? 'G' : c == 4 ? 'T' : 'N';
+}
+
+inline unsigned nblk(uint64_t n) { return (unsigned)((n + 255) / 256); }
+
+void put_i64(std::string &o, int64_t v) { char b[24]; o.append(b, std::snprintf(b, sizeof b, "%lld", (long long)v)); }
+
+}  // namespace
+
+int fmg_unitig_device(const fmg_index_s *idx, const OvDevice &D, int min_match, const char *out_path, uint64_t *n_unitigs) {
+    const uint64_t n = D.n_seq;
+    if (n_unitigs) *n_unitigs = 0;
+    if (n == 0 || n >= kNone) return 1;
+    UG_TRY(cudaSetDevice(idx->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
+    if (!idx->ovc) idx->ovc = new fmg_ovcache_s;
+    fmg_ovcache_s &H = *idx->ovc;
+    cudaStream_t st = nullptr;                       // legacy default stream: ordered after the pass (which synchronised its streams)
+    Dev d_succ, d_pred, d_row, d_tail, d_flags, d_ptr[2], d_dn[2], d_db[2], d_cnt, d_len, d_nei, d_tmp, d_meta, d_unei, d_useq, d_ucov, d_diff;
+    UG_TRY(d_succ.alloc(n * 4)); UG_TRY(d_pred.alloc(n * 4)); UG_TRY(d_row.alloc(n * 4)); UG_TRY(d_tail.alloc(n * 4)); UG_TRY(d_flags.alloc(64));
+    for (int k = 0; k < 2; ++k) { UG_TRY(d_ptr[k].alloc(n * 4)); UG_TRY(d_dn[k].alloc(n * 4)); UG_TRY(d_db[k].alloc(n * 8)); }
+    UG_TRY(d_cnt.alloc((n + 1) * 8)); UG_TRY(d_len.alloc((n + 1) * 8)); UG_TRY(d_nei.alloc((n + 1) * 8));
+    UG_TRY(H.ctrl.need(64));
+    uint32_t *h_flags = H.ctrl.as<uint32_t>();
+    G g;
+    g.pack = D.pack.as<OvPack>(); g.spill = D.spill.as<uint4>(); g.ext = D.ext.as<uint8_t>(); g.rank_of_row = D.rank.as<int64_t>();
+    g.n = n; g.min_match = min_match;
+    g.succ = d_succ.as<uint32_t>(); g.pred = d_pred.as<uint32_t>(); g.row_of_rank = d_row.as<uint32_t>(); g.tail_of = d_tail.as<uint32_t>();
+    g.flags = d_flags.as<uint32_t>(); g.counts = d_flags.as<unsigned long long>() + 1;
+    UG_TRY(cudaMemsetAsync(d_flags.p, 0, 64, st));
+    UG_TRY(cudaMemsetAsync(d_pred.p, 0xff, n * 4, st));
+    UG_TRY(cudaMemsetAsync(d_tail.p, 0xff, n * 4, st));
+    k_links<<<nblk(n), 256, 0, st>>>(g);
+    k_pred<<<nblk(n), 256, 0, st>>>(g);
+    k_jump_init<<<nblk(n), 256, 0, st>>>(g, d_ptr[0].as<uint32_t>(), d_dn[0].as<uint32_t>(), d_db[0].as<uint64_t>());
+    g_launches += 3;
+    UG_TRY(cudaGetLastError());
+    int cur = 0, rounds = 0;
+    for (;; ++rounds) {
+        UG_TRY(cudaMemcpyAsync(h_flags, d_flags.p, 4, cudaMemcpyDeviceToHost, st));
+        UG_TRY(cudaStreamSynchronize(st));
+        const uint32_t f = *h_flags;
+        if (f & (UGF_NONINJ | UGF_ASYM | UGF_NOTNODE)) {
+            if (fmg_verbose >= 3) std::fprintf(stderr, "[M::%s] irregular link graph (flags %x): falling back to the host walk\n", __func__, f);
+            return 1;
+        }
+        if (rounds > 0 && !(f & UGF_CHANGED)) break;
+        if (rounds >= 40) {
+            if (fmg_verbose >= 3) std::fprintf(stderr, "[M::%s] the link graph has a cycle: falling back to the host walk\n", __func__);
+            return 1;
+        }
+        UG_TRY(cudaMemsetAsync(d_flags.p, 0, 4, st));
+        // two jumps per flag read-back (a converged jump is the identity)
+        for (int r = 0; r < 2; ++r) {
+            k_jump<<<nblk(n), 256, 0, st>>>(n, d_ptr[cur].as<uint32_t>(), d_dn[cur].as<uint32_t>(), d_db[cur].as<uint64_t>(),
+                                            d_ptr[cur ^ 1].as<uint32_t>(), d_dn[cur ^ 1].as<uint32_t>(), d_db[cur ^ 1].as<uint64_t>(), g.flags);
+            ++g_launches;
+            cur ^= 1;
+        }
+        UG_TRY(cudaGetLastError());
+    }
+    const uint32_t *head = d_ptr[cur].as<uint32_t>(), *dn = d_dn[cur].as<uint32_t>();
+    const uint64_t *db = d_db[cur].as<uint64_t>();
+    const double t_rank = since(t0);
+    k_tails<<<nblk(n), 256, 0, st>>>(g, head);
+    uint64_t *e_cnt = d_cnt.as<uint64_t>(), *e_len = d_len.as<uint64_t>(), *e_nei = d_nei.as<uint64_t>();
+    k_select<<<nblk(n), 256, 0, st>>>(g, dn, db, e_cnt, e_len, e_nei);
+    g_launches += 2;
+    UG_TRY(cudaGetLastError());
+    // exclusive scans (n + 1 items: the last one is the total); e_cnt keeps the flags, the offsets go to the other buffers
+    Dev d_uidx, d_uoff, d_noff;
+    UG_TRY(d_uidx.alloc((n + 1) * 8)); UG_TRY(d_uoff.alloc((n + 1) * 8)); UG_TRY(d_noff.alloc((n + 1) * 8));
+    UG_TRY(cudaMemsetAsync(e_cnt + n, 0, 8, st)); UG_TRY(cudaMemsetAsync(e_len + n, 0, 8, st)); UG_TRY(cudaMemsetAsync(e_nei + n, 0, 8, st));
+    size_t need = 0;
+    UG_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, e_cnt, d_uidx.as<uint64_t>(), n + 1, st));
+    UG_TRY(d_tmp.alloc(need + 256));
+    UG_TRY(cub::DeviceScan::ExclusiveSum(d_tmp.p, need, e_cnt, d_uidx.as<uint64_t>(), n + 1, st));
+    UG_TRY(cub::DeviceScan::ExclusiveSum(d_tmp.p, need, e_len, d_uoff.as<uint64_t>(), n + 1, st));
+    UG_TRY(cub::DeviceScan::ExclusiveSum(d_tmp.p, need, e_nei, d_noff.as<uint64_t>(), n + 1, st));
+    g_launches += 3;
+    uint64_t *h_tot = H.ctrl.as<uint64_t>() + 1;
+    UG_TRY(cudaMemcpyAsync(h_tot + 3, d_flags.as<uint64_t>() + 1, 16, cudaMemcpyDeviceToHost, st));
+    UG_TRY(cudaMemcpyAsync(h_tot + 0, d_uidx.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    UG_TRY(cudaMemcpyAsync(h_tot + 1, d_uoff.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    UG_TRY(cudaMemcpyAsync(h_tot + 2, d_noff.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    UG_TRY(cudaStreamSynchronize(st));
+    const uint64_t n_u = h_tot[0], total = h_tot[1], n_nei = h_tot[2];
+    if (h_tot[3] != h_tot[4]) {
+        if (fmg_verbose >= 3)
+            std::fprintf(stderr, "[M::%s] %llu of %llu reads lie on cycles of the link graph: falling back to the host walk\n", __func__,
+                         (unsigned long long)(h_tot[3] - h_tot[4]), (unsigned long long)h_tot[3]);
+        return 1;
+    }
+    UG_TRY(d_meta.alloc(std::max<uint64_t>(n_u, 1) * sizeof(UMeta))); UG_TRY(d_unei.alloc(std::max<uint64_t>(n_nei, 1) * sizeof(UNei)));
+    UG_TRY(d_useq.alloc(total + 1)); UG_TRY(d_ucov.alloc(total + 1)); UG_TRY(d_diff.alloc((total + 1) * 4));
+    UG_TRY(cudaMemsetAsync(d_diff.p, 0, (total + 1) * 4, st));
+    k_emit_meta<<<nblk(n), 256, 0, st>>>(g, dn, db, e_cnt, d_uidx.as<uint64_t>(), d_uoff.as<uint64_t>(), d_noff.as<uint64_t>(), d_meta.as<UMeta>(), d_unei.as<UNei>());
+    k_emit_nodes<<<nblk(n), 256, 0, st>>>(g, idx->view, head, db, e_cnt, d_uoff.as<uint64_t>(), d_useq.as<uint8_t>(), d_diff.as<int32_t>());
+    g_launches += 2;
+    UG_TRY(cudaGetLastError());
+    if (total) {
+        size_t need2 = 0;
+        UG_TRY(cub::DeviceScan::InclusiveSum(nullptr, need2, d_diff.as<int32_t>(), d_diff.as<int32_t>(), total, st));
+        if (need2 > need) UG_TRY(d_tmp.alloc(need2 + 256));
+        UG_TRY(cub::DeviceScan::InclusiveSum(d_tmp.p, need2, d_diff.as<int32_t>(), d_diff.as<int32_t>(), total, st));
+        k_emit_text<<<nblk(total), 256, 0, st>>>(total, d_diff.as<int32_t>(), d_useq.as<uint8_t>(), d_ucov.as<uint8_t>());
+        g_launches += 2;
+        UG_TRY(cudaGetLastError());
+    }
+    UG_TRY(H.umeta.need(std::max<uint64_t>(n_u, 1) * sizeof(UMeta))); UG_TRY(H.unei.need(std::max<uint64_t>(n_nei, 1) * sizeof(UNei)));
+    UG_TRY(H.useq.need(total + 1)); UG_TRY(H.ucov.need(total + 1));
+    if (n_u) UG_TRY(cudaMemcpyAsync(H.umeta.p, d_meta.p, n_u * sizeof(UMeta), cudaMemcpyDeviceToHost, st));
+    if (n_nei) UG_TRY(cudaMemcpyAsync(H.unei.p, d_unei.p, n_nei * sizeof(UNei), cudaMemcpyDeviceToHost, st));
+    if (total) {
+        UG_TRY(cudaMemcpyAsync(H.useq.p, d_useq.p, total, cudaMemcpyDeviceToHost, st));
+        UG_TRY(cudaMemcpyAsync(H.ucov.p, d_ucov.p, total, cudaMemcpyDeviceToHost, st));
+    }
+    UG_TRY(cudaStreamSynchronize(st));
+    const double t_dev = since(t0);
+
+    // ---- MAG text (mag_v_write, mag.c:149-174), formatted by all host cores in unitig order.  A regular file is written
+    // by the same threads with pwrite at the offsets the part sizes give (the page-cache copy is the cost of the output).
+    const bool to_stdout = std::strcmp(out_path, "-") == 0;
+    int fd = -1;
+    if (!to_stdout) {
+        fd = ::open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (fd < 0) {
+            if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] cannot write '%s'\n", __func__, out_path);
+            return -1;
+        }
+    }
+    const UMeta *meta = H.umeta.as<UMeta>();
+    const UNei *nei = H.unei.as<UNei>();
+    const char *useq = H.useq.as<char>(), *ucov = H.ucov.as<char>();
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    if (const char *e = std::getenv("FMG_THREADS")) nt = (unsigned)std::max(1, std::atoi(e));
+    if (n_u < 4096) nt = 1;
+    std::vector<std::string> parts(nt);
+    auto fmt = [&](unsigned t) {
+        const uint64_t a = n_u * t / nt, b = n_u * (t + 1) / nt;
+        std::string &o = parts[t];
+        uint64_t bytes = 0;
+        for (uint64_t u = a; u < b; ++u) bytes += 2ull * meta[u].len + 64 + 24ull * (meta[u].n0 + meta[u].n1);
+        o.reserve(bytes);
+        for (uint64_t u = a; u < b; ++u) {
+            const UMeta &m = meta[u];
+            o += '@'; put_i64(o, (int64_t)m.k0); o += ':'; put_i64(o, (int64_t)m.k1); o += '\t'; put_i64(o, m.nsr);
+            const UNei *e = nei + m.nei_off;
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t c = j ? m.n1 : m.n0;
+                o += '\t';
+                for (uint32_t i = 0; i < c; ++i) { put_i64(o, (int64_t)e[i].x); o += ','; put_i64(o, (int32_t)e[i].ovlp); o += ';'; }
+                if (c == 0) o += '.';
+                e += c;
+            }
+            o += '\n';
+            o.append(useq + m.seq_off, m.len);
+            o += "\n+\n";
+            o.append(ucov + m.seq_off, m.len);
+            o += '\n';
+        }
+    };
+    std::atomic<int> io_fail{0};
+    auto put = [&](unsigned t, uint64_t off) {
+        const std::string &o = parts[t];
+        for (size_t done = 0; done < o.size();) {
+            const ssize_t w = ::pwrite(fd, o.data() + done, o.size() - done, (off_t)(off + done));
+            if (w <= 0) { io_fail = 1; return; }
+            done += (size_t)w;
+        }
+    };
+    auto run_all = [&](auto fn) {
+        if (nt == 1) { fn(0u); return; }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(fn, t);
+        for (auto &x : th) x.join();
+    };
+    run_all(fmt);
+    if (to_stdout) {
+        for (const std::string &o : parts) std::fwrite(o.data(), 1, o.size(), stdout);
+        std::fflush(stdout);
+    } else {
+        std::vector<uint64_t> off(nt + 1, 0);
+        for (unsigned t = 0; t < nt; ++t) off[t + 1] = off[t] + parts[t].size();
+        run_all([&](unsigned t) { put(t, off[t]); });
+        ::close(fd);
+        if (io_fail) {
+            if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] short write to '%s'\n", __func__, out_path);
+            return -1;
+        }
+    }
+    if (n_unitigs) *n_unitigs = n_u;
+    if (fmg_verbose >= 4)
+        std::fprintf(stderr, "[M::%s] %llu unitigs, %llu bases from %llu sequences: chains %.3f s (%d jump rounds), assembly + copies %.3f s, text %.3f s\n", __func__,
+                     (unsigned long long)n_u, (unsigned long long)total, (unsigned long long)n, t_rank, 2 * rounds, t_dev - t_rank, since(t0) - t_dev);
+    return 0;
+}
+
+extern "C" {
+
+// fm6_unitig (unitig.c:378-407) + main_unitig (cmd.c:184-216): overlap records of every sequence on the GPU, then the
+// walk; MAG records go to `out_path` ("-" = stdout).  max_len = upper bound of the sequence length in the index
+// (0: estimate from the symbol counts, grown on demand).
+int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *out_path, uint64_t *n_unitigs) {
+    if (!idx) return -1;
+    if (n_unitigs) *n_unitigs = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    // 1. records stay in HBM and the unitigs are assembled there (unitig_gpu.cu)
+    const char *force_host = std::getenv("FMG_UNITIG_HOST");
+    if (!force_host || !*force_host || *force_host == '0') {
+        int rc;
+        {
+            fmg::OvDevice D;
+            rc = fmg_overlap_pass(idx, min_match, max_len, &D, nullptr);
+            if (rc != 0) return rc;
+            const auto t1 = std::chrono::steady_clock::now();
+            rc = fmg_unitig_device(idx, D, min_match, out_path, n_unitigs);
+            if (rc == 0 && fmg_verbose >= 3)
+                std::fprintf(stderr, "[M::%s] %llu sequences: overlap records %.3f s, unitig assembly + output %.3f s (GPU)\n", __func__,
+                             (unsigned long long)D.n_seq, secs(t0, t1), secs(t1, std::chrono::steady_clock::now()));
+            max_len = D.max_len;
+        }
+        if (rc <= 0) return rc;
+    }
+    // 2. an irregular link graph (or FMG_UNITIG_HOST=1): records to the host, walk in the reference's seed order
+    const auto t1 = std::chrono::steady_clock::now();
+    OvHost R;
+    const int rc0 = fmg_overlap_all(idx, min_match, max_len, &R);
+    if (rc0 != 0) return rc0;
+    const auto t2 = std::chrono::steady_clock::now();
+    const int rc = fmg_unitig_walk(R, min_match, out_path, n_unitigs);
+    if (fmg_verbose >= 3)
+        std::fprintf(stderr, "[M::%s] %llu sequences: overlap records %.3f s (GPU, incl. copies), unitig walk + output %.3f s (host)\n", __func__,
+                     (unsigned long long)R.n_seq, secs(t1, t2), secs(t2, std::chrono::steady_clock::now()));
+    return rc;
+}
+
+} // extern "C"

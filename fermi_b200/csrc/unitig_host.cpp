@@ -251,23 +251,4 @@ int fmg_unitig_assemble(uint64_t n_seq, int max_len, int min_match, const int64_
     return fmg_unitig_walk(R, min_match, out_path, n_unitigs);
 }
 
-// fm6_unitig (unitig.c:378-407) + main_unitig (cmd.c:184-216): overlap records of every sequence on the GPU, then the
-// walk; MAG records go to `out_path` ("-" = stdout).  max_len = upper bound of the sequence length in the index
-// (0: estimate from the symbol counts, grown on demand).
-int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *out_path, uint64_t *n_unitigs) {
-    if (!idx) return -1;
-    if (n_unitigs) *n_unitigs = 0;
-    const auto t0 = std::chrono::steady_clock::now();
-    OvHost R;
-    const int rc0 = fmg_overlap_all(idx, min_match, max_len, &R);
-    if (rc0 != 0) return rc0;
-    const auto t1 = std::chrono::steady_clock::now();
-    const int rc = fmg_unitig_walk(R, min_match, out_path, n_unitigs);
-    const auto t2 = std::chrono::steady_clock::now();
-    if (fmg_verbose >= 3)
-        std::fprintf(stderr, "[M::%s] %llu sequences: overlap records %.3f s (GPU, incl. copies), unitig walk + output %.3f s (host)\n", __func__,
-                     (unsigned long long)R.n_seq, std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count());
-    return rc;
-}
-
 } // extern "C"

@@ -154,9 +154,9 @@ def test_record_slot_overflow_is_rerun_not_truncated(fb, oracle, tmp_path):
 
 
 @pytest.mark.parametrize("case", golden_cases())
-def test_overlap_records_and_unitigs_match_reference(fb, case, tmp_path):
-    """k_retrieve + k_overlap against the reference's fm_retrieve / fm6_is_contained / fm6_get_nei records, and the
-    unitig set of fmg_unitig against `fermi unitig -t1` (canonicalised MAG records)."""
+def test_overlap_records_and_unitigs_match_reference(fb, case, tmp_path, monkeypatch):
+    """the four overlap phases against the reference's fm_retrieve / fm6_is_contained / fm6_get_nei records, and the
+    unitig set of fmg_unitig -- device assembly and host walk -- against `fermi unitig -t1` (canonicalised MAG records)."""
     g, fmd = _load(case)
     idx = fb.FmdIndex(fb.Fmd.restore(fmd), 0)
     max_len = int(g["ov_rec"][:, 1].max()) + 8
@@ -164,28 +164,37 @@ def test_overlap_records_and_unitigs_match_reference(fb, case, tmp_path):
     assert np.array_equal(o["rec"][:, :9], g["ov_rec"])
     assert np.array_equal(o["nei"], g["ov_nei"]) and np.array_equal(o["nei_off"], g["ov_off"])
     out = str(tmp_path / "u.mag")
-    n = fb.fm6_unitig(idx, int(g["ov_min"]), out)
-    ours = H.parse_mag(open(out).read())
     ref = H.parse_mag(open(os.path.join(H.GOLDEN_DIR, case + ".mag")).read())
-    assert n == len(ref) and H.canonical_mag(ours) == H.canonical_mag(ref)
+    for host in ("0", "1"):
+        monkeypatch.setenv("FMG_UNITIG_HOST", host)
+        n = fb.fm6_unitig(idx, int(g["ov_min"]), out)
+        ours = H.parse_mag(open(out).read())
+        assert n == len(ref) and H.canonical_mag(ours) == H.canonical_mag(ref), "host walk" if host == "1" else "device assembly"
     idx.close()
 
 
 @pytest.mark.skipif(H.ref_fermi_binary() is None, reason="oracle/_ref/fermi did not travel with the repo")
-@pytest.mark.parametrize("err", [0.0, 0.01])
-def test_unitig_20k_reads_vs_reference_binary(fb, tmp_path, err):
-    """BASELINE config 3 in miniature: unitig -l50 over 20k x 100 bp reads (10x), set-equal to the reference."""
-    genome = fb.synth_genome(31, 200000)
-    reads = fb.synth_reads(32, genome, 20000, 100, err)
+@pytest.mark.parametrize("err,cov,circular", [(0.0, 10, False), (0.01, 10, False), (0.02, 40, False), (0.0, 12, True)])
+def test_unitig_20k_reads_vs_reference_binary(fb, tmp_path, monkeypatch, err, cov, circular):
+    """BASELINE config 3 in miniature: unitig -l50 over 20k x 100 bp reads, set-equal to the reference -- through the device
+    assembly (unitig_gpu.cu) and through the host walk.  The circular case (reads wrap around a 20 kb plasmid, error-free)
+    makes the link graph one cycle, which the device path hands to the host walk."""
+    n_reads = 20000 if not circular else 2400
+    genome = fb.synth_genome(31, n_reads * 100 // cov)
+    src = np.concatenate([genome, genome[:100]]) if circular else genome
+    reads = fb.synth_reads(32, src, n_reads, 100, err)
     fmd = fb.fm_build(fb.fmd_text(reads), 0)
     fn = str(tmp_path / "r.fmd")
     fmd.dump(fn)
-    ref = H.parse_mag(H.reference_unitig(fn, 50, 4))
+    ref = H.parse_mag(H.reference_unitig(fn, 50, 1))
     idx = fb.FmdIndex(fmd, 0)
     out = str(tmp_path / "u.mag")
-    n = fb.fm6_unitig(idx, 50, out)
-    assert n == len(ref)
-    assert H.canonical_mag(H.parse_mag(open(out).read())) == H.canonical_mag(ref)
+    for host in ("0", "1"):
+        monkeypatch.setenv("FMG_UNITIG_HOST", host)
+        monkeypatch.setenv("FMG_THREADS", "1" if circular else "8")     # a cycle is cut where the first seed meets it
+        n = fb.fm6_unitig(idx, 50, out)
+        assert n == len(ref)
+        assert H.canonical_mag(H.parse_mag(open(out).read())) == H.canonical_mag(ref), "host walk" if host == "1" else "device assembly"
     idx.close()
 
 
