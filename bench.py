@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--unitig-reads", type=int, default=10_000_000, help="reads of the unitig leg (BASELINE config 3); 0 disables it")
+    ap.add_argument("--unitig-ref-reads", type=int, default=500_000, help="reads of the bounded reference sample of the unitig leg")
     return ap.parse_args()
 
 
@@ -156,6 +158,75 @@ def count_locates(fmd_file, reads, cores):
     O.destroy(h)
     n = len(reads)
     return nloc / n, next_ / n, int(mo[-1]) / n
+
+
+# ----------------------------------------------------------------------------------- unitig leg (BASELINE config 3)
+UNITIG_GENOME_SEED, UNITIG_READ_SEED, UNITIG_COV, UNITIG_MIN = 41, 42, 10, 50
+# block lookups (rld_locate_blk calls) per input read of `fermi unitig -l50 -t1` on error-free 10x 100 bp reads, measured with
+# a counter in the reference at 1/100 scale: 306 rank2a + ~120 rank1a -> 423 lookups
+UNITIG_LOCATES_PER_READ = 423.0
+
+
+def unitig_index(fb, n_reads, read_len, device):
+    genome = fb.synth_genome(UNITIG_GENOME_SEED, n_reads * read_len // UNITIG_COV)
+    reads = fb.synth_reads(UNITIG_READ_SEED, genome, n_reads, read_len, 0.0)
+    t = time.time()
+    bwt = fb.fm_build_bwt(fb.fmd_text(reads), device)
+    t_bwt = time.time() - t
+    t = time.time()
+    fmd = fb.Fmd.from_bwt(bwt)
+    return fmd, t_bwt, time.time() - t
+
+
+def unitig_leg(fb, a, device, peak, peak_src):
+    """`fermi unitig -l50` (fm6_unitig, unitig.c:378) over the FMD-index of n x 100 bp error-free 10x reads, end to end through
+    the C-ABI call a user makes: overlap records + unitig assembly on the GPU, results copied to the host and written as MAG
+    text.  Next to it the unmodified reference binary (`fermi unitig -l50 -t<nproc>`) on a bounded sample built the same way."""
+    import helpers as H
+    L = a.read_len
+    fmd, t_bwt, t_enc = unitig_index(fb, a.unitig_reads, L, device)
+    idx = fb.FmdIndex(fmd, device)
+    out = os.path.join(tempfile.gettempdir(), "fermi_b200_bench_unitig.mag")
+    launches0 = fb.launch_count()
+    fb.fm6_unitig(idx, UNITIG_MIN, out)                    # warm-up: scratch pool, pinned result buffers
+    launches = fb.launch_count() - launches0
+    times, n_u = [], 0
+    for _ in range(3):
+        t = time.perf_counter()
+        n_u = fb.fm6_unitig(idx, UNITIG_MIN, out)
+        times.append(time.perf_counter() - t)
+    secs = sum(times) / len(times)
+    st = fb.overlap_stats()
+    k_ms = st["contained"] + st["neighbours"] + st["left_chain"] + st["left_lists"]
+    bytes_per_read = UNITIG_LOCATES_PER_READ * 128 + L
+    achieved = a.unitig_reads * bytes_per_read / (k_ms / 1e3) / 1e9
+    res = {"workload": "fermi unitig -l%d: FMD-index of %d x %d bp error-free reads (%dx), %d sequences, %d symbols" %
+                       (UNITIG_MIN, a.unitig_reads, L, UNITIG_COV, int(fmd.mcnt[1]), int(fmd.mcnt[0])),
+           "value": a.unitig_reads / secs, "unit": "reads/s", "seconds": secs, "unitigs": int(n_u), "mag_bytes": os.path.getsize(out),
+           "api": "fmg_unitig (records + assembly on the GPU, MAG text written to a file)", "gpu_launches_per_call": int(launches),
+           "setup": {"gpu_bwt_s": round(t_bwt, 2), "rld_encode_s": round(t_enc, 2)},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "kernel": "k_ov_chain<1> + k_ov_lists<2> + k_ov_chain<3> + k_ov_lists<4>", "kernel_ms": k_ms, "kernel_ms_by_phase": st,
+                        "algorithmic_bytes_per_read": bytes_per_read, "locates_per_read": UNITIG_LOCATES_PER_READ,
+                        "locates_source": "SURVEY.md 8d: counter in the reference's rld_locate_blk, `unitig -l50 -t1`, error-free 10x, 1/100 scale",
+                        "peak_source": peak_src}}
+    idx.close()
+    del fmd
+    fb.release_cache()
+    ref_bin = H.ref_fermi_binary()
+    if ref_bin and a.unitig_ref_reads > 0 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rfmd, _, _ = unitig_index(fb, a.unitig_ref_reads, L, device)
+        fn = os.path.join(tempfile.gettempdir(), "fermi_b200_bench_unitig_ref.fmd")
+        rfmd.dump(fn)
+        t = time.perf_counter()
+        with open(out + ".ref", "wb") as fh:
+            subprocess.run([ref_bin, "unitig", "-l", str(UNITIG_MIN), "-t", str(cores), fn], stdout=fh, stderr=subprocess.DEVNULL, check=True)
+        dt = time.perf_counter() - t
+        res["cpu_baseline"] = {"value": a.unitig_ref_reads / dt, "unit": "reads/s", "cores": cores, "kind": "reference",
+                               "sample": "fermi unitig -l%d -t%d on the index of %d reads generated the same way (incl. loading the .fmd), %.1f s wall"
+                                         % (UNITIG_MIN, cores, a.unitig_ref_reads, dt)}
+    return res
 
 
 # ----------------------------------------------------------------------------------- reference arm
@@ -361,6 +432,18 @@ def run_ours(a):
         if world == 1 and not a.no_cpu_baseline:
             cb, _, _ = cpu_smem_rate(fn, h_reads.numpy(), a.cpu_seconds, cores)
             out["cpu_baseline"] = cb
+        if world == 1 and a.unitig_reads > 0:
+            # the second half of the metric (overlap / unitig): its own index, so the SMEM buffers go first
+            del d_reads, d_off, d_boff, h_reads, h_off
+            if e2e:
+                del h_mem, h_moff
+            idx.close()
+            fb.release_cache()
+            torch.cuda.empty_cache()
+            try:
+                out["unitig"] = unitig_leg(fb, a, local, peak, peak_src)
+            except Exception as exc:                       # the SMEM line stands on its own
+                out["unitig"] = {"error": repr(exc)}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

@@ -246,6 +246,13 @@ def fm6_unitig(idx, min_match, out_path, max_len=0):
     return n.value
 
 
+def overlap_stats():
+    """kernel milliseconds of the last fm6_unitig overlap pass: dict(contained, neighbours, left_chain, left_lists, pack, batches)"""
+    ms = (C.c_double * 8)()
+    lib().fmg_overlap_stats(ms)
+    return {"contained": ms[1], "neighbours": ms[2], "left_chain": ms[3], "left_lists": ms[4], "pack": ms[5], "batches": int(ms[7])}
+
+
 def fm_build_bwt(text, device=0):
     """BWT of the FMD text on the GPU (replaces fm_bwtgen/ksa_bwt, build.c:5, ksa.c:231)."""
     text = np.ascontiguousarray(text, np.uint8)
@@ -339,6 +346,11 @@ def fm_ropebwt(reads, device=0):
 
 def launch_count():
     return int(lib().fmg_launch_count())
+
+
+def release_cache():
+    """return the device scratch the library keeps between calls to the driver"""
+    lib().fmg_release_cache()
 
 
 # ------------------------------------------------------------------ synthetic data (host helpers)

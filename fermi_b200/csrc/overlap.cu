@@ -166,6 +166,14 @@ static int lists_blocks_per_sm(bool wide) {
 
 namespace fmg { Pool g_pool; }
 
+// CUDA-event durations of the kernels of the last whole-index pass (bench.py's roofline figure for the unitig path)
+static std::mutex g_stats_lock;
+static double g_pass_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+extern "C" void fmg_overlap_stats(double ms[8]) {
+    std::lock_guard<std::mutex> g(g_stats_lock);
+    for (int k = 0; k < 8; ++k) ms[k] = g_pass_ms[k];
+}
+
 extern "C" void fmg_release_cache(void) { g_pool.release(); }
 
 void fmg_ovcache_destroy(fmg_ovcache_s *p) { delete p; }
@@ -242,7 +250,7 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
         for (uint64_t row0 = 0; row0 < n_seq; row0 += batch, ++b) {
             const int64_t m = (int64_t)std::min<uint64_t>(batch, n_seq - row0);
             cudaEvent_t *ev = nullptr;
-            if (fmg_verbose >= 4) {
+            {
                 const size_t e0 = phase_ev.size();
                 phase_ev.resize(e0 + 8, nullptr);
                 for (int k = 0; k < 8; ++k) OV_TRY(cudaEventCreate(&phase_ev[e0 + k]));
@@ -291,8 +299,14 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
                     cudaEventElapsedTime(&ms, phase_ev[e0 + k], phase_ev[e0 + k + 1]);
                     tot[k] += ms;
                 }
-            std::fprintf(stderr, "[M::%s] kernels over %zu batches (ms): memset %.1f, retrieve + contained %.1f, neighbours %.1f, left chain %.1f, left lists %.1f, pack %.1f, seed rows (+ wait for the copy engine) %.1f\n",
-                         __func__, phase_ev.size() / 8, tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], tot[6]);
+            if (fmg_verbose >= 4)
+                std::fprintf(stderr, "[M::%s] kernels over %zu batches (ms): memset %.1f, retrieve + contained %.1f, neighbours %.1f, left chain %.1f, left lists %.1f, pack %.1f, seed rows (+ wait for the copy engine) %.1f\n",
+                             __func__, phase_ev.size() / 8, tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], tot[6]);
+            {
+                std::lock_guard<std::mutex> g(g_stats_lock);
+                for (int k = 0; k < 7; ++k) g_pass_ms[k] = tot[k];
+                g_pass_ms[7] = (double)(phase_ev.size() / 8);
+            }
             for (cudaEvent_t e : phase_ev) cudaEventDestroy(e);
             phase_ev.clear();
         }

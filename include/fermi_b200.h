@@ -122,9 +122,16 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
  * per-GPU record shards): MAG text as written by mag_v_write (mag.c:149-174) to out_path ("-" = stdout) */
 int fmg_unitig_assemble(uint64_t n_seq, int max_len, int min_match, const int64_t *rec, const fmg_intv_t *nei,
                         const uint64_t *nei_off, const uint8_t *seq, const uint8_t *ext, const char *out_path, uint64_t *n_unitigs);
-/* fm6_unitig (unitig.c:378-407) / `fermi unitig -l min_match`: records on the GPU, then the walk. The set of
- * MAG records equals that of the reference after canonicalisation. max_len 0 = estimate. */
+/* fm6_unitig (unitig.c:378-407) / `fermi unitig -l min_match`: overlap records of every sequence and the unitigs themselves
+ * (link graph + pointer jumping) on the GPU; an irregular link graph (cycle, one-sided link) or FMG_UNITIG_HOST=1 takes
+ * the records to the host and walks them in the reference's seed order (fmg_unitig_assemble).  The set of MAG records
+ * equals that of the reference after canonicalisation. max_len 0 = estimate. */
 int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *out_path, uint64_t *n_unitigs);
+
+/* CUDA-event durations (ms, summed over the batches) of the kernels of the last fmg_unitig overlap pass on this process:
+ * ms[1] fm_retrieve + fm6_is_contained chain, ms[2] fm6_get_nei, ms[3] / ms[4] check_left_simple chain / candidate loop,
+ * ms[5] record packing, ms[6] seed rows, ms[0] set-up, ms[7] = number of batches */
+void fmg_overlap_stats(double ms[8]);
 
 /* ------------------------------------------------------------------ `fermi correct`: k-mer collection
  * fm6_traverse (exact.c:141-171) + ec_collect (correct.c:35-87) for all 4^SUF_LEN suffixes, as a breadth-first
