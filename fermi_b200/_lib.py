@@ -54,6 +54,7 @@ _PROTOS = {
     "fmg_unitig_assemble": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, u64p, C.c_void_p, C.c_void_p, C.c_char_p, u64p]),
     "fmg_unitig": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, u64p]),
     "fmg_overlap_stats": (None, [C.POINTER(C.c_double)]),
+    "fmg_seqsort": (C.c_int, [C.c_void_p, u64p, C.POINTER(C.c_int64)]),
     "fmg_ec_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, vpp, u64p, C.POINTER(C.c_int64)]),
     "fmg_ec_kmer_length": (C.c_int, [C.c_uint64]),
     # construction + synthetic data

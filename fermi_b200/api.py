@@ -246,6 +246,15 @@ def fm6_unitig(idx, min_match, out_path, max_len=0):
     return n.value
 
 
+def fm6_seqsort(idx):
+    """fm6_seqsort (seqsort.c:37) / `fermi seqrank`: (sorted[mcnt[1]], (zeros, contained, duplicates))."""
+    n = int(idx.fmd.mcnt[1])
+    out = np.zeros(max(n, 1), np.uint64)
+    st = (C.c_int64 * 3)()
+    _check(lib().fmg_seqsort(idx.h, _p(out, u64p), st), "fm6_seqsort")
+    return out[:n], (int(st[0]), int(st[1]), int(st[2]))
+
+
 def overlap_stats():
     """kernel milliseconds of the last fm6_unitig overlap pass: dict(contained, neighbours, left_chain, left_lists, pack, batches)"""
     ms = (C.c_double * 8)()

@@ -4,7 +4,8 @@
 //   recode   cmd.c:674-685   RLE\6 / RLD -> RLD .fmd
 //   chkbwt   cmd.c:47-120    marginal counts (-p prints the BWT)
 //   exact    cmd.c:292-333   SMEMs of every read (GPU), same SQ/EM text as fermi
-//   unitig   cmd.c:184-216   MAG records (GPU overlap records + record walk)
+//   unitig   cmd.c:184-216   MAG records (GPU overlap records + unitig assembly)
+//   seqrank  cmd.c:486-505   rank table of fm6_seqsort (GPU fm6_retrieve of every read)
 //   kmers    correct.c:305-360  the collect phase of `correct`: "collected N informative and M ambiguous k-mers"
 // Host code only parses files and formats text; all index arithmetic happens in the library's CUDA kernels.
 #include <cstdio>
@@ -238,13 +239,16 @@ int main_exact(int argc, char *argv[]) {
 
 int main_unitig(int argc, char *argv[]) {
     int c, min_match = 30, device = 0, max_len = 0;
-    while ((c = getopt(argc, argv, "Ml:t:d:L:")) >= 0) {
+    while ((c = getopt(argc, argv, "Ml:t:d:L:r:")) >= 0) {
         if (c == 'l') min_match = atoi(optarg); else if (c == 'd') device = atoi(optarg); else if (c == 'L') max_len = atoi(optarg);
         else if (c == 't') setenv("FMG_THREADS", optarg, 1);
+        // -r FILE (cmd.c:195): the rank file only lets the reference index its `used` bitmap by row instead of by rank
+        // (unitig.c:22-36,282); the unitigs are the same, so the file is accepted and not needed here
     }
     if (optind + 1 > argc) {
         std::fprintf(stderr, "\nUsage:   fermi-b200 unitig [options] <reads.fmd>\n\nOptions: -l INT      min match [%d]\n"
-                             "         -t INT      number of host threads of the unitig walk [all]\n         -d INT      CUDA device [0]\n\n", min_match);
+                             "         -t INT      number of host threads of the unitig walk [all]\n         -r FILE     rank file (accepted, not needed)\n"
+                             "         -d INT      CUDA device [0]\n\n", min_match);
         return 1;
     }
     fmg_fmd_t *e = fmg_fmd_restore(argv[optind]);
@@ -252,6 +256,27 @@ int main_unitig(int argc, char *argv[]) {
     fmg_index_t *idx = fmg_index_upload(e, device);
     if (!idx) return 1;
     const int rc = fmg_unitig(idx, min_match, max_len, "-", nullptr);
+    fmg_index_free(idx);
+    fmg_fmd_destroy(e);
+    return rc != 0;
+}
+
+int main_seqsort(int argc, char *argv[]) {              // cmd.c:486-505: the rank table as raw 64-bit words on stdout
+    int c, device = 0;
+    while ((c = getopt(argc, argv, "t:d:")) >= 0) if (c == 'd') device = atoi(optarg);
+    if (optind == argc) { std::fprintf(stderr, "Usage: fermi-b200 seqrank [-d device] <reads.fmd>\n"); return 1; }
+    fmg_fmd_t *e = fmg_fmd_restore(argv[optind]);
+    fmg_index_t *idx = e ? fmg_index_upload(e, device) : nullptr;
+    if (!idx) return 1;
+    uint64_t info[17];
+    fmg_fmd_info(e, info);
+    std::vector<uint64_t> sorted(info[1] ? info[1] : 1);
+    int64_t st[3];
+    const int rc = fmg_seqsort(idx, sorted.data(), st);
+    if (rc == 0) {
+        std::fprintf(stderr, "[M::%s] #zeros=%ld, #contained=%ld, #duplicates=%ld\n", "fm6_seqsort", (long)st[0], (long)st[1], (long)st[2]);   // seqsort.c:66
+        std::fwrite(sorted.data(), 8, info[1], stdout);
+    }
     fmg_index_free(idx);
     fmg_fmd_destroy(e);
     return rc != 0;
@@ -288,6 +313,7 @@ int usage() {
     std::fprintf(stderr, "         chkbwt     marginal counts / print the BWT\n");
     std::fprintf(stderr, "         exact      find supermaximal exact matches\n");
     std::fprintf(stderr, "         unitig     construct unitigs\n");
+    std::fprintf(stderr, "         seqrank    compute the rank of sequences\n");
     std::fprintf(stderr, "         kmers      k-mer collection of `correct`\n\n");
     return 1;
 }
@@ -305,6 +331,7 @@ int main(int argc, char *argv[]) {                    // main.c:63-138
     else if (cmd == "chkbwt") ret = main_chkbwt(argc - 1, argv + 1);
     else if (cmd == "exact") ret = main_exact(argc - 1, argv + 1);
     else if (cmd == "unitig") ret = main_unitig(argc - 1, argv + 1);
+    else if (cmd == "seqsort" || cmd == "seqrank") ret = main_seqsort(argc - 1, argv + 1);      // main.c:108-109
     else if (cmd == "kmers") ret = main_kmers(argc - 1, argv + 1);
     else { std::fprintf(stderr, "[E::%s] unrecognized command '%s'\n", __func__, argv[1]); return 1; }
     if (ret == 0 && fmg_verbose >= 3) {

@@ -28,6 +28,7 @@ namespace fmg {
 struct OverlapArgs {
     OccView ix;
     int min_match;
+    int mode;                   // 0: unitig records; 1: fm6_retrieve for seqsort (seqsort.c:12-35): phase 1 only, no candidate lists, no length cut
     int64_t n;                  // sequences in this batch
     // phase 1 spells the sequences itself (fm_retrieve, exact.c:59-70, fused with the backward search of fm6_is_contained)
     const uint64_t *ids;        // BWT rows (sentinel ranks) of the batch, or nullptr for row t = first + t * step
@@ -215,8 +216,8 @@ struct OvLane {
     FMG_HD void phase_contained(int64_t t) {
         int64_t *rec = A.rec + t * OV_NREC;
         const int min_match = A.min_match;
-        uint8_t *out = A.seq + (size_t)t * A.max_len;
-        Cand *list = list0(t);
+        uint8_t *out = A.mode == 0 ? A.seq + (size_t)t * A.max_len : nullptr;
+        Cand *list = A.mode == 0 ? list0(t) : nullptr;
         ovf = false;
         uint64_t k = A.ids ? A.ids[t] : A.first + (uint64_t)t * A.step;
         int n = 0, np = 0, ret = 0;
@@ -248,20 +249,27 @@ struct OvLane {
                     intv0 = ok(0);
                     break;
                 }
-                if (n >= min_match && size(0) != 0) { ik.info = (U)n; push(list, A.pcap, np, ik); }
+                if (A.mode == 0 && n >= min_match && size(0) != 0) { ik.info = (U)n; push(list, A.pcap, np, ik); }
                 ik = ok(c);
             } else {
                 if (last) break;                              // an empty sequence
                 ik = base_intv<U>(A.ix, c);
             }
-            if (n < A.max_len) out[n] = (uint8_t)c;
+            if (A.mode == 0 && n < A.max_len) out[n] = (uint8_t)c;
             ++n;
         }
         A.ret[t] = (int64_t)k;
+        for (int q = 0; q < OV_NREC; ++q) rec[q] = 0;
+        if (A.mode != 0) {                                            // fm6_retrieve (exact.c:100-127): k, k2 and the containment flags
+            extend(intv0, 0);
+            if (intv0.x2 != size(0)) ret = -1;
+            intv0 = ok(0);
+            rec[OV_LEN] = n; rec[OV_CONTAINED] = ret; rec[OV_X0] = (int64_t)intv0.x0; rec[OV_X1] = (int64_t)intv0.x1; rec[OV_X2] = (int64_t)intv0.x2;
+            return;
+        }
         const int L = n <= A.max_len ? n : -n;
         A.len[t] = L;
         for (int a = 0, b = (n < A.max_len ? n : A.max_len) - 1; a < b; ++a, --b) { const uint8_t x = out[a]; out[a] = out[b]; out[b] = x; }   // seq_reverse (unitig.c:285)
-        for (int q = 0; q < OV_NREC; ++q) rec[q] = 0;
         rec[OV_LEN] = L; rec[OV_RBEG] = -1; rec[OV_LEFT] = 1;
         A.nei_cnt[t] = 0;
         A.np0[t] = -1;

@@ -125,6 +125,21 @@ __global__ void __launch_bounds__(256) k_seq_odd(const uint8_t *__restrict__ seq
     out[i] = seq[(2 * row + 1) * max_len + col];
 }
 
+// fm6_seqsort (seqsort.c:12-35): from fm6_retrieve's k / k2 / containment of every even row i, the rank table
+//   sorted[k] = i << 2 | flag,  sorted[rank of the reverse complement] = (i | 1) << 2 | flag
+__global__ void __launch_bounds__(256) k_seqsort_scatter(int64_t n, uint64_t row0, const int64_t *__restrict__ rec, const int64_t *__restrict__ ret,
+                                                        uint64_t *__restrict__ sorted) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t *r = rec + t * OV_NREC;
+    const uint64_t i = row0 + 2 * (uint64_t)t, k = (uint64_t)ret[t];
+    const uint64_t x0 = (uint64_t)r[OV_X0], x1 = (uint64_t)r[OV_X1], x2 = (uint64_t)r[OV_X2];
+    const uint64_t flag = (uint64_t)(r[OV_CONTAINED] != 0) << 1 | (uint64_t)(x2 > 1 && k != x0);
+    sorted[k] = i << 2 | flag;
+    if (x0 != x1) sorted[x1 + (k - x0)] = (i | 1) << 2 | flag;        // seq and reverse complement are different
+    else sorted[k + 1] = (i | 1) << 2 | flag;
+}
+
 // the record compaction kernels of the SMEM path (fmg_cuda.cu) are reused for the neighbour slots
 int fmg_compact_slots(const uint32_t *cnt, int64_t n, int cap, const uint4 *slots, uint4 *mem, uint64_t *mem_off, uint64_t *tile_sum,
                       unsigned long long *ctrl, cudaStream_t st);
@@ -258,7 +273,7 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
                 OV_TRY(cudaEventRecord(ev[0], s_run));
             }
             OverlapArgs O;
-            O.ix = idx->view; O.min_match = min_match; O.n = m; O.seq = d_seq.as<uint8_t>(); O.len = d_len.as<int32_t>(); O.max_len = max_len;
+            O.ix = idx->view; O.min_match = min_match; O.mode = 0; O.n = m; O.seq = d_seq.as<uint8_t>(); O.len = d_len.as<int32_t>(); O.max_len = max_len;
             O.ids = nullptr; O.first = row0; O.step = 1; O.ret = d_ret.as<int64_t>() + row0;
             O.P0 = d_P0.p; O.pcap = pcap; O.np0 = d_np0.as<int32_t>(); O.A = d_A.p; O.B = d_B.p; O.cap = cap; O.cat = d_cat.as<int32_t>();
             O.rec = d_rec.as<int64_t>(); O.nei = d_slots.as<uint4>(); O.nei_cap = nei_cap; O.nei_cnt = d_cnt.as<uint32_t>();
@@ -357,6 +372,50 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
 
 extern "C" {
 
+// fm6_seqsort (seqsort.c:37-70) / `fermi seqrank`: sorted[mcnt[1]] as the reference fills it; stats = #zeros, #contained, #duplicates
+int fmg_seqsort(const fmg_index_t *idx, uint64_t *sorted, int64_t stats[3]) {
+    if (!idx || !sorted) return -1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] no CUDA device available; libfermi_b200 has no CPU path\n", __func__);
+        return -1;
+    }
+    OV_TRY(cudaSetDevice(idx->device));
+    const uint64_t n_seq = idx->mcnt[1];
+    const bool wide = idx->view.n_sym + 256 >= (1ull << 32) || std::getenv("FMG_FORCE_WIDE") != nullptr;
+    Dev d_sorted, d_rec, d_ret, d_cnt, d_np0, d_len;
+    OV_TRY(d_sorted.alloc(std::max<uint64_t>(n_seq, 1) * 8));
+    OV_TRY(cudaMemset(d_sorted.p, 0, std::max<uint64_t>(n_seq, 1) * 8));         // calloc in the reference (seqsort.c:49)
+    const int64_t batch = 1 << 22;
+    const int64_t n_even = (int64_t)((n_seq + 1) / 2), nb_max = std::min<int64_t>(batch, std::max<int64_t>(n_even, 1));
+    OV_TRY(d_rec.alloc((size_t)nb_max * OV_NREC * 8)); OV_TRY(d_ret.alloc((size_t)nb_max * 8)); OV_TRY(d_cnt.alloc((size_t)nb_max * 4));
+    OV_TRY(d_np0.alloc((size_t)nb_max * 4)); OV_TRY(d_len.alloc((size_t)nb_max * 4));
+    for (int64_t t0 = 0; t0 < n_even; t0 += batch) {
+        const int64_t m = std::min(batch, n_even - t0);
+        OverlapArgs O;
+        std::memset(&O, 0, sizeof O);
+        O.ix = idx->view; O.min_match = 0; O.mode = 1; O.n = m; O.max_len = 0;
+        O.ids = nullptr; O.first = 2 * (uint64_t)t0; O.step = 2; O.ret = d_ret.as<int64_t>(); O.len = d_len.as<int32_t>();
+        O.np0 = d_np0.as<int32_t>(); O.rec = d_rec.as<int64_t>(); O.nei_cnt = d_cnt.as<uint32_t>();
+        const unsigned gch = (unsigned)((m + OVCH_BLOCK - 1) / OVCH_BLOCK);
+        if (wide) k_ov_chain<uint64_t, 1><<<gch, OVCH_BLOCK>>>(O); else k_ov_chain<uint32_t, 1><<<gch, OVCH_BLOCK>>>(O);
+        k_seqsort_scatter<<<(unsigned)((m + 255) / 256), 256>>>(m, 2 * (uint64_t)t0, d_rec.as<int64_t>(), d_ret.as<int64_t>(), d_sorted.as<uint64_t>());
+        g_launches += 2;
+        OV_TRY(cudaGetLastError());
+    }
+    OV_TRY(cudaMemcpy(sorted, d_sorted.p, n_seq * 8, cudaMemcpyDeviceToHost));
+    if (stats) {                                                                    // the tally fm6_seqsort prints (seqsort.c:61-68)
+        stats[0] = stats[1] = stats[2] = 0;
+        for (uint64_t i = 0; i < n_seq; ++i)
+            if (sorted[i] == 0) ++stats[0];
+            else if (sorted[i] & 2) ++stats[1];
+            else if (sorted[i] & 1) ++stats[2];
+        if (fmg_verbose >= 3)
+            std::fprintf(stderr, "[M::%s] #zeros=%ld, #contained=%ld, #duplicates=%ld\n", __func__, (long)stats[0], (long)stats[1], (long)stats[2]);
+    }
+    return 0;
+}
+
 int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const uint64_t *ids, uint64_t first, uint64_t step,
                       int max_len, int64_t *rec, fmg_intv_t **nei, uint64_t *nei_off, uint8_t *seq, int32_t *len, uint8_t *ext) {
     if (!idx || n < 0 || max_len <= 0 || !rec || !nei || !nei_off) return -1;
@@ -395,7 +454,7 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
         OV_TRY(d_P0.alloc((size_t)n * pcap * esz)); OV_TRY(d_A.alloc((size_t)n_lanes * cap * esz)); OV_TRY(d_B.alloc((size_t)n_lanes * cap * esz));
         OV_TRY(d_cat.alloc((size_t)n_lanes * cap * 8)); OV_TRY(d_slots.alloc((size_t)n * nei_cap * 32)); OV_TRY(d_mem.alloc((size_t)n * nei_cap * 32));
         OverlapArgs O;
-        O.ix = idx->view; O.min_match = min_match; O.n = n; O.seq = d_seq.as<uint8_t>(); O.len = d_len.as<int32_t>(); O.max_len = max_len;
+        O.ix = idx->view; O.min_match = min_match; O.mode = 0; O.n = n; O.seq = d_seq.as<uint8_t>(); O.len = d_len.as<int32_t>(); O.max_len = max_len;
         O.ids = ids ? d_ids.as<uint64_t>() : nullptr; O.first = first; O.step = step; O.ret = d_ret.as<int64_t>();
         O.P0 = d_P0.p; O.pcap = pcap; O.np0 = d_np0.as<int32_t>(); O.A = d_A.p; O.B = d_B.p; O.cap = cap; O.cat = d_cat.as<int32_t>();
         O.rec = d_rec.as<int64_t>(); O.nei = d_slots.as<uint4>(); O.nei_cap = nei_cap; O.nei_cnt = d_cnt.as<uint32_t>();

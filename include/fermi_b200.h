@@ -128,6 +128,11 @@ int fmg_unitig_assemble(uint64_t n_seq, int max_len, int min_match, const int64_
  * equals that of the reference after canonicalisation. max_len 0 = estimate. */
 int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *out_path, uint64_t *n_unitigs);
 
+/* fm6_seqsort (seqsort.c:37-70) / `fermi seqrank`: sorted[mcnt[1]] exactly as the reference fills it (fm6_retrieve, exact.c:100-127,
+ * of every even BWT row on the GPU: sorted[rank] = row << 2 | contained << 1 | duplicate); stats (may be NULL) = #zeros,
+ * #contained, #duplicates as fm6_seqsort reports them.  The array is what `fermi unitig -r` / `fermi remap -r` load. */
+int fmg_seqsort(const fmg_index_t *idx, uint64_t *sorted, int64_t stats[3]);
+
 /* CUDA-event durations (ms, summed over the batches) of the kernels of the last fmg_unitig overlap pass on this process:
  * ms[1] fm_retrieve + fm6_is_contained chain, ms[2] fm6_get_nei, ms[3] / ms[4] check_left_simple chain / candidate loop,
  * ms[5] record packing, ms[6] seed rows, ms[0] set-up, ms[7] = number of batches */

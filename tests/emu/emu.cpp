@@ -106,7 +106,7 @@ int emu_overlap(const void *_x, int min_match, int64_t n, const uint64_t *ids, i
     std::vector<uint64_t> P0((size_t)n * pcap * 4), A((size_t)n_lanes * cap * 4), B((size_t)n_lanes * cap * 4);
     std::vector<int32_t> cat((size_t)n_lanes * cap * 2), np0(n);
     OverlapArgs O;
-    O.ix = x->view; O.min_match = min_match; O.n = n; O.seq = seq; O.len = len; O.max_len = max_len;
+    O.ix = x->view; O.min_match = min_match; O.mode = 0; O.n = n; O.seq = seq; O.len = len; O.max_len = max_len;
     O.ids = ids; O.first = 0; O.step = 1; O.ret = ret.data();
     O.P0 = P0.data(); O.pcap = pcap; O.np0 = np0.data(); O.A = A.data(); O.B = B.data(); O.cap = cap; O.cat = cat.data();
     O.rec = rec; O.nei = reinterpret_cast<uint4 *>(nei); O.nei_cap = nei_cap; O.nei_cnt = nei_cnt; O.ext = ext; O.next = nullptr;

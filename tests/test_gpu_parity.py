@@ -2,6 +2,7 @@
 from the unmodified reference and against the oracle on fresh seeded inputs.  Bit-exact everywhere
 (integer work): SA intervals, bi-intervals, SMEM records, BWT bytes."""
 import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -196,6 +197,35 @@ def test_unitig_20k_reads_vs_reference_binary(fb, tmp_path, monkeypatch, err, co
         assert n == len(ref)
         assert H.canonical_mag(H.parse_mag(open(out).read())) == H.canonical_mag(ref), "host walk" if host == "1" else "device assembly"
     idx.close()
+
+
+@pytest.mark.skipif(H.ref_fermi_binary() is None, reason="oracle/_ref/fermi did not travel with the repo")
+@pytest.mark.parametrize("err,dup", [(0.0, 0), (0.01, 300)])
+def test_seqrank_equals_reference_seqsort(fb, tmp_path, monkeypatch, err, dup):
+    """fmg_seqsort (fm6_retrieve of every read on the GPU) == the bytes `fermi seqsort` writes (seqsort.c:12-70): ranks,
+    contained and duplicate flags, with duplicated reads, palindromes and reads contained in longer ones in the input."""
+    genome = fb.synth_genome(51, 150000)
+    reads = list(fb.synth_reads(52, genome, 15000, 100, err))
+    reads += [reads[i].copy() for i in range(dup)]                                   # exact duplicates
+    reads += [r[10:70].copy() for r in reads[:200]]                                  # contained in a longer read
+    pal = np.array([1, 2, 3, 4] * 10, np.uint8)
+    reads.append(np.concatenate([pal, (5 - pal)[::-1]]))                             # equals its own reverse complement
+    fmd = fb.fm_build(H.fmd_text(reads), 0)
+    fn = str(tmp_path / "r.fmd")
+    fmd.dump(fn)
+    ref = np.frombuffer(subprocess.run([H.ref_fermi_binary(), "seqsort", "-t", "4", fn], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                       check=True).stdout, np.uint64)
+    idx = fb.FmdIndex(fmd, 0)
+    for wide in ("", "1"):
+        if wide:
+            monkeypatch.setenv("FMG_FORCE_WIDE", "1")
+        ours, st = fb.fm6_seqsort(idx)
+        assert np.array_equal(ours, ref)
+        assert st == (int((ref == 0).sum()), int(((ref & 2) != 0).sum()), int((((ref & 2) == 0) & ((ref & 1) != 0) & (ref != 0)).sum()))
+    idx.close()
+    cli = os.path.join(H.ROOT, "fermi_b200", "bin", "fermi-b200")
+    out = subprocess.run([cli, "seqrank", fn], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+    assert out == ref.tobytes()
 
 
 def test_bcr_bwt_equals_suffix_sort_and_reference(fb, tmp_path):
