@@ -59,6 +59,10 @@ _PROTOS = {
     "fmg_ec_kmer_length": (C.c_int, [C.c_uint64]),
     # construction + synthetic data
     "fmg_build_bwt": (C.c_int, [C.c_int, C.c_int64, u8p, u8p]),
+    "fmg_build_fmd": (C.c_void_p, [C.c_int, C.c_int64, u8p]),
+    "fmg_fmd_from_bwt_device": (C.c_void_p, [C.c_int, C.c_int64, u8p]),
+    "fmg_bcr_want_fmd": (C.c_int, [C.c_void_p, C.c_int]),
+    "fmg_bcr_fmd": (C.c_void_p, [C.c_void_p]),
     "fmg_bcr_init": (C.c_void_p, [C.c_int]),
     "fmg_bcr_append": (C.c_int, [C.c_void_p, C.c_int, u8p]),
     "fmg_bcr_append_batch": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, u8p]),

@@ -42,6 +42,12 @@ class Fmd:
         return cls(lib().fmg_fmd_from_bwt(len(bwt), _p(bwt, u8p)))
 
     @classmethod
+    def from_bwt_device(cls, bwt, device=0):
+        """fm_bwtenc (build.c:11) with the RLD encoder on the GPU (rld_enc.cu); byte-identical to from_bwt."""
+        bwt = np.ascontiguousarray(bwt, np.uint8)
+        return cls(lib().fmg_fmd_from_bwt_device(device, len(bwt), _p(bwt, u8p)))
+
+    @classmethod
     def from_rle6(cls, rle):
         rle = np.ascontiguousarray(rle, np.uint8)
         return cls(lib().fmg_fmd_from_rle6(len(rle), _p(rle, u8p)))
@@ -270,9 +276,13 @@ def fm_build_bwt(text, device=0):
     return bwt
 
 
-def fm_build(text, device=0):
-    """fm_build (build.c:33): text -> Fmd."""
-    return Fmd.from_bwt(fm_build_bwt(text, device))
+def fm_build(text, device=0, host_encode=False):
+    """fm_build (build.c:33): text -> Fmd.  Suffix sort, BWT and the RLD encoder all run on the GPU (fmg_build_fmd);
+    host_encode=True takes the BWT to the host and encodes it there (fm_bwtenc as serial host code)."""
+    if host_encode:
+        return Fmd.from_bwt(fm_build_bwt(text, device))
+    text = np.ascontiguousarray(text, np.uint8)
+    return Fmd(lib().fmg_build_fmd(device, len(text), _p(text, u8p)))
 
 
 def fm6_ec_collect(idx, w=-1, min_occ=3):
@@ -302,6 +312,12 @@ class Bcr:
 
     def build(self):
         _check(lib().fmg_bcr_build(self.h), "bcr_build")
+
+    def build_fmd(self):
+        """`fermi ropebwt | fermi recode`: BCR and the RLD encoder on the GPU; returns the Fmd (the BWT itself is not copied out)."""
+        _check(lib().fmg_bcr_want_fmd(self.h, 1), "bcr_want_fmd")
+        _check(lib().fmg_bcr_build(self.h), "bcr_build")
+        return Fmd(lib().fmg_bcr_fmd(self.h))
 
     def bwt(self):
         n = lib().fmg_bcr_size(self.h)

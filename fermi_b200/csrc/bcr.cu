@@ -22,7 +22,12 @@
 #include <cstring>
 #include <atomic>
 #include <vector>
+#include <memory>
+#include "fmd_host.hpp"
 #include "../../include/fermi_b200.h"
+
+int fmg_rld_encode_device(const uint8_t *d_bwt, uint64_t n, fmg::FmdImage *out);     // rld_enc.cu
+struct fmg_fmd_s { fmg::FmdImage img; };
 
 extern std::atomic<uint64_t> g_launches;
 
@@ -192,6 +197,9 @@ struct fmg_bcr_s {
     int max_len = 0;
     std::vector<uint8_t> bwt;        // result (host), one nt6 byte per symbol
     bool built = false;
+    bool want_fmd = false;           // encode the .fmd image on the device instead of copying the BWT out (fmg_bcr_fmd)
+    std::unique_ptr<fmg::FmdImage> img;
+    uint64_t n_sym = 0;
 };
 
 static int bcr_build_device(fmg_bcr_s *b) {
@@ -254,8 +262,14 @@ static int bcr_build_device(fmg_bcr_s *b) {
         if (fmg_verbose >= 4) std::fprintf(stderr, "[M::fmg_bcr_build] cycle %d: %llu symbols, %llu sequences still active\n", pos, (unsigned long long)m, (unsigned long long)n_act);
     }
     BCR_TRY(cudaGetLastError());
-    b->bwt.resize(m);
-    BCR_TRY(cudaMemcpy(b->bwt.data(), d_bwt[cur].p, m, cudaMemcpyDeviceToHost));
+    b->n_sym = m;
+    if (b->want_fmd) {
+        b->img.reset(new fmg::FmdImage);
+        if (fmg_rld_encode_device(d_bwt[cur].as<uint8_t>(), m, b->img.get()) != 0) return -1;
+    } else {
+        b->bwt.resize(m);
+        BCR_TRY(cudaMemcpy(b->bwt.data(), d_bwt[cur].p, m, cudaMemcpyDeviceToHost));
+    }
     b->built = true;
     return 0;
 }
@@ -309,17 +323,29 @@ int fmg_bcr_build(fmg_bcr_t *b) {
     return bcr_build_device(b);
 }
 
-int64_t fmg_bcr_size(const fmg_bcr_t *b) { return b && b->built ? (int64_t)b->bwt.size() : -1; }
+int64_t fmg_bcr_size(const fmg_bcr_t *b) { return b && b->built ? (int64_t)b->n_sym : -1; }
+
+// ask fmg_bcr_build for the RLD-encoded .fmd image (encoded on the device) instead of the plain BWT
+int fmg_bcr_want_fmd(fmg_bcr_t *b, int on) { if (!b) return -1; b->want_fmd = on != 0; return 0; }
+
+// the image built by fmg_bcr_build after fmg_bcr_want_fmd(b, 1): `fermi ropebwt | fermi recode` in one step; the caller owns it
+fmg_fmd_t *fmg_bcr_fmd(fmg_bcr_t *b) {
+    if (!b || !b->built || !b->img) return nullptr;
+    fmg_fmd_t *e = new fmg_fmd_s;
+    e->img = std::move(*b->img);
+    b->img.reset();
+    return e;
+}
 
 int fmg_bcr_bwt(const fmg_bcr_t *b, uint8_t *bwt) {
-    if (!b || !b->built) return -1;
+    if (!b || !b->built || b->bwt.size() != b->n_sym) return -1;
     std::memcpy(bwt, b->bwt.data(), b->bwt.size());
     return 0;
 }
 
 // the byte run-length stream of bcr_itr_next / `fermi ropebwt -b` (ropebwt.c:127-144): bytes len<<3|sym, len <= 31
 int fmg_bcr_rle(const fmg_bcr_t *b, uint8_t **rle, int64_t *n) {
-    if (!b || !b->built) return -1;
+    if (!b || !b->built || b->bwt.size() != b->n_sym) return -1;
     std::vector<uint8_t> out;
     const std::vector<uint8_t> &w = b->bwt;
     for (size_t i = 0; i < w.size();) {

@@ -13,7 +13,11 @@
 #include <cstdio>
 #include <cstdint>
 #include <atomic>
+#include "fmd_host.hpp"
 #include "../../include/fermi_b200.h"
+
+int fmg_rld_encode_device(const uint8_t *d_bwt, uint64_t n, fmg::FmdImage *out);     // rld_enc.cu
+struct fmg_fmd_s { fmg::FmdImage img; };
 
 extern std::atomic<uint64_t> g_launches;
 
@@ -106,7 +110,7 @@ struct DevBuf {
     template <class T> T *as() { return static_cast<T *>(p); }
 };
 
-int build_bwt_device(uint32_t n, const uint8_t *h_text, uint8_t *h_bwt) {
+int build_bwt_device(uint32_t n, const uint8_t *h_text, uint8_t *h_bwt, fmg::FmdImage *img) {
     DevBuf dT, dSA, dRank, dKeyA, dKeyB, dValA, dValB, dPosA, dPosB, dHead, dTied, dTmp, dCount;
     BW_TRY(dT.alloc(n)); BW_TRY(dSA.alloc((size_t)n * 4)); BW_TRY(dRank.alloc((size_t)n * 4));
     BW_TRY(dKeyA.alloc((size_t)n * 8)); BW_TRY(dKeyB.alloc((size_t)n * 8));
@@ -195,7 +199,8 @@ int build_bwt_device(uint32_t n, const uint8_t *h_text, uint8_t *h_bwt) {
     // BWT (reuse tied[] as the output buffer)
     k_gather_bwt<<<blocks_for(n), kThreads>>>(T, sa, n, tied); ++g_launches;
     BW_TRY(cudaGetLastError());
-    BW_TRY(cudaMemcpy(h_bwt, tied, n, cudaMemcpyDeviceToHost));
+    if (h_bwt) BW_TRY(cudaMemcpy(h_bwt, tied, n, cudaMemcpyDeviceToHost));
+    if (img && fmg_rld_encode_device(tied, n, img) != 0) return -1;      // the BWT never leaves the device
     return 0;
 }
 
@@ -212,5 +217,41 @@ extern "C" int fmg_build_bwt(int device, int64_t n, const uint8_t *text, uint8_t
         return -1;
     }
     if (cudaSetDevice(device) != cudaSuccess) return -1;
-    return build_bwt_device((uint32_t)n, text, bwt);
+    return build_bwt_device((uint32_t)n, text, bwt, nullptr);
+}
+
+// fm_build (build.c:33-50) entirely on the device: suffix sort, BWT and RLD encoding; only the .fmd image comes back
+extern "C" fmg_fmd_t *fmg_build_fmd(int device, int64_t n, const uint8_t *text) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] no CUDA device available; libfermi_b200 has no CPU path\n", __func__);
+        return nullptr;
+    }
+    if (n <= 0 || n >= 0xffffffffll || text[n - 1] != 0) {
+        if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] text must have 1..2^32-2 symbols and end with a sentinel\n", __func__);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    fmg_fmd_t *e = new fmg_fmd_s;
+    if (build_bwt_device((uint32_t)n, text, nullptr, &e->img) != 0) { delete e; return nullptr; }
+    return e;
+}
+
+// fm_bwtenc (build.c:11-31) on the device for a BWT that lives on the host: copy in, encode, image out
+extern "C" fmg_fmd_t *fmg_fmd_from_bwt_device(int device, int64_t n, const uint8_t *bwt) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || n <= 0 || !bwt) {
+        if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] no CUDA device available (or empty input); libfermi_b200 has no CPU path\n", __func__);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    uint8_t *d = nullptr;
+    if (cudaMalloc(&d, (size_t)n) != cudaSuccess) return nullptr;
+    fmg_fmd_t *e = nullptr;
+    if (cudaMemcpy(d, bwt, (size_t)n, cudaMemcpyHostToDevice) == cudaSuccess) {
+        e = new fmg_fmd_s;
+        if (fmg_rld_encode_device(d, (uint64_t)n, &e->img) != 0) { delete e; e = nullptr; }
+    }
+    cudaFree(d);
+    return e;
 }

@@ -152,6 +152,12 @@ int fmg_ec_kmer_length(uint64_t n_symbols);
  * sorting on the GPU; replaces fm_build / ksa_bwt (build.c:33-50, ksa.c:231-242) for texts that fit
  * one GPU.  `text` = nt6 bytes with 0 sentinels (n < 2^32); `bwt` receives n symbols. */
 int fmg_build_bwt(int device, int64_t n, const uint8_t *text, uint8_t *bwt);
+/* fm_build (build.c:33-50) entirely on the device: suffix sort, BWT and the RLD encoder (rld_enc / enc_next_block /
+ * rld_enc_finish, rld.c:111-236, as parallel segment chasing + one thread per 64-byte block); the image is byte-identical
+ * to what fmg_fmd_from_bwt / the reference produce.  NULL on failure. */
+fmg_fmd_t *fmg_build_fmd(int device, int64_t n, const uint8_t *text);
+/* fm_bwtenc (build.c:11-31) on the device for a BWT held by the host (n nt6 symbols) */
+fmg_fmd_t *fmg_fmd_from_bwt_device(int device, int64_t n, const uint8_t *bwt);
 
 /* BCR construction (bcr.h:43-49: bcr_init / bcr_append / bcr_build / bcr_itr_next / bcr_destroy), for collections of
  * any total size that fits HBM.  Sequences are nt6 codes 1..4 (no N, like bcr_append, ropebwt.c:98); they are
@@ -165,6 +171,10 @@ int        fmg_bcr_build(fmg_bcr_t *b);                                 /* bcr_b
 int64_t    fmg_bcr_size(const fmg_bcr_t *b);                            /* symbols in the BWT, -1 before the build */
 int        fmg_bcr_bwt(const fmg_bcr_t *b, uint8_t *bwt);               /* one nt6 byte per symbol */
 int        fmg_bcr_rle(const fmg_bcr_t *b, uint8_t **rle, int64_t *n);  /* bcr_itr_next stream: bytes len<<3|sym (ropebwt.c:127-144) */
+/* `fermi ropebwt | fermi recode` in one step: after fmg_bcr_want_fmd(b, 1), fmg_bcr_build RLD-encodes the BWT on the device
+ * (the plain BWT is not copied out: fmg_bcr_bwt / fmg_bcr_rle then fail) and fmg_bcr_fmd hands the image to the caller */
+int        fmg_bcr_want_fmd(fmg_bcr_t *b, int on);
+fmg_fmd_t *fmg_bcr_fmd(fmg_bcr_t *b);
 void       fmg_bcr_destroy(fmg_bcr_t *b);                               /* bcr_destroy, bcr.c:342 */
 
 /* ------------------------------------------------------------------ synthetic data

@@ -228,6 +228,49 @@ def test_seqrank_equals_reference_seqsort(fb, tmp_path, monkeypatch, err, dup):
     assert out == ref.tobytes()
 
 
+def _same_fmd(a, b, tmp_path):
+    fa, fb_ = str(tmp_path / "a.fmd"), str(tmp_path / "b.fmd")
+    a.dump(fa)
+    b.dump(fb_)
+    return open(fa, "rb").read() == open(fb_, "rb").read()
+
+
+def test_device_rld_encoder_is_byte_identical(fb, tmp_path):
+    """rld_enc.cu (speculative block chain + one thread per block) writes the same .fmd bytes as the serial host encoder
+    (and hence as the reference, tests/test_oracle.py): golden BWTs, one-symbol and tiny inputs, runs >= 0x8000 symbols
+    (7 x u32 block headers), 1-symbol runs only, and a stream longer than one 2^23-word chunk (shortened chunk-end blocks)."""
+    rng = np.random.RandomState(9)
+    cases = [np.array([0], np.uint8), np.array([3, 3, 3, 0], np.uint8), rng.randint(0, 6, size=777).astype(np.uint8)]
+    for case in golden_cases():
+        cases.append(fb.Fmd.restore(os.path.join(H.GOLDEN_DIR, case + ".fmd")).decode_bwt())
+    long_runs = np.concatenate([np.full(l, s, np.uint8) for l, s in zip(rng.choice([1, 5, 300, 40000, 70000, 1 << 20], size=400), rng.randint(0, 6, size=400))])
+    cases.append(long_runs)
+    cases.append(np.tile(np.array([1, 2, 3, 4, 0, 5], np.uint8), 200000))                       # no run longer than 1: 4-bit codes
+    cases.append(rng.randint(1, 5, size=150_000_000).astype(np.uint8))                           # ~80 MB of stream: crosses a chunk end
+    for bwt in cases:
+        dev, host = fb.Fmd.from_bwt_device(bwt, 0), fb.Fmd.from_bwt(bwt)
+        assert dev.n_bytes == host.n_bytes and dev.n_frames == host.n_frames and list(dev.mcnt) == list(host.mcnt)
+        assert _same_fmd(dev, host, tmp_path), "n=%d" % len(bwt)
+    assert cases[-1].size and fb.Fmd.from_bwt(cases[-1]).n_bytes > (1 << 26)
+
+
+def test_build_and_bcr_with_device_encoder(fb, tmp_path):
+    """fm_build / Bcr.build_fmd keep the BWT on the device (suffix sort or BCR, then rld_enc.cu): same .fmd bytes as the
+    host-encoded path and as the golden file the reference built."""
+    g, fmd = _load("reads10x")
+    text = g["text"]
+    assert _same_fmd(fb.fm_build(text, 0), fb.fm_build(text, 0, host_encode=True), tmp_path)
+    assert open(str(tmp_path / "a.fmd"), "rb").read() == open(fmd, "rb").read()
+    reads = text[text != 0].reshape(-1, 100)[0::2]
+    b = fb.Bcr(0)
+    both = np.empty((2 * len(reads), 100), np.uint8)
+    both[0::2], both[1::2] = reads, 5 - reads[:, ::-1]
+    b.append_batch(both)
+    e = b.build_fmd()
+    e.dump(str(tmp_path / "c.fmd"))
+    assert open(str(tmp_path / "c.fmd"), "rb").read() == open(fmd, "rb").read()
+
+
 def test_bcr_bwt_equals_suffix_sort_and_reference(fb, tmp_path):
     """GPU BCR (fmg_bcr_*) == naive BWT on small/ragged inputs, == the GPU suffix-sort builder on 40k reads, and the
     RLD-encoded result is byte-identical to the golden .fmd the reference built with SA-IS."""
