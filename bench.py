@@ -171,11 +171,8 @@ def unitig_index(fb, n_reads, read_len, device):
     genome = fb.synth_genome(UNITIG_GENOME_SEED, n_reads * read_len // UNITIG_COV)
     reads = fb.synth_reads(UNITIG_READ_SEED, genome, n_reads, read_len, 0.0)
     t = time.time()
-    bwt = fb.fm_build_bwt(fb.fmd_text(reads), device)
-    t_bwt = time.time() - t
-    t = time.time()
-    fmd = fb.Fmd.from_bwt(bwt)
-    return fmd, t_bwt, time.time() - t
+    fmd = fb.fm_build(fb.fmd_text(reads), device)          # suffix sort, BWT and RLD encoding on the GPU
+    return fmd, time.time() - t
 
 
 def unitig_leg(fb, a, device, peak, peak_src):
@@ -184,7 +181,7 @@ def unitig_leg(fb, a, device, peak, peak_src):
     text.  Next to it the unmodified reference binary (`fermi unitig -l50 -t<nproc>`) on a bounded sample built the same way."""
     import helpers as H
     L = a.read_len
-    fmd, t_bwt, t_enc = unitig_index(fb, a.unitig_reads, L, device)
+    fmd, t_build = unitig_index(fb, a.unitig_reads, L, device)
     idx = fb.FmdIndex(fmd, device)
     out = os.path.join(tempfile.gettempdir(), "fermi_b200_bench_unitig.mag")
     launches0 = fb.launch_count()
@@ -204,7 +201,7 @@ def unitig_leg(fb, a, device, peak, peak_src):
                        (UNITIG_MIN, a.unitig_reads, L, UNITIG_COV, int(fmd.mcnt[1]), int(fmd.mcnt[0])),
            "value": a.unitig_reads / secs, "unit": "reads/s", "seconds": secs, "unitigs": int(n_u), "mag_bytes": os.path.getsize(out),
            "api": "fmg_unitig (records + assembly on the GPU, MAG text written to a file)", "gpu_launches_per_call": int(launches),
-           "setup": {"gpu_bwt_s": round(t_bwt, 2), "rld_encode_s": round(t_enc, 2)},
+           "setup": {"gpu_build_fmd_s": round(t_build, 2)},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                         "kernel": "k_ov_chain<1> + k_ov_lists<2> + k_ov_chain<3> + k_ov_lists<4>", "kernel_ms": k_ms, "kernel_ms_by_phase": st,
                         "algorithmic_bytes_per_read": bytes_per_read, "locates_per_read": UNITIG_LOCATES_PER_READ,
@@ -216,7 +213,7 @@ def unitig_leg(fb, a, device, peak, peak_src):
     ref_bin = H.ref_fermi_binary()
     if ref_bin and a.unitig_ref_reads > 0 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        rfmd, _, _ = unitig_index(fb, a.unitig_ref_reads, L, device)
+        rfmd, _ = unitig_index(fb, a.unitig_ref_reads, L, device)
         fn = os.path.join(tempfile.gettempdir(), "fermi_b200_bench_unitig_ref.fmd")
         rfmd.dump(fn)
         t = time.perf_counter()
@@ -301,13 +298,12 @@ def run_ours(a):
     if rank == 0 and not os.path.exists(fn):
         text = fb.fmd_text(recs)
         t1 = time.time()
-        bwt = fb.fm_build_bwt(text, local)
+        fmd = fb.fm_build(text, local)                 # suffix sort, BWT and RLD encoding on the GPU
         t2 = time.time()
-        fmd = fb.Fmd.from_bwt(bwt)
         fmd.dump(fn + ".tmp")
         os.replace(fn + ".tmp", fn)
-        log("index: %d symbols, GPU BWT %.1f s, RLD encode + write %.1f s" % (len(text), t2 - t1, time.time() - t2))
-        del text, bwt, fmd
+        log("index: %d symbols, GPU build (BWT + RLD encoding) %.1f s, write %.1f s" % (len(text), t2 - t1, time.time() - t2))
+        del text, fmd
     barrier()
     fmd = fb.Fmd.restore(fn)
     t1 = time.time()

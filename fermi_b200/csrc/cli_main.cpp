@@ -102,9 +102,7 @@ int main_build(int argc, char *argv[]) {
         text += rd.seq; text += '\0';
     }
     if (text.empty()) { std::fprintf(stderr, "[E::%s] no sequence in the input\n", __func__); return 1; }
-    std::vector<uint8_t> bwt(text.size());
-    if (fmg_build_bwt(device, (int64_t)text.size(), (const uint8_t *)text.data(), bwt.data())) return 1;
-    fmg_fmd_t *e = fmg_fmd_from_bwt((int64_t)bwt.size(), bwt.data());
+    fmg_fmd_t *e = fmg_build_fmd(device, (int64_t)text.size(), (const uint8_t *)text.data());    // suffix sort + BWT + RLD encoding on the GPU
     const int rc = e ? fmg_fmd_dump(e, out) : 1;
     fmg_fmd_destroy(e);
     return rc != 0;
@@ -113,11 +111,16 @@ int main_build(int argc, char *argv[]) {
 int main_ropebwt(int argc, char *argv[]) {
     int c, bin = 0, fwd = 1, rev = 1, odd = 1, device = 0;
     const char *out = "-";
-    while ((c = getopt(argc, argv, "a:bNtFROo:d:v:")) >= 0) {          // -a bcr is the only algorithm; -N (cut at N) is always on; -t accepted
+    int fmd = 0;
+    while ((c = getopt(argc, argv, "a:bNtFROo:d:v:r")) >= 0) {         // -a bcr is the only algorithm; -N (cut at N) is always on; -t accepted
         if (c == 'b') bin = 1; else if (c == 'F') fwd = 0; else if (c == 'R') rev = 0; else if (c == 'O') odd = 0;
-        else if (c == 'o') out = optarg; else if (c == 'd') device = atoi(optarg);
+        else if (c == 'o') out = optarg; else if (c == 'd') device = atoi(optarg); else if (c == 'r') fmd = 1;
     }
-    if (optind == argc) { std::fprintf(stderr, "Usage: fermi-b200 ropebwt [-b] [-F] [-R] [-O] [-o out] <in.fq.gz>\n"); return 1; }
+    if (optind == argc) {
+        std::fprintf(stderr, "Usage: fermi-b200 ropebwt [-b] [-r] [-F] [-R] [-O] [-o out] <in.fq.gz>\n"
+                             "       -r writes the RLD-encoded .fmd directly (= `fermi ropebwt -b | fermi recode`, encoded on the GPU)\n");
+        return 1;
+    }
     SeqReader rd(argv[optind]);
     if (!rd.fp) { std::fprintf(stderr, "[E::%s] Fail to open the input file.\n", __func__); return 1; }
     fmg_bcr_t *b = fmg_bcr_init(device);
@@ -132,6 +135,15 @@ int main_ropebwt(int argc, char *argv[]) {
         size_t st = 0;
         for (size_t j = 0; j <= rd.seq.size(); ++j)               // cut at ambiguous bases (ropebwt.c:107-116)
             if (j == rd.seq.size() || rd.seq[j] == 5 || rd.seq[j] == 0) { if (j > st) insert1(rd.seq.substr(st, j - st)); st = j + 1; }
+    }
+    if (fmd) {
+        fmg_bcr_want_fmd(b, 1);
+        if (fmg_bcr_build(b)) return 1;
+        fmg_fmd_t *e = fmg_bcr_fmd(b);
+        const int rc = e ? fmg_fmd_dump(e, out) : 1;
+        fmg_fmd_destroy(e);
+        fmg_bcr_destroy(b);
+        return rc != 0;
     }
     if (fmg_bcr_build(b)) return 1;
     FILE *fp = std::strcmp(out, "-") ? std::fopen(out, "wb") : stdout;

@@ -354,8 +354,10 @@ def test_command_line_front_end(fb, tmp_path):
     run("build", "-fo", a, fa)
     run("ropebwt", "-a", "bcr", "-bN", "-o", rle, fa)
     run("recode", rle, b)
+    c = str(tmp_path / "c.fmd")
+    run("ropebwt", "-a", "bcr", "-rN", "-o", c, fa)            # BCR + RLD encoding on the GPU in one step
     want = open(fmd, "rb").read()
-    assert open(a, "rb").read() == want and open(b, "rb").read() == want
+    assert open(a, "rb").read() == want and open(b, "rb").read() == want and open(c, "rb").read() == want
 
 
 def test_gpu_transcode_equals_host_builder(fb, monkeypatch, tmp_path):
