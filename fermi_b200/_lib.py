@@ -55,6 +55,11 @@ _PROTOS = {
     "fmg_unitig": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, u64p]),
     "fmg_overlap_stats": (None, [C.POINTER(C.c_double)]),
     "fmg_seqsort": (C.c_int, [C.c_void_p, u64p, C.POINTER(C.c_int64)]),
+    "fmg_overlap_shard": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                    C.c_void_p, C.c_uint64, u64p]),
+    "fmg_overlap_rebase": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "fmg_unitig_from_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                         C.c_char_p, u64p]),
     "fmg_ec_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, vpp, u64p, C.POINTER(C.c_int64)]),
     "fmg_ec_kmer_length": (C.c_int, [C.c_uint64]),
     # construction + synthetic data

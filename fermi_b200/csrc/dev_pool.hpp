@@ -61,16 +61,32 @@ struct OvDevice {
     uint64_t n_seq = 0, ext_total = 0, spill_total = 0;
     int max_len = 0;
 };
+
+// a shard of the pass written into caller-owned device buffers (multi-GPU: fmg_overlap_shard)
+struct OvShard {
+    uint64_t row_lo, row_hi;        // BWT rows [row_lo, row_hi)
+    void *pack;                     // OvPack[n_seq], zeroed by the caller; only the ranks of the shard's rows are written
+    int64_t *rank;                  // row_hi - row_lo
+    uint8_t *ext; uint64_t ext_cap;
+    void *spill; uint64_t spill_cap;        // entries of 32 bytes
+    uint64_t ext_total, spill_total;        // out (the need, when a capacity was too small)
+    int max_len;                            // out
+};
+// raw view of device-resident records for the assembly
+struct OvDevView {
+    const void *pack; const int64_t *rank; const uint8_t *ext; const void *spill;
+    uint64_t n_seq, ext_total, spill_total;
+};
 }  // namespace fmg
 
 struct fmg_index_s;
 struct OvHost;
 // Overlap records of every sequence of the index: into `dev` (kept in HBM for the device unitig assembly) and / or
 // into `host` (pinned arrays for the host walk); either may be nullptr.  Returns 0, or -1 on a CUDA error.
-int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, fmg::OvDevice *dev, OvHost *host);
+int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, fmg::OvDevice *dev, OvHost *host, fmg::OvShard *shard = nullptr);
 // unitig_gpu.cu: unitigs from the device-resident records; 0 = written, 1 = the link graph is irregular (cycles or
 // one-sided links: the caller falls back to the host walk, which reproduces the reference's seed order), -1 = error
-int fmg_unitig_device(const fmg_index_s *idx, const fmg::OvDevice &D, int min_match, const char *out_path, uint64_t *n_unitigs);
+int fmg_unitig_device(const fmg_index_s *idx, const fmg::OvDevView &D, int min_match, const char *out_path, uint64_t *n_unitigs);
 
 // Pinned host arrays of the whole-index pass and of the device unitig assembly.  Page-locking gigabytes costs more
 // than the pass itself, so the arrays stay with the index handle and are reused (grown on demand) by the next call.

@@ -203,8 +203,8 @@ int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *
     return out ? fmg_overlap_pass(idx, min_match, max_len, nullptr, out) : -1;
 }
 
-int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevice *dev_out, OvHost *out) {
-    if (!idx || (!out && !dev_out)) return -1;
+int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevice *dev_out, OvHost *out, OvShard *shard) {
+    if (!idx || (!out && !dev_out && !shard) || (shard && (out || dev_out))) return -1;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] no CUDA device available; libfermi_b200 has no CPU path\n", __func__);
@@ -242,6 +242,9 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
     // fmg_verbose >= 4: 8 events per batch = [start | (unused) | retrieve + contained | neighbours | left chain | left lists | pack | seed rows]
     std::vector<cudaEvent_t> phase_ev;
     uint64_t ext_cap = std::max<uint64_t>(n_seq * 24, 1 << 20), spill_cap = std::max<uint64_t>(n_seq, 1 << 16);
+    const uint64_t row_lo = shard ? shard->row_lo : 0, row_hi = shard ? shard->row_hi : n_seq;
+    if (shard) { ext_cap = shard->ext_cap; spill_cap = shard->spill_cap; }
+    if (row_lo > row_hi || row_hi > n_seq || (row_lo & 1)) return -1;          // shards start at a read (even row)
     OV_TRY(H.ctrl.need(OVC_N * 8));
     unsigned long long *h_ctrl = static_cast<unsigned long long *>(H.ctrl.p);
     Dev d_pack, d_ret, d_extout, d_spill, d_ctrl, d_seq, d_len, d_rec, d_ext, d_cnt, d_slots, d_P0, d_np0, d_A, d_B, d_cat, d_odd[2];
@@ -249,8 +252,16 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
         const int pcap = std::max(8, max_len - min_match + 8) * pcap_mul;
         const size_t esz = wide ? 32 : 16;
         const uint64_t n_odd_all = n_seq / 2;
-        OV_TRY(d_pack.alloc(n_seq * sizeof(OvPack))); OV_TRY(d_ret.alloc(n_seq * 8));
-        OV_TRY(d_extout.alloc(ext_cap)); OV_TRY(d_spill.alloc(spill_cap * 32)); OV_TRY(d_ctrl.alloc(OVC_N * 8));
+        if (!shard) {
+            OV_TRY(d_pack.alloc(n_seq * sizeof(OvPack))); OV_TRY(d_ret.alloc(n_seq * 8));
+            OV_TRY(d_extout.alloc(ext_cap)); OV_TRY(d_spill.alloc(spill_cap * 32));
+        }
+        OV_TRY(d_ctrl.alloc(OVC_N * 8));
+        // the four output arrays: the pass's own, or the caller's shard buffers (rank[] is addressed by absolute row)
+        OvPack *o_pack = shard ? static_cast<OvPack *>(shard->pack) : d_pack.as<OvPack>();
+        int64_t *o_ret = shard ? shard->rank - row_lo : d_ret.as<int64_t>();
+        uint8_t *o_ext = shard ? shard->ext : d_extout.as<uint8_t>();
+        uint4 *o_spill = shard ? static_cast<uint4 *>(shard->spill) : d_spill.as<uint4>();
         OV_TRY(d_seq.alloc((size_t)nb_max * max_len)); OV_TRY(d_len.alloc((size_t)nb_max * 4)); OV_TRY(d_rec.alloc((size_t)nb_max * OV_NREC * 8));
         OV_TRY(d_ext.alloc((size_t)nb_max * max_len)); OV_TRY(d_cnt.alloc((size_t)(nb_max + 1) * 4)); OV_TRY(d_slots.alloc((size_t)nb_max * nei_cap * 32));
         OV_TRY(d_P0.alloc((size_t)nb_max * pcap * esz)); OV_TRY(d_np0.alloc((size_t)nb_max * 4));
@@ -260,10 +271,10 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
         if (out) OV_TRY(H.seq.need(std::max<uint64_t>(n_odd_all, 1) * (uint64_t)max_len));
         OV_TRY(cudaMemsetAsync(d_ctrl.p, 0, OVC_N * 8, s_run));
         // records of sequences that overflow are not written: keep the array defined
-        OV_TRY(cudaMemsetAsync(d_pack.p, 0, n_seq * sizeof(OvPack), s_run));
+        if (!shard) OV_TRY(cudaMemsetAsync(d_pack.p, 0, n_seq * sizeof(OvPack), s_run));
         int64_t b = 0;
-        for (uint64_t row0 = 0; row0 < n_seq; row0 += batch, ++b) {
-            const int64_t m = (int64_t)std::min<uint64_t>(batch, n_seq - row0);
+        for (uint64_t row0 = row_lo; row0 < row_hi; row0 += batch, ++b) {
+            const int64_t m = (int64_t)std::min<uint64_t>(batch, row_hi - row0);
             cudaEvent_t *ev = nullptr;
             {
                 const size_t e0 = phase_ev.size();
@@ -274,17 +285,17 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
             }
             OverlapArgs O;
             O.ix = idx->view; O.min_match = min_match; O.mode = 0; O.n = m; O.seq = d_seq.as<uint8_t>(); O.len = d_len.as<int32_t>(); O.max_len = max_len;
-            O.ids = nullptr; O.first = row0; O.step = 1; O.ret = d_ret.as<int64_t>() + row0;
+            O.ids = nullptr; O.first = row0; O.step = 1; O.ret = o_ret + row0;
             O.P0 = d_P0.p; O.pcap = pcap; O.np0 = d_np0.as<int32_t>(); O.A = d_A.p; O.B = d_B.p; O.cap = cap; O.cat = d_cat.as<int32_t>();
             O.rec = d_rec.as<int64_t>(); O.nei = d_slots.as<uint4>(); O.nei_cap = nei_cap; O.nei_cnt = d_cnt.as<uint32_t>();
             O.ext = d_ext.as<uint8_t>(); O.next = nullptr;
             unsigned long long *c2 = d_ctrl.as<unsigned long long>() + OVC_NEXT;       // OVC_NEXT, OVC_NEXT2: the work counters
             OV_TRY(wide ? launch_phases<uint64_t>(O, grid, c2, s_run, ev ? ev + 1 : nullptr) : launch_phases<uint32_t>(O, grid, c2, s_run, ev ? ev + 1 : nullptr));
             PackArgs P;
-            P.n = m; P.rec = d_rec.as<int64_t>(); P.ret = d_ret.as<int64_t>() + row0; P.len = d_len.as<int32_t>(); P.nei_cnt = d_cnt.as<uint32_t>();
+            P.n = m; P.rec = d_rec.as<int64_t>(); P.ret = o_ret + row0; P.len = d_len.as<int32_t>(); P.nei_cnt = d_cnt.as<uint32_t>();
             P.nei_slots = d_slots.as<uint4>(); P.nei_cap = nei_cap; P.ext = d_ext.as<uint8_t>(); P.max_len = max_len;
-            P.pack = d_pack.as<OvPack>(); P.n_seq = n_seq; P.ext_out = d_extout.as<uint8_t>(); P.ext_cap = ext_cap;
-            P.spill_out = d_spill.as<uint4>(); P.spill_cap = spill_cap; P.ctrl = d_ctrl.as<unsigned long long>();
+            P.pack = o_pack; P.n_seq = n_seq; P.ext_out = o_ext; P.ext_cap = ext_cap;
+            P.spill_out = o_spill; P.spill_cap = spill_cap; P.ctrl = d_ctrl.as<unsigned long long>();
             k_ov_pack<<<(unsigned)((m + 255) / 256), 256, 0, s_run>>>(P);
             ++g_launches;
             OV_TRY(cudaGetLastError());
@@ -334,6 +345,10 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
             if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] cannot represent the overlap records (flags %llx, cap=%d, nei_cap=%d)\n", __func__, flags, cap, nei_cap);
             return -1;
         }
+        if (shard && (flags & (OVF_EXT | OVF_SPILL))) {        // the caller owns these buffers: report the need
+            shard->ext_total = h_ctrl[OVC_EXT] + (h_ctrl[OVC_EXT] >> 3) + 4096; shard->spill_total = h_ctrl[OVC_SPILL] + (h_ctrl[OVC_SPILL] >> 3) + 256;
+            return 1;
+        }
         if (too_long) { max_len = (int)too_long + 8; cap = std::max(cap, 4 * max_len); }
         if (flags & OVF_LIST) cap *= 4, pcap_mul *= 4;
         if (flags & (OVF_LIST | OVF_NEI)) nei_cap *= 4;
@@ -362,6 +377,7 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
         out->ext = static_cast<const uint8_t *>(H.ext.p); out->spill = static_cast<const fmg_intv_t *>(H.spill.p);
         out->ext_total = ext_total; out->spill_total = spill_total;
     }
+    if (shard) { shard->ext_total = ext_total; shard->spill_total = spill_total; shard->max_len = max_len; }
     if (dev_out) {
         dev_out->pack.swap(d_pack); dev_out->rank.swap(d_ret); dev_out->ext.swap(d_extout); dev_out->spill.swap(d_spill);
         dev_out->n_seq = n_seq; dev_out->ext_total = ext_total; dev_out->spill_total = spill_total; dev_out->max_len = max_len;

@@ -243,7 +243,7 @@ void put_i64(std::string &o, int64_t v) { char b[24]; o.append(b, std::snprintf(
 
 }  // namespace
 
-int fmg_unitig_device(const fmg_index_s *idx, const OvDevice &D, int min_match, const char *out_path, uint64_t *n_unitigs) {
+int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match, const char *out_path, uint64_t *n_unitigs) {
     const uint64_t n = D.n_seq;
     if (n_unitigs) *n_unitigs = 0;
     if (n == 0 || n >= kNone) return 1;
@@ -260,7 +260,7 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevice &D, int min_match, 
     UG_TRY(H.ctrl.need(64));
     uint32_t *h_flags = H.ctrl.as<uint32_t>();
     G g;
-    g.pack = D.pack.as<OvPack>(); g.spill = D.spill.as<uint4>(); g.ext = D.ext.as<uint8_t>(); g.rank_of_row = D.rank.as<int64_t>();
+    g.pack = static_cast<const OvPack *>(D.pack); g.spill = static_cast<const uint4 *>(D.spill); g.ext = D.ext; g.rank_of_row = D.rank;
     g.n = n; g.min_match = min_match;
     g.succ = d_succ.as<uint32_t>(); g.pred = d_pred.as<uint32_t>(); g.row_of_rank = d_row.as<uint32_t>(); g.tail_of = d_tail.as<uint32_t>();
     g.flags = d_flags.as<uint32_t>(); g.counts = d_flags.as<unsigned long long>() + 1;
@@ -452,7 +452,8 @@ int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *o
             rc = fmg_overlap_pass(idx, min_match, max_len, &D, nullptr);
             if (rc != 0) return rc;
             const auto t1 = std::chrono::steady_clock::now();
-            rc = fmg_unitig_device(idx, D, min_match, out_path, n_unitigs);
+            const fmg::OvDevView V = {D.pack.p, D.rank.as<int64_t>(), D.ext.as<uint8_t>(), D.spill.p, D.n_seq, D.ext_total, D.spill_total};
+            rc = fmg_unitig_device(idx, V, min_match, out_path, n_unitigs);
             if (rc == 0 && fmg_verbose >= 3)
                 std::fprintf(stderr, "[M::%s] %llu sequences: overlap records %.3f s, unitig assembly + output %.3f s (GPU)\n", __func__,
                              (unsigned long long)D.n_seq, secs(t0, t1), secs(t1, std::chrono::steady_clock::now()));
@@ -471,6 +472,48 @@ int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *o
         std::fprintf(stderr, "[M::%s] %llu sequences: overlap records %.3f s (GPU, incl. copies), unitig walk + output %.3f s (host)\n", __func__,
                      (unsigned long long)R.n_seq, secs(t1, t2), secs(t2, std::chrono::steady_clock::now()));
     return rc;
+}
+
+// ---- multi-GPU: shards of the records in caller-owned device buffers (the caller runs the collective, e.g. NCCL through
+// torch.distributed: all-reduce of the disjointly filled pack array, all-gather of the rank / ext / spill shards)
+__global__ void __launch_bounds__(256) k_ov_rebase(OvPack *pack, const int64_t *__restrict__ rank, uint64_t n_rows, uint64_t ext_base, uint64_t spill_base) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows) return;
+    OvPack *p = pack + rank[t];
+    if (p->nnei == 1) p->ext_first += ext_base;
+    else if (p->nnei > 1) p->nx0 += spill_base;
+}
+
+int fmg_overlap_shard(const fmg_index_t *idx, int min_match, int max_len, uint64_t row_lo, uint64_t row_hi, void *d_pack, int64_t *d_rank,
+                      uint8_t *d_ext, uint64_t ext_cap, void *d_spill, uint64_t spill_cap, uint64_t totals[2]) {
+    if (!idx || !d_pack || !d_rank || !d_ext || !d_spill || !totals) return -1;
+    fmg::OvShard S;
+    S.row_lo = row_lo; S.row_hi = row_hi; S.pack = d_pack; S.rank = d_rank; S.ext = d_ext; S.ext_cap = ext_cap; S.spill = d_spill; S.spill_cap = spill_cap;
+    S.ext_total = S.spill_total = 0; S.max_len = 0;
+    const int rc = fmg_overlap_pass(idx, min_match, max_len, nullptr, nullptr, &S);
+    totals[0] = S.ext_total; totals[1] = S.spill_total;
+    return rc;
+}
+
+int fmg_overlap_rebase(const fmg_index_t *idx, void *d_pack, const int64_t *d_rank, uint64_t n_rows, uint64_t ext_base, uint64_t spill_base) {
+    if (!idx || !d_pack || !d_rank) return -1;
+    UG_TRY(cudaSetDevice(idx->device));
+    if (n_rows && (ext_base || spill_base)) {
+        k_ov_rebase<<<nblk(n_rows), 256>>>(static_cast<OvPack *>(d_pack), d_rank, n_rows, ext_base, spill_base);
+        ++g_launches;
+        UG_TRY(cudaGetLastError());
+    }
+    UG_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+int fmg_unitig_from_device(const fmg_index_t *idx, int min_match, const void *d_pack, const int64_t *d_rank, const uint8_t *d_ext, uint64_t ext_total,
+                           const void *d_spill, uint64_t spill_total, const char *out_path, uint64_t *n_unitigs) {
+    if (!idx || !d_pack || !d_rank || !out_path) return -1;
+    UG_TRY(cudaSetDevice(idx->device));
+    UG_TRY(cudaDeviceSynchronize());
+    const fmg::OvDevView V = {d_pack, d_rank, d_ext, d_spill, idx->mcnt[1], ext_total, spill_total};
+    return fmg_unitig_device(idx, V, min_match, out_path, n_unitigs);
 }
 
 } // extern "C"

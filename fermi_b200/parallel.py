@@ -77,6 +77,73 @@ def unitig_distributed(idx, min_match, out_path, max_len, overlap_fn=None, group
     return None
 
 
+def unitig_distributed_device(idx, min_match, out_path, max_len=0, group=None):
+    """`fermi unitig` over all ranks with everything in HBM: every rank computes the packed overlap records of its range of BWT
+    rows on its GPU (fmg_overlap_shard), ONE exchange merges the shards -- an all-reduce(sum) of the rank-indexed 64-byte
+    record array, which the shards fill disjointly, and all-gathers of the rank / appended-base / fork-neighbour shards --
+    and rank 0 assembles the unitigs on its GPU (fmg_unitig_from_device) and writes the MAG file.  NCCL only.
+    Returns the number of unitigs on rank 0 (None elsewhere)."""
+    import ctypes as C
+    from ._lib import lib
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = _device()
+    L = lib()
+    n_seq = int(idx.mcnt[1])
+    lo, hi = shard_range(n_seq // 2, rank, world)             # shards of whole reads: rows 2i (read) and 2i+1 (reverse complement)
+    lo, hi = 2 * lo, (2 * hi if rank < world - 1 else n_seq)
+    m = hi - lo
+    pack = torch.zeros(n_seq * 8, dtype=torch.int64, device=dev)
+    rnk = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
+    ext_cap, spill_cap = max(32 * m, 1 << 16), max(2 * m, 1 << 12)
+    tot = (C.c_uint64 * 2)()
+    while True:
+        ext = torch.empty(ext_cap, dtype=torch.uint8, device=dev)
+        spill = torch.empty(spill_cap * 4, dtype=torch.int64, device=dev)
+        rc = L.fmg_overlap_shard(idx.h, int(min_match), int(max_len), lo, hi, pack.data_ptr(), rnk.data_ptr(), ext.data_ptr(), ext_cap,
+                                 spill.data_ptr(), spill_cap, tot)
+        if rc == 1:                                           # capacities too small: the call reports the need
+            pack.zero_()
+            ext_cap, spill_cap = max(ext_cap, int(tot[0])), max(spill_cap, int(tot[1]))
+            continue
+        if rc != 0:
+            raise RuntimeError("fermi_b200: fmg_overlap_shard failed (see stderr)")
+        break
+    sizes = torch.tensor([m, int(tot[0]), int(tot[1])], dtype=torch.int64, device=dev)
+    all_sizes = torch.empty(world * 3, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_sizes, sizes, group=group)                      # shard sizes
+    all_sizes = all_sizes.view(world, 3).cpu()
+    rows, exts, spills = all_sizes[:, 0].tolist(), all_sizes[:, 1].tolist(), all_sizes[:, 2].tolist()
+    if L.fmg_overlap_rebase(idx.h, pack.data_ptr(), rnk.data_ptr(), m, sum(exts[:rank]), sum(spills[:rank])) != 0:
+        raise RuntimeError("fermi_b200: fmg_overlap_rebase failed")
+    dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)                        # the records: disjoint shards, so sum = union
+
+    def gather(t, counts, width=1):
+        pad = max(max(counts), 1) * width
+        buf = torch.zeros(pad, dtype=t.dtype, device=dev)
+        buf[: counts[rank] * width] = t[: counts[rank] * width]
+        out = torch.empty(world * pad, dtype=t.dtype, device=dev)
+        dist.all_gather_into_tensor(out, buf, group=group)
+        return torch.cat([out[r * pad: r * pad + counts[r] * width] for r in range(world)]) if world > 1 else out[: counts[0] * width]
+
+    rank_all = gather(rnk, rows)
+    ext_all = gather(ext, exts)
+    spill_all = gather(spill, spills, 4)
+    n = None
+    if rank == 0:
+        nu = C.c_uint64()
+        rc = L.fmg_unitig_from_device(idx.h, int(min_match), pack.data_ptr(), rank_all.data_ptr(), ext_all.data_ptr() if len(ext_all) else 0,
+                                      sum(exts), spill_all.data_ptr() if len(spill_all) else 0, sum(spills), str(out_path).encode(), C.byref(nu))
+        if rc == 1:                                           # irregular link graph: the single-GPU path with the host walk
+            from . import api
+            n = api.fm6_unitig(idx, min_match, out_path, max_len)
+        elif rc != 0:
+            raise RuntimeError("fermi_b200: fmg_unitig_from_device failed")
+        else:
+            n = int(nu.value)
+    torch.cuda.synchronize()
+    return n
+
+
 def allgather_counts(n_local, group=None):
     """per-rank unit counts -> (counts, exclusive offsets): global numbering of sharded SMEM results."""
     world = dist.get_world_size(group)

@@ -128,6 +128,23 @@ int fmg_unitig_assemble(uint64_t n_seq, int max_len, int min_match, const int64_
  * equals that of the reference after canonicalisation. max_len 0 = estimate. */
 int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *out_path, uint64_t *n_unitigs);
 
+/* Multi-GPU `fermi unitig`: the sequences (BWT rows) are sharded over the GPUs the way fm6_unitig stripes its threads
+ * (unitig.c:394-404), every GPU holding the whole index.  All pointers are DEVICE pointers owned by the caller, who also runs
+ * the one exchange of the path (fermi_b200/parallel.py does it with NCCL through torch.distributed):
+ *   fmg_overlap_shard   records of rows [row_lo, row_hi) (row_lo even): d_pack = n_seq x 64-byte records indexed by sequence rank,
+ *                       zeroed by the caller, only this shard's entries are written; d_rank[row - row_lo] = rank of the row;
+ *                       d_ext / d_spill (32-byte entries) = appended bases / neighbour lists of forks, addressed by the records with
+ *                       shard-local offsets; totals = {ext bytes, spill entries} used.  Returns 1 when ext_cap / spill_cap are too
+ *                       small (totals = the need).
+ *   fmg_overlap_rebase  adds this shard's bases (exclusive prefix sums of all shards' totals) to the offsets in its records
+ *   -- all-reduce(sum) of d_pack (disjointly filled), all-gather of d_rank, d_ext, d_spill in rank order --
+ *   fmg_unitig_from_device  unitig assembly on one GPU from the merged arrays; 0 = MAG written, 1 = irregular link graph (run fmg_unitig) */
+int fmg_overlap_shard(const fmg_index_t *idx, int min_match, int max_len, uint64_t row_lo, uint64_t row_hi, void *d_pack, int64_t *d_rank,
+                      uint8_t *d_ext, uint64_t ext_cap, void *d_spill, uint64_t spill_cap, uint64_t totals[2]);
+int fmg_overlap_rebase(const fmg_index_t *idx, void *d_pack, const int64_t *d_rank, uint64_t n_rows, uint64_t ext_base, uint64_t spill_base);
+int fmg_unitig_from_device(const fmg_index_t *idx, int min_match, const void *d_pack, const int64_t *d_rank, const uint8_t *d_ext, uint64_t ext_total,
+                           const void *d_spill, uint64_t spill_total, const char *out_path, uint64_t *n_unitigs);
+
 /* fm6_seqsort (seqsort.c:37-70) / `fermi seqrank`: sorted[mcnt[1]] exactly as the reference fills it (fm6_retrieve, exact.c:100-127,
  * of every even BWT row on the GPU: sorted[rank] = row << 2 | contained << 1 | duplicate); stats (may be NULL) = #zeros,
  * #contained, #duplicates as fm6_seqsort reports them.  The array is what `fermi unitig -r` / `fermi remap -r` load. */

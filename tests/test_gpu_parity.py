@@ -199,6 +199,53 @@ def test_unitig_20k_reads_vs_reference_binary(fb, tmp_path, monkeypatch, err, co
     idx.close()
 
 
+@pytest.mark.parametrize("err,shards", [(0.0, 2), (0.01, 3)])
+def test_sharded_records_merge_to_the_single_gpu_unitigs(fb, tmp_path, err, shards):
+    """The multi-GPU data path on one GPU: the records of row shards (fmg_overlap_shard) in separate device buffers, offsets
+    rebased, the record arrays merged by summation and the side arrays by concatenation -- what the NCCL all-reduce and
+    all-gather of fermi_b200.parallel.unitig_distributed_device do -- then fmg_unitig_from_device == fm6_unitig."""
+    import ctypes as C
+    import torch
+    from fermi_b200._lib import lib
+    from fermi_b200.parallel import shard_range
+    L = lib()
+    genome = fb.synth_genome(81, 300000)
+    reads = fb.synth_reads(82, genome, 30000, 100, err)
+    idx = fb.FmdIndex(fb.fm_build(fb.fmd_text(reads), 0), 0)
+    n_seq = int(idx.fmd.mcnt[1])
+    dev = torch.device("cuda", 0)
+    packs, ranks, exts, spills, tots = [], [], [], [], []
+    for r in range(shards):
+        lo, hi = shard_range(n_seq // 2, r, shards)
+        lo, hi = 2 * lo, 2 * hi
+        pack = torch.zeros(n_seq * 8, dtype=torch.int64, device=dev)
+        rnk = torch.empty(hi - lo, dtype=torch.int64, device=dev)
+        ext_cap, spill_cap = 64, 8                                     # too small on purpose: the call must report the need
+        tot = (C.c_uint64 * 2)()
+        for attempt in range(3):
+            ext = torch.empty(ext_cap, dtype=torch.uint8, device=dev)
+            spill = torch.empty(spill_cap * 4, dtype=torch.int64, device=dev)
+            rc = L.fmg_overlap_shard(idx.h, 50, 0, lo, hi, pack.data_ptr(), rnk.data_ptr(), ext.data_ptr(), ext_cap, spill.data_ptr(), spill_cap, tot)
+            if rc != 1:
+                break
+            pack.zero_()
+            ext_cap, spill_cap = int(tot[0]), int(tot[1])
+        assert rc == 0 and attempt == 1
+        assert L.fmg_overlap_rebase(idx.h, pack.data_ptr(), rnk.data_ptr(), hi - lo, sum(t[0] for t in tots), sum(t[1] for t in tots)) == 0
+        packs.append(pack); ranks.append(rnk); exts.append(ext[: int(tot[0])]); spills.append(spill[: 4 * int(tot[1])]); tots.append((int(tot[0]), int(tot[1])))
+    pack = torch.stack(packs).sum(0)
+    rank_all, ext_all, spill_all = torch.cat(ranks), torch.cat(exts), torch.cat(spills)
+    assert sorted(rank_all.cpu().tolist()) == list(range(n_seq))
+    out, single = str(tmp_path / "m.mag"), str(tmp_path / "s.mag")
+    nu = C.c_uint64()
+    rc = L.fmg_unitig_from_device(idx.h, 50, pack.data_ptr(), rank_all.data_ptr(), ext_all.data_ptr(), len(ext_all), spill_all.data_ptr() if len(spill_all) else 0,
+                                  len(spill_all) // 4, out.encode(), C.byref(nu))
+    assert rc == 0
+    n = fb.fm6_unitig(idx, 50, single)
+    assert nu.value == n and H.canonical_mag(H.parse_mag(open(out).read())) == H.canonical_mag(H.parse_mag(open(single).read()))
+    idx.close()
+
+
 @pytest.mark.skipif(H.ref_fermi_binary() is None, reason="oracle/_ref/fermi did not travel with the repo")
 @pytest.mark.parametrize("err,dup", [(0.0, 0), (0.01, 300)])
 def test_seqrank_equals_reference_seqsort(fb, tmp_path, monkeypatch, err, dup):

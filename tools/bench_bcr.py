@@ -16,6 +16,7 @@ ap.add_argument("--len", type=int, default=150)
 ap.add_argument("--cov", type=float, default=30.0)
 ap.add_argument("--ref-reads", type=int, default=500000)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--fmd", action="store_true", help="also time BCR + RLD encoding on the GPU (`ropebwt | recode` in one step)")
 a = ap.parse_args()
 L = a.len | 1 if False else a.len
 genome = fb.synth_genome(61, int(a.reads * L / a.cov))
@@ -32,6 +33,12 @@ for it in range(2):
         if a.check:
             res["equals_suffix_sort"] = bool(np.array_equal(b.bwt(), fb.fm_build_bwt(fb.fmd_text(reads), 0)))
     b.close()
+if a.fmd:
+    b = fb.Bcr(0)
+    b.append_batch(both)
+    t = time.time(); e = b.build_fmd(); t_fmd = time.time() - t
+    res.update({"build_fmd_s": t_fmd, "fmd_bytes": int(e.n_bytes), "fmd_symbols_per_s": res["symbols"] / t_fmd})
+    b.close(); e.close()
 if a.ref_reads and H.ref_fermi_binary():
     fa = os.path.join(tempfile.gettempdir(), "bench_bcr.fa")
     with open(fa, "w") as fh:

@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--reads", type=int, default=1000000)
 ap.add_argument("--err", type=float, default=0.0)
 ap.add_argument("--check", action="store_true", help="compare with a single-GPU fm6_unitig on rank 0")
+ap.add_argument("--host-gather", action="store_true", help="the round-1 path: records to the host, all-gather, host walk on rank 0")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -26,12 +27,13 @@ if rank == 0:
 dist.barrier()
 idx = fb.FmdIndex(fb.Fmd.restore(fn), local)
 out = os.path.join(tempfile.gettempdir(), "unitig_multi.mag")
-for it in range(2):
+for it in range(3):
     dist.barrier(); torch.cuda.synchronize(); t = time.time()
-    n = parallel.unitig_distributed(idx, 50, out, 108)
+    n = parallel.unitig_distributed(idx, 50, out, 108) if a.host_gather else parallel.unitig_distributed_device(idx, 50, out)
     dist.barrier(); dt = time.time() - t
 if rank == 0:
-    res = {"n_gpus": world, "reads": a.reads, "unitigs": n, "seconds": dt, "reads_per_s": a.reads / dt}
+    res = {"n_gpus": world, "reads": a.reads, "err": a.err, "path": "host gather" if a.host_gather else "device (NCCL all-reduce + all-gather, GPU assembly)",
+           "unitigs": n, "seconds": dt, "reads_per_s": a.reads / dt}
     if a.check:
         import helpers as H
         single = out + ".single"
