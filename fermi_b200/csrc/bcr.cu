@@ -43,8 +43,9 @@ namespace {
         }                                                                                               \
     } while (0)
 
-constexpr int kTile = 2048;          // output symbols per block of the merge pass
-constexpr int kThreads = 256;        // 8 symbols per thread
+constexpr int kTile = 4096;          // output symbols per block of the merge pass
+constexpr int kThreads = 256;
+constexpr int kPer = kTile / kThreads;   // 16 symbols per thread: one 16-byte vector
 
 struct Vec4 { uint64_t v[4]; };      // occurrences of A,C,G,T
 struct Vec4Add { __host__ __device__ Vec4 operator()(const Vec4 &a, const Vec4 &b) const { Vec4 r; for (int i = 0; i < 4; ++i) r.v[i] = a.v[i] + b.v[i]; return r; } };
@@ -79,62 +80,99 @@ __global__ void k_bcr_iota(Item *item, uint64_t n) {
     if (k < n) { item[k].f = k; item[k].id = (uint32_t)k; item[k].pad = 0; }
 }
 
-__device__ __forceinline__ uint64_t lower_bound_f(const Item *item, uint64_t n, uint64_t q) {
-    uint64_t lo = 0, hi = n;
-    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (item[mid].f < q) lo = mid + 1; else hi = mid; }
-    return lo;
+// tile_lo[t] = first insert whose position falls into output tile t or later (the inserts are sorted by position): every
+// insert fills the entries between its predecessor's tile and its own -- one coalesced pass instead of a binary search
+// over the whole insert list at the start of every tile
+__global__ void k_bcr_bounds(const Item *__restrict__ item, uint64_t n_act, uint64_t n_tiles, uint64_t *__restrict__ tile_lo) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_act) return;
+    const uint64_t t1 = item[k].f / kTile;
+    const uint64_t t0 = k ? item[k - 1].f / kTile + 1 : 0;
+    for (uint64_t t = t0; t <= t1; ++t) tile_lo[t] = k;
+    if (k == n_act - 1) for (uint64_t t = t1 + 1; t <= n_tiles; ++t) tile_lo[t] = n_act;
 }
 
 // One tile of the new BWT: old symbols and inserts merged, the tile's A/C/G/T histogram, and for every insert
-// the number of equal symbols before it inside the tile.
+// the number of equal symbols before it inside the tile.  16 output symbols per thread: the old symbols a tile keeps are
+// one contiguous piece of the old array, staged in shared memory with aligned 16-byte loads; a thread whose 16 positions
+// hold no insert (most of them: one insert per pos symbols in cycle pos) copies 16 staged bytes with word operations, and
+// every thread writes one 16-byte vector.
+__device__ __forceinline__ uint64_t count_acgt(uint32_t w) {       // packed 4 x 16-bit counts of A,C,G,T among 4 symbol bytes
+    uint64_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t c = (w >> (8 * i)) & 0xffu;
+        if (c >= 1 && c <= 4) r += 1ull << (16 * (c - 1));
+    }
+    return r;
+}
+
 __global__ void __launch_bounds__(kThreads) k_bcr_merge(const uint8_t *__restrict__ old_bwt, uint64_t m_new, const Item *__restrict__ item,
-                                                        const uint8_t *__restrict__ sym, uint64_t n_act, uint8_t *__restrict__ new_bwt,
+                                                        const uint8_t *__restrict__ sym, const uint64_t *__restrict__ tile_lo, uint8_t *__restrict__ new_bwt,
                                                         Vec4 *__restrict__ tile_hist, uint32_t *__restrict__ rank_in_tile) {
-    __shared__ uint8_t s_sym[kTile], s_flag[kTile];
-    __shared__ uint64_t s_k[2];
+    __shared__ __align__(16) uint8_t s_sym[kTile];
+    __shared__ __align__(16) uint8_t s_src[kTile + 32];
+    __shared__ __align__(16) uint8_t s_flag[kTile];
     __shared__ uint32_t s_warp_ins[kThreads / 32];
     __shared__ uint64_t s_warp_cnt[kThreads / 32];
     const uint64_t q0 = (uint64_t)blockIdx.x * kTile;
     const int tid = threadIdx.x;
-    if (tid < 2) s_k[tid] = lower_bound_f(item, n_act, tid == 0 ? q0 : (q0 + kTile < m_new ? q0 + kTile : m_new));
-    for (int j = tid; j < kTile; j += kThreads) s_flag[j] = 0;
+    const uint64_t k_lo = tile_lo[blockIdx.x], k_hi = tile_lo[blockIdx.x + 1];
+    reinterpret_cast<uint4 *>(s_flag)[tid] = make_uint4(0, 0, 0, 0);
+    // the old symbols this tile keeps
+    const uint64_t src_lo = q0 - k_lo;            // old symbols before this tile
+    const uint64_t tile_len = q0 + kTile <= m_new ? (uint64_t)kTile : m_new - q0;
+    const uint64_t n_src = tile_len - (k_hi - k_lo);
+    const uint64_t a0 = src_lo & ~15ull;
+    const int shift = (int)(src_lo - a0);
+    for (uint64_t v = tid; v * 16 < n_src + shift; v += kThreads)
+        reinterpret_cast<uint4 *>(s_src)[v] = *reinterpret_cast<const uint4 *>(old_bwt + a0 + v * 16);
     __syncthreads();
-    const uint64_t k_lo = s_k[0], k_hi = s_k[1];
     for (uint64_t k = k_lo + tid; k < k_hi; k += kThreads) {
         const int j = (int)(item[k].f - q0);
         s_flag[j] = 1; s_sym[j] = sym[k];
     }
     __syncthreads();
-    // inserts before each thread's 8 positions
-    const int j0 = tid * 8;
-    uint32_t my_ins = 0;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) my_ins += s_flag[j0 + t];
+    // inserts before each thread's 16 positions
+    const int j0 = tid * kPer;
+    const uint4 fl = reinterpret_cast<const uint4 *>(s_flag)[tid];
+    const uint32_t my_ins = (((fl.x + fl.y + fl.z + fl.w) * 0x01010101u) >> 24);      // flag bytes are 0/1: at most 16
     uint32_t incl = my_ins;
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
     if ((tid & 31) == 31) s_warp_ins[tid >> 5] = incl;
     __syncthreads();
     uint32_t ins_before = incl - my_ins;
     for (int w = 0; w < (tid >> 5); ++w) ins_before += s_warp_ins[w];
-    // fill the old symbols
-    const uint64_t src0 = q0 - k_lo;            // old symbols before this tile
-    {
+    // the thread's 16 output symbols in four words
+    uint32_t o[4];
+    const bool full = q0 + j0 + kPer <= m_new;
+    if (my_ins == 0 && full) {                     // plain copy of 16 staged bytes starting at an arbitrary byte offset
+        const int sb = shift + j0 - (int)ins_before;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(s_src) + (sb >> 2);
+        const int sh = (sb & 3) * 8;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+        o[0] = __funnelshift_r(w0, w1, sh); o[1] = __funnelshift_r(w1, w2, sh);
+        o[2] = __funnelshift_r(w2, w3, sh); o[3] = __funnelshift_r(w3, w4, sh);
+    } else {
+        const uint4 sy = reinterpret_cast<const uint4 *>(s_sym)[tid];
+        const uint32_t syw[4] = {sy.x, sy.y, sy.z, sy.w}, flw[4] = {fl.x, fl.y, fl.z, fl.w};
         uint32_t ib = ins_before;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
+        for (int t = 0; t < kPer; ++t) {
             const int j = j0 + t;
+            uint32_t c = 7;
             if (q0 + j < m_new) {
-                if (s_flag[j]) ++ib;
-                else s_sym[j] = old_bwt[src0 + (uint64_t)(j - ib)];
-            } else s_sym[j] = 7;
+                if ((flw[t >> 2] >> (8 * (t & 3))) & 1u) { c = (syw[t >> 2] >> (8 * (t & 3))) & 0xffu; ++ib; }
+                else c = s_src[shift + (j - (int)ib)];
+            }
+            if ((t & 3) == 0) o[t >> 2] = 0;
+            o[t >> 2] |= c << (8 * (t & 3));
         }
     }
-    // packed A/C/G/T counts of the thread's 8 symbols (4 x 16 bit) and their block-wide exclusive prefix
-    uint64_t my_cnt = 0;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) { const uint32_t c = s_sym[j0 + t]; if (c >= 1 && c <= 4) my_cnt += 1ull << (16 * (c - 1)); }
+    // packed A/C/G/T counts of the thread's symbols (4 x 16 bit) and their block-wide exclusive prefix
+    const uint64_t my_cnt = count_acgt(o[0]) + count_acgt(o[1]) + count_acgt(o[2]) + count_acgt(o[3]);
     uint64_t cincl = my_cnt;
-    for (int o = 1; o < 32; o <<= 1) { const uint64_t v = __shfl_up_sync(0xffffffffu, cincl, o); if ((tid & 31) >= o) cincl += v; }
+    for (int q = 1; q < 32; q <<= 1) { const uint64_t v = __shfl_up_sync(0xffffffffu, cincl, q); if ((tid & 31) >= q) cincl += v; }
     if ((tid & 31) == 31) s_warp_cnt[tid >> 5] = cincl;
     __syncthreads();
     uint64_t cnt_before = cincl - my_cnt;
@@ -146,23 +184,23 @@ __global__ void __launch_bounds__(kThreads) k_bcr_merge(const uint8_t *__restric
         tile_hist[blockIdx.x] = h;
     }
     // rank of every insert among equal symbols inside the tile
-    {
+    if (my_ins) {
+        const uint32_t flw[4] = {fl.x, fl.y, fl.z, fl.w};
         uint64_t run = cnt_before;
         uint32_t ib = ins_before;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const int j = j0 + t;
-            const uint32_t c = s_sym[j];
-            if (s_flag[j]) {
+        for (int t = 0; t < kPer; ++t) {
+            const uint32_t c = (o[t >> 2] >> (8 * (t & 3))) & 0xffu;
+            if ((flw[t >> 2] >> (8 * (t & 3))) & 1u) {
                 rank_in_tile[k_lo + ib] = (c >= 1 && c <= 4) ? (uint32_t)((run >> (16 * (c - 1))) & 0xffff) : 0u;
                 ++ib;
             }
             if (c >= 1 && c <= 4) run += 1ull << (16 * (c - 1));
         }
     }
-    // write the tile (8 bytes per thread)
-    if (q0 + j0 + 8 <= m_new) *reinterpret_cast<uint2 *>(new_bwt + q0 + j0) = *reinterpret_cast<const uint2 *>(s_sym + j0);
-    else for (int t = 0; t < 8; ++t) if (q0 + j0 + t < m_new) new_bwt[q0 + j0 + t] = s_sym[j0 + t];
+    // write the tile (16 bytes per thread)
+    if (full) *reinterpret_cast<uint4 *>(new_bwt + q0 + j0) = make_uint4(o[0], o[1], o[2], o[3]);
+    else for (int t = 0; t < kPer; ++t) if (q0 + j0 + t < m_new) new_bwt[q0 + j0 + t] = (uint8_t)(o[t >> 2] >> (8 * (t & 3)));
 }
 
 // LF mapping of every insert: position of the extended suffix in the next cycle's BWT (bcr.c:442 + set_bwt bookkeeping)
@@ -207,14 +245,15 @@ static int bcr_build_device(fmg_bcr_s *b) {
     const uint64_t total = b->seq.size() + n_seq;
     if (n_seq == 0) { b->built = true; return 0; }
     if (n_seq >= 0xffffffffull) { if (fmg_verbose >= 1) std::fprintf(stderr, "[E::fmg_bcr_build] more than 2^32-1 sequences\n"); return -1; }
-    DevBuf d_seq, d_off, d_bwt[2], d_item[2], d_sym[2], d_rank, d_hist, d_pref, d_total, d_tmp;
+    DevBuf d_seq, d_off, d_bwt[2], d_item[2], d_sym[2], d_rank, d_hist, d_pref, d_total, d_tmp, d_lo;
     BCR_TRY(d_seq.reserve(b->seq.size())); BCR_TRY(d_off.reserve((n_seq + 1) * 8));
     BCR_TRY(cudaMemcpy(d_seq.p, b->seq.data(), b->seq.size(), cudaMemcpyHostToDevice));
     BCR_TRY(cudaMemcpy(d_off.p, b->off.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice));
-    BCR_TRY(d_bwt[0].reserve(total + 8)); BCR_TRY(d_bwt[1].reserve(total + 8));
+    BCR_TRY(d_bwt[0].reserve(total + 64)); BCR_TRY(d_bwt[1].reserve(total + 64));         // the merge stages whole 16-byte words
     BCR_TRY(d_item[0].reserve(n_seq * sizeof(Item))); BCR_TRY(d_item[1].reserve(n_seq * sizeof(Item)));
     BCR_TRY(d_sym[0].reserve(n_seq)); BCR_TRY(d_sym[1].reserve(n_seq)); BCR_TRY(d_rank.reserve(n_seq * 4));
     const uint64_t max_tiles = (total + kTile - 1) / kTile;
+    BCR_TRY(d_lo.reserve((max_tiles + 2) * 8));
     BCR_TRY(d_hist.reserve(max_tiles * sizeof(Vec4))); BCR_TRY(d_pref.reserve(max_tiles * sizeof(Vec4))); BCR_TRY(d_total.reserve(sizeof(Vec4)));
     size_t tmp_scan = 0, tmp_sort = 0;
     {
@@ -235,7 +274,8 @@ static int bcr_build_device(fmg_bcr_s *b) {
     for (int pos = 0; n_act > 0; ++pos) {
         const uint64_t m_new = m + n_act, n_tiles = (m_new + kTile - 1) / kTile;
         k_bcr_symbols<<<blocks_for(n_act, 256), 256>>>(items.Current(), n_act, d_seq.as<uint8_t>(), d_off.as<uint64_t>(), pos, syms.Current()); ++g_launches;
-        k_bcr_merge<<<(unsigned)n_tiles, kThreads>>>(d_bwt[cur].as<uint8_t>(), m_new, items.Current(), syms.Current(), n_act, d_bwt[cur ^ 1].as<uint8_t>(),
+        k_bcr_bounds<<<blocks_for(n_act, 256), 256>>>(items.Current(), n_act, n_tiles, d_lo.as<uint64_t>()); ++g_launches;
+        k_bcr_merge<<<(unsigned)n_tiles, kThreads>>>(d_bwt[cur].as<uint8_t>(), m_new, items.Current(), syms.Current(), d_lo.as<uint64_t>(), d_bwt[cur ^ 1].as<uint8_t>(),
                                                      d_hist.as<Vec4>(), d_rank.as<uint32_t>()); ++g_launches;
         size_t need = d_tmp.cap;
         Vec4 zero{};
