@@ -23,6 +23,7 @@
 #include <atomic>
 #include <vector>
 #include <memory>
+#include <chrono>
 #include "fmd_host.hpp"
 #include "../../include/fermi_b200.h"
 
@@ -233,10 +234,9 @@ struct fmg_bcr_s {
     std::vector<uint8_t> seq;        // appended sequences, nt6 1..4
     std::vector<uint64_t> off{0};
     int max_len = 0;
-    std::vector<uint8_t> bwt;        // result (host), one nt6 byte per symbol
+    DevBuf d_bwt;                    // result: one nt6 byte per symbol, kept in HBM; copied out / RLD-encoded on request
     bool built = false;
-    bool want_fmd = false;           // encode the .fmd image on the device instead of copying the BWT out (fmg_bcr_fmd)
-    std::unique_ptr<fmg::FmdImage> img;
+    bool want_fmd = false;           // kept for callers of fmg_bcr_want_fmd (the image is encoded on request either way)
     uint64_t n_sym = 0;
 };
 
@@ -245,6 +245,8 @@ static int bcr_build_device(fmg_bcr_s *b) {
     const uint64_t total = b->seq.size() + n_seq;
     if (n_seq == 0) { b->built = true; return 0; }
     if (n_seq >= 0xffffffffull) { if (fmg_verbose >= 1) std::fprintf(stderr, "[E::fmg_bcr_build] more than 2^32-1 sequences\n"); return -1; }
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
     DevBuf d_seq, d_off, d_bwt[2], d_item[2], d_sym[2], d_rank, d_hist, d_pref, d_total, d_tmp, d_lo;
     BCR_TRY(d_seq.reserve(b->seq.size())); BCR_TRY(d_off.reserve((n_seq + 1) * 8));
     BCR_TRY(cudaMemcpy(d_seq.p, b->seq.data(), b->seq.size(), cudaMemcpyHostToDevice));
@@ -265,6 +267,7 @@ static int bcr_build_device(fmg_bcr_s *b) {
     }
     BCR_TRY(d_tmp.reserve(tmp_scan > tmp_sort ? tmp_scan : tmp_sort));
 
+    const double t_in = since();
     cub::DoubleBuffer<uint8_t> syms(d_sym[0].as<uint8_t>(), d_sym[1].as<uint8_t>());
     cub::DoubleBuffer<Item> items(d_item[0].as<Item>(), d_item[1].as<Item>());
     k_bcr_iota<<<blocks_for(n_seq, 256), 256>>>(items.Current(), n_seq); ++g_launches;
@@ -302,15 +305,14 @@ static int bcr_build_device(fmg_bcr_s *b) {
         if (fmg_verbose >= 4) std::fprintf(stderr, "[M::fmg_bcr_build] cycle %d: %llu symbols, %llu sequences still active\n", pos, (unsigned long long)m, (unsigned long long)n_act);
     }
     BCR_TRY(cudaGetLastError());
+    BCR_TRY(cudaDeviceSynchronize());
+    const double t_cycles = since();
     b->n_sym = m;
-    if (b->want_fmd) {
-        b->img.reset(new fmg::FmdImage);
-        if (fmg_rld_encode_device(d_bwt[cur].as<uint8_t>(), m, b->img.get()) != 0) return -1;
-    } else {
-        b->bwt.resize(m);
-        BCR_TRY(cudaMemcpy(b->bwt.data(), d_bwt[cur].p, m, cudaMemcpyDeviceToHost));
-    }
+    std::swap(b->d_bwt.p, d_bwt[cur].p); std::swap(b->d_bwt.cap, d_bwt[cur].cap);     // the BWT stays in HBM with the handle
     b->built = true;
+    if (fmg_verbose >= 3)
+        std::fprintf(stderr, "[M::fmg_bcr_build] %llu sequences, %llu symbols: allocation + copy in %.3f s, %d cycles %.3f s\n", (unsigned long long)n_seq,
+                     (unsigned long long)m, t_in, b->max_len + 1, t_cycles - t_in);
     return 0;
 }
 
@@ -365,32 +367,33 @@ int fmg_bcr_build(fmg_bcr_t *b) {
 
 int64_t fmg_bcr_size(const fmg_bcr_t *b) { return b && b->built ? (int64_t)b->n_sym : -1; }
 
-// ask fmg_bcr_build for the RLD-encoded .fmd image (encoded on the device) instead of the plain BWT
+// kept for source compatibility: the image is encoded on request from the BWT that stays in HBM
 int fmg_bcr_want_fmd(fmg_bcr_t *b, int on) { if (!b) return -1; b->want_fmd = on != 0; return 0; }
 
-// the image built by fmg_bcr_build after fmg_bcr_want_fmd(b, 1): `fermi ropebwt | fermi recode` in one step; the caller owns it
+// `fermi ropebwt | fermi recode` in one step: the BWT in HBM through the RLD encoder on the device; the caller owns the image
 fmg_fmd_t *fmg_bcr_fmd(fmg_bcr_t *b) {
-    if (!b || !b->built || !b->img) return nullptr;
+    if (!b || !b->built || !b->n_sym || cudaSetDevice(b->device) != cudaSuccess) return nullptr;
     fmg_fmd_t *e = new fmg_fmd_s;
-    e->img = std::move(*b->img);
-    b->img.reset();
+    if (fmg_rld_encode_device(b->d_bwt.as<uint8_t>(), b->n_sym, &e->img) != 0) { delete e; return nullptr; }
     return e;
 }
 
 int fmg_bcr_bwt(const fmg_bcr_t *b, uint8_t *bwt) {
-    if (!b || !b->built || b->bwt.size() != b->n_sym) return -1;
-    std::memcpy(bwt, b->bwt.data(), b->bwt.size());
+    if (!b || !b->built || cudaSetDevice(b->device) != cudaSuccess) return -1;
+    if (b->n_sym && cudaMemcpy(bwt, b->d_bwt.p, b->n_sym, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return 0;
 }
 
 // the byte run-length stream of bcr_itr_next / `fermi ropebwt -b` (ropebwt.c:127-144): bytes len<<3|sym, len <= 31
 int fmg_bcr_rle(const fmg_bcr_t *b, uint8_t **rle, int64_t *n) {
-    if (!b || !b->built || b->bwt.size() != b->n_sym) return -1;
+    if (!b || !b->built) return -1;
+    std::unique_ptr<uint8_t[]> w(new uint8_t[b->n_sym ? b->n_sym : 1]);
+    if (fmg_bcr_bwt(b, w.get()) != 0) return -1;
     std::vector<uint8_t> out;
-    const std::vector<uint8_t> &w = b->bwt;
-    for (size_t i = 0; i < w.size();) {
+    out.reserve(b->n_sym / 2 + 16);
+    for (size_t i = 0; i < b->n_sym;) {
         size_t j = i;
-        while (j < w.size() && w[j] == w[i] && j - i < 31) ++j;
+        while (j < b->n_sym && w[j] == w[i] && j - i < 31) ++j;
         out.push_back((uint8_t)((j - i) << 3 | w[i]));
         i = j;
     }
