@@ -239,7 +239,14 @@ __global__ void __launch_bounds__(256) k_emit_text(uint64_t total, const int32_t
 
 inline unsigned nblk(uint64_t n) { return (unsigned)((n + 255) / 256); }
 
-void put_i64(std::string &o, int64_t v) { char b[24]; o.append(b, std::snprintf(b, sizeof b, "%lld", (long long)v)); }
+void put_i64(std::string &o, int64_t v) {            // decimal digits without going through printf (several per unitig)
+    char b[24];
+    int n = 24;
+    uint64_t u = v < 0 ? 0 - (uint64_t)v : (uint64_t)v;
+    do { b[--n] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) b[--n] = '-';
+    o.append(b + n, 24 - n);
+}
 
 }  // namespace
 

@@ -133,7 +133,14 @@ struct Walker {
 };
 
 
-void append_i64(std::string &o, int64_t v) { char b[24]; o.append(b, std::snprintf(b, sizeof b, "%lld", (long long)v)); }
+void append_i64(std::string &o, int64_t v) {
+    char b[24];
+    int n = 24;
+    uint64_t u = v < 0 ? 0 - (uint64_t)v : (uint64_t)v;
+    do { b[--n] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) b[--n] = '-';
+    o.append(b + n, 24 - n);
+}
 
 // mag_v_write, mag.c:149-174
 void write_mag(std::string &o, const uint64_t k[2], int nsr, const std::vector<Nei> nei[2], const std::string &seq, const std::string &cov) {

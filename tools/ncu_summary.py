@@ -1,10 +1,10 @@
 #!/usr/bin/env python
-"""Print the handful of ncu raw-page metrics we track for one kernel capture.
-usage: tools/ncu_summary.py gpurun_out/prof_iter_raw.csv"""
+"""Print the handful of ncu raw-page metrics we track, one block per captured kernel.
+usage: tools/ncu_summary.py gpurun_out/prof_iter_raw.csv   (from `ncu -i X.ncu-rep --page raw --csv`)"""
 import csv
 import sys
 rows = list(csv.reader(open(sys.argv[1])))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units = rows[0], rows[1]
 KEYS = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
         'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed.sum',
@@ -15,6 +15,14 @@ KEYS = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'l1tex__data_pipe_lsu_wavefronts.sum',
         'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
         'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum']
-for h, u, v in zip(hdr, units, vals):
-    if h in KEYS or ('issue_stalled' in h and h.endswith('.ratio') and float(v or 0) > 0.1):
-        print("%-90s %-14s %s" % (h, u, v))
+for vals in rows[2:]:
+    if len(vals) != len(hdr):
+        continue
+    for h, u, v in zip(hdr, units, vals):
+        try:
+            big = 'issue_stalled' in h and h.endswith('.ratio') and float(v or 0) > 0.1
+        except ValueError:
+            big = False
+        if h in KEYS or big:
+            print("%-90s %-14s %s" % (h, u, v))
+    print()
