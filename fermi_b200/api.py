@@ -296,6 +296,11 @@ def fm6_ec_collect(idx, w=-1, min_occ=3):
     return out, (int(cnt[0]), int(cnt[1]))
 
 
+def ec_kmer_length(n_symbols):
+    """k-mer length fm6_ec_correct picks for an index of n_symbols (correct.c:313-318)."""
+    return int(lib().fmg_ec_kmer_length(int(n_symbols)))
+
+
 class Bcr:
     """bcr_t (bcr.h:43-49): append sequences, build the BWT on the GPU, read it back."""
 

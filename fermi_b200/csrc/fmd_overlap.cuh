@@ -1,7 +1,6 @@
 // Device-side core of the overlap path of `fermi unitig` (unitig.c:38-204):
-//   retrieve_one    fm_retrieve (exact.c:59-70): LF walk that spells one indexed sequence
-//   OvLane          per sequence: fm6_is_contained (unitig.c:77-91) -> fm6_get_nei (unitig.c:93-179)
-//                   -> check_left_simple (unitig.c:186-204), in four phases (see OvLane)
+//   OvLane          per sequence: fm_retrieve (exact.c:59-70) fused with fm6_is_contained (unitig.c:77-91) -> fm6_get_nei
+//                   (unitig.c:93-179) -> check_left_simple (unitig.c:186-204), in four phases (see OvLane)
 // Everything the unitig walk (unitig_unidir / unitig1, unitig.c:227-317) asks the index is a pure function
 // of ONE read: its right neighbours, the consensus extension towards them and the simple left check of a
 // unique neighbour.  The GPU computes that record for every sequence of the index in parallel; the walk
@@ -485,45 +484,6 @@ template <typename U, int PHASE>
 FMG_HD void overlap_chain(const OverlapArgs &A, int64_t t) {
     OvLane<U, false, PHASE> ln(A, 0);
     if (PHASE == 1) ln.phase_contained(t); else ln.phase_left1(t);
-}
-
-// ---------------------------------------------------------------------------------------------
-// fm_retrieve (exact.c:59-70): LF walk from sentinel rank x; one block load per base.
-// Writes the sequence in reading order to seq[t*max_len ..], its length to len[t] (clipped reads are
-// flagged by len[t] = -(true length)) and the returned k to ret[t].
-struct RetrieveArgs {
-    OccView ix;
-    int64_t n;
-    const uint64_t *ids;        // sentinel ranks, or nullptr for ids[t] = first + t*step
-    uint64_t first, step;
-    uint8_t *seq; int max_len;
-    int32_t *len;
-    int64_t *ret;
-};
-
-FMG_HD void retrieve_one(const RetrieveArgs &A, int64_t t) {
-    uint64_t k = A.ids ? A.ids[t] : A.first + (uint64_t)t * A.step;
-    uint8_t *out = A.seq + (size_t)t * A.max_len;
-    int n = 0;
-    for (;;) {
-        const Blk B = load_blk(A.ix, k);
-        uint32_t rel[6];
-        rank_rel(B, k, rel);                              // counts in [superblock_start, k)
-        const uint32_t w = ((uint32_t)k >> 5) & 3u, bit = (uint32_t)k & 31u;
-        const uint32_t p0 = w == 0 ? B.lo.v[4] : w == 1 ? B.lo.v[5] : w == 2 ? B.lo.v[6] : B.lo.v[7];
-        const uint32_t p1 = w == 0 ? B.hi.v[0] : w == 1 ? B.hi.v[1] : w == 2 ? B.hi.v[2] : B.hi.v[3];
-        const uint32_t p2 = w == 0 ? B.hi.v[4] : w == 1 ? B.hi.v[5] : w == 2 ? B.hi.v[6] : B.hi.v[7];
-        const int c = (int)((p0 >> bit & 1u) | (p1 >> bit & 1u) << 1 | (p2 >> bit & 1u) << 2);     // BWT[k]
-        // rank of c in BWT[0..k] is rel+1, so LF(k) = C[c] + rel (exact.c:66)
-        k = ld_u64(A.ix.cs + (k >> kSuperShift) * 8 + c) + pick6(rel, c);
-        if (c == 0 || c > 5) break;
-        if (n < A.max_len) out[n] = (uint8_t)c;
-        ++n;
-    }
-    A.ret[t] = (int64_t)k;
-    const int m = n < A.max_len ? n : A.max_len;
-    for (int a = 0, b = m - 1; a < b; ++a, --b) { const uint8_t x = out[a]; out[a] = out[b]; out[b] = x; }   // seq_reverse (unitig.c:285)
-    A.len[t] = n <= A.max_len ? n : -n;
 }
 
 } // namespace fmg
