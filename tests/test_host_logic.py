@@ -15,6 +15,23 @@ def _load(case):
     return np.load(os.path.join(H.GOLDEN_DIR, case + ".npz")), os.path.join(H.GOLDEN_DIR, case + ".fmd")
 
 
+def test_plain_c_client_links_and_runs(product_lib, tmp_path):
+    """include/fermi_b200.h is valid C99 and a C program (what fermi's own mains are) links every entry point and drives the
+    host-side container calls; tests/c_abi/abi_check.c also lists every declared symbol, checked against the header here."""
+    import subprocess
+    src = os.path.join(H.ROOT, "tests", "c_abi", "abi_check.c")
+    hdr = open(os.path.join(H.ROOT, "include", "fermi_b200.h")).read()
+    declared = set(re.findall(r"\b(fmg_[a-z0-9_]+)\s*\(", hdr))
+    listed = set(re.findall(r"\(anyfn_t\)(fmg_[a-z0-9_]+)", open(src).read()))
+    assert declared == listed, sorted(declared ^ listed)
+    exe = str(tmp_path / "abi_check")
+    libdir = os.path.join(H.ROOT, "fermi_b200", "lib")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + os.path.join(H.ROOT, "include"), "-o", exe, src,
+                    "-L" + libdir, "-lfermi_b200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe, str(tmp_path / "t.fmd")], stdout=subprocess.PIPE, check=True).stdout.decode()
+    assert out.startswith("ok %d symbols" % len(declared))
+
+
 def test_library_exports_every_declared_symbol(product_lib):
     hdr = open(os.path.join(H.ROOT, "include", "fermi_b200.h")).read()
     declared = set(re.findall(r"\b(fmg_[a-z0-9_]+)\s*\(", hdr))
