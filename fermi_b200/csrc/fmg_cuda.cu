@@ -401,6 +401,18 @@ fmg_smem_session_t *fmg_smem_session_create(const fmg_index_t *idx, int64_t max_
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_smem<uint32_t>, SMEM_BLOCK, 0);
     if (per_sm < 1) per_sm = 1;
     s->grid = idx->n_sm * per_sm;
+    // long queries (contigs, unitigs: fm6_remap, `exact` on assemblies): every lane needs 2 x (2 len + 2) candidate slots, so
+    // the lane count shrinks until the two lists fit a fixed share of HBM; the kernel hands out reads to however many lanes run
+    {
+        const size_t per_lane = (size_t)2 * s->cap * (s->wide ? 32 : 16), budget = (size_t)24 << 30;
+        const int64_t max_blocks = (int64_t)(budget / (per_lane * SMEM_BLOCK));
+        if (max_blocks < 1) {
+            if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] queries of %d bases need more candidate scratch than fits\n", __func__, max_len);
+            delete s;
+            return nullptr;
+        }
+        if (s->grid > max_blocks) s->grid = (int)max_blocks;
+    }
     s->n_lanes = s->grid * SMEM_BLOCK;
     const int64_t n_tiles = (max_reads + 1 + kScanTile - 1) / kScanTile;
     bool ok = false;

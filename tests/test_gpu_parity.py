@@ -154,6 +154,34 @@ def test_record_slot_overflow_is_rerun_not_truncated(fb, oracle, tmp_path):
     idx.close()
 
 
+@pytest.mark.timeout(180)
+def test_smem_long_queries_vs_oracle(fb, oracle, tmp_path):
+    """queries far longer than reads (contigs against a read index: what fm6_remap and `exact` on assemblies send): the lane count
+    shrinks so that the per-lane candidate lists fit, the records stay bit-exact."""
+    genome = fb.synth_genome(91, 400000)
+    reads = fb.synth_reads(92, genome, 40000, 100, 0.0)
+    fmd = fb.fm_build(fb.fmd_text(reads), 0)
+    fn = str(tmp_path / "r.fmd")
+    fmd.dump(fn)
+    idx = fb.FmdIndex(fmd, 0)
+    rng = np.random.RandomState(4)
+    contigs = []
+    for L in (200000, 60000, 15000, 100):
+        s0 = rng.randint(0, len(genome) - L)
+        c = genome[s0: s0 + L].copy()
+        sub = rng.randint(0, L, size=L // 300 + 1)                      # substitutions break the matches (an N as the first base of a
+        c[sub] = 1 + (c[sub] % 4)                                       # match is undefined behaviour in the reference: not used here)
+        contigs.append(c)
+    seq = np.concatenate(contigs)
+    off = np.concatenate([[0], np.cumsum([len(c) for c in contigs])]).astype(np.uint64)
+    h = oracle.load(fn)
+    orec, omo, _, _, _ = oracle.smem(h, seq, off, 0, 4)
+    rec, mo = fb.fm6_smem(idx, seq, off, 0)
+    assert len(rec) > 1000 and np.array_equal(mo, omo) and np.array_equal(rec, orec)
+    oracle.destroy(h)
+    idx.close()
+
+
 @pytest.mark.parametrize("case", golden_cases())
 def test_overlap_records_and_unitigs_match_reference(fb, case, tmp_path, monkeypatch):
     """the four overlap phases against the reference's fm_retrieve / fm6_is_contained / fm6_get_nei records, and the
