@@ -12,7 +12,9 @@
 #define SMEM_DEFAULT_OUT_CAP 64
 // overlap kernels: list-chasing phases (persistent lanes) and chain phases (one sequence per thread)
 #define OVLP_BLOCK 128
+#ifndef OVLP_MIN_BLOCKS
 #define OVLP_MIN_BLOCKS 4
+#endif
 #define OVCH_BLOCK 128
 
 struct fmg_fmd_s { fmg::FmdImage img; };
