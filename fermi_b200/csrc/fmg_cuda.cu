@@ -623,25 +623,35 @@ int fmg_smem_batch_into(const fmg_index_t *idx, int64_t n, const uint8_t *seq, c
     if (n <= 0) return 0;
     if (batch_reads <= 0) batch_reads = 1 << 20;
     batch_reads = std::min<int64_t>(batch_reads, n);
-    int max_len = 1;
     uint64_t max_bytes = 1;
     for (int64_t b = 0; b < n; b += batch_reads) {
         const int64_t e = std::min(n, b + batch_reads);
         max_bytes = std::max<uint64_t>(max_bytes, off[e] - off[b]);
     }
-    for (int64_t i = 0; i < n; ++i) max_len = std::max<int>(max_len, (int)(off[i + 1] - off[i]));
+    // The longest read sizes the per-lane candidate lists.  Scanning all n lengths up front would sit in front of the first
+    // kernel (10 ms for 10 M reads), so only the first batch is scanned here; every later batch is scanned just before it is
+    // issued, while the GPU works on its predecessors, and a longer read than the pipeline was built for rebuilds it.
+    auto batch_max_len = [&](int64_t b) {
+        int m = 1;
+        const int64_t lo = b * batch_reads, hi = std::min(n, lo + batch_reads);
+        for (int64_t i = lo; i < hi; ++i) m = std::max<int>(m, (int)(off[i + 1] - off[i]));
+        return m;
+    };
+    int max_len = batch_max_len(0);
 
     // one pipeline per index, rebuilt only when a call needs larger batches or longer reads
     std::lock_guard<std::mutex> guard(idx->pipe_lock);
-    if (idx->pipe && (idx->pipe->batch_reads < batch_reads || idx->pipe->max_len < max_len || idx->pipe->max_bytes < max_bytes)) {
-        fmg_pipe_destroy(idx->pipe);
-        idx->pipe = nullptr;
-    }
-    if (!idx->pipe) idx->pipe = pipe_create(idx, batch_reads, max_len, max_bytes);
-    if (!idx->pipe) return -1;
-    fmg_pipe_s &P = *idx->pipe;
-    cudaStream_t s_in = P.s_in, s_run = P.s_run, s_out = P.s_out;
-    BatchBuf *buf = P.buf;
+    auto ensure_pipe = [&](int need_len) -> bool {
+        if (idx->pipe && (idx->pipe->batch_reads < batch_reads || idx->pipe->max_len < need_len || idx->pipe->max_bytes < max_bytes)) {
+            fmg_pipe_destroy(idx->pipe);
+            idx->pipe = nullptr;
+        }
+        if (!idx->pipe) idx->pipe = pipe_create(idx, batch_reads, need_len, max_bytes);
+        return idx->pipe != nullptr;
+    };
+    if (!ensure_pipe(max_len)) return -1;
+    cudaStream_t s_in = idx->pipe->s_in, s_run = idx->pipe->s_run, s_out = idx->pipe->s_out;
+    BatchBuf *buf = idx->pipe->buf;
     int rc = -1;
     uint64_t total = 0;
     bool short_cap = false;
@@ -686,8 +696,20 @@ int fmg_smem_batch_into(const fmg_index_t *idx, int64_t n, const uint8_t *seq, c
         };
         bool fail = false;
         for (int64_t b = 0; b <= n_batches && !fail; ++b) {
+            bool drained = false;
+            if (b >= 1 && b < n_batches) {
+                const int ml = batch_max_len(b);
+                if (ml > idx->pipe->max_len) {
+                    // a longer read than any before: finish what is in flight, then rebuild the sessions for it
+                    if (drain(b - 1)) { fail = true; break; }
+                    drained = true;
+                    CUDA_TRY(cudaStreamSynchronize(s_out), fail = true; break);
+                    if (!ensure_pipe(ml)) { fail = true; break; }
+                    s_in = idx->pipe->s_in; s_run = idx->pipe->s_run; s_out = idx->pipe->s_out; buf = idx->pipe->buf;
+                }
+            }
             if (b < n_batches && issue(b)) { fail = true; break; }
-            if (b >= 1 && drain(b - 1)) { fail = true; break; }
+            if (b >= 1 && !drained && drain(b - 1)) { fail = true; break; }
         }
         if (fail) break;
         CUDA_TRY(cudaStreamSynchronize(s_out), break);

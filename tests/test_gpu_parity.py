@@ -115,7 +115,8 @@ def test_ragged_empty_and_multibatch(fb, oracle):
     reads = [g["q"][i % 300][: rng.randint(0, 101)] for i in range(3000)]
     reads[0] = reads[0][:0]
     reads[17] = g["q"][17][:1]
-    seq = np.concatenate(reads).astype(np.uint8)
+    reads[2900] = np.concatenate([g["q"][5], g["q"][6], g["q"][7][:37]])      # longer than anything before it: the pipeline, sized by
+    seq = np.concatenate(reads).astype(np.uint8)                               # the batches seen so far, must rebuild itself mid-call
     off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.uint64)
     idx = fb.FmdIndex(fb.Fmd.restore(fmd_path), 0)
     h = oracle.load(fmd_path)
