@@ -36,6 +36,7 @@ struct fmg_index_s {
     mutable std::mutex pipe_lock;
     // pinned host arrays of the last whole-index overlap pass (overlap.cu: fmg_overlap_all), reused between calls
     mutable fmg_ovcache_s *ovc = nullptr;
+    mutable std::mutex ov_lock;          // one overlap pass / unitig assembly at a time per index handle (they share ovc)
 };
 
 // occ_build.cu: build the occ blocks of `img` in the HBM of the current device; fills d_blocks/d_cs/n_blocks/bytes

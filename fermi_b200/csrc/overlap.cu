@@ -211,6 +211,7 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
         return -1;
     }
     OV_TRY(cudaSetDevice(idx->device));
+    std::lock_guard<std::mutex> ov_guard(idx->ov_lock);
     const uint64_t n_seq = idx->mcnt[1];
     if (max_len <= 0) max_len = (int)((idx->mcnt[0] - n_seq + n_seq - 1) / (n_seq ? n_seq : 1)) + 8;
     if (!idx->ovc) idx->ovc = new fmg_ovcache_s;

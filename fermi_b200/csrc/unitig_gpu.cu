@@ -24,6 +24,7 @@
 #include <unistd.h>
 #include <atomic>
 #include <chrono>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -255,6 +256,7 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
     if (n_unitigs) *n_unitigs = 0;
     if (n == 0 || n >= kNone) return 1;
     UG_TRY(cudaSetDevice(idx->device));
+    std::lock_guard<std::mutex> ov_guard(idx->ov_lock);
     const auto t0 = std::chrono::steady_clock::now();
     auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
     if (!idx->ovc) idx->ovc = new fmg_ovcache_s;
