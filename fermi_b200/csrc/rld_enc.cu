@@ -6,12 +6,9 @@
 // current block iff the payload bits used so far plus its width stay BELOW the payload size (rld.c:164), the payload
 // size depends on the header width (7 x u16, or 7 x u32 when the previous block held >= 0x8000 symbols, rld.c:119-124)
 // and on whether the block is the last of a 2^23-word chunk (one word less, rld.h:66).  So where block b+1 starts is a
-// function of where block b starts -- a serial chain over ~n/100 blocks.  It is cut into segments of kSeg runs that
-// are chased speculatively in parallel: every segment assumes an entry state (first run of a block, header width, block
-// number), chases its blocks, and hands its exit state to the next segment; rounds repeat until no segment's entry
-// changes.  Greedy packings started a few runs apart fall into step after a handful of blocks, so the fixpoint -- which is
-// exactly the serial result, by induction from segment 0 -- arrives after a few rounds.  Then one thread per block packs
-// its codes and header into registers and writes the 64 bytes.
+// function of where block b starts -- a serial chain over ~n/100 blocks.  It is resolved exactly by pointer doubling over
+// the runs (see k_jump0 .. k_fill_blocks below); then one thread per block packs its codes and header into registers and
+// writes the 64 bytes.
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 #include <cstdio>
@@ -42,7 +39,6 @@ extern std::atomic<uint64_t> g_launches;
 namespace {
 
 constexpr int kTile = 256 * 16;              // symbols per thread block in the run detection
-constexpr int kSeg = 4096;                   // runs per speculative segment
 constexpr uint64_t kChunkBlocks = 1ull << 20; // blocks per 2^23-word chunk (rld.h:9-10)
 
 __device__ __forceinline__ int ilog2_u32(uint32_t v) { return 31 - __clz(v); }
@@ -126,38 +122,82 @@ __device__ __forceinline__ uint64_t next_block(const Chain &c, uint64_t r, int h
     return lo;
 }
 
-struct SegState { uint64_t run; uint64_t blk; int h; };
+// ---- the chain by pointer doubling.  Almost every block has a 7 x u16 header and the full payload ("regular"): for those,
+// where the next block starts is a function of where this one starts alone, jump[r] = next_block(r) - r.  K rounds of
+// doubling give every run the start of the block 2^K blocks further on (as a distance, with a flag that is set when one of
+// those blocks holds >= 0x8000 symbols, i.e. changes the header width of its successor).  One warp then walks the chain in
+// groups of 2^K blocks -- one table look-up per regular group, block by block through a group with a flagged block or with
+// the shortened last block of a 2^23-word chunk (which is always the last block of its group) -- and finally one thread per
+// group fills in the block starts between two anchors with the exact rule.
+constexpr int kJumpLog = 10;
+constexpr uint64_t kGroup = 1ull << kJumpLog;     // divides kChunkBlocks
+constexpr uint32_t kBig = 1u << 31;
 
-// chase the blocks of one segment from its entry state; returns the exit state = entry of the next segment
-__device__ __forceinline__ SegState chase(const Chain &c, SegState s, uint64_t seg_end, uint64_t *bstart) {
-    while (s.run < seg_end) {
-        if (bstart) bstart[s.blk] = s.run;
-        const uint64_t nx = next_block(c, s.run, s.h, s.blk);
-        s.h = c.pos[nx] - c.pos[s.run] >= 0x8000;
-        s.run = nx;
-        ++s.blk;
-    }
-    return s;
+__global__ void __launch_bounds__(256) k_jump0(Chain c, uint32_t *__restrict__ jump) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > c.n_runs) return;
+    if (r == c.n_runs) { jump[r] = 0; return; }                  // the end of the chain is absorbing
+    const uint64_t nx = next_block(c, r, 0, 0);
+    jump[r] = (uint32_t)(nx - r) | (c.pos[nx] - c.pos[r] >= 0x8000 ? kBig : 0u);
 }
 
-// One round: segment s chases its blocks from its entry state (ent_run[s], ent_h[s]) numbered from blk0[s], records how many
-// it holds and hands its exit to segment s+1.  Block numbers only matter for the shortened last block of a chunk; they come
-// from a scan of n_blk between rounds.  A round that changes no entry and no count has reached the serial answer.
-__global__ void __launch_bounds__(128) k_seg_chase(Chain c, uint64_t n_seg, uint64_t *ent_run, uint8_t *ent_h, const uint64_t *__restrict__ blk0,
-                                                  uint64_t *n_blk, unsigned long long *changed, uint64_t *bstart) {
-    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_seg) return;
-    SegState e;
-    e.run = ent_run[s]; e.blk = blk0[s]; e.h = ent_h[s];
-    const uint64_t seg_end = min(c.n_runs, (s + 1) * (uint64_t)kSeg);
-    const SegState x = chase(c, e, seg_end, bstart);
-    if (bstart) return;
-    const uint64_t nb = x.blk - e.blk;
-    bool chg = false;
-    if (n_blk[s] != nb) { n_blk[s] = nb; chg = true; }
-    // slot n_seg holds the end of the chain
-    if (ent_run[s + 1] != x.run || ent_h[s + 1] != (uint8_t)x.h) { ent_run[s + 1] = x.run; ent_h[s + 1] = (uint8_t)x.h; chg = true; }
-    if (chg) atomicAdd(changed, 1ull);
+__global__ void __launch_bounds__(256) k_jump_double(uint64_t n_runs, const uint32_t *__restrict__ in, uint32_t *__restrict__ out) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_runs) return;
+    const uint32_t a = in[r], b = in[r + (a & ~kBig)];
+    out[r] = ((a & ~kBig) + (b & ~kBig)) | ((a | b) & kBig);
+}
+
+// next_block with the 32 lanes of a warp probing the <= 100 candidate ends at once (one round trip instead of seven)
+__device__ __forceinline__ uint64_t next_block_warp(const Chain &c, uint64_t r, int h, uint64_t b, int lane) {
+    const int words = ((b + 1) % kChunkBlocks == 0 ? 7 : 8) - (h ? kHeaderWords32 : kHeaderWords16);
+    const uint64_t limit = c.W[r] + (uint64_t)words * 64 - 1;
+    uint64_t best = r + 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint64_t t = r + 1 + (uint64_t)(q * 32 + lane);
+        const bool ok = t <= c.n_runs && t <= r + 100 && c.W[t] <= limit;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (m) best = r + 1 + (uint64_t)(q * 32 + (31 - __clz(m)));      // W is increasing: the fitting ends are a prefix
+    }
+    return best;
+}
+
+// anchors[g] = first run of block g * 2^K (bit 63: that block has a 7 x u32 header); *n_groups = number of anchors
+__global__ void __launch_bounds__(32) k_anchor_chase(Chain c, const uint32_t *__restrict__ jumpK, uint64_t *anchors, uint64_t *n_groups) {
+    const int lane = threadIdx.x;
+    uint64_t r = 0, g = 0;
+    int h = 0;
+    while (r < c.n_runs) {
+        if (lane == 0) anchors[g] = r | (uint64_t)h << 63;
+        const uint32_t j = jumpK[r];
+        if (h == 0 && !(j & kBig) && (g + 1) % (kChunkBlocks / kGroup) != 0) r += j;
+        else
+            for (uint64_t i = 0; i < kGroup && r < c.n_runs; ++i) {
+                const uint64_t nx = next_block_warp(c, r, h, g * kGroup + i, lane);
+                h = c.pos[nx] - c.pos[r] >= 0x8000;
+                r = nx;
+            }
+        ++g;
+    }
+    if (lane == 0) *n_groups = g;
+}
+
+// block starts of one group from its anchor with the exact rule; the last group reports how many blocks it holds
+__global__ void __launch_bounds__(128) k_fill_blocks(Chain c, const uint64_t *__restrict__ anchors, uint64_t n_groups, uint64_t *__restrict__ bstart,
+                                                    uint64_t *last_count, uint8_t *last_h) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    uint64_t r = anchors[g] & ~(1ull << 63), i = 0;
+    int h = (int)(anchors[g] >> 63);
+    for (; i < kGroup && r < c.n_runs; ++i) {
+        const uint64_t b = g * kGroup + i;
+        bstart[b] = r;
+        const uint64_t nx = next_block(c, r, h, b);
+        h = c.pos[nx] - c.pos[r] >= 0x8000;
+        r = nx;
+    }
+    if (g == n_groups - 1) { *last_count = i; *last_h = (uint8_t)h; }
 }
 
 // ---- one thread per block: header (counts of the previous block, rld.c:111-134) + codes, 64 bytes
@@ -254,47 +294,34 @@ int fmg_rld_encode_device(const uint8_t *d_bwt, uint64_t n, FmdImage *out) {
     c.W = d_W.as<uint64_t>(); c.pos = d_pos.as<uint64_t>(); c.n_runs = n_runs;
     const double t_runs = since(t0);
 
-    // ---- speculative segments until the entry states and block counts stop changing
-    const uint64_t n_seg = (n_runs + kSeg - 1) / kSeg;
-    Dev &d_ent = d_run[0], &d_blk0 = d_blk[0], &d_nblk = d_blk[1], &d_eh = d_h[0];
-    RE_TRY(d_ent.alloc((n_seg + 1) * 8)); RE_TRY(d_blk0.alloc((n_seg + 1) * 8)); RE_TRY(d_nblk.alloc((n_seg + 1) * 8));
-    RE_TRY(d_eh.alloc(n_seg + 1)); RE_TRY(d_chg.alloc(8));
-    {   // initial guess: every segment starts a block at its first run with a 16-bit header
-        std::vector<uint64_t> r0(n_seg + 1);
-        for (uint64_t s = 0; s <= n_seg; ++s) r0[s] = std::min<uint64_t>(s * kSeg, n_runs);
-        RE_TRY(cudaMemcpy(d_ent.p, r0.data(), (n_seg + 1) * 8, cudaMemcpyHostToDevice));
-        RE_TRY(cudaMemset(d_blk0.p, 0, (n_seg + 1) * 8));
-        RE_TRY(cudaMemset(d_nblk.p, 0, (n_seg + 1) * 8));
-        RE_TRY(cudaMemset(d_eh.p, 0, n_seg + 1));
+    // ---- the block chain: jump distances, K doublings, anchors every 2^K blocks, block starts
+    const uint64_t max_groups = n_runs / kGroup + 2;                     // every block holds at least one run
+    Dev &d_j0 = d_run[0], &d_j1 = d_run[1], &d_anchor = d_blk[0], &d_cnt = d_blk[1];
+    RE_TRY(d_j0.alloc((n_runs + 2) * 4)); RE_TRY(d_j1.alloc((n_runs + 2) * 4)); RE_TRY(d_anchor.alloc(max_groups * 8)); RE_TRY(d_cnt.alloc(64));
+    k_jump0<<<grid_for(n_runs + 1, 256), 256>>>(c, d_j0.as<uint32_t>());
+    uint32_t *ja = d_j0.as<uint32_t>(), *jb = d_j1.as<uint32_t>();
+    for (int k = 0; k < kJumpLog; ++k) {
+        k_jump_double<<<grid_for(n_runs + 1, 256), 256>>>(n_runs, ja, jb);
+        std::swap(ja, jb);
     }
-    size_t need3 = 0;
-    RE_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need3, d_nblk.as<uint64_t>(), d_blk0.as<uint64_t>(), n_seg + 1));
-    if (need3 > need) { RE_TRY(d_tmp.alloc(need3 + 256)); need = need3; }
-    int rounds = 0;
-    for (;; ++rounds) {
-        if (rounds > 4096) {
-            if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] the block chain did not settle after %d rounds\n", __func__, rounds);
-            return -2;
-        }
-        RE_TRY(cudaMemset(d_chg.p, 0, 8));
-        // entries are updated in place: a slot rewritten during this round is read by its owner now or in the next round, and the
-        // loop only ends after a round in which nothing was rewritten (then every read was of settled values)
-        k_seg_chase<<<grid_for(n_seg, 128), 128>>>(c, n_seg, d_ent.as<uint64_t>(), d_eh.as<uint8_t>(), d_blk0.as<uint64_t>(), d_nblk.as<uint64_t>(),
-                                                   d_chg.as<unsigned long long>(), nullptr);
-        ++g_launches;
-        unsigned long long chg = 0;
-        RE_TRY(cudaMemcpy(&chg, d_chg.p, 8, cudaMemcpyDeviceToHost));
-        if (chg == 0) break;
-        RE_TRY(cub::DeviceScan::ExclusiveSum(d_tmp.p, need3, d_nblk.as<uint64_t>(), d_blk0.as<uint64_t>(), n_seg + 1));
-        ++g_launches;
+    k_anchor_chase<<<1, 32>>>(c, ja, d_anchor.as<uint64_t>(), d_cnt.as<uint64_t>());
+    g_launches += kJumpLog + 2;
+    uint64_t n_groups = 0;
+    RE_TRY(cudaMemcpy(&n_groups, d_cnt.p, 8, cudaMemcpyDeviceToHost));
+    if (n_groups == 0 || n_groups > max_groups) {
+        if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] the block chain has an impossible length\n", __func__);
+        return -2;
     }
-    uint64_t n_blocks = 0;
-    RE_TRY(cudaMemcpy(&n_blocks, d_blk0.as<uint64_t>() + n_seg, 8, cudaMemcpyDeviceToHost));
-    uint8_t h_last = 0;
-    RE_TRY(cudaMemcpy(&h_last, d_eh.as<uint8_t>() + n_seg, 1, cudaMemcpyDeviceToHost));
-    RE_TRY(d_bstart.alloc((n_blocks + 1) * 8));
-    k_seg_chase<<<grid_for(n_seg, 128), 128>>>(c, n_seg, d_ent.as<uint64_t>(), d_eh.as<uint8_t>(), d_blk0.as<uint64_t>(), nullptr, nullptr, d_bstart.as<uint64_t>());
+    RE_TRY(d_bstart.alloc((n_groups * kGroup + 1) * 8));
+    k_fill_blocks<<<grid_for(n_groups, 128), 128>>>(c, d_anchor.as<uint64_t>(), n_groups, d_bstart.as<uint64_t>(), d_cnt.as<uint64_t>() + 1,
+                                                    reinterpret_cast<uint8_t *>(d_cnt.as<uint64_t>() + 2));
     ++g_launches;
+    uint64_t tail[2] = {0, 0};
+    RE_TRY(cudaMemcpy(tail, d_cnt.as<uint64_t>() + 1, 16, cudaMemcpyDeviceToHost));
+    const uint64_t n_blocks = (n_groups - 1) * kGroup + tail[0];
+    const uint8_t h_last = (uint8_t)(tail[1] & 0xff);
+    const int rounds = kJumpLog - 1;
+    const uint64_t n_seg = n_groups;
     const double t_chain = since(t0);
 
     // ---- pack
@@ -311,7 +338,7 @@ int fmg_rld_encode_device(const uint8_t *d_bwt, uint64_t n, FmdImage *out) {
     out->finish_counts();
     out->build_frames();                      // rld_rank_index (rld.c:186-224): one pass over the block headers, host
     if (fmg_verbose >= 4)
-        std::fprintf(stderr, "[M::%s] %llu symbols, %llu runs, %llu blocks: runs %.3f s, block chain %.3f s (%d rounds over %llu segments), pack + copy + directory %.3f s\n",
+        std::fprintf(stderr, "[M::%s] %llu symbols, %llu runs, %llu blocks: runs %.3f s, block chain %.3f s (%d doublings, %llu groups), pack + copy + directory %.3f s\n",
                      __func__, (unsigned long long)n, (unsigned long long)n_runs, (unsigned long long)n_blocks, t_runs, t_chain - t_runs, rounds + 1,
                      (unsigned long long)n_seg, since(t0) - t_chain);
     return 0;
