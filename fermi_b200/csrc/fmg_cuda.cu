@@ -623,18 +623,28 @@ int fmg_smem_batch_into(const fmg_index_t *idx, int64_t n, const uint8_t *seq, c
     if (n <= 0) return 0;
     if (batch_reads <= 0) batch_reads = 1 << 20;
     batch_reads = std::min<int64_t>(batch_reads, n);
-    uint64_t max_bytes = 1;
-    for (int64_t b = 0; b < n; b += batch_reads) {
-        const int64_t e = std::min(n, b + batch_reads);
-        max_bytes = std::max<uint64_t>(max_bytes, off[e] - off[b]);
+    // Batch boundaries.  The first copy in and the last copy out cannot overlap any kernel, so a call of several full batches
+    // starts and ends with short ones (1/4, 1/2, 1, 1, ..., 1/2, 1/4 of batch_reads): the exposed copies shrink fourfold.
+    std::vector<int64_t> cut{0};
+    {
+        const int64_t q = batch_reads / 4, h = batch_reads / 2;
+        if (n >= 3 * batch_reads && q >= 1024) {
+            cut.push_back(q); cut.push_back(q + h);
+            const int64_t tail = h + q, body_end = n - tail;
+            for (int64_t p0 = q + h; p0 < body_end;) { p0 = std::min(body_end, p0 + batch_reads); cut.push_back(p0); }
+            cut.push_back(n - q); cut.push_back(n);
+        } else
+            for (int64_t p0 = 0; p0 < n;) { p0 = std::min(n, p0 + batch_reads); cut.push_back(p0); }
     }
+    const int64_t n_batches = (int64_t)cut.size() - 1;
+    uint64_t max_bytes = 1;
+    for (int64_t b = 0; b < n_batches; ++b) max_bytes = std::max<uint64_t>(max_bytes, off[cut[b + 1]] - off[cut[b]]);
     // The longest read sizes the per-lane candidate lists.  Scanning all n lengths up front would sit in front of the first
     // kernel (10 ms for 10 M reads), so only the first batch is scanned here; every later batch is scanned just before it is
     // issued, while the GPU works on its predecessors, and a longer read than the pipeline was built for rebuilds it.
     auto batch_max_len = [&](int64_t b) {
         int m = 1;
-        const int64_t lo = b * batch_reads, hi = std::min(n, lo + batch_reads);
-        for (int64_t i = lo; i < hi; ++i) m = std::max<int>(m, (int)(off[i + 1] - off[i]));
+        for (int64_t i = cut[b]; i < cut[b + 1]; ++i) m = std::max<int>(m, (int)(off[i + 1] - off[i]));
         return m;
     };
     int max_len = batch_max_len(0);
@@ -656,10 +666,9 @@ int fmg_smem_batch_into(const fmg_index_t *idx, int64_t n, const uint8_t *seq, c
     uint64_t total = 0;
     bool short_cap = false;
     do {
-        const int64_t n_batches = (n + batch_reads - 1) / batch_reads;
         auto issue = [&](int64_t b) -> int {          // H2D + kernels of batch b
             BatchBuf &B = buf[b & 1];
-            B.first = b * batch_reads; B.count = std::min(batch_reads, n - B.first);
+            B.first = cut[b]; B.count = cut[b + 1] - cut[b];
             const uint64_t o0 = off[B.first], nb = off[B.first + B.count] - o0;
             // the device buffers of this slot are free once the D2H of batch b-2 has finished
             CUDA_TRY(cudaStreamWaitEvent(s_in, B.d2h_done, 0), return -1);
