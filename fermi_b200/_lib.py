@@ -61,6 +61,7 @@ _PROTOS = {
     "fmg_unitig_from_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                          C.c_char_p, u64p]),
     "fmg_ec_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, vpp, u64p, C.POINTER(C.c_int64)]),
+    "fmg_ec_collect_part": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, vpp, u64p, C.POINTER(C.c_int64)]),
     "fmg_ec_kmer_length": (C.c_int, [C.c_uint64]),
     # construction + synthetic data
     "fmg_build_bwt": (C.c_int, [C.c_int, C.c_int64, u8p, u8p]),

@@ -285,12 +285,13 @@ def fm_build(text, device=0, host_encode=False):
     return Fmd(lib().fmg_build_fmd(device, len(text), _p(text, u8p)))
 
 
-def fm6_ec_collect(idx, w=-1, min_occ=3):
-    """ec_collect (correct.c:35-87) over the whole trie: returns (triples u64[] sorted = suffix<<40|key<<8|val, cnt[2])."""
+def fm6_ec_collect(idx, w=-1, min_occ=3, part=0, n_parts=1):
+    """ec_collect (correct.c:35-87) over the whole trie: returns (triples u64[] sorted = suffix<<40|key<<8|val, cnt[2]).
+    n_parts > 1: only the subtrees of the suffixes s with s % n_parts == part (one GPU's share)."""
     p = C.c_void_p()
     n = C.c_uint64()
     cnt = (C.c_int64 * 2)()
-    _check(lib().fmg_ec_collect(idx.h, int(w), int(min_occ), C.byref(p), C.byref(n), cnt), "fm6_ec_collect")
+    _check(lib().fmg_ec_collect_part(idx.h, int(w), int(min_occ), int(part), int(n_parts), C.byref(p), C.byref(n), cnt), "fm6_ec_collect")
     out = np.frombuffer(C.string_at(p.value, n.value * 8), np.uint64).copy() if n.value else np.zeros(0, np.uint64)
     lib().fmg_free(p)
     return out, (int(cnt[0]), int(cnt[1]))

@@ -41,23 +41,28 @@ template <typename U> struct Frontier { U *x0, *x1, *x2; uint64_t *path; };
 // keeps every non-empty child, exact.c:158-164; below it ec_collect prunes with min_occ, correct.c:77-82)
 template <typename U>
 __global__ void __launch_bounds__(256) k_trie_expand(OccView ix, Frontier<U> in, uint64_t n_in, int depth, uint64_t thr,
-                                                     Frontier<U> out, unsigned long long *n_out, uint64_t cap_out) {
+                                                     Frontier<U> out, unsigned long long *n_out, uint64_t cap_out, uint32_t part, uint32_t n_parts) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_in) return;
     const U x0 = in.x0[i], x1 = in.x1[i], x2 = in.x2[i];
     const uint64_t path = in.path[i];
     Ext6T<U> e;
     extend6<U>(ix, x1, x0, x2, e);                       // backward: far = x[0], near = x[1]
+    // n_parts > 1 (set on the level that completes the suffix): keep only the subtrees of suffixes s with s % n_parts == part --
+    // the unit the reference hands to its threads (correct.c:346-350) and this library to its GPUs
     int n_child = 0;
 #pragma unroll
-    for (int c = 1; c <= 4; ++c) n_child += e.size[c] >= thr;
+    for (int c = 1; c <= 4; ++c) {
+        if (n_parts > 1 && (uint32_t)((path | (uint64_t)(c - 1) << (2 * depth)) % n_parts) != part) e.size[c] = 0;
+        n_child += e.size[c] >= thr && e.size[c] != 0;
+    }
     if (n_child == 0) return;
     const unsigned long long base = atomicAdd(n_out, (unsigned long long)n_child);      // (ptxas aggregates per warp)
     if (base + n_child > cap_out) return;               // overflow: detected by the host from *n_out
     int k = 0;
 #pragma unroll
     for (int c = 1; c <= 4; ++c)
-        if (e.size[c] >= thr) {
+        if (e.size[c] >= thr && e.size[c] != 0) {
             out.x0[base + k] = far_of(ix, e, c); out.x1[base + k] = e.near[c]; out.x2[base + k] = e.size[c];
             out.path[base + k] = path | (uint64_t)(c - 1) << (2 * depth);
             ++k;
@@ -105,7 +110,8 @@ template <typename U> struct FrontierBuf {
 };
 
 template <typename U>
-int ec_collect_impl(const fmg_index_s *idx, int w, int suf_len, uint64_t min_occ, uint64_t **triples, uint64_t *n_triples, int64_t cnt[2]) {
+int ec_collect_impl(const fmg_index_s *idx, int w, int suf_len, uint64_t min_occ, uint32_t part, uint32_t n_parts, uint64_t **triples, uint64_t *n_triples,
+                    int64_t cnt[2]) {
     const OccView &ix = idx->view;
     FrontierBuf<U> fb[2];
     unsigned long long *d_ctr = nullptr, h_ctr[4];
@@ -136,7 +142,9 @@ int ec_collect_impl(const fmg_index_s *idx, int w, int suf_len, uint64_t min_occ
         for (;;) {
             if (fb[cur ^ 1].cap < n_cur + (n_cur >> 1)) EC_TRY(fb[cur ^ 1].reserve(n_cur + (n_cur >> 1)));   // grown further on demand below
             EC_TRY(cudaMemset(d_ctr, 0, 4 * sizeof(unsigned long long)));
-            k_trie_expand<U><<<(unsigned)((n_cur + 255) / 256), 256>>>(ix, fb[cur].view(), n_cur, depth, thr, fb[cur ^ 1].view(), d_ctr, fb[cur ^ 1].cap);
+            // children of this level sit at depth + 1: the suffix (the first suf_len bases) is complete when depth + 1 == suf_len
+            k_trie_expand<U><<<(unsigned)((n_cur + 255) / 256), 256>>>(ix, fb[cur].view(), n_cur, depth, thr, fb[cur ^ 1].view(), d_ctr, fb[cur ^ 1].cap,
+                                                                       part, depth + 1 == suf_len ? n_parts : 1u);
             ++g_launches;
             EC_TRY(cudaMemcpy(h_ctr, d_ctr, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
             if (h_ctr[0] <= fb[cur ^ 1].cap) break;
@@ -182,7 +190,11 @@ int fmg_ec_kmer_length(uint64_t n_symbols) {      // fm6_ec_correct, correct.c:3
 }
 
 int fmg_ec_collect(const fmg_index_t *idx, int w, int min_occ, uint64_t **triples, uint64_t *n_triples, int64_t cnt[2]) {
-    if (!idx || !triples || !n_triples || !cnt) return -1;
+    return fmg_ec_collect_part(idx, w, min_occ, 0, 1, triples, n_triples, cnt);
+}
+
+int fmg_ec_collect_part(const fmg_index_t *idx, int w, int min_occ, int part, int n_parts, uint64_t **triples, uint64_t *n_triples, int64_t cnt[2]) {
+    if (!idx || !triples || !n_triples || !cnt || n_parts < 1 || part < 0 || part >= n_parts) return -1;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] no CUDA device available; libfermi_b200 has no CPU path\n", __func__);
@@ -193,8 +205,12 @@ int fmg_ec_collect(const fmg_index_t *idx, int w, int min_occ, uint64_t **triple
     if (w < 2 || w > 27) { if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] k-mer length %d out of range [2,27]\n", __func__, w); return -1; }
     const int suf_len = w > 15 ? w - 15 : 1;        // compute_SUF, correct.c:319
     const bool wide = idx->view.n_sym + 256 >= (1ull << 32) || std::getenv("FMG_FORCE_WIDE") != nullptr;
-    return wide ? ec_collect_impl<uint64_t>(idx, w, suf_len, (uint64_t)min_occ, triples, n_triples, cnt)
-                : ec_collect_impl<uint32_t>(idx, w, suf_len, (uint64_t)min_occ, triples, n_triples, cnt);
+    if (suf_len == 1 && n_parts > 1) {                  // the depth-1 nodes are set up on the host: a suffix of one base cannot be filtered on a level
+        if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] k-mer length %d has one-base suffixes: nothing to shard\n", __func__, w);
+        return -1;
+    }
+    return wide ? ec_collect_impl<uint64_t>(idx, w, suf_len, (uint64_t)min_occ, (uint32_t)part, (uint32_t)n_parts, triples, n_triples, cnt)
+                : ec_collect_impl<uint32_t>(idx, w, suf_len, (uint64_t)min_occ, (uint32_t)part, (uint32_t)n_parts, triples, n_triples, cnt);
 }
 
 } // extern "C"

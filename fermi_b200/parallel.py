@@ -144,6 +144,29 @@ def unitig_distributed_device(idx, min_match, out_path, max_len=0, group=None):
     return n
 
 
+def ec_collect_distributed(idx, w=-1, min_occ=3, group=None):
+    """The k-mer collection of `fermi correct` over all ranks: rank r expands the trie subtrees of the suffixes s with
+    s % world == r on its GPU (the reference stripes the same units over its threads, correct.c:346-350), one all-gather
+    brings the (suffix, key, val) triples and the two counters together.  Returns (sorted triples, (cnt0, cnt1)) on every rank."""
+    from . import api
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    tri, cnt = api.fm6_ec_collect(idx, w, min_occ, part=rank, n_parts=world)
+    dev = _device()
+    sizes = torch.tensor([len(tri), cnt[0], cnt[1]], dtype=torch.int64, device=dev)
+    all_sizes = torch.empty(world * 3, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_sizes, sizes, group=group)
+    all_sizes = all_sizes.view(world, 3).cpu()
+    counts = all_sizes[:, 0].tolist()
+    pad = max(max(counts), 1)
+    buf = torch.zeros(pad, dtype=torch.int64, device=dev)
+    buf[: len(tri)] = torch.from_numpy(tri.view(np.int64)).to(dev)
+    out = torch.empty(world * pad, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    merged = torch.cat([out[r * pad: r * pad + counts[r]] for r in range(world)])
+    res = np.sort(merged.cpu().numpy().view(np.uint64))
+    return res, (int(all_sizes[:, 1].sum()), int(all_sizes[:, 2].sum()))
+
+
 def allgather_counts(n_local, group=None):
     """per-rank unit counts -> (counts, exclusive offsets): global numbering of sharded SMEM results."""
     world = dist.get_world_size(group)

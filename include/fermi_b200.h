@@ -162,6 +162,9 @@ void fmg_overlap_stats(double ms[8]);
  * stores in solid[suffix] (correct.c:71-75); cnt[0], cnt[1] as in correct.c:59,66.  The host fills khash from them
  * and runs ec_fix (correct.c:121-300) unchanged. */
 int fmg_ec_collect(const fmg_index_t *idx, int w, int min_occ, uint64_t **triples, uint64_t *n_triples, int64_t cnt[2]);
+/* the share of one GPU: only the subtrees of the suffixes s with s % n_parts == part (the unit of work the reference hands to
+ * its threads, correct.c:346-350); the union over all parts is the result of fmg_ec_collect and cnt adds up.  Needs w >= 17. */
+int fmg_ec_collect_part(const fmg_index_t *idx, int w, int min_occ, int part, int n_parts, uint64_t **triples, uint64_t *n_triples, int64_t cnt[2]);
 int fmg_ec_kmer_length(uint64_t n_symbols);
 
 /* ------------------------------------------------------------------ index construction

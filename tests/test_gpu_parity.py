@@ -391,6 +391,25 @@ def test_ec_collect_matches_reference(fb, case, monkeypatch):
     idx.close()
 
 
+def test_ec_collect_parts_add_up(fb):
+    """the per-GPU shares of the k-mer collection (suffix s goes to part s % n_parts) are disjoint and their union -- triples and
+    counters -- is the single-GPU result (which the tests above pin to the reference)."""
+    genome = fb.synth_genome(73, 400000)
+    reads = fb.synth_reads(74, genome, 40000, 100, 0.01)
+    idx = fb.FmdIndex(fb.fm_build(fb.fmd_text(reads), 0), 0)
+    full, cnt = fb.fm6_ec_collect(idx, 18, 2)
+    assert len(full) > 100000
+    for n_parts in (2, 3, 8):
+        parts = [fb.fm6_ec_collect(idx, 18, 2, part=r, n_parts=n_parts) for r in range(n_parts)]
+        tri = np.sort(np.concatenate([p[0] for p in parts]))
+        assert np.array_equal(tri, full)
+        assert sum(p[1][0] for p in parts) == cnt[0] and sum(p[1][1] for p in parts) == cnt[1]
+        assert all(len(p[0]) > 0 for p in parts)
+        suf = [set(((p[0] >> np.uint64(40)) % np.uint64(n_parts)).tolist()) for p in parts]
+        assert all(s_ == {r} for r, s_ in enumerate(suf))
+    idx.close()
+
+
 def test_ec_collect_100k_reads_vs_oracle(fb, oracle, tmp_path):
     genome = fb.synth_genome(71, 500000)
     reads = fb.synth_reads(72, genome, 50000, 100, 0.01)
