@@ -292,7 +292,7 @@ def fm6_ec_collect(idx, w=-1, min_occ=3, part=0, n_parts=1):
     n = C.c_uint64()
     cnt = (C.c_int64 * 2)()
     _check(lib().fmg_ec_collect_part(idx.h, int(w), int(min_occ), int(part), int(n_parts), C.byref(p), C.byref(n), cnt), "fm6_ec_collect")
-    out = np.frombuffer(C.string_at(p.value, n.value * 8), np.uint64).copy() if n.value else np.zeros(0, np.uint64)
+    out = np.ctypeslib.as_array(C.cast(p, u64p), shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint64)     # one copy out of the malloc'd result
     lib().fmg_free(p)
     return out, (int(cnt[0]), int(cnt[1]))
 

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 #include <cstdio>
+#include <chrono>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -18,6 +19,7 @@
 #include <cmath>
 #include "fmd_device.cuh"
 #include "fmg_internal.hpp"
+#include "dev_pool.hpp"
 #include "../../include/fermi_b200.h"
 
 using namespace fmg;
@@ -95,15 +97,18 @@ __global__ void __launch_bounds__(256) k_ec_emit(OccView ix, Frontier<U> in, uin
     if (rest <= 7 && r >= (double)min_occ) atomicAdd(ctr + 2, 1ull);
 }
 
+// frontier storage comes from the library's device pool (dev_pool.hpp) and grows geometrically: a level that does not fit is
+// run again, and cudaMalloc / cudaFree of gigabyte buffers on every level cost more than the expansion itself
 template <typename U> struct FrontierBuf {
+    fmg::Dev xs, ps;
     U *x = nullptr; uint64_t *path = nullptr; uint64_t cap = 0;
-    ~FrontierBuf() { cudaFree(x); cudaFree(path); }
     cudaError_t reserve(uint64_t n) {
         if (n <= cap) return cudaSuccess;
-        cudaFree(x); cudaFree(path); x = nullptr; path = nullptr; cap = 0;
-        cudaError_t err = cudaMalloc(&x, n * 3 * sizeof(U));
-        if (err == cudaSuccess) err = cudaMalloc(&path, n * 8);
-        if (err == cudaSuccess) cap = n;
+        if (n < 2 * cap) n = 2 * cap;
+        cap = 0; x = nullptr; path = nullptr;
+        cudaError_t err = xs.alloc(n * 3 * sizeof(U));
+        if (err == cudaSuccess) err = ps.alloc(n * 8);
+        if (err == cudaSuccess) { cap = n; x = xs.template as<U>(); path = ps.template as<uint64_t>(); }
         return err;
     }
     Frontier<U> view() const { return Frontier<U>{x, x + cap, x + 2 * cap, path}; }
@@ -113,6 +118,8 @@ template <typename U>
 int ec_collect_impl(const fmg_index_s *idx, int w, int suf_len, uint64_t min_occ, uint32_t part, uint32_t n_parts, uint64_t **triples, uint64_t *n_triples,
                     int64_t cnt[2]) {
     const OccView &ix = idx->view;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
     FrontierBuf<U> fb[2];
     unsigned long long *d_ctr = nullptr, h_ctr[4];
     uint64_t *d_tri = nullptr;
@@ -157,8 +164,11 @@ int ec_collect_impl(const fmg_index_s *idx, int w, int suf_len, uint64_t min_occ
     cnt[0] = cnt[1] = 0;
     *n_triples = 0;
     *triples = nullptr;
+    const double t_expand = since();
     if (n_cur > 0) {
-        EC_TRY(cudaMalloc(&d_tri, n_cur * 8));
+        fmg::Dev b_tri, b_sorted, b_tmp;
+        EC_TRY(b_tri.alloc(n_cur * 8));
+        d_tri = b_tri.as<uint64_t>();
         EC_TRY(cudaMemset(d_ctr, 0, 4 * sizeof(unsigned long long)));
         k_ec_emit<U><<<(unsigned)((n_cur + 255) / 256), 256>>>(ix, fb[cur].view(), n_cur, suf_len, min_occ, d_tri, d_ctr);
         ++g_launches;
@@ -167,16 +177,19 @@ int ec_collect_impl(const fmg_index_s *idx, int w, int suf_len, uint64_t min_occ
         cnt[0] = (int64_t)h_ctr[1]; cnt[1] = (int64_t)h_ctr[2];
         *triples = (uint64_t *)std::malloc((h_ctr[0] ? h_ctr[0] : 1) * 8);
         if (h_ctr[0]) {                                               // canonical order: by suffix, then key (radix sort on the device)
-            uint64_t *d_sorted = nullptr; void *d_tmp = nullptr; size_t need = 0;
-            EC_TRY(cudaMalloc(&d_sorted, h_ctr[0] * 8));
+            size_t need = 0;
+            EC_TRY(b_sorted.alloc(h_ctr[0] * 8));
+            uint64_t *d_sorted = b_sorted.as<uint64_t>();
             EC_TRY(cub::DeviceRadixSort::SortKeys(nullptr, need, d_tri, d_sorted, (int64_t)h_ctr[0]));
-            EC_TRY(cudaMalloc(&d_tmp, need));
-            EC_TRY(cub::DeviceRadixSort::SortKeys(d_tmp, need, d_tri, d_sorted, (int64_t)h_ctr[0]));
+            EC_TRY(b_tmp.alloc(need));
+            EC_TRY(cub::DeviceRadixSort::SortKeys(b_tmp.p, need, d_tri, d_sorted, (int64_t)h_ctr[0]));
             EC_TRY(cudaMemcpy(*triples, d_sorted, h_ctr[0] * 8, cudaMemcpyDeviceToHost));
-            cudaFree(d_sorted); cudaFree(d_tmp);
         }
     } else *triples = (uint64_t *)std::malloc(8);
-    cudaFree(d_tri); cudaFree(d_ctr);
+    cudaFree(d_ctr);
+    if (fmg_verbose >= 3)
+        std::fprintf(stderr, "[M::fmg_ec_collect] k=%d: %llu k-mers; trie expansion %.3f s, emit + sort + copy out %.3f s\n", w, (unsigned long long)*n_triples,
+                     t_expand, since() - t_expand);
     return 0;
 }
 
