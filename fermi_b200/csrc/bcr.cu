@@ -341,14 +341,15 @@ int fmg_bcr_append(fmg_bcr_t *b, int len, const uint8_t *seq) {
 
 int fmg_bcr_append_batch(fmg_bcr_t *b, int64_t n, int len, const uint8_t *seqs) {
     if (!b || len < 1 || n < 0) return -1;
-    const size_t base = b->seq.size();
-    b->seq.insert(b->seq.end(), seqs, seqs + (size_t)n * len);
-    for (size_t i = base; i < b->seq.size(); ++i)
-        if (b->seq[i] < 1 || b->seq[i] > 4) {
-            if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] only A/C/G/T (nt6 1..4) are supported\n", __func__);
-            b->seq.resize(base);
-            return -1;
-        }
+    const size_t base = b->seq.size(), add = (size_t)n * len;
+    unsigned bad = 0;                                     // branch-free so that the compiler vectorises the scan of gigabytes
+    for (size_t i = 0; i < add; ++i) bad |= (unsigned)(uint8_t)(seqs[i] - 1) > 3u;
+    if (bad) {
+        if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] only A/C/G/T (nt6 1..4) are supported\n", __func__);
+        return -1;
+    }
+    b->seq.insert(b->seq.end(), seqs, seqs + add);
+    b->off.reserve(b->off.size() + (size_t)n);
     for (int64_t i = 1; i <= n; ++i) b->off.push_back(base + (size_t)i * len);
     if (len > b->max_len) b->max_len = len;
     return 0;
