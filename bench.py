@@ -284,7 +284,9 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL writes its banner / debug lines to stdout by default; stdout carries the one JSON line only
+        # stdout carries the one JSON line only: NCCL_DEBUG=VERSION (set on the GPU boxes) makes NCCL printf its banner there
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 

@@ -16,7 +16,9 @@ ap.add_argument("--check", action="store_true", help="compare with the single-GP
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")        # keep stdout for the JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # keep stdout for the JSON line (the banner is a printf)
+    os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 fn = os.path.join(tempfile.gettempdir(), "ec_multi_%d_%d.fmd" % (a.reads, a.len))
 if rank == 0:

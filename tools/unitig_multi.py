@@ -18,7 +18,9 @@ ap.add_argument("--host-gather", action="store_true", help="the round-1 path: re
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")        # keep stdout for the JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # keep stdout for the JSON line (the banner is a printf)
+    os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 fn = os.path.join(tempfile.gettempdir(), "unitig_multi_%d.fmd" % a.reads)
 if rank == 0:
