@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define FMG_VERSION "0.1-r1"
+#define FMG_VERSION "0.2-r1"
 
 extern int fmg_verbose;                                   /* fm_verbose, utils.c:8 */
 
@@ -49,7 +49,7 @@ int64_t    fmg_fmd_decode_bwt(const fmg_fmd_t *e, uint8_t *out); /* main_chkbwt 
 
 /* ------------------------------------------------------------------ device index
  * fmg_index_upload copies the .fmd image to the HBM of `device` and builds the query layout
- * there ("occ blocks": 128-byte lines of 256 symbols = mid-line cumulative counts + 3 bit planes).
+ * there ("occ blocks": 64-byte blocks of 128 symbols = mid-block cumulative counts + 3 bit planes).
  * Replaces holding an rld_t for queries: rld_restore + rld_rank_index (rld.c:186-224,288). */
 typedef struct fmg_index_s fmg_index_t;
 
