@@ -94,27 +94,38 @@ FMG_HD bool ov_pack(const int64_t *rec, uint64_t nx0, uint64_t nx1, uint64_t nx2
 template <typename U> struct Ok6 { IntvT<U> v[6]; };
 
 // TAG gives every kernel its own copy of the function (ptxas 12.9 crashes on a noinline function shared by two entries)
+// What most call sites need of an extension: the size of ok[0] and the interval of ONE selected symbol.  These come back in
+// registers; all six intervals are only written (through `all`, to the caller's stack) where a call site walks over them.
+template <typename U> struct ExtSel { U s0, ssel, x0, x1; int any; };
+
 template <typename U, int TAG>
-FMG_NOINLINE bool ext_sync(const OccView &ix, bool active, U x0, U x1, U x2, int back, Ok6<U> *out) {
+FMG_NOINLINE ExtSel<U> ext_sync(const OccView &ix, bool active, U x0, U x1, U x2, int back, int csel, Ok6<U> *all) {
+    ExtSel<U> R;
+    R.s0 = R.ssel = R.x0 = R.x1 = 0;
 #if defined(__CUDA_ARCH__)
-    const bool any = __any_sync(0xffffffffu, active);
+    R.any = __any_sync(0xffffffffu, active);
 #else
-    const bool any = active;
+    R.any = active;
 #endif
     if (active) {
         Ext6T<U> e;
         extend6<U>(ix, back ? x1 : x0, back ? x0 : x1, x2, e);
         const uint64_t *row = ix.cs + e.sbk * 8;
+        const U nr = pick6(e.near, csel), fr = (U)(ld_u64(row + csel) + pick6(e.relk, csel));
+        R.s0 = e.size[0]; R.ssel = pick6(e.size, csel);
+        R.x0 = back ? fr : nr; R.x1 = back ? nr : fr;
+        if (all) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            const U fr = (U)(ld_u64(row + c) + e.relk[c]);
-            out->v[c].x0 = back ? fr : e.near[c];
-            out->v[c].x1 = back ? e.near[c] : fr;
-            out->v[c].x2 = e.size[c];
-            out->v[c].info = 0;
+            for (int c = 0; c < 6; ++c) {
+                const U f6 = (U)(ld_u64(row + c) + e.relk[c]);
+                all->v[c].x0 = back ? f6 : e.near[c];
+                all->v[c].x1 = back ? e.near[c] : f6;
+                all->v[c].x2 = e.size[c];
+                all->v[c].info = 0;
+            }
         }
     }
-    return any;
+    return R;
 }
 
 template <typename U> struct OvBits {     // packing of the candidate `info` word (unitig.c:132,150)
@@ -150,7 +161,8 @@ struct OvLane {
     Cand *P, *Q;      // lane lists (phases 2 and 4)
     int32_t *cat;
     bool ovf;
-    Ok6<U> r, em;     // SYNC: ok[0..5] of the last extension; em = those of the last forward extension of phase 2
+    Ok6<U> r, em;     // SYNC: ok[0..5] of the last full extension; em = those of the last forward extension of phase 2
+    ExtSel<U> rs;     // SYNC: size of ok[0] and the selected interval of the last extension (registers)
     Ext6T<U> e;       // !SYNC: the same, before the far coordinates are formed
     int eback;
 
@@ -158,9 +170,12 @@ struct OvLane {
         : A(a), P(static_cast<Cand *>(a.A) + (size_t)lane * a.cap), Q(static_cast<Cand *>(a.B) + (size_t)lane * a.cap),
           cat(a.cat + (size_t)lane * a.cap * 2), ovf(false), eback(0) {}
 
-    FMG_HD void ext_to(const Cand &k, int back, Ok6<U> *dst) { ext_sync<U, TAG>(A.ix, true, k.x0, k.x1, k.x2, back, dst); }
+    // SYNC only: all six intervals into *dst (+ rs for symbol 0) / only rs for the selected symbol
+    FMG_HD void ext_to(const Cand &k, int back, Ok6<U> *dst) { rs = ext_sync<U, TAG>(A.ix, true, k.x0, k.x1, k.x2, back, 0, dst); }
+    FMG_HD void extend_sel(const Cand &k, int back, int csel) { rs = ext_sync<U, TAG>(A.ix, true, k.x0, k.x1, k.x2, back, csel, nullptr); }
+    FMG_HD Cand sel() const { Cand o; o.x0 = rs.x0; o.x1 = rs.x1; o.x2 = rs.ssel; o.info = 0; return o; }
     FMG_HD void extend(const Cand &k, int back) {
-        if (SYNC) ext_sync<U, TAG>(A.ix, true, k.x0, k.x1, k.x2, back, &r);
+        if (SYNC) rs = ext_sync<U, TAG>(A.ix, true, k.x0, k.x1, k.x2, back, 0, &r);
         else { extend6<U>(A.ix, back ? k.x1 : k.x0, back ? k.x0 : k.x1, k.x2, e); eback = back; }
     }
     FMG_HD U size(int c) const { return SYNC ? r.v[c].x2 : pick6(e.size, c); }
@@ -332,12 +347,12 @@ struct OvLane {
                     if (cj < 0) break;
                     p.info = (U)((p.info & BT::pos_mask) | ((U)cj << BT::cat_shift));
                     ext_to(p, 0, &em);                                   // forward extension; ok[1..4] stay in `em` across the probes
-                    const U s0 = em.v[0].x2;
+                    const U s0 = rs.s0;
                     if (s0 != 0 && ori_l != sl) {                        // some (partial) reads end here
-                        extend(em.v[0], 1);                              // fm6_extend0(ok[0], back)
-                        if (size(0) != 0) {                              // bounded by sentinels on both sides: a full read
-                            if (s0 == p.x2 && p.x2 == size(0)) {         // not contained in a longer read
-                                Cand nb = ok(0);                         // fm6_extend0's ok0 (x[0] = tk[0]; cnt[0] is 0)
+                        extend_sel(sel(), 1, 0);                         // fm6_extend0(ok[0], back)
+                        if (rs.s0 != 0) {                                // bounded by sentinels on both sides: a full read
+                            if (s0 == p.x2 && p.x2 == rs.s0) {           // not contained in a longer read
+                                Cand nb = sel();                         // fm6_extend0's ok0 (x[0] = tk[0]; cnt[0] is 0)
                                 nb.info = (U)(ori_l - (int)(p.info & BT::pos_mask));
                                 for (int i = j; i < npc && pcat[i] == cj; ++i) pcat[i] = -1;
                                 if (more) cn = pcat[j + 1];              // the request above may predate the masking
@@ -354,8 +369,8 @@ struct OvLane {
                     for (int c = 1; c < 5; ++c) {                        // collect extensible intervals
                         Cand kc = em.v[c];
                         if (kc.x2 == 0) continue;
-                        extend(kc, 1);                                   // fm6_extend0(ok[c], back)
-                        if (size(0) != 0) {                              // left end still bounded by a sentinel
+                        extend_sel(kc, 1, 0);                            // fm6_extend0(ok[c], back)
+                        if (rs.s0 != 0) {                                // left end still bounded by a sentinel
                             kc.info = (U)((p.info & ~BT::base_mask) | ((U)c << BT::pos_bits));
                             const U hi = (U)(kc.info >> BT::pos_bits);
                             if (nq == 0) first_base = c;
@@ -454,9 +469,9 @@ struct OvLane {
             const int npc = np < pcap ? np : pcap, c = sq[i];
             for (int j = 0; j < npc; ++j) {
                 const Cand p = ld_cand(prev + j);
-                extend(p, 1);
-                if ((U)(size(0) + size(c)) != p.x2) { left = -1; break; }       // potential backward bifurcation
-                push(curr, A.cap, nq, ok(c));
+                extend_sel(p, 1, c);
+                if ((U)(rs.s0 + rs.ssel) != p.x2) { left = -1; break; }         // potential backward bifurcation
+                push(curr, A.cap, nq, sel());
             }
             prev = curr; curr = curr == P ? Q : P;
             pcap = A.cap;
@@ -476,7 +491,7 @@ FMG_HD void overlap_lane_sync(const OverlapArgs &A, int64_t lane, FetchFn fetch)
         if (t >= A.n) break;
         if (PHASE == 2) ln.phase_nei(t); else ln.phase_left2(t);
     }
-    while (ext_sync<U, PHASE>(A.ix, false, 0, 0, 0, 0, &ln.r)) {}
+    while (ext_sync<U, PHASE>(A.ix, false, 0, 0, 0, 0, 0, nullptr).any) {}
 }
 
 // chain phases: one sequence per thread
