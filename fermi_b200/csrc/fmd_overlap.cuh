@@ -95,17 +95,18 @@ template <typename U> struct Ok6 { IntvT<U> v[6]; };
 
 // TAG gives every kernel its own copy of the function (ptxas 12.9 crashes on a noinline function shared by two entries)
 // What most call sites need of an extension: the size of ok[0] and the interval of ONE selected symbol.  These come back in
-// registers; all six intervals are only written (through `all`, to the caller's stack) where a call site walks over them.
-template <typename U> struct ExtSel { U s0, ssel, x0, x1; int any; };
+// registers together with a mask of the non-empty base extensions; the intervals of those (ok[1..4], usually one) are only
+// written -- through `kids`, to the caller's stack -- where a call site walks over them.
+template <typename U> struct ExtSel { U s0, ssel, x0, x1; int flags; };       // flags: bit 0 = some lane of the warp was active, bits 1..4 = ok[c] is not empty
 
 template <typename U, int TAG>
-FMG_NOINLINE ExtSel<U> ext_sync(const OccView &ix, bool active, U x0, U x1, U x2, int back, int csel, Ok6<U> *all) {
+FMG_NOINLINE ExtSel<U> ext_sync(const OccView &ix, bool active, U x0, U x1, U x2, int back, int csel, Ok6<U> *kids) {
     ExtSel<U> R;
     R.s0 = R.ssel = R.x0 = R.x1 = 0;
 #if defined(__CUDA_ARCH__)
-    R.any = __any_sync(0xffffffffu, active);
+    R.flags = __any_sync(0xffffffffu, active) ? 1 : 0;
 #else
-    R.any = active;
+    R.flags = active ? 1 : 0;
 #endif
     if (active) {
         Ext6T<U> e;
@@ -114,14 +115,16 @@ FMG_NOINLINE ExtSel<U> ext_sync(const OccView &ix, bool active, U x0, U x1, U x2
         const U nr = pick6(e.near, csel), fr = (U)(ld_u64(row + csel) + pick6(e.relk, csel));
         R.s0 = e.size[0]; R.ssel = pick6(e.size, csel);
         R.x0 = back ? fr : nr; R.x1 = back ? nr : fr;
-        if (all) {
 #pragma unroll
-            for (int c = 0; c < 6; ++c) {
+        for (int c = 1; c < 5; ++c) {
+            if (e.size[c] == 0) continue;
+            R.flags |= 1 << c;
+            if (kids) {
                 const U f6 = (U)(ld_u64(row + c) + e.relk[c]);
-                all->v[c].x0 = back ? f6 : e.near[c];
-                all->v[c].x1 = back ? e.near[c] : f6;
-                all->v[c].x2 = e.size[c];
-                all->v[c].info = 0;
+                kids->v[c].x0 = back ? f6 : e.near[c];
+                kids->v[c].x1 = back ? e.near[c] : f6;
+                kids->v[c].x2 = e.size[c];
+                kids->v[c].info = 0;
             }
         }
     }
@@ -161,8 +164,8 @@ struct OvLane {
     Cand *P, *Q;      // lane lists (phases 2 and 4)
     int32_t *cat;
     bool ovf;
-    Ok6<U> r, em;     // SYNC: ok[0..5] of the last full extension; em = those of the last forward extension of phase 2
-    ExtSel<U> rs;     // SYNC: size of ok[0] and the selected interval of the last extension (registers)
+    Ok6<U> em;        // SYNC: the non-empty ok[1..4] of the last extension that asked for them (phase 2)
+    ExtSel<U> rs;     // SYNC: size of ok[0], the selected interval and the mask of non-empty ok[1..4] of the last extension (registers)
     Ext6T<U> e;       // !SYNC: the same, before the far coordinates are formed
     int eback;
 
@@ -170,17 +173,14 @@ struct OvLane {
         : A(a), P(static_cast<Cand *>(a.A) + (size_t)lane * a.cap), Q(static_cast<Cand *>(a.B) + (size_t)lane * a.cap),
           cat(a.cat + (size_t)lane * a.cap * 2), ovf(false), eback(0) {}
 
-    // SYNC only: all six intervals into *dst (+ rs for symbol 0) / only rs for the selected symbol
-    FMG_HD void ext_to(const Cand &k, int back, Ok6<U> *dst) { rs = ext_sync<U, TAG>(A.ix, true, k.x0, k.x1, k.x2, back, 0, dst); }
+    // SYNC phases: rs for the selected symbol, with (ext_kids) or without (extend_sel) the non-empty ok[1..4] in `em`
+    FMG_HD void ext_kids(const Cand &k, int back, int csel) { rs = ext_sync<U, TAG>(A.ix, true, k.x0, k.x1, k.x2, back, csel, &em); }
     FMG_HD void extend_sel(const Cand &k, int back, int csel) { rs = ext_sync<U, TAG>(A.ix, true, k.x0, k.x1, k.x2, back, csel, nullptr); }
     FMG_HD Cand sel() const { Cand o; o.x0 = rs.x0; o.x1 = rs.x1; o.x2 = rs.ssel; o.info = 0; return o; }
-    FMG_HD void extend(const Cand &k, int back) {
-        if (SYNC) rs = ext_sync<U, TAG>(A.ix, true, k.x0, k.x1, k.x2, back, 0, &r);
-        else { extend6<U>(A.ix, back ? k.x1 : k.x0, back ? k.x0 : k.x1, k.x2, e); eback = back; }
-    }
-    FMG_HD U size(int c) const { return SYNC ? r.v[c].x2 : pick6(e.size, c); }
+    // chain phases (!SYNC): the plain inlined extension
+    FMG_HD void extend(const Cand &k, int back) { extend6<U>(A.ix, back ? k.x1 : k.x0, back ? k.x0 : k.x1, k.x2, e); eback = back; }
+    FMG_HD U size(int c) const { return pick6(e.size, c); }
     FMG_HD Cand ok(int c) const {
-        if (SYNC) return r.v[c];
         Cand o;
         const U nr = pick6(e.near, c), fr = far_of(A.ix, e, c);
         o.x0 = eback ? fr : nr; o.x1 = eback ? nr : fr; o.x2 = pick6(e.size, c); o.info = 0;
@@ -346,8 +346,9 @@ struct OvLane {
                 do {
                     if (cj < 0) break;
                     p.info = (U)((p.info & BT::pos_mask) | ((U)cj << BT::cat_shift));
-                    ext_to(p, 0, &em);                                   // forward extension; ok[1..4] stay in `em` across the probes
+                    ext_kids(p, 0, 0);                                   // forward extension; the non-empty ok[1..4] stay in `em` across the probes
                     const U s0 = rs.s0;
+                    const int kids = rs.flags;
                     if (s0 != 0 && ori_l != sl) {                        // some (partial) reads end here
                         extend_sel(sel(), 1, 0);                         // fm6_extend0(ok[0], back)
                         if (rs.s0 != 0) {                                // bounded by sentinels on both sides: a full read
@@ -367,8 +368,8 @@ struct OvLane {
                         }
                     }
                     for (int c = 1; c < 5; ++c) {                        // collect extensible intervals
+                        if (!(kids >> c & 1)) continue;
                         Cand kc = em.v[c];
-                        if (kc.x2 == 0) continue;
                         extend_sel(kc, 1, 0);                            // fm6_extend0(ok[c], back)
                         if (rs.s0 != 0) {                                // left end still bounded by a sentinel
                             kc.info = (U)((p.info & ~BT::base_mask) | ((U)c << BT::pos_bits));
@@ -420,19 +421,20 @@ struct OvLane {
         const int rbeg = ori_l - (int)nei0.info;
         if (nnei == 1 && is_forked) {             // contained reads forked the path: rebuild it along the one neighbour
             Cand k0 = base_intv<U>(A.ix, 0);
-            for (int i = rbeg; i < ori_l; ++i) { extend(k0, 0); k0 = ok(comp6(sq[i])); }
+            for (int i = rbeg; i < ori_l; ++i) { extend_sel(k0, 0, comp6(sq[i])); k0 = sel(); }
             int i = ori_l;
             for (; i < sl; ++i) {
                 int c0 = -1, hits = 0;
-                extend(k0, 0);
+                ext_kids(k0, 0, 0);
                 for (int c = 1; c < 5; ++c) {
-                    const Cand kc = ok(c);
-                    if (kc.x2 != 0 && kc.x0 <= nei0.x0 && kc.x0 + kc.x2 >= nei0.x0 + nei0.x2) ++hits, c0 = c;
+                    if (!(rs.flags >> c & 1)) continue;
+                    const Cand kc = em.v[c];
+                    if (kc.x0 <= nei0.x0 && kc.x0 + kc.x2 >= nei0.x0 + nei0.x2) ++hits, c0 = c;
                 }
-                if (hits == 0 && size(0) != 0) break;
+                if (hits == 0 && rs.s0 != 0) break;
                 if (hits != 1) { ovf = true; break; }                    // the reference asserts hits == 1 (unitig.c:171)
                 xt[i - ori_l] = (uint8_t)comp6(c0);
-                k0 = ok(c0);
+                k0 = em.v[c0];
             }
             sl = i;
         }
@@ -491,7 +493,7 @@ FMG_HD void overlap_lane_sync(const OverlapArgs &A, int64_t lane, FetchFn fetch)
         if (t >= A.n) break;
         if (PHASE == 2) ln.phase_nei(t); else ln.phase_left2(t);
     }
-    while (ext_sync<U, PHASE>(A.ix, false, 0, 0, 0, 0, 0, nullptr).any) {}
+    while (ext_sync<U, PHASE>(A.ix, false, 0, 0, 0, 0, 0, nullptr).flags & 1) {}
 }
 
 // chain phases: one sequence per thread

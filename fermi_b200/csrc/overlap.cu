@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(OVCH_BLOCK) k_ov_chain(OverlapArgs A) {
 
 // phases 2 and 4: persistent lanes, sequences handed out by atomicAdd, every extension behind a warp vote
 template <typename U, int PHASE>
-__global__ void __launch_bounds__(OVLP_BLOCK, OVLP_MIN_BLOCKS) k_ov_lists(OverlapArgs A) {
+__global__ void __launch_bounds__(OVLP_BLOCK, OVLP_MIN_BLOCKS) k_ov_lists(const __grid_constant__ OverlapArgs A) {     // &A.ix is taken: no stack copy
     const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     overlap_lane_sync<U, PHASE>(A, lane, [&]() -> int64_t { return (int64_t)atomicAdd(A.next, 1ull); });
 }
