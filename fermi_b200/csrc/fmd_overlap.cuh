@@ -89,15 +89,16 @@ FMG_HD bool ov_pack(const int64_t *rec, uint64_t nx0, uint64_t nx1, uint64_t nx2
     return (uint64_t)rec[OV_X2] < (1ull << 32) && nx2 < (1ull << 32) && rec[OV_NNEI] < 65536 && rec[OV_LEN] < (1ll << 31) && rec[OV_SLEN] < (1ll << 31);
 }
 
-// All six result intervals of fm6_extend (exact.c:72-88), info = 0.  Computed inside ext_sync, i.e. while the warp is
-// converged, so that the (divergent) callers only index the array.
+// Result intervals of fm6_extend (exact.c:72-88) indexed by symbol, info = 0: storage for the ok[1..4] a call site walks over.
 template <typename U> struct Ok6 { IntvT<U> v[6]; };
 
-// TAG gives every kernel its own copy of the function (ptxas 12.9 crashes on a noinline function shared by two entries)
 // What most call sites need of an extension: the size of ok[0] and the interval of ONE selected symbol.  These come back in
 // registers together with a mask of the non-empty base extensions; the intervals of those (ok[1..4], usually one) are only
-// written -- through `kids`, to the caller's stack -- where a call site walks over them.
+// written -- through `kids`, to the caller's stack -- where a call site walks over them.  Everything is computed inside
+// ext_sync, i.e. while the warp is converged, so that the (divergent) callers only pick values.
 template <typename U> struct ExtSel { U s0, ssel, x0, x1; int flags; };       // flags: bit 0 = some lane of the warp was active, bits 1..4 = ok[c] is not empty
+
+// TAG gives every kernel its own copy of the function (ptxas 12.9 crashes on a noinline function shared by two entries)
 
 template <typename U, int TAG>
 FMG_NOINLINE ExtSel<U> ext_sync(const OccView &ix, bool active, U x0, U x1, U x2, int back, int csel, Ok6<U> *kids) {
