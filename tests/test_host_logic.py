@@ -50,6 +50,28 @@ def test_device_entry_points_fail_loudly_without_gpu(product_lib):
         fb.FmdIndex(f, 0)
     with pytest.raises(RuntimeError):
         fb.fm_build_bwt(np.array([1, 2, 0, 3, 4, 0], np.uint8))
+    # the builders that encode on the device, BCR and the device RLD encoder: no CPU path either
+    with pytest.raises((RuntimeError, IOError)):
+        fb.fm_build(np.array([1, 2, 0, 3, 4, 0], np.uint8))
+    with pytest.raises((RuntimeError, IOError)):
+        fb.Fmd.from_bwt_device(np.array([1, 2, 0, 3, 4, 0], np.uint8))
+    b = fb.Bcr(0)
+    b.append(np.array([1, 2, 3], np.uint8))
+    with pytest.raises(RuntimeError):
+        b.build()
+    b.close()
+
+
+def test_unitig_assemble_rejects_inconsistent_records(product_lib, tmp_path):
+    """fmg_unitig_assemble packs the records it is handed by rank: a rank outside the index is an error, not a crash."""
+    import fermi_b200 as fb
+    n = 4
+    rec = np.zeros((n, 10), np.int64)
+    rec[:, 0] = [0, 1, 2, 7]                     # rank 7 of 4 sequences
+    rec[:, 1] = 60
+    o = dict(rec=rec, nei=np.zeros(0, fb.INTV), nei_off=np.zeros(n + 1, np.uint64), seq=np.ones((n, 64), np.uint8), ext=np.zeros((n, 64), np.uint8))
+    with pytest.raises(RuntimeError):
+        fb.fm6_unitig_assemble(n, 50, o, str(tmp_path / "x.mag"))
 
 
 @pytest.mark.parametrize("case", golden_cases())
