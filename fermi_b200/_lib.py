@@ -57,7 +57,12 @@ _PROTOS = {
     "fmg_seqsort": (C.c_int, [C.c_void_p, u64p, C.POINTER(C.c_int64)]),
     "fmg_overlap_shard": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                     C.c_void_p, C.c_uint64, u64p]),
-    "fmg_overlap_rebase": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "fmg_overlap_merge": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fmg_overlap_left_fix": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "fmg_unitig_part": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "fmg_magpart_write": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int]),
+    "fmg_magpart_free": (None, [C.c_void_p]),
     "fmg_unitig_from_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                          C.c_char_p, u64p]),
     "fmg_ec_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, vpp, u64p, C.POINTER(C.c_int64)]),

@@ -262,10 +262,10 @@ def fm6_seqsort(idx):
 
 
 def overlap_stats():
-    """kernel milliseconds of the last fm6_unitig overlap pass: dict(contained, neighbours, left_chain, left_lists, pack, batches)"""
+    """kernel milliseconds of the last overlap pass: dict(contained, neighbours, left_fix, left_rows, pack, batches)"""
     ms = (C.c_double * 8)()
     lib().fmg_overlap_stats(ms)
-    return {"contained": ms[1], "neighbours": ms[2], "left_chain": ms[3], "left_lists": ms[4], "pack": ms[5], "batches": int(ms[7])}
+    return {"contained": ms[1], "neighbours": ms[2], "left_fix": ms[3], "left_rows": int(ms[4]), "pack": ms[5], "batches": int(ms[7])}
 
 
 def fm_build_bwt(text, device=0):

@@ -129,13 +129,13 @@ int build_bwt_device(uint32_t n, const uint8_t *h_text, uint8_t *h_bwt, fmg::Fmd
     {
         cub::DoubleBuffer<uint64_t> dk(dKeyA.as<uint64_t>(), dKeyB.as<uint64_t>());
         cub::DoubleBuffer<uint32_t> dv(dValA.as<uint32_t>(), dValB.as<uint32_t>());
-        BW_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, (int)n, 0, 64));
+        BW_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, (int64_t)n, 0, 64));
         tmp_bytes = need;
-        BW_TRY(cub::DeviceScan::InclusiveScan(nullptr, need, head, head, cub::Max(), (int)n));
+        BW_TRY(cub::DeviceScan::InclusiveScan(nullptr, need, head, head, cub::Max(), (int64_t)n));
         tmp_bytes = need > tmp_bytes ? need : tmp_bytes;
-        BW_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, head, head, (int)n));
+        BW_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, head, head, (int64_t)n));
         tmp_bytes = need > tmp_bytes ? need : tmp_bytes;
-        BW_TRY(cub::DeviceSelect::Flagged(nullptr, need, sa, tied, sa, count, (int)n));
+        BW_TRY(cub::DeviceSelect::Flagged(nullptr, need, sa, tied, sa, count, (int64_t)n));
         tmp_bytes = need > tmp_bytes ? need : tmp_bytes;
     }
     BW_TRY(dTmp.alloc(tmp_bytes));
@@ -143,7 +143,7 @@ int build_bwt_device(uint32_t n, const uint8_t *h_text, uint8_t *h_bwt, fmg::Fmd
     // sentinel ordinals (exclusive prefix count of zeros); head[] is reused as the ordinal array
     k_is_sentinel<<<blocks_for(n), kThreads>>>(T, n, head); ++g_launches;
     need = tmp_bytes;
-    BW_TRY(cub::DeviceScan::ExclusiveSum(dTmp.p, need, head, head, (int)n));
+    BW_TRY(cub::DeviceScan::ExclusiveSum(dTmp.p, need, head, head, (int64_t)n));
     uint32_t last_ord = 0;
     BW_TRY(cudaMemcpy(&last_ord, head + (n - 1), 4, cudaMemcpyDeviceToHost));
     const uint32_t n_sent = last_ord + 1;       // T[n-1] is a sentinel
@@ -156,11 +156,11 @@ int build_bwt_device(uint32_t n, const uint8_t *h_text, uint8_t *h_bwt, fmg::Fmd
     cub::DoubleBuffer<uint32_t> vals(dValA.as<uint32_t>(), dValB.as<uint32_t>());
     k_init_keys<<<blocks_for(n), kThreads>>>(T, head, n, K, B, keys.Current(), vals.Current()); ++g_launches;
     need = tmp_bytes;
-    BW_TRY(cub::DeviceRadixSort::SortPairs(dTmp.p, need, keys, vals, (int)n, 0, 3 * K + B));
+    BW_TRY(cub::DeviceRadixSort::SortPairs(dTmp.p, need, keys, vals, (int64_t)n, 0, 3 * K + B));
     BW_TRY(cudaMemcpyAsync(sa, vals.Current(), (size_t)n * 4, cudaMemcpyDeviceToDevice));
     k_group_heads<<<blocks_for(n), kThreads>>>(keys.Current(), n, nullptr, head); ++g_launches;
     need = tmp_bytes;
-    BW_TRY(cub::DeviceScan::InclusiveScan(dTmp.p, need, head, head, cub::Max(), (int)n));
+    BW_TRY(cub::DeviceScan::InclusiveScan(dTmp.p, need, head, head, cub::Max(), (int64_t)n));
     k_set_rank<<<blocks_for(n), kThreads>>>(keys.Current(), vals.Current(), head, n, rank, tied); ++g_launches;
 
     // active list = (position in SA, suffix) of every suffix still tied with a neighbour
@@ -172,9 +172,9 @@ int build_bwt_device(uint32_t n, const uint8_t *h_text, uint8_t *h_bwt, fmg::Fmd
         // compact (pos, val) by tied[]
         uint32_t m2 = 0;
         need = tmp_bytes;
-        BW_TRY(cub::DeviceSelect::Flagged(dTmp.p, need, pos.Current(), tied, pos.Alternate(), count, (int)m));
+        BW_TRY(cub::DeviceSelect::Flagged(dTmp.p, need, pos.Current(), tied, pos.Alternate(), count, (int64_t)m));
         need = tmp_bytes;
-        BW_TRY(cub::DeviceSelect::Flagged(dTmp.p, need, vals.Current(), tied, vals.Alternate(), count, (int)m));
+        BW_TRY(cub::DeviceSelect::Flagged(dTmp.p, need, vals.Current(), tied, vals.Alternate(), count, (int64_t)m));
         BW_TRY(cudaMemcpy(&m2, count, 4, cudaMemcpyDeviceToHost));
         pos.selector ^= 1; vals.selector ^= 1;
         if (fmg_verbose >= 4)
@@ -187,11 +187,11 @@ int build_bwt_device(uint32_t n, const uint8_t *h_text, uint8_t *h_bwt, fmg::Fmd
         }
         k_double_keys<<<blocks_for(m), kThreads>>>(vals.Current(), m, rank, n, h, keys.Current()); ++g_launches;
         need = tmp_bytes;
-        BW_TRY(cub::DeviceRadixSort::SortPairs(dTmp.p, need, keys, vals, (int)m, 0, 64));
+        BW_TRY(cub::DeviceRadixSort::SortPairs(dTmp.p, need, keys, vals, (int64_t)m, 0, 64));
         k_scatter_sa<<<blocks_for(m), kThreads>>>(pos.Current(), vals.Current(), m, sa); ++g_launches;
         k_group_heads<<<blocks_for(m), kThreads>>>(keys.Current(), m, pos.Current(), head); ++g_launches;
         need = tmp_bytes;
-        BW_TRY(cub::DeviceScan::InclusiveScan(dTmp.p, need, head, head, cub::Max(), (int)m));
+        BW_TRY(cub::DeviceScan::InclusiveScan(dTmp.p, need, head, head, cub::Max(), (int64_t)m));
         k_set_rank<<<blocks_for(m), kThreads>>>(keys.Current(), vals.Current(), head, m, rank, tied); ++g_launches;
         h = h > (1u << 30) ? 0xffffffffu : h * 2;
         ++round;

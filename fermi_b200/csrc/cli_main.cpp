@@ -259,7 +259,7 @@ int main_unitig(int argc, char *argv[]) {
     }
     if (optind + 1 > argc) {
         std::fprintf(stderr, "\nUsage:   fermi-b200 unitig [options] <reads.fmd>\n\nOptions: -l INT      min match [%d]\n"
-                             "         -t INT      number of host threads of the unitig walk [all]\n         -r FILE     rank file (accepted, not needed)\n"
+                             "         -t INT      number of host threads of the unitig walk [1]\n         -r FILE     rank file (accepted, not needed)\n"
                              "         -d INT      CUDA device [0]\n\n", min_match);
         return 1;
     }

@@ -86,7 +86,11 @@ struct OvHost;
 int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, fmg::OvDevice *dev, OvHost *host, fmg::OvShard *shard = nullptr);
 // unitig_gpu.cu: unitigs from the device-resident records; 0 = written, 1 = the link graph is irregular (cycles or
 // one-sided links: the caller falls back to the host walk, which reproduces the reference's seed order), -1 = error
-int fmg_unitig_device(const fmg_index_s *idx, const fmg::OvDevView &D, int min_match, const char *out_path, uint64_t *n_unitigs);
+// part / n_parts: only the chains whose head rank % n_parts == part are emitted (several GPUs share the emission); sink != nullptr
+// keeps the MAG text in memory instead of writing it
+struct fmg_magpart_s;
+int fmg_unitig_device(const fmg_index_s *idx, const fmg::OvDevView &D, int min_match, const char *out_path, uint64_t *n_unitigs,
+                      uint32_t part, uint32_t n_parts, fmg_magpart_s *sink);
 
 // Pinned host arrays of the whole-index pass and of the device unitig assembly.  Page-locking gigabytes costs more
 // than the pass itself, so the arrays stay with the index handle and are reused (grown on demand) by the next call.

@@ -117,6 +117,50 @@ FMG_HD Blk load_blk(const OccView &ix, uint64_t p) {
     return r;
 }
 
+// 64-byte block gather for a CONVERGED warp (all 32 lanes call it; `need` = this lane wants the block at position p).
+// A warp-level load instruction costs one L1-miss request per distinct 128-byte line it touches, and the rate of those requests
+// -- not bytes -- is what bounds dependent random gathers from an index that does not fit L2 (tools/micro/gather_bench2.cu on a
+// B200, 1 GB array: two ld.v8 per thread 27 G blocks/s; both 32-byte halves of a block requested by two adjacent lanes in ONE
+// instruction 53 G blocks/s).  So lanes work in pairs: instruction 1 fetches the blocks of the even lanes (even lane: lower
+// half, odd lane: upper half), instruction 2 those of the odd lanes, and eight shuffles hand each lane the half it lacks.
+// The gather is split in two so that several of them can be in flight: pair_issue puts the two loads of a block on the wire,
+// pair_finish (which waits for the data) shuffles the halves into place.
+struct PairReq { Vec8 r0, r1; };
+FMG_HD PairReq pair_issue(const OccView &ix, uint64_t p, bool need) {
+    PairReq q;
+#if defined(__CUDA_ARCH__)
+    constexpr uint32_t kNoBlk = 0xffffffffu;                       // block numbers fit 32 bits (checked at upload)
+    const uint32_t b = need ? (uint32_t)(p >> kBlkShift) : kNoBlk;
+    const uint32_t pb = __shfl_xor_sync(0xffffffffu, b, 1);
+    const uint32_t odd = threadIdx.x & 1u;
+    const uint32_t be = odd ? pb : b, bo = odd ? b : pb;
+    const Vec8 z = {{0, 0, 0, 0, 0, 0, 0, 0}};
+    q.r0 = z; q.r1 = z;
+    if (be != kNoBlk) q.r0 = ld256_nc(ix.blocks + (uint64_t)be * kBlkWords + odd * 8u);
+    if (bo != kNoBlk) q.r1 = ld256_nc(ix.blocks + (uint64_t)bo * kBlkWords + odd * 8u);
+#else
+    if (need) { const Blk B = load_blk(ix, p); q.r0 = B.lo; q.r1 = B.hi; }
+    else { memset(&q, 0, sizeof q); }
+#endif
+    return q;
+}
+FMG_HD Blk pair_finish(const PairReq &q) {
+    Blk r;
+#if defined(__CUDA_ARCH__)
+    const uint32_t odd = threadIdx.x & 1u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? q.r0.v[i] : q.r1.v[i], 1);
+        r.lo.v[i] = odd ? got : q.r0.v[i];
+        r.hi.v[i] = odd ? q.r1.v[i] : got;
+    }
+#else
+    r.lo = q.r0; r.hi = q.r1;
+#endif
+    return r;
+}
+FMG_HD Blk load_blk_pair(const OccView &ix, uint64_t p, bool need) { return pair_finish(pair_issue(ix, p, need)); }
+
 // positions where the 3-bit symbol (p2 p1 p0) equals SYM; p2m / np2m are p2 / ~p2 already ANDed with the mask
 template <int SYM>
 FMG_HD uint32_t match32(uint32_t p0, uint32_t p1, uint32_t p2m, uint32_t np2m) {
@@ -189,6 +233,57 @@ FMG_HD void extend6_with(const OccView &ix, U x_near, uint64_t pk, uint64_t pl, 
     e.near[2] = e.near[3] + e.size[3];
     e.near[1] = e.near[2] + e.size[2];
     e.near[5] = e.near[1] + e.size[1];
+}
+
+// the same from the two rank results (rel counts at pk = x_far and pl = x_far + size)
+template <typename U>
+FMG_HD void extend6_rel(const OccView &ix, U x_near, uint64_t pk, uint64_t pl, const uint32_t rk[6], const uint32_t rl[6], Ext6T<U> &e) {
+    const uint64_t sbk = pk >> kSuperShift, sbl = pl >> kSuperShift;
+    e.sbk = sbk;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { e.relk[c] = rk[c]; e.size[c] = (U)rl[c] - (U)rk[c]; }
+    if (sbk != sbl) {
+        const uint64_t *ck = ix.cs + sbk * 8, *cl = ix.cs + sbl * 8;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) e.size[c] += (U)(ld_u64(cl + c) - ld_u64(ck + c));
+    }
+    e.near[0] = x_near;
+    e.near[4] = e.near[0] + e.size[0];
+    e.near[3] = e.near[4] + e.size[4];
+    e.near[2] = e.near[3] + e.size[3];
+    e.near[1] = e.near[2] + e.size[2];
+    e.near[5] = e.near[1] + e.size[1];
+}
+
+FMG_HD bool warp_any(bool v) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(0xffffffffu, v);      // also the reconvergence point of the 32 lanes
+#else
+    return v;
+#endif
+}
+
+// fm6_extend for a CONVERGED warp: every lane calls, `active` lanes get their extension; the blocks come through
+// load_blk_pair (half the L1-miss requests of extend6)
+template <typename U>
+FMG_HD void extend6_conv(const OccView &ix, bool active, U x_near, U x_far, U size, Ext6T<U> &e) {
+    const uint64_t pk = x_far, pl = (uint64_t)x_far + size;
+    const bool two = active && (pk >> kBlkShift) != (pl >> kBlkShift);
+    // one lane in a dozen needs a second block, so most warps do: both gathers are issued before either is waited for
+    const bool any_two = warp_any(two);
+    const PairReq qk = pair_issue(ix, pk, active);
+    PairReq ql;
+    if (any_two) ql = pair_issue(ix, pl, two);
+    uint32_t rk[6], rl[6];
+    {
+        const Blk bk = pair_finish(qk);
+        if (active) { rank_rel(bk, pk, rk); if (!two) rank_rel(bk, pl, rl); }
+    }
+    if (any_two) {
+        const Blk bl = pair_finish(ql);
+        if (two) rank_rel(bl, pl, rl);
+    }
+    if (active) extend6_rel<U>(ix, x_near, pk, pl, rk, rl, e);
 }
 
 template <typename U>
@@ -297,14 +392,6 @@ struct SmemArgs {
 };
 
 enum { PH_FETCH = 0, PH_BEGIN, PH_START_BWD, PH_FWD, PH_FWD_TAIL, PH_BWD, PH_DONE };
-
-FMG_HD bool warp_any(bool v) {
-#if defined(__CUDA_ARCH__)
-    return __any_sync(0xffffffffu, v);      // also the reconvergence point of the 32 lanes
-#else
-    return v;
-#endif
-}
 
 // Loop shape (per trip):  [divergent, short]  advance the lane's state machine to its next extension request
 //                         [warp vote]         leave when no lane has a request; reconverges the warp

@@ -31,22 +31,44 @@ extern std::atomic<uint64_t> g_launches;
         }                                                                                             \
     } while (0)
 
-// phases 1 and 3: one sequence per thread, a straight chain of extensions (converged for equal-length reads)
+// phase 1 is run by whole warps (paired block loads, fmd_device.cuh: load_blk_pair): threads past the end of the batch take part
+// without a sequence.  Phase 3: one sequence per thread, a straight chain of extensions.
 template <typename U, int PHASE>
-__global__ void __launch_bounds__(OVCH_BLOCK) k_ov_chain(OverlapArgs A) {
+__global__ void __launch_bounds__(OVCH_BLOCK) k_ov_chain(const __grid_constant__ OverlapArgs A) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < A.n) overlap_chain<U, PHASE>(A, t);
+    if (PHASE == 1) overlap_chain<U, 1>(A, t, t < A.n);
+    else if (t < A.n) overlap_chain<U, PHASE>(A, t);
 }
 
-// phases 2 and 4: persistent lanes, sequences handed out by atomicAdd, every extension behind a warp vote
+// phases 2 and 4: persistent lanes, sequences handed out by atomicAdd, every extension behind a warp vote; the level lists of
+// phase 2 start in (dynamic) shared memory
 template <typename U, int PHASE>
 __global__ void __launch_bounds__(OVLP_BLOCK, OVLP_MIN_BLOCKS) k_ov_lists(const __grid_constant__ OverlapArgs A) {     // &A.ix is taken: no stack copy
     const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     overlap_lane_sync<U, PHASE>(A, lane, [&]() -> int64_t { return (int64_t)atomicAdd(A.next, 1ull); });
 }
+// phase 2 (fm6_get_nei): persistent lanes of the flat state machine nei_lane, one converged gather per trip; the first entries of
+// the level lists in (dynamic) shared memory
+// MINB = resident blocks per SM the register allocation aims at (4: 128 registers, 5: 96, 6: 80 with some spilling); the best one is
+// a measured choice (FMG_NEI_BLOCKS overrides it for experiments)
+template <typename U, int MINB>
+__global__ void __launch_bounds__(OVLP_BLOCK, MINB) k_ov_nei(const __grid_constant__ OverlapArgs A) {
+    extern __shared__ uint4 fmg_ov_shared[];
+    const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    nei_lane<U>(A, lane, [&]() -> int64_t { return (int64_t)atomicAdd(A.next, 1ull); }, fmg_ov_shared, (int)blockDim.x, (int)threadIdx.x);
+}
+static int nei_minb() {
+    static const int v = [] { const char *e = std::getenv("FMG_NEI_BLOCKS"); const int x = e ? std::atoi(e) : 5; return x <= 4 ? 4 : x >= 6 ? 6 : 5; }();
+    return v;
+}
+template <typename U> static const void *nei_kernel() {
+    const int m = nei_minb();
+    return m == 4 ? (const void *)k_ov_nei<U, 4> : m == 6 ? (const void *)k_ov_nei<U, 6> : (const void *)k_ov_nei<U, 5>;
+}
+template <typename U> static constexpr size_t lists_shared_bytes() { return NeiLists<U>::shared_bytes(OVLP_BLOCK); }
 
 // ---- whole-index pass (fmg_overlap_all): per-batch records -> rank-indexed packed records + compact ext / spill arrays
-enum { OVC_NEXT = 0, OVC_NEXT2, OVC_EXT, OVC_SPILL, OVC_FLAGS, OVC_MAXLEN, OVC_N };
+enum { OVC_NEXT = 0, OVC_NEXT2, OVC_EXT, OVC_SPILL, OVC_FLAGS, OVC_MAXLEN, OVC_NLEFT, OVC_N };
 enum { OVF_LIST = 1, OVF_NEI = 2, OVF_EXT = 4, OVF_SPILL = 8, OVF_FIELD = 16, OVF_RANK = 32 };
 
 struct PackArgs {
@@ -57,7 +79,8 @@ struct PackArgs {
     const uint32_t *nei_cnt;
     const uint4 *nei_slots; int nei_cap;
     const uint8_t *ext; int max_len;
-    OvPack *pack; uint64_t n_seq;
+    OvPack *pack; uint64_t n_seq;       // by_row == 0: n_seq records indexed by rank; by_row == 1: the records of this batch in row order
+    int by_row;
     uint8_t *ext_out; uint64_t ext_cap;
     uint4 *spill_out; uint64_t spill_cap;
     unsigned long long *ctrl;
@@ -109,7 +132,7 @@ __global__ void __launch_bounds__(256) k_ov_pack(PackArgs A) {
             }
             OvPack o;
             if (!ov_pack(rec, nx0, nx1, nx2, be, &o)) flags |= OVF_FIELD;
-            uint4 *dst = reinterpret_cast<uint4 *>(A.pack + k);
+            uint4 *dst = reinterpret_cast<uint4 *>(A.pack + (A.by_row ? (uint64_t)t : k));
             const uint4 *src = reinterpret_cast<const uint4 *>(&o);
             dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
         }
@@ -117,12 +140,45 @@ __global__ void __launch_bounds__(256) k_ov_pack(PackArgs A) {
     if (flags) atomicOr(A.ctrl + OVC_FLAGS, (unsigned long long)flags);
 }
 
-// the sequences of the odd rows (the seeds of unitig_core, unitig.c:333-334) of a batch whose first row is even
-__global__ void __launch_bounds__(256) k_seq_odd(const uint8_t *__restrict__ seq, int max_len, int64_t n_odd, uint8_t *__restrict__ out) {
+// ---- the deferred left check.  check_left (unitig.c:206-225) only decides something when check_left_simple (unitig.c:186-204)
+// fails AND the reverse complement of the neighbour has more than one right neighbour; whether a record links to its unique
+// neighbour therefore depends on OV_LEFT only if pack[nx1].nnei > 1 (unitig_gpu.cu: links / stop_nei, unitig_host.cpp).  The pass
+// computes the records without the left check (phases 1 and 2) and evaluates it afterwards for exactly those rows -- none to
+// a few per mille on error-free reads, where phases 3 and 4 used to cost a third of the kernel time for every sequence.
+__global__ void __launch_bounds__(256) k_left_select(const OvPack *__restrict__ pack, const int64_t *__restrict__ rank_of_row, uint64_t row_lo, uint64_t row_hi,
+                                                    uint64_t *ids, unsigned long long *count) {
+    const uint64_t row = row_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool want = false;
+    if (row < row_hi) {
+        const OvPack p = pack[rank_of_row[row]];
+        want = p.nnei == 1 && p.contained == 0 && p.rbeg >= 0 && p.left == 1 && pack[p.nx1].nnei > 1;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) ids[base + __popc(m & ((1u << lane) - 1u))] = row;
+}
+
+__global__ void __launch_bounds__(256) k_left_patch(int64_t n, const int64_t *__restrict__ rec, const int64_t *__restrict__ ret, const uint32_t *__restrict__ nei_cnt, int nei_cap,
+                                                   OvPack *pack, unsigned long long *ctrl) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t *r = rec + t * OV_NREC;
+    if (r[OV_CONTAINED] == -100 || nei_cnt[t] > (uint32_t)nei_cap) { atomicOr(ctrl + OVC_FLAGS, (unsigned long long)OVF_LIST); return; }
+    pack[ret[t]].left = (int8_t)r[OV_LEFT];
+}
+
+// the sequences of the odd rows (the seeds of unitig_core, unitig.c:333-334) of a batch whose first row is even, left-aligned
+// for the host walk (the rows of the batch are right-aligned, fmd_overlap.cuh: OverlapArgs::seq_of)
+__global__ void __launch_bounds__(256) k_seq_odd(const uint8_t *__restrict__ seq, const int32_t *__restrict__ len, int max_len, int64_t n_odd, uint8_t *__restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_odd * max_len) return;
     const int64_t row = i / max_len, col = i - row * max_len;
-    out[i] = seq[(2 * row + 1) * max_len + col];
+    const int l = len[2 * row + 1], lc = l < 0 ? max_len : l;
+    out[i] = col < lc ? seq[(2 * row + 2) * max_len - lc + col] : 0;
 }
 
 // fm6_seqsort (seqsort.c:12-35): from fm6_retrieve's k / k2 / containment of every even row i, the rank table
@@ -145,9 +201,10 @@ int fmg_compact_slots(const uint32_t *cnt, int64_t n, int cap, const uint4 *slot
                       unsigned long long *ctrl, cudaStream_t st);
 int64_t fmg_compact_tiles(int64_t n);
 
-// the four phases of the overlap record over one batch, back to back on `st`; ctrl2 = two work counters (zeroed here)
+// phases 1 + 2 (the record without the left check) and phases 3 + 4 (check_left_simple) over one batch, back to back on `st`;
+// ctrl2 = two work counters (zeroed by launch_records)
 template <typename U>
-static cudaError_t launch_phases(OverlapArgs O, int grid, unsigned long long *ctrl2, cudaStream_t st, cudaEvent_t *ev = nullptr) {
+static cudaError_t launch_records(OverlapArgs O, int grid, unsigned long long *ctrl2, cudaStream_t st, cudaEvent_t *ev = nullptr) {
     cudaError_t e = cudaMemsetAsync(ctrl2, 0, 16, st);
     if (e != cudaSuccess) return e;
     const unsigned gch = (unsigned)((O.n + OVCH_BLOCK - 1) / OVCH_BLOCK);
@@ -156,30 +213,78 @@ static cudaError_t launch_phases(OverlapArgs O, int grid, unsigned long long *ct
     k_ov_chain<U, 1><<<gch, OVCH_BLOCK, 0, st>>>(O);
     if (ev) cudaEventRecord(ev[1], st);
     O.next = ctrl2;
-    k_ov_lists<U, 2><<<g, OVLP_BLOCK, 0, st>>>(O);
+    {
+        void *kargs[] = {(void *)&O};
+        e = cudaLaunchKernel(nei_kernel<U>(), dim3((unsigned)g), dim3(OVLP_BLOCK), kargs, lists_shared_bytes<U>(), st);
+        if (e != cudaSuccess) return e;
+    }
     if (ev) cudaEventRecord(ev[2], st);
+    g_launches += 2;
+    return cudaGetLastError();
+}
+template <typename U>
+static cudaError_t launch_left(OverlapArgs O, int grid, unsigned long long *ctrl2, cudaStream_t st) {
+    const unsigned gch = (unsigned)((O.n + OVCH_BLOCK - 1) / OVCH_BLOCK);
+    const int g = (int)std::min<int64_t>(grid, (O.n + OVLP_BLOCK - 1) / OVLP_BLOCK);
     k_ov_chain<U, 3><<<gch, OVCH_BLOCK, 0, st>>>(O);
-    if (ev) cudaEventRecord(ev[3], st);
     O.next = ctrl2 + 1;
     k_ov_lists<U, 4><<<g, OVLP_BLOCK, 0, st>>>(O);
-    if (ev) cudaEventRecord(ev[4], st);
-    g_launches += 4;
+    g_launches += 2;
     return cudaGetLastError();
 }
 
 static int lists_blocks_per_sm(bool wide) {
     int a = 0, b = 0;
     if (wide) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_ov_lists<uint64_t, 2>, OVLP_BLOCK, 0);
+        cudaFuncSetAttribute(nei_kernel<uint64_t>(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lists_shared_bytes<uint64_t>());
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, nei_kernel<uint64_t>(), OVLP_BLOCK, lists_shared_bytes<uint64_t>());
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_ov_lists<uint64_t, 4>, OVLP_BLOCK, 0);
     } else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_ov_lists<uint32_t, 2>, OVLP_BLOCK, 0);
+        cudaFuncSetAttribute(nei_kernel<uint32_t>(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lists_shared_bytes<uint32_t>());
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, nei_kernel<uint32_t>(), OVLP_BLOCK, lists_shared_bytes<uint32_t>());
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_ov_lists<uint32_t, 4>, OVLP_BLOCK, 0);
     }
     return std::max(1, std::max(a, b));       // lane scratch is sized for the larger grid
 }
 
+// narrow (32-bit) candidate entries pack the read position in 16 bits (fmd_overlap.cuh: OvBits): sequences of 64 kb or more, or
+// an index of 2^32 symbols, need the wide kernels
+static bool ov_wide(const fmg_index_s *idx, int max_len) {
+    return idx->view.n_sym + 256 >= (1ull << 32) || max_len >= 65536 || std::getenv("FMG_FORCE_WIDE") != nullptr;
+}
+static inline int round8(int v) { return (v + 7) & ~7; }
+
 namespace fmg { Pool g_pool; }
+
+// device scratch of the phase kernels for batches of up to `nb` rows
+struct OvScratch {
+    Dev seq, len, rec, ext, cnt, slots, P0, S0, np0, A, B, cat, S;
+    int max_len = 0, pcap = 0, cap = 0, nei_cap = 0, grid = 0;
+    bool wide = false;
+    cudaError_t alloc(int64_t nb, int max_len_, int pcap_, int cap_, int nei_cap_, bool wide_, int grid_) {
+        max_len = max_len_; pcap = pcap_; cap = cap_; nei_cap = nei_cap_; wide = wide_; grid = grid_;
+        const size_t esz = wide ? 32 : 16;
+        const int64_t n_lanes = (int64_t)grid * OVLP_BLOCK;
+        cudaError_t e;
+#define OVS_A(call) if ((e = (call)) != cudaSuccess) return e
+        OVS_A(seq.alloc((size_t)nb * max_len)); OVS_A(len.alloc((size_t)nb * 4)); OVS_A(rec.alloc((size_t)nb * OV_NREC * 8));
+        OVS_A(ext.alloc((size_t)nb * max_len)); OVS_A(cnt.alloc((size_t)(nb + 1) * 4)); OVS_A(slots.alloc((size_t)nb * nei_cap * 32));
+        OVS_A(P0.alloc((size_t)nb * pcap * esz)); OVS_A(S0.alloc((size_t)nb * pcap * (esz / 4))); OVS_A(np0.alloc((size_t)nb * 4));
+        OVS_A(A.alloc((size_t)n_lanes * cap * esz)); OVS_A(B.alloc((size_t)n_lanes * cap * esz)); OVS_A(cat.alloc((size_t)n_lanes * cap * 8));
+        OVS_A(S.alloc((size_t)n_lanes * cap * 2 * (esz / 4)));
+#undef OVS_A
+        return cudaSuccess;
+    }
+    OverlapArgs args(const fmg_index_s *idx, int min_match, int64_t m) const {
+        OverlapArgs O;
+        O.ix = idx->view; O.min_match = min_match; O.mode = 0; O.n = m; O.seq = seq.as<uint8_t>(); O.len = len.as<int32_t>(); O.max_len = max_len;
+        O.ids = nullptr; O.first = 0; O.step = 1; O.ret = nullptr;
+        O.P0 = P0.p; O.S0 = S0.p; O.pcap = pcap; O.np0 = np0.as<int32_t>(); O.A = A.p; O.B = B.p; O.cap = cap; O.cat = cat.as<int32_t>(); O.S = S.p;
+        O.rec = rec.as<int64_t>(); O.nei = slots.as<uint4>(); O.nei_cap = nei_cap; O.nei_cnt = cnt.as<uint32_t>();
+        O.ext = ext.as<uint8_t>(); O.next = nullptr;
+        return O;
+    }
+};
 
 // CUDA-event durations of the kernels of the last whole-index pass (bench.py's roofline figure for the unitig path)
 static std::mutex g_stats_lock;
@@ -193,12 +298,54 @@ extern "C" void fmg_release_cache(void) { g_pool.release(); }
 
 void fmg_ovcache_destroy(fmg_ovcache_s *p) { delete p; }
 
+// The deferred left check over rows [row_lo, row_hi) of a COMPLETE rank-indexed record array (see k_left_select): selected rows
+// are recomputed through all four phases in batches and their OV_LEFT is patched into `pack`.  Returns 0, 1 when a scratch
+// capacity was exceeded (the caller re-runs with larger ones), -1 on a CUDA error; *n_left = rows evaluated, *ms = device time.
+static int left_fix(const fmg_index_s *idx, int min_match, const OvScratch &S, int64_t nb_max, OvPack *pack, const int64_t *rank_of_row, uint64_t row_lo, uint64_t row_hi,
+                    unsigned long long *d_ctrl, unsigned long long *h_ctrl, cudaStream_t st, uint64_t *n_left, double *ms) {
+    *n_left = 0; *ms = 0;
+    if (row_hi <= row_lo) return 0;
+    Dev d_ids, d_ret;
+    OV_TRY(d_ids.alloc((row_hi - row_lo) * 8));
+    OV_TRY(d_ret.alloc((size_t)nb_max * 8));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    OV_TRY(cudaEventCreate(&e0)); OV_TRY(cudaEventCreate(&e1));
+    struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{e0, e1};
+    OV_TRY(cudaEventRecord(e0, st));
+    OV_TRY(cudaMemsetAsync(d_ctrl + OVC_NLEFT, 0, 8, st));
+    k_left_select<<<(unsigned)((row_hi - row_lo + 255) / 256), 256, 0, st>>>(pack, rank_of_row, row_lo, row_hi, d_ids.as<uint64_t>(), d_ctrl + OVC_NLEFT);
+    ++g_launches;
+    OV_TRY(cudaGetLastError());
+    OV_TRY(cudaMemcpyAsync(h_ctrl + OVC_NLEFT, d_ctrl + OVC_NLEFT, 8, cudaMemcpyDeviceToHost, st));
+    OV_TRY(cudaStreamSynchronize(st));
+    const uint64_t n = h_ctrl[OVC_NLEFT];
+    *n_left = n;
+    for (uint64_t o = 0; o < n; o += (uint64_t)nb_max) {
+        const int64_t m = (int64_t)std::min<uint64_t>((uint64_t)nb_max, n - o);
+        OverlapArgs O = S.args(idx, min_match, m);
+        O.ids = d_ids.as<uint64_t>() + o; O.ret = d_ret.as<int64_t>();
+        unsigned long long *c2 = d_ctrl + OVC_NEXT;
+        OV_TRY(S.wide ? launch_records<uint64_t>(O, S.grid, c2, st) : launch_records<uint32_t>(O, S.grid, c2, st));
+        OV_TRY(S.wide ? launch_left<uint64_t>(O, S.grid, c2, st) : launch_left<uint32_t>(O, S.grid, c2, st));
+        k_left_patch<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(m, S.rec.as<int64_t>(), d_ret.as<int64_t>(), S.cnt.as<uint32_t>(), S.nei_cap, pack, d_ctrl);
+        ++g_launches;
+        OV_TRY(cudaGetLastError());
+    }
+    OV_TRY(cudaEventRecord(e1, st));
+    OV_TRY(cudaMemcpyAsync(h_ctrl + OVC_FLAGS, d_ctrl + OVC_FLAGS, 8, cudaMemcpyDeviceToHost, st));
+    OV_TRY(cudaStreamSynchronize(st));
+    float f = 0;
+    cudaEventElapsedTime(&f, e0, e1);
+    *ms = f;
+    return h_ctrl[OVC_FLAGS] ? 1 : 0;
+}
+
 // Overlap records of EVERY sequence of the index (fm_retrieve + fm6_is_contained + fm6_get_nei + check_left_simple per
 // BWT row, unitig.c:77-204) for the unitig walk.  Rows are processed in batches queued back to back on one stream with
-// no host synchronisation in between: the four overlap phases -> k_ov_pack scatter the batch into device-resident,
-// rank-indexed 64-byte records plus compact ext / spill arrays; the seed sequences of batch b travel to pinned host
-// memory on a second stream while batch b+1 computes.  Overflow of any scratch or output capacity is flagged on the
-// device and answered by ONE re-run of the whole pass with larger capacities.
+// no host synchronisation in between: phases 1 + 2 -> k_ov_pack scatter the batch into device-resident, rank-indexed
+// 64-byte records plus compact ext / spill arrays; the seed sequences of batch b travel to pinned host memory on a second
+// stream while batch b+1 computes; the left check follows for the rows where it matters (left_fix).  Overflow of any scratch
+// or output capacity is flagged on the device and answered by ONE re-run of the whole pass with larger capacities.
 int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *out) {
     return out ? fmg_overlap_pass(idx, min_match, max_len, nullptr, out) : -1;
 }
@@ -214,14 +361,11 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
     std::lock_guard<std::mutex> ov_guard(idx->ov_lock);
     const uint64_t n_seq = idx->mcnt[1];
     if (max_len <= 0) max_len = (int)((idx->mcnt[0] - n_seq + n_seq - 1) / (n_seq ? n_seq : 1)) + 8;
+    max_len = round8(max_len);
     if (!idx->ovc) idx->ovc = new fmg_ovcache_s;
     fmg_ovcache_s &H = *idx->ovc;
-    const bool wide = idx->view.n_sym + 256 >= (1ull << 32) || std::getenv("FMG_FORCE_WIDE") != nullptr;
-    const int per_sm = lists_blocks_per_sm(wide);
     const int64_t batch = 1 << 21;                           // even, so that the odd rows of a batch are its local odd rows
     const int64_t nb_max = (int64_t)std::min<uint64_t>(batch, n_seq ? n_seq : 1);
-    const int grid = (int)std::min<int64_t>((int64_t)idx->n_sm * per_sm, (nb_max + OVLP_BLOCK - 1) / OVLP_BLOCK);
-    const int64_t n_lanes = (int64_t)grid * OVLP_BLOCK;
     const auto t0 = std::chrono::steady_clock::now();
     auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
 
@@ -240,7 +384,8 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
     }
 
     int cap = 4 * max_len, nei_cap = 8, pcap_mul = 1;
-    // fmg_verbose >= 4: 8 events per batch = [start | (unused) | retrieve + contained | neighbours | left chain | left lists | pack | seed rows]
+    // 6 events per batch = [start | retrieve + contained | neighbours | pack | seed rows | end]
+    constexpr int kEv = 6;
     std::vector<cudaEvent_t> phase_ev;
     uint64_t ext_cap = std::max<uint64_t>(n_seq * 24, 1 << 20), spill_cap = std::max<uint64_t>(n_seq, 1 << 16);
     const uint64_t row_lo = shard ? shard->row_lo : 0, row_hi = shard ? shard->row_hi : n_seq;
@@ -248,63 +393,57 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
     if (row_lo > row_hi || row_hi > n_seq || (row_lo & 1)) return -1;          // shards start at a read (even row)
     OV_TRY(H.ctrl.need(OVC_N * 8));
     unsigned long long *h_ctrl = static_cast<unsigned long long *>(H.ctrl.p);
-    Dev d_pack, d_ret, d_extout, d_spill, d_ctrl, d_seq, d_len, d_rec, d_ext, d_cnt, d_slots, d_P0, d_np0, d_A, d_B, d_cat, d_odd[2];
+    Dev d_pack, d_ret, d_extout, d_spill, d_ctrl, d_odd[2];
+    OvScratch S;
+    uint64_t n_left = 0;
+    double left_ms = 0;
     for (int attempt = 0;; ++attempt) {
+        const bool wide = ov_wide(idx, max_len);
+        const int per_sm = lists_blocks_per_sm(wide);
+        const int grid = (int)std::min<int64_t>((int64_t)idx->n_sm * per_sm, (nb_max + OVLP_BLOCK - 1) / OVLP_BLOCK);
         const int pcap = std::max(8, max_len - min_match + 8) * pcap_mul;
-        const size_t esz = wide ? 32 : 16;
         const uint64_t n_odd_all = n_seq / 2;
         if (!shard) {
             OV_TRY(d_pack.alloc(n_seq * sizeof(OvPack))); OV_TRY(d_ret.alloc(n_seq * 8));
             OV_TRY(d_extout.alloc(ext_cap)); OV_TRY(d_spill.alloc(spill_cap * 32));
         }
         OV_TRY(d_ctrl.alloc(OVC_N * 8));
-        // the four output arrays: the pass's own, or the caller's shard buffers (rank[] is addressed by absolute row)
+        // the four output arrays: the pass's own (records by rank), or the caller's shard buffers (records in row order; rank[] is addressed by absolute row)
         OvPack *o_pack = shard ? static_cast<OvPack *>(shard->pack) : d_pack.as<OvPack>();
         int64_t *o_ret = shard ? shard->rank - row_lo : d_ret.as<int64_t>();
         uint8_t *o_ext = shard ? shard->ext : d_extout.as<uint8_t>();
         uint4 *o_spill = shard ? static_cast<uint4 *>(shard->spill) : d_spill.as<uint4>();
-        OV_TRY(d_seq.alloc((size_t)nb_max * max_len)); OV_TRY(d_len.alloc((size_t)nb_max * 4)); OV_TRY(d_rec.alloc((size_t)nb_max * OV_NREC * 8));
-        OV_TRY(d_ext.alloc((size_t)nb_max * max_len)); OV_TRY(d_cnt.alloc((size_t)(nb_max + 1) * 4)); OV_TRY(d_slots.alloc((size_t)nb_max * nei_cap * 32));
-        OV_TRY(d_P0.alloc((size_t)nb_max * pcap * esz)); OV_TRY(d_np0.alloc((size_t)nb_max * 4));
-        OV_TRY(d_A.alloc((size_t)n_lanes * cap * esz)); OV_TRY(d_B.alloc((size_t)n_lanes * cap * esz));
-        OV_TRY(d_cat.alloc((size_t)n_lanes * cap * 8));
+        OV_TRY(S.alloc(nb_max, max_len, pcap, cap, nei_cap, wide, grid));
         for (int k = 0; k < 2; ++k) OV_TRY(d_odd[k].alloc((size_t)(nb_max / 2 + 1) * max_len));
         if (out) OV_TRY(H.seq.need(std::max<uint64_t>(n_odd_all, 1) * (uint64_t)max_len));
         OV_TRY(cudaMemsetAsync(d_ctrl.p, 0, OVC_N * 8, s_run));
         // records of sequences that overflow are not written: keep the array defined
         if (!shard) OV_TRY(cudaMemsetAsync(d_pack.p, 0, n_seq * sizeof(OvPack), s_run));
+        else if (row_hi > row_lo) OV_TRY(cudaMemsetAsync(o_pack, 0, (row_hi - row_lo) * sizeof(OvPack), s_run));
         int64_t b = 0;
         for (uint64_t row0 = row_lo; row0 < row_hi; row0 += batch, ++b) {
             const int64_t m = (int64_t)std::min<uint64_t>(batch, row_hi - row0);
-            cudaEvent_t *ev = nullptr;
-            {
-                const size_t e0 = phase_ev.size();
-                phase_ev.resize(e0 + 8, nullptr);
-                for (int k = 0; k < 8; ++k) OV_TRY(cudaEventCreate(&phase_ev[e0 + k]));
-                ev = &phase_ev[e0];
-                OV_TRY(cudaEventRecord(ev[0], s_run));
-            }
-            OverlapArgs O;
-            O.ix = idx->view; O.min_match = min_match; O.mode = 0; O.n = m; O.seq = d_seq.as<uint8_t>(); O.len = d_len.as<int32_t>(); O.max_len = max_len;
-            O.ids = nullptr; O.first = row0; O.step = 1; O.ret = o_ret + row0;
-            O.P0 = d_P0.p; O.pcap = pcap; O.np0 = d_np0.as<int32_t>(); O.A = d_A.p; O.B = d_B.p; O.cap = cap; O.cat = d_cat.as<int32_t>();
-            O.rec = d_rec.as<int64_t>(); O.nei = d_slots.as<uint4>(); O.nei_cap = nei_cap; O.nei_cnt = d_cnt.as<uint32_t>();
-            O.ext = d_ext.as<uint8_t>(); O.next = nullptr;
+            const size_t e0 = phase_ev.size();
+            phase_ev.resize(e0 + kEv, nullptr);
+            for (int k = 0; k < kEv; ++k) OV_TRY(cudaEventCreate(&phase_ev[e0 + k]));
+            cudaEvent_t *ev = &phase_ev[e0];
+            OverlapArgs O = S.args(idx, min_match, m);
+            O.first = row0; O.ret = o_ret + row0;
             unsigned long long *c2 = d_ctrl.as<unsigned long long>() + OVC_NEXT;       // OVC_NEXT, OVC_NEXT2: the work counters
-            OV_TRY(wide ? launch_phases<uint64_t>(O, grid, c2, s_run, ev ? ev + 1 : nullptr) : launch_phases<uint32_t>(O, grid, c2, s_run, ev ? ev + 1 : nullptr));
+            OV_TRY(wide ? launch_records<uint64_t>(O, grid, c2, s_run, ev) : launch_records<uint32_t>(O, grid, c2, s_run, ev));
             PackArgs P;
-            P.n = m; P.rec = d_rec.as<int64_t>(); P.ret = o_ret + row0; P.len = d_len.as<int32_t>(); P.nei_cnt = d_cnt.as<uint32_t>();
-            P.nei_slots = d_slots.as<uint4>(); P.nei_cap = nei_cap; P.ext = d_ext.as<uint8_t>(); P.max_len = max_len;
-            P.pack = o_pack; P.n_seq = n_seq; P.ext_out = o_ext; P.ext_cap = ext_cap;
+            P.n = m; P.rec = S.rec.as<int64_t>(); P.ret = o_ret + row0; P.len = S.len.as<int32_t>(); P.nei_cnt = S.cnt.as<uint32_t>();
+            P.nei_slots = S.slots.as<uint4>(); P.nei_cap = nei_cap; P.ext = S.ext.as<uint8_t>(); P.max_len = max_len;
+            P.pack = shard ? o_pack + (row0 - row_lo) : o_pack; P.n_seq = n_seq; P.by_row = shard ? 1 : 0; P.ext_out = o_ext; P.ext_cap = ext_cap;
             P.spill_out = o_spill; P.spill_cap = spill_cap; P.ctrl = d_ctrl.as<unsigned long long>();
             k_ov_pack<<<(unsigned)((m + 255) / 256), 256, 0, s_run>>>(P);
             ++g_launches;
             OV_TRY(cudaGetLastError());
-            if (ev) OV_TRY(cudaEventRecord(ev[6], s_run));
+            OV_TRY(cudaEventRecord(ev[3], s_run));
             const int64_t n_odd = out ? m / 2 : 0;             // the seed sequences only travel for the host walk
             if (n_odd) {
                 OV_TRY(cudaStreamWaitEvent(s_run, copy_done[b & 1], 0));     // the staging buffer of batch b-2 has left the device
-                k_seq_odd<<<(unsigned)((n_odd * max_len + 255) / 256), 256, 0, s_run>>>(d_seq.as<uint8_t>(), max_len, n_odd, d_odd[b & 1].as<uint8_t>());
+                k_seq_odd<<<(unsigned)((n_odd * max_len + 255) / 256), 256, 0, s_run>>>(S.seq.as<uint8_t>(), S.len.as<int32_t>(), max_len, n_odd, d_odd[b & 1].as<uint8_t>());
                 ++g_launches;
                 OV_TRY(cudaGetLastError());
                 OV_TRY(cudaEventRecord(run_done[b & 1], s_run));
@@ -313,26 +452,33 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
                                        cudaMemcpyDeviceToHost, s_copy));
                 OV_TRY(cudaEventRecord(copy_done[b & 1], s_copy));
             }
-            if (ev) OV_TRY(cudaEventRecord(ev[7], s_run));
+            OV_TRY(cudaEventRecord(ev[4], s_run));
         }
         OV_TRY(cudaMemcpyAsync(h_ctrl, d_ctrl.p, OVC_N * 8, cudaMemcpyDeviceToHost, s_run));
         OV_TRY(cudaStreamSynchronize(s_run));
-        const unsigned long long flags = h_ctrl[OVC_FLAGS], too_long = h_ctrl[OVC_MAXLEN];
+        unsigned long long flags = h_ctrl[OVC_FLAGS];
+        const unsigned long long too_long = h_ctrl[OVC_MAXLEN];
+        // the left check where it decides a link; a shard cannot know (the records of other rows are elsewhere): its caller runs fmg_overlap_left_fix on the merged array
+        if (!flags && !too_long && !shard) {
+            const int rc = left_fix(idx, min_match, S, nb_max, o_pack, o_ret, row_lo, row_hi, d_ctrl.as<unsigned long long>(), h_ctrl, s_run, &n_left, &left_ms);
+            if (rc < 0) return -1;
+            if (rc == 1) flags |= OVF_LIST;
+        }
         if (!phase_ev.empty()) {
-            double tot[7] = {0, 0, 0, 0, 0, 0, 0};
-            for (size_t e0 = 0; e0 + 8 <= phase_ev.size(); e0 += 8)
-                for (int k = 0; k < 7; ++k) {
+            double tot[kEv] = {0, 0, 0, 0, 0, 0};
+            for (size_t e0 = 0; e0 + kEv <= phase_ev.size(); e0 += kEv)
+                for (int k = 0; k < 4; ++k) {
                     float ms = 0;
                     cudaEventElapsedTime(&ms, phase_ev[e0 + k], phase_ev[e0 + k + 1]);
                     tot[k] += ms;
                 }
             if (fmg_verbose >= 4)
-                std::fprintf(stderr, "[M::%s] kernels over %zu batches (ms): memset %.1f, retrieve + contained %.1f, neighbours %.1f, left chain %.1f, left lists %.1f, pack %.1f, seed rows (+ wait for the copy engine) %.1f\n",
-                             __func__, phase_ev.size() / 8, tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], tot[6]);
+                std::fprintf(stderr, "[M::%s] kernels over %zu batches (ms): retrieve + contained %.1f, neighbours %.1f, pack %.1f, seed rows (+ wait for the copy engine) %.1f; left check of %llu rows %.1f\n",
+                             __func__, phase_ev.size() / kEv, tot[0], tot[1], tot[2], tot[3], (unsigned long long)n_left, left_ms);
             {
                 std::lock_guard<std::mutex> g(g_stats_lock);
-                for (int k = 0; k < 7; ++k) g_pass_ms[k] = tot[k];
-                g_pass_ms[7] = (double)(phase_ev.size() / 8);
+                g_pass_ms[0] = 0; g_pass_ms[1] = tot[0]; g_pass_ms[2] = tot[1]; g_pass_ms[3] = left_ms; g_pass_ms[4] = (double)n_left;
+                g_pass_ms[5] = tot[2]; g_pass_ms[6] = tot[3]; g_pass_ms[7] = (double)(phase_ev.size() / kEv);
             }
             for (cudaEvent_t e : phase_ev) cudaEventDestroy(e);
             phase_ev.clear();
@@ -350,7 +496,7 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
             shard->ext_total = h_ctrl[OVC_EXT] + (h_ctrl[OVC_EXT] >> 3) + 4096; shard->spill_total = h_ctrl[OVC_SPILL] + (h_ctrl[OVC_SPILL] >> 3) + 256;
             return 1;
         }
-        if (too_long) { max_len = (int)too_long + 8; cap = std::max(cap, 4 * max_len); }
+        if (too_long) { max_len = round8((int)too_long + 8); cap = std::max(cap, 4 * max_len); }
         if (flags & OVF_LIST) cap *= 4, pcap_mul *= 4;
         if (flags & (OVF_LIST | OVF_NEI)) nei_cap *= 4;
         // the totals keep counting past the capacity, so they are the true need unless other sequences were skipped
@@ -387,6 +533,46 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
     return 0;
 }
 
+// the left check over ALL rows of a merged, rank-indexed record array in caller-owned device memory (multi-GPU path: every rank
+// runs it on its copy after the exchange; fmg_overlap_pass does the same internally for a single GPU)
+int fmg_overlap_left_fix_dev(const fmg_index_s *idx, int min_match, int max_len, void *d_pack, const int64_t *d_rank_of_row, uint64_t *n_left_out) {
+    if (!idx || !d_pack || !d_rank_of_row) return -1;
+    OV_TRY(cudaSetDevice(idx->device));
+    std::lock_guard<std::mutex> ov_guard(idx->ov_lock);
+    const uint64_t n_seq = idx->mcnt[1];
+    if (max_len <= 0) max_len = (int)((idx->mcnt[0] - n_seq + n_seq - 1) / (n_seq ? n_seq : 1)) + 8;
+    max_len = round8(max_len);
+    if (!idx->ovc) idx->ovc = new fmg_ovcache_s;
+    fmg_ovcache_s &H = *idx->ovc;
+    OV_TRY(H.ctrl.need(OVC_N * 8));
+    unsigned long long *h_ctrl = static_cast<unsigned long long *>(H.ctrl.p);
+    const int64_t nb_max = (int64_t)std::min<uint64_t>(1 << 21, n_seq ? n_seq : 1);
+    Dev d_ctrl;
+    OV_TRY(d_ctrl.alloc(OVC_N * 8));
+    int cap = 4 * max_len, nei_cap = 8, pcap_mul = 1;
+    uint64_t n_left = 0;
+    for (int attempt = 0;; ++attempt) {
+        const bool wide = ov_wide(idx, max_len);
+        const int per_sm = lists_blocks_per_sm(wide);
+        const int grid = (int)std::min<int64_t>((int64_t)idx->n_sm * per_sm, (nb_max + OVLP_BLOCK - 1) / OVLP_BLOCK);
+        OvScratch S;
+        OV_TRY(S.alloc(nb_max, max_len, std::max(8, max_len - min_match + 8) * pcap_mul, cap, nei_cap, wide, grid));
+        OV_TRY(cudaMemset(d_ctrl.p, 0, OVC_N * 8));
+        double ms = 0;
+        const int rc = left_fix(idx, min_match, S, nb_max, static_cast<OvPack *>(d_pack), d_rank_of_row, 0, n_seq, d_ctrl.as<unsigned long long>(), h_ctrl, nullptr, &n_left, &ms);
+        if (rc < 0) return -1;
+        {
+            std::lock_guard<std::mutex> g(g_stats_lock);
+            g_pass_ms[3] = ms; g_pass_ms[4] = (double)n_left;
+        }
+        if (rc == 0) break;
+        if (attempt == 6) return -1;
+        cap *= 4; pcap_mul *= 4; nei_cap *= 4;
+    }
+    if (n_left_out) *n_left_out = n_left;
+    return 0;
+}
+
 extern "C" {
 
 // fm6_seqsort (seqsort.c:37-70) / `fermi seqrank`: sorted[mcnt[1]] as the reference fills it; stats = #zeros, #contained, #duplicates
@@ -399,7 +585,7 @@ int fmg_seqsort(const fmg_index_t *idx, uint64_t *sorted, int64_t stats[3]) {
     }
     OV_TRY(cudaSetDevice(idx->device));
     const uint64_t n_seq = idx->mcnt[1];
-    const bool wide = idx->view.n_sym + 256 >= (1ull << 32) || std::getenv("FMG_FORCE_WIDE") != nullptr;
+    const bool wide = ov_wide(idx, 0);
     Dev d_sorted, d_rec, d_ret, d_cnt, d_np0, d_len;
     OV_TRY(d_sorted.alloc(std::max<uint64_t>(n_seq, 1) * 8));
     OV_TRY(cudaMemset(d_sorted.p, 0, std::max<uint64_t>(n_seq, 1) * 8));         // calloc in the reference (seqsort.c:49)
@@ -445,48 +631,41 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
     nei_off[0] = 0;
     *nei = nullptr;
     if (n == 0) { *nei = (fmg_intv_t *)std::malloc(32); return 0; }
-    const bool wide = idx->view.n_sym + 256 >= (1ull << 32) || std::getenv("FMG_FORCE_WIDE") != nullptr;
+    const int ml = round8(max_len);                              // row stride on the device
+    const bool wide = ov_wide(idx, ml);
 
-    Dev d_ids, d_seq, d_len, d_ret, d_rec, d_ext, d_cnt, d_slots, d_mem, d_off, d_tiles, d_ctrl, d_A, d_B, d_cat;
-    OV_TRY(d_seq.alloc((size_t)n * max_len)); OV_TRY(d_len.alloc((size_t)n * 4)); OV_TRY(d_ret.alloc((size_t)n * 8));
-    OV_TRY(d_rec.alloc((size_t)n * OV_NREC * 8)); OV_TRY(d_ext.alloc((size_t)n * max_len)); OV_TRY(d_cnt.alloc((size_t)(n + 1) * 4));
+    Dev d_ids, d_ret, d_mem, d_off, d_tiles, d_ctrl;
+    OV_TRY(d_ret.alloc((size_t)n * 8));
     OV_TRY(d_off.alloc((size_t)(n + 1) * 8)); OV_TRY(d_tiles.alloc((size_t)fmg_compact_tiles(n) * 8)); OV_TRY(d_ctrl.alloc(64));
     if (ids) { OV_TRY(d_ids.alloc((size_t)n * 8)); OV_TRY(cudaMemcpy(d_ids.p, ids, (size_t)n * 8, cudaMemcpyHostToDevice)); }
 
     const auto t0 = std::chrono::steady_clock::now();
     auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
-    const auto t1 = std::chrono::steady_clock::now();
-    // ---- overlap records; scratch capacities grow until nothing overflows
+    // ---- overlap records (all four phases for every sequence); scratch capacities grow until nothing overflows
     const int per_sm = lists_blocks_per_sm(wide);
     const int grid = (int)std::min<int64_t>((int64_t)idx->n_sm * per_sm, (n + OVLP_BLOCK - 1) / OVLP_BLOCK);
-    const int64_t n_lanes = (int64_t)grid * OVLP_BLOCK;
-    int cap = 4 * max_len, nei_cap = 8, pcap = std::max(8, max_len - min_match + 8);
+    int cap = 4 * ml, nei_cap = 8, pcap = std::max(8, ml - min_match + 8);
     int64_t *h_rec = rec;
     std::vector<uint32_t> h_cnt(n);
-    Dev d_P0, d_np0;
     std::vector<int32_t> h_len(n);
-    OV_TRY(d_np0.alloc((size_t)n * 4));
+    OvScratch S;
     for (int attempt = 0;; ++attempt) {
-        const size_t esz = wide ? 32 : 16;
-        OV_TRY(d_P0.alloc((size_t)n * pcap * esz)); OV_TRY(d_A.alloc((size_t)n_lanes * cap * esz)); OV_TRY(d_B.alloc((size_t)n_lanes * cap * esz));
-        OV_TRY(d_cat.alloc((size_t)n_lanes * cap * 8)); OV_TRY(d_slots.alloc((size_t)n * nei_cap * 32)); OV_TRY(d_mem.alloc((size_t)n * nei_cap * 32));
-        OverlapArgs O;
-        O.ix = idx->view; O.min_match = min_match; O.mode = 0; O.n = n; O.seq = d_seq.as<uint8_t>(); O.len = d_len.as<int32_t>(); O.max_len = max_len;
+        OV_TRY(S.alloc(n, ml, pcap, cap, nei_cap, wide, grid));
+        OV_TRY(d_mem.alloc((size_t)n * nei_cap * 32));
+        OverlapArgs O = S.args(idx, min_match, n);
         O.ids = ids ? d_ids.as<uint64_t>() : nullptr; O.first = first; O.step = step; O.ret = d_ret.as<int64_t>();
-        O.P0 = d_P0.p; O.pcap = pcap; O.np0 = d_np0.as<int32_t>(); O.A = d_A.p; O.B = d_B.p; O.cap = cap; O.cat = d_cat.as<int32_t>();
-        O.rec = d_rec.as<int64_t>(); O.nei = d_slots.as<uint4>(); O.nei_cap = nei_cap; O.nei_cnt = d_cnt.as<uint32_t>();
-        O.ext = d_ext.as<uint8_t>(); O.next = nullptr;
-        OV_TRY(wide ? launch_phases<uint64_t>(O, grid, d_ctrl.as<unsigned long long>(), nullptr) : launch_phases<uint32_t>(O, grid, d_ctrl.as<unsigned long long>(), nullptr));
+        OV_TRY(wide ? launch_records<uint64_t>(O, grid, d_ctrl.as<unsigned long long>(), nullptr) : launch_records<uint32_t>(O, grid, d_ctrl.as<unsigned long long>(), nullptr));
+        OV_TRY(wide ? launch_left<uint64_t>(O, grid, d_ctrl.as<unsigned long long>(), nullptr) : launch_left<uint32_t>(O, grid, d_ctrl.as<unsigned long long>(), nullptr));
         OV_TRY(cudaDeviceSynchronize());
-        if (fmg_verbose >= 4) std::fprintf(stderr, "[M::%s] overlap phases (attempt %d) %.3f s for %lld sequences\n", __func__, attempt, since(t1), (long long)n);
-        OV_TRY(cudaMemcpy(h_len.data(), d_len.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        if (fmg_verbose >= 4) std::fprintf(stderr, "[M::%s] overlap phases (attempt %d) %.3f s for %lld sequences\n", __func__, attempt, since(t0), (long long)n);
+        OV_TRY(cudaMemcpy(h_len.data(), S.len.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
         for (int64_t i = 0; i < n; ++i)
-            if (h_len[i] < 0) {
-                if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] a sequence of %d bases exceeds max_len=%d\n", __func__, -h_len[i], max_len);
+            if (h_len[i] < 0 || h_len[i] > max_len) {
+                if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] a sequence of %d bases exceeds max_len=%d\n", __func__, h_len[i] < 0 ? -h_len[i] : h_len[i], max_len);
                 return 2;
             }
-        OV_TRY(cudaMemcpy(h_rec, d_rec.p, (size_t)n * OV_NREC * 8, cudaMemcpyDeviceToHost));
-        OV_TRY(cudaMemcpy(h_cnt.data(), d_cnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        OV_TRY(cudaMemcpy(h_rec, S.rec.p, (size_t)n * OV_NREC * 8, cudaMemcpyDeviceToHost));
+        OV_TRY(cudaMemcpy(h_cnt.data(), S.cnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
         bool list_ovf = false, nei_ovf = false;
         for (int64_t i = 0; i < n; ++i) {
             if (h_rec[i * OV_NREC + OV_CONTAINED] == -100) list_ovf = true;
@@ -507,15 +686,25 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
     for (int64_t i = 0; i < n; ++i) h_rec[i * OV_NREC + OV_K] = h_ret[i];
 
     // ---- neighbour slots -> dense array + offsets
-    if (fmg_compact_slots(d_cnt.as<uint32_t>(), n, nei_cap, d_slots.as<uint4>(), d_mem.as<uint4>(), d_off.as<uint64_t>(),
+    if (fmg_compact_slots(S.cnt.as<uint32_t>(), n, nei_cap, S.slots.as<uint4>(), d_mem.as<uint4>(), d_off.as<uint64_t>(),
                           d_tiles.as<uint64_t>(), d_ctrl.as<unsigned long long>(), nullptr)) return -1;
     OV_TRY(cudaMemcpy(nei_off, d_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost));
     const uint64_t tot = nei_off[n];
     *nei = (fmg_intv_t *)std::malloc((tot ? tot : 1) * 32);
     if (tot) OV_TRY(cudaMemcpy(*nei, d_mem.p, tot * 32, cudaMemcpyDeviceToHost));
-    if (seq) OV_TRY(cudaMemcpy(seq, d_seq.p, (size_t)n * max_len, cudaMemcpyDeviceToHost));
+    if (seq || ext) {                                            // device rows: stride ml, sequences right-aligned -> caller's n x max_len, left-aligned
+        std::vector<uint8_t> h((size_t)n * ml);
+        if (seq) {
+            OV_TRY(cudaMemcpy(h.data(), S.seq.p, (size_t)n * ml, cudaMemcpyDeviceToHost));
+            std::memset(seq, 0, (size_t)n * max_len);
+            for (int64_t i = 0; i < n; ++i) std::memcpy(seq + (size_t)i * max_len, h.data() + (size_t)(i + 1) * ml - h_len[i], (size_t)h_len[i]);
+        }
+        if (ext) {
+            OV_TRY(cudaMemcpy(h.data(), S.ext.p, (size_t)n * ml, cudaMemcpyDeviceToHost));
+            for (int64_t i = 0; i < n; ++i) std::memcpy(ext + (size_t)i * max_len, h.data() + (size_t)i * ml, (size_t)max_len);
+        }
+    }
     if (len) std::memcpy(len, h_len.data(), (size_t)n * 4);
-    if (ext) OV_TRY(cudaMemcpy(ext, d_ext.p, (size_t)n * max_len, cudaMemcpyDeviceToHost));
     if (fmg_verbose >= 4) std::fprintf(stderr, "[M::%s] batch total %.3f s\n", __func__, since(t0));
     return 0;
 }

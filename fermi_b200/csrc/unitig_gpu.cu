@@ -162,7 +162,7 @@ __device__ __forceinline__ uint32_t stop_nei(const G &g, uint64_t u, UNei *out) 
 
 // one orientation per chain: the head h emits when h <= rc(tail)
 __global__ void __launch_bounds__(256) k_select(G g, const uint32_t *__restrict__ dn, const uint64_t *__restrict__ db,
-                                               uint64_t *e_cnt, uint64_t *e_len, uint64_t *e_nei) {
+                                               uint64_t *e_cnt, uint64_t *e_len, uint64_t *e_nei, uint32_t part, uint32_t n_parts) {
     const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= g.n) return;
     uint64_t c = 0, l = 0, m = 0;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) k_select(G g, const uint32_t *__restrict_
         const uint32_t t = g.tail_of[h];
         const OvPack pt = g.pack[t];
         atomicAdd(g.counts + 1, (unsigned long long)dn[t] + 1);
-        if (h <= pt.x1) {
+        if (h <= pt.x1 && (n_parts <= 1 || (uint32_t)(h % n_parts) == part)) {      // several GPUs: the chains are dealt out by head rank
             c = 1;
             l = db[t] + pt.len;
             m = stop_nei(g, ph.x1, nullptr) + stop_nei(g, t, nullptr);
@@ -251,7 +251,44 @@ void put_i64(std::string &o, int64_t v) {            // decimal digits without g
 
 }  // namespace
 
-int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match, const char *out_path, uint64_t *n_unitigs) {
+// MAG text of one part of the unitigs, held by the caller between the two steps of a multi-GPU run (all ranks learn the sizes
+// of all parts before they write them side by side into one file)
+struct fmg_magpart_s { std::vector<std::string> parts; uint64_t bytes = 0; };
+
+static int write_parts(const std::vector<std::string> &parts, const char *out_path, uint64_t offset, bool truncate, const char *who) {
+    int fd = ::open(out_path, truncate ? (O_WRONLY | O_CREAT | O_TRUNC) : (O_WRONLY | O_CREAT), 0644);
+    if (fd < 0) {
+        if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] cannot write '%s'\n", who, out_path);
+        return -1;
+    }
+    const unsigned nt = (unsigned)parts.size();
+    std::vector<uint64_t> off(nt + 1, offset);
+    for (unsigned t = 0; t < nt; ++t) off[t + 1] = off[t] + parts[t].size();
+    std::atomic<int> io_fail{0};
+    auto put = [&](unsigned t) {
+        const std::string &o = parts[t];
+        for (size_t done = 0; done < o.size();) {
+            const ssize_t w = ::pwrite(fd, o.data() + done, o.size() - done, (off_t)(off[t] + done));
+            if (w <= 0) { io_fail = 1; return; }
+            done += (size_t)w;
+        }
+    };
+    if (nt <= 1) { if (nt) put(0); }
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(put, t);
+        for (auto &x : th) x.join();
+    }
+    ::close(fd);
+    if (io_fail) {
+        if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] short write to '%s'\n", who, out_path);
+        return -1;
+    }
+    return 0;
+}
+
+int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match, const char *out_path, uint64_t *n_unitigs,
+                      uint32_t part, uint32_t n_parts, fmg_magpart_s *sink) {
     const uint64_t n = D.n_seq;
     if (n_unitigs) *n_unitigs = 0;
     if (n == 0 || n >= kNone) return 1;
@@ -310,7 +347,7 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
     const double t_rank = since(t0);
     k_tails<<<nblk(n), 256, 0, st>>>(g, head);
     uint64_t *e_cnt = d_cnt.as<uint64_t>(), *e_len = d_len.as<uint64_t>(), *e_nei = d_nei.as<uint64_t>();
-    k_select<<<nblk(n), 256, 0, st>>>(g, dn, db, e_cnt, e_len, e_nei);
+    k_select<<<nblk(n), 256, 0, st>>>(g, dn, db, e_cnt, e_len, e_nei, part, n_parts);
     g_launches += 2;
     UG_TRY(cudaGetLastError());
     // exclusive scans (n + 1 items: the last one is the total); e_cnt keeps the flags, the offsets go to the other buffers
@@ -366,22 +403,16 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
 
     // ---- MAG text (mag_v_write, mag.c:149-174), formatted by all host cores in unitig order.  A regular file is written
     // by the same threads with pwrite at the offsets the part sizes give (the page-cache copy is the cost of the output).
-    const bool to_stdout = std::strcmp(out_path, "-") == 0;
-    int fd = -1;
-    if (!to_stdout) {
-        fd = ::open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
-        if (fd < 0) {
-            if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] cannot write '%s'\n", __func__, out_path);
-            return -1;
-        }
-    }
+    const bool to_stdout = !sink && std::strcmp(out_path, "-") == 0;
     const UMeta *meta = H.umeta.as<UMeta>();
     const UNei *nei = H.unei.as<UNei>();
     const char *useq = H.useq.as<char>(), *ucov = H.ucov.as<char>();
-    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency() / std::max(1u, n_parts), 32u));
     if (const char *e = std::getenv("FMG_THREADS")) nt = (unsigned)std::max(1, std::atoi(e));
     if (n_u < 4096) nt = 1;
-    std::vector<std::string> parts(nt);
+    std::vector<std::string> local_parts;
+    std::vector<std::string> &parts = sink ? sink->parts : local_parts;
+    parts.assign(nt, std::string());
     auto fmt = [&](unsigned t) {
         const uint64_t a = n_u * t / nt, b = n_u * (t + 1) / nt;
         std::string &o = parts[t];
@@ -406,35 +437,19 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
             o += '\n';
         }
     };
-    std::atomic<int> io_fail{0};
-    auto put = [&](unsigned t, uint64_t off) {
-        const std::string &o = parts[t];
-        for (size_t done = 0; done < o.size();) {
-            const ssize_t w = ::pwrite(fd, o.data() + done, o.size() - done, (off_t)(off + done));
-            if (w <= 0) { io_fail = 1; return; }
-            done += (size_t)w;
-        }
-    };
-    auto run_all = [&](auto fn) {
-        if (nt == 1) { fn(0u); return; }
+    if (nt == 1) fmt(0u);
+    else {
         std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; ++t) th.emplace_back(fn, t);
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(fmt, t);
         for (auto &x : th) x.join();
-    };
-    run_all(fmt);
-    if (to_stdout) {
+    }
+    if (sink) {
+        sink->bytes = 0;
+        for (const std::string &o : parts) sink->bytes += o.size();
+    } else if (to_stdout) {
         for (const std::string &o : parts) std::fwrite(o.data(), 1, o.size(), stdout);
         std::fflush(stdout);
-    } else {
-        std::vector<uint64_t> off(nt + 1, 0);
-        for (unsigned t = 0; t < nt; ++t) off[t + 1] = off[t] + parts[t].size();
-        run_all([&](unsigned t) { put(t, off[t]); });
-        ::close(fd);
-        if (io_fail) {
-            if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] short write to '%s'\n", __func__, out_path);
-            return -1;
-        }
-    }
+    } else if (write_parts(parts, out_path, 0, true, __func__) != 0) return -1;
     if (n_unitigs) *n_unitigs = n_u;
     if (fmg_verbose >= 4)
         std::fprintf(stderr, "[M::%s] %llu unitigs, %llu bases from %llu sequences: chains %.3f s (%d jump rounds), assembly + copies %.3f s, text %.3f s\n", __func__,
@@ -462,7 +477,7 @@ int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *o
             if (rc != 0) return rc;
             const auto t1 = std::chrono::steady_clock::now();
             const fmg::OvDevView V = {D.pack.p, D.rank.as<int64_t>(), D.ext.as<uint8_t>(), D.spill.p, D.n_seq, D.ext_total, D.spill_total};
-            rc = fmg_unitig_device(idx, V, min_match, out_path, n_unitigs);
+            rc = fmg_unitig_device(idx, V, min_match, out_path, n_unitigs, 0, 1, nullptr);
             if (rc == 0 && fmg_verbose >= 3)
                 std::fprintf(stderr, "[M::%s] %llu sequences: overlap records %.3f s, unitig assembly + output %.3f s (GPU)\n", __func__,
                              (unsigned long long)D.n_seq, secs(t0, t1), secs(t1, std::chrono::steady_clock::now()));
@@ -483,37 +498,80 @@ int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *o
     return rc;
 }
 
-// ---- multi-GPU: shards of the records in caller-owned device buffers (the caller runs the collective, e.g. NCCL through
-// torch.distributed: all-reduce of the disjointly filled pack array, all-gather of the rank / ext / spill shards)
-__global__ void __launch_bounds__(256) k_ov_rebase(OvPack *pack, const int64_t *__restrict__ rank, uint64_t n_rows, uint64_t ext_base, uint64_t spill_base) {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_rows) return;
-    OvPack *p = pack + rank[t];
-    if (p->nnei == 1) p->ext_first += ext_base;
-    else if (p->nnei > 1) p->nx0 += spill_base;
+} // extern "C"
+
+// ---- multi-GPU `fermi unitig` (fermi_b200/parallel.py drives it with NCCL through torch.distributed):
+//   fmg_overlap_shard      every GPU: records of its rows, in row order, into caller-owned device buffers
+//   -- one all-gather of the record / rank / ext / spill shards, each padded to the largest shard --
+//   fmg_overlap_merge      every GPU: gathered shards -> the rank-indexed record array the assembly chases
+//   fmg_overlap_left_fix   every GPU: the deferred left check (overlap.cu: left_fix) on the merged array
+//   fmg_unitig_part        every GPU: link graph + pointer jumping over all records, then emission and MAG text of the chains
+//                          it owns (head rank % n_parts == part)
+//   -- all-gather of the text sizes --
+//   fmg_magpart_write      every GPU: its text at its offset of the one output file
+struct MergeArgs {
+    int n_shards;
+    uint64_t rows[64];              // rows of each shard (shards are consecutive row ranges, in order)
+    uint64_t row_pad, ext_pad, spill_pad;   // slot sizes of the gathered arrays (rows, bytes, entries per shard)
+};
+__global__ void __launch_bounds__(256) k_ov_merge(MergeArgs M, const OvPack *__restrict__ rec_all, const int64_t *__restrict__ rank_all, uint64_t n_seq,
+                                                 OvPack *pack, int64_t *rank_of_row, uint32_t *flags) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;       // index into the padded gathered arrays
+    const uint64_t s = i / M.row_pad, t = i - s * M.row_pad;
+    if (s >= (uint64_t)M.n_shards || t >= M.rows[s]) return;
+    uint64_t row = t;
+    for (uint64_t q = 0; q < s; ++q) row += M.rows[q];
+    const int64_t r = rank_all[i];
+    rank_of_row[row] = r;
+    OvPack p = rec_all[i];
+    if (p.nnei == 1) p.ext_first += s * M.ext_pad;
+    else if (p.nnei > 1) p.nx0 += s * M.spill_pad;
+    if ((uint64_t)r >= n_seq) { atomicOr(flags, 1u); return; }
+    uint4 *dst = reinterpret_cast<uint4 *>(pack + r);
+    const uint4 *src = reinterpret_cast<const uint4 *>(&p);
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
 }
 
-int fmg_overlap_shard(const fmg_index_t *idx, int min_match, int max_len, uint64_t row_lo, uint64_t row_hi, void *d_pack, int64_t *d_rank,
+int fmg_overlap_left_fix_dev(const fmg_index_s *idx, int min_match, int max_len, void *d_pack, const int64_t *d_rank_of_row, uint64_t *n_left_out);
+
+extern "C" {
+
+int fmg_overlap_shard(const fmg_index_t *idx, int min_match, int max_len, uint64_t row_lo, uint64_t row_hi, void *d_rec, int64_t *d_rank,
                       uint8_t *d_ext, uint64_t ext_cap, void *d_spill, uint64_t spill_cap, uint64_t totals[2]) {
-    if (!idx || !d_pack || !d_rank || !d_ext || !d_spill || !totals) return -1;
+    if (!idx || !d_rec || !d_rank || !d_ext || !d_spill || !totals) return -1;
     fmg::OvShard S;
-    S.row_lo = row_lo; S.row_hi = row_hi; S.pack = d_pack; S.rank = d_rank; S.ext = d_ext; S.ext_cap = ext_cap; S.spill = d_spill; S.spill_cap = spill_cap;
+    S.row_lo = row_lo; S.row_hi = row_hi; S.pack = d_rec; S.rank = d_rank; S.ext = d_ext; S.ext_cap = ext_cap; S.spill = d_spill; S.spill_cap = spill_cap;
     S.ext_total = S.spill_total = 0; S.max_len = 0;
     const int rc = fmg_overlap_pass(idx, min_match, max_len, nullptr, nullptr, &S);
     totals[0] = S.ext_total; totals[1] = S.spill_total;
     return rc;
 }
 
-int fmg_overlap_rebase(const fmg_index_t *idx, void *d_pack, const int64_t *d_rank, uint64_t n_rows, uint64_t ext_base, uint64_t spill_base) {
-    if (!idx || !d_pack || !d_rank) return -1;
+int fmg_overlap_merge(const fmg_index_t *idx, int n_shards, const uint64_t *rows, uint64_t row_pad, uint64_t ext_pad, uint64_t spill_pad,
+                      const void *d_rec_all, const int64_t *d_rank_all, void *d_pack, int64_t *d_rank_of_row) {
+    if (!idx || n_shards < 1 || n_shards > 64 || !rows || !d_rec_all || !d_rank_all || !d_pack || !d_rank_of_row) return -1;
     UG_TRY(cudaSetDevice(idx->device));
-    if (n_rows && (ext_base || spill_base)) {
-        k_ov_rebase<<<nblk(n_rows), 256>>>(static_cast<OvPack *>(d_pack), d_rank, n_rows, ext_base, spill_base);
-        ++g_launches;
-        UG_TRY(cudaGetLastError());
-    }
-    UG_TRY(cudaDeviceSynchronize());
-    return 0;
+    const uint64_t n_seq = idx->mcnt[1];
+    MergeArgs M;
+    M.n_shards = n_shards; M.row_pad = row_pad ? row_pad : 1; M.ext_pad = ext_pad; M.spill_pad = spill_pad;
+    uint64_t tot = 0;
+    for (int q = 0; q < n_shards; ++q) { M.rows[q] = rows[q]; tot += rows[q]; if (rows[q] > M.row_pad) return -1; }
+    if (tot != n_seq) return -1;
+    Dev d_flag;
+    UG_TRY(d_flag.alloc(4));
+    UG_TRY(cudaMemset(d_flag.p, 0, 4));
+    UG_TRY(cudaMemset(d_pack, 0, n_seq * sizeof(OvPack)));
+    k_ov_merge<<<nblk(M.row_pad * (uint64_t)n_shards), 256>>>(M, static_cast<const OvPack *>(d_rec_all), d_rank_all, n_seq, static_cast<OvPack *>(d_pack), d_rank_of_row,
+                                                           d_flag.as<uint32_t>());
+    ++g_launches;
+    UG_TRY(cudaGetLastError());
+    uint32_t f = 0;
+    UG_TRY(cudaMemcpy(&f, d_flag.p, 4, cudaMemcpyDeviceToHost));
+    return f ? -1 : 0;
+}
+
+int fmg_overlap_left_fix(const fmg_index_t *idx, int min_match, int max_len, void *d_pack, const int64_t *d_rank_of_row, uint64_t *n_left) {
+    return fmg_overlap_left_fix_dev(idx, min_match, max_len, d_pack, d_rank_of_row, n_left);
 }
 
 int fmg_unitig_from_device(const fmg_index_t *idx, int min_match, const void *d_pack, const int64_t *d_rank, const uint8_t *d_ext, uint64_t ext_total,
@@ -522,7 +580,29 @@ int fmg_unitig_from_device(const fmg_index_t *idx, int min_match, const void *d_
     UG_TRY(cudaSetDevice(idx->device));
     UG_TRY(cudaDeviceSynchronize());
     const fmg::OvDevView V = {d_pack, d_rank, d_ext, d_spill, idx->mcnt[1], ext_total, spill_total};
-    return fmg_unitig_device(idx, V, min_match, out_path, n_unitigs);
+    return fmg_unitig_device(idx, V, min_match, out_path, n_unitigs, 0, 1, nullptr);
 }
+
+int fmg_unitig_part(const fmg_index_t *idx, int min_match, const void *d_pack, const int64_t *d_rank_of_row, const uint8_t *d_ext, const void *d_spill,
+                    int part, int n_parts, fmg_magpart_t **out, uint64_t *n_unitigs, uint64_t *n_bytes) {
+    if (!idx || !d_pack || !d_rank_of_row || !out || part < 0 || n_parts < 1 || part >= n_parts) return -1;
+    *out = nullptr;
+    UG_TRY(cudaSetDevice(idx->device));
+    UG_TRY(cudaDeviceSynchronize());
+    fmg_magpart_s *sink = new fmg_magpart_s;
+    const fmg::OvDevView V = {d_pack, d_rank_of_row, d_ext, d_spill, idx->mcnt[1], 0, 0};
+    const int rc = fmg_unitig_device(idx, V, min_match, "", n_unitigs, (uint32_t)part, (uint32_t)n_parts, sink);
+    if (rc != 0) { delete sink; return rc; }
+    if (n_bytes) *n_bytes = sink->bytes;
+    *out = sink;
+    return 0;
+}
+
+int fmg_magpart_write(const fmg_magpart_t *p, const char *path, uint64_t offset, int truncate) {
+    if (!p || !path) return -1;
+    return write_parts(p->parts, path, offset, truncate != 0, __func__);
+}
+
+void fmg_magpart_free(fmg_magpart_t *p) { delete p; }
 
 } // extern "C"

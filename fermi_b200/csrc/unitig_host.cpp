@@ -172,8 +172,9 @@ int fmg_unitig_walk(const OvHost &R, int min_match, const char *out_path, uint64
     }
     const auto tw0 = std::chrono::steady_clock::now();
     int n_threads = 1;
+    // one thread by default, like `fermi unitig` (-t 1, cmd.c:186): on an irregular link graph the result depends on the seed
+    // order, and only the single-thread walk reproduces the reference record for record; FMG_THREADS / -t opts in to more
     if (const char *e = std::getenv("FMG_THREADS")) n_threads = std::atoi(e);
-    else n_threads = (int)std::min<unsigned>(std::thread::hardware_concurrency(), 32u);
     if (n_threads < 1 || n_seq < 64) n_threads = 1;
     Bits used(n_seq), bend(n_seq), visited(n_seq);
     std::vector<uint64_t> counts(n_threads, 0);

@@ -77,71 +77,132 @@ def unitig_distributed(idx, min_match, out_path, max_len, overlap_fn=None, group
     return None
 
 
-def unitig_distributed_device(idx, min_match, out_path, max_len=0, group=None):
-    """`fermi unitig` over all ranks with everything in HBM: every rank computes the packed overlap records of its range of BWT
-    rows on its GPU (fmg_overlap_shard), ONE exchange merges the shards -- an all-reduce(sum) of the rank-indexed 64-byte
-    record array, which the shards fill disjointly, and all-gathers of the rank / appended-base / fork-neighbour shards --
-    and rank 0 assembles the unitigs on its GPU (fmg_unitig_from_device) and writes the MAG file.  NCCL only.
-    Returns the number of unitigs on rank 0 (None elsewhere)."""
+def unitig_shard_rows(n_seq, rank, world):
+    """rows [lo, hi) of `rank`: shards of whole reads (row 2i = the read, row 2i+1 = its reverse complement)"""
+    lo, hi = shard_range(n_seq // 2, rank, world)
+    return 2 * lo, (2 * hi if rank < world - 1 else n_seq)
+
+
+def overlap_shard_device(idx, min_match, lo, hi, max_len=0):
+    """fmg_overlap_shard into torch buffers: (rec int64[m*8], rank int64[m], ext uint8[], spill int64[], ext_total, spill_total)"""
     import ctypes as C
     from ._lib import lib
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    dev = _device()
     L = lib()
-    n_seq = int(idx.mcnt[1])
-    lo, hi = shard_range(n_seq // 2, rank, world)             # shards of whole reads: rows 2i (read) and 2i+1 (reverse complement)
-    lo, hi = 2 * lo, (2 * hi if rank < world - 1 else n_seq)
+    dev = torch.device("cuda", torch.cuda.current_device())
     m = hi - lo
-    pack = torch.zeros(n_seq * 8, dtype=torch.int64, device=dev)
+    rec = torch.empty(max(m, 1) * 8, dtype=torch.int64, device=dev)
     rnk = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
     ext_cap, spill_cap = max(32 * m, 1 << 16), max(2 * m, 1 << 12)
     tot = (C.c_uint64 * 2)()
     while True:
         ext = torch.empty(ext_cap, dtype=torch.uint8, device=dev)
         spill = torch.empty(spill_cap * 4, dtype=torch.int64, device=dev)
-        rc = L.fmg_overlap_shard(idx.h, int(min_match), int(max_len), lo, hi, pack.data_ptr(), rnk.data_ptr(), ext.data_ptr(), ext_cap,
+        rc = L.fmg_overlap_shard(idx.h, int(min_match), int(max_len), lo, hi, rec.data_ptr(), rnk.data_ptr(), ext.data_ptr(), ext_cap,
                                  spill.data_ptr(), spill_cap, tot)
         if rc == 1:                                           # capacities too small: the call reports the need
-            pack.zero_()
             ext_cap, spill_cap = max(ext_cap, int(tot[0])), max(spill_cap, int(tot[1]))
             continue
         if rc != 0:
             raise RuntimeError("fermi_b200: fmg_overlap_shard failed (see stderr)")
-        break
-    sizes = torch.tensor([m, int(tot[0]), int(tot[1])], dtype=torch.int64, device=dev)
+        return rec, rnk, ext, spill, int(tot[0]), int(tot[1])
+
+
+def unitig_distributed_device(idx, min_match, out_path, max_len=0, group=None, timings=None):
+    """`fermi unitig` over all ranks with everything in HBM (NCCL only).  Every rank computes the packed overlap records of its
+    range of BWT rows on its GPU (fmg_overlap_shard); ONE all-gather (four tensors: records, ranks, appended bases, fork
+    neighbour lists, each shard padded to the largest) gives every rank all records; every rank merges them into the
+    rank-indexed array (fmg_overlap_merge), evaluates the deferred left checks (fmg_overlap_left_fix), builds the link graph
+    and assembles + formats the unitigs whose chain head it owns (fmg_unitig_part: head rank % world == rank); after an
+    all-gather of the text sizes every rank writes its text at its offset of the one MAG file.  Returns the total number of
+    unitigs (on every rank).  `timings` (dict) receives wall-clock seconds of the stages, measured with device synchronisation."""
+    import ctypes as C
+    import time
+    from ._lib import lib
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = _device()
+    L = lib()
+    n_seq = int(idx.mcnt[1])
+    t = [time.perf_counter()]
+
+    def lap():
+        torch.cuda.synchronize()
+        t.append(time.perf_counter())
+
+    lo, hi = unitig_shard_rows(n_seq, rank, world)
+    m = hi - lo
+    rec, rnk, ext, spill, ext_tot, spill_tot = overlap_shard_device(idx, min_match, lo, hi, max_len)
+    lap()
+    sizes = torch.tensor([m, ext_tot, spill_tot], dtype=torch.int64, device=dev)
     all_sizes = torch.empty(world * 3, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(all_sizes, sizes, group=group)                      # shard sizes
     all_sizes = all_sizes.view(world, 3).cpu()
-    rows, exts, spills = all_sizes[:, 0].tolist(), all_sizes[:, 1].tolist(), all_sizes[:, 2].tolist()
-    if L.fmg_overlap_rebase(idx.h, pack.data_ptr(), rnk.data_ptr(), m, sum(exts[:rank]), sum(spills[:rank])) != 0:
-        raise RuntimeError("fermi_b200: fmg_overlap_rebase failed")
-    dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)                        # the records: disjoint shards, so sum = union
+    rows = all_sizes[:, 0].tolist()
+    row_pad, ext_pad, spill_pad = max(int(all_sizes[:, 0].max()), 1), max(int(all_sizes[:, 1].max()), 1), max(int(all_sizes[:, 2].max()), 1)
 
-    def gather(t, counts, width=1):
-        pad = max(max(counts), 1) * width
-        buf = torch.zeros(pad, dtype=t.dtype, device=dev)
-        buf[: counts[rank] * width] = t[: counts[rank] * width]
-        out = torch.empty(world * pad, dtype=t.dtype, device=dev)
-        dist.all_gather_into_tensor(out, buf, group=group)
-        return torch.cat([out[r * pad: r * pad + counts[r] * width] for r in range(world)]) if world > 1 else out[: counts[0] * width]
+    def gather(src, n_used, pad, width=1):
+        buf = src
+        if src.numel() < pad * width:                         # the shard buffer is smaller than the largest shard: pad a copy
+            buf = torch.zeros(pad * width, dtype=src.dtype, device=dev)
+            buf[: n_used * width] = src[: n_used * width]
+        out = torch.empty(world * pad * width, dtype=src.dtype, device=dev)
+        dist.all_gather_into_tensor(out, buf[: pad * width], group=group)
+        return out
 
-    rank_all = gather(rnk, rows)
-    ext_all = gather(ext, exts)
-    spill_all = gather(spill, spills, 4)
-    n = None
-    if rank == 0:
-        nu = C.c_uint64()
-        rc = L.fmg_unitig_from_device(idx.h, int(min_match), pack.data_ptr(), rank_all.data_ptr(), ext_all.data_ptr() if len(ext_all) else 0,
-                                      sum(exts), spill_all.data_ptr() if len(spill_all) else 0, sum(spills), str(out_path).encode(), C.byref(nu))
-        if rc == 1:                                           # irregular link graph: the single-GPU path with the host walk
+    rec_all = gather(rec, m, row_pad, 8)                      # the one exchange of the path: 64-byte records ...
+    rank_all = gather(rnk, m, row_pad)                        # ... their ranks ...
+    ext_all = gather(ext, ext_tot, ext_pad)                   # ... appended bases ...
+    spill_all = gather(spill, spill_tot, spill_pad, 4)        # ... and the neighbour lists of forks
+    lap()
+    pack = torch.empty(n_seq * 8, dtype=torch.int64, device=dev)
+    rank_of_row = torch.empty(n_seq, dtype=torch.int64, device=dev)
+    c_rows = (C.c_uint64 * world)(*rows)
+    if L.fmg_overlap_merge(idx.h, world, c_rows, row_pad, ext_pad, spill_pad, rec_all.data_ptr(), rank_all.data_ptr(), pack.data_ptr(),
+                           rank_of_row.data_ptr()) != 0:
+        raise RuntimeError("fermi_b200: fmg_overlap_merge failed")
+    del rec_all, rank_all
+    n_left = C.c_uint64()
+    if L.fmg_overlap_left_fix(idx.h, int(min_match), int(max_len), pack.data_ptr(), rank_of_row.data_ptr(), C.byref(n_left)) != 0:
+        raise RuntimeError("fermi_b200: fmg_overlap_left_fix failed")
+    lap()
+    part, nu, nb = C.c_void_p(), C.c_uint64(), C.c_uint64()
+    rc = L.fmg_unitig_part(idx.h, int(min_match), pack.data_ptr(), rank_of_row.data_ptr(), ext_all.data_ptr(), spill_all.data_ptr(), rank, world,
+                           C.byref(part), C.byref(nu), C.byref(nb))
+    lap()
+    state = torch.tensor([rc, int(nu.value), int(nb.value)], dtype=torch.int64, device=dev)
+    all_state = torch.empty(world * 3, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_state, state, group=group)                      # text sizes (and whether the graph was regular)
+    all_state = all_state.view(world, 3).cpu()
+    if int(all_state[:, 0].max()) == 1 or int(all_state[:, 0].min()) < 0:
+        # irregular link graph (the same on every rank: they hold the same records): the single-GPU path with the host walk
+        if part:
+            L.fmg_magpart_free(part)
+        if int(all_state[:, 0].min()) < 0:
+            raise RuntimeError("fermi_b200: fmg_unitig_part failed")
+        n = None
+        if rank == 0:
             from . import api
             n = api.fm6_unitig(idx, min_match, out_path, max_len)
-        elif rc != 0:
-            raise RuntimeError("fermi_b200: fmg_unitig_from_device failed")
-        else:
-            n = int(nu.value)
-    torch.cuda.synchronize()
-    return n
+        res = torch.tensor([n if n is not None else 0], dtype=torch.int64, device=dev)
+        dist.broadcast(res, 0, group=group)
+        if timings is not None:
+            timings.update(records=t[1] - t[0], exchange=t[2] - t[1], merge_left=t[3] - t[2], assembly=t[4] - t[3], write=0.0, host_walk=True,
+                           left_rows=int(n_left.value))
+        return int(res[0])
+    sizes_b = all_state[:, 2].tolist()
+    path = str(out_path).encode()
+    if rank == 0:
+        with open(out_path, "wb") as fh:                      # the file exists and is empty before anyone writes into it
+            fh.truncate(sum(sizes_b))
+    dist.barrier(group=group)
+    if L.fmg_magpart_write(part, path, sum(sizes_b[:rank]), 0) != 0:
+        raise RuntimeError("fermi_b200: fmg_magpart_write failed")
+    L.fmg_magpart_free(part)
+    dist.barrier(group=group)
+    lap()
+    if timings is not None:
+        timings.update(records=t[1] - t[0], exchange=t[2] - t[1], merge_left=t[3] - t[2], assembly=t[4] - t[3], write=t[5] - t[4], host_walk=False,
+                       left_rows=int(n_left.value), exchange_bytes=int(8 * (world - 1) * (row_pad * 9) + (world - 1) * (ext_pad + spill_pad * 32)))
+    return int(all_state[:, 1].sum())
 
 
 def ec_collect_distributed(idx, w=-1, min_occ=3, group=None):

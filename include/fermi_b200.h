@@ -130,18 +130,32 @@ int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *o
 
 /* Multi-GPU `fermi unitig`: the sequences (BWT rows) are sharded over the GPUs the way fm6_unitig stripes its threads
  * (unitig.c:394-404), every GPU holding the whole index.  All pointers are DEVICE pointers owned by the caller, who also runs
- * the one exchange of the path (fermi_b200/parallel.py does it with NCCL through torch.distributed):
- *   fmg_overlap_shard   records of rows [row_lo, row_hi) (row_lo even): d_pack = n_seq x 64-byte records indexed by sequence rank,
- *                       zeroed by the caller, only this shard's entries are written; d_rank[row - row_lo] = rank of the row;
- *                       d_ext / d_spill (32-byte entries) = appended bases / neighbour lists of forks, addressed by the records with
- *                       shard-local offsets; totals = {ext bytes, spill entries} used.  Returns 1 when ext_cap / spill_cap are too
- *                       small (totals = the need).
- *   fmg_overlap_rebase  adds this shard's bases (exclusive prefix sums of all shards' totals) to the offsets in its records
- *   -- all-reduce(sum) of d_pack (disjointly filled), all-gather of d_rank, d_ext, d_spill in rank order --
- *   fmg_unitig_from_device  unitig assembly on one GPU from the merged arrays; 0 = MAG written, 1 = irregular link graph (run fmg_unitig) */
-int fmg_overlap_shard(const fmg_index_t *idx, int min_match, int max_len, uint64_t row_lo, uint64_t row_hi, void *d_pack, int64_t *d_rank,
+ * the exchanges of the path (fermi_b200/parallel.py does it with NCCL through torch.distributed):
+ *   fmg_overlap_shard   records of rows [row_lo, row_hi) (row_lo even), in ROW order: d_rec = (row_hi - row_lo) x 64-byte records,
+ *                       d_rank[row - row_lo] = rank of the row; d_ext / d_spill (32-byte entries) = appended bases / neighbour lists of
+ *                       forks, addressed by the records with shard-local offsets; totals = {ext bytes, spill entries} used.  Returns 1
+ *                       when ext_cap / spill_cap are too small (totals = the need).
+ *   -- ONE all-gather of the four arrays, every shard padded to row_pad rows / ext_pad bytes / spill_pad entries --
+ *   fmg_overlap_merge   gathered shards (n_shards <= 64 consecutive row ranges of rows[s] rows) -> d_pack = n_seq x 64-byte records
+ *                       indexed by sequence rank (the layout the assembly chases), d_rank_of_row = n_seq ranks; offsets are rebased onto
+ *                       the padded gathered ext / spill arrays, which stay as they are
+ *   fmg_overlap_left_fix  check_left_simple (unitig.c:186-204) for the records where it decides a link (the reverse complement of the
+ *                       unique neighbour has several neighbours): needs the merged array, patches OV_LEFT in it; *n_left = rows evaluated
+ *   fmg_unitig_part     link graph + pointer jumping over all records, then emission + MAG text (mag_v_write, mag.c:149-174) of the chains
+ *                       with head rank % n_parts == part, kept in memory; 0 = ok, 1 = irregular link graph (run fmg_unitig on one GPU)
+ *   -- all-gather of the text sizes --
+ *   fmg_magpart_write   the text of this part at `offset` of the output file (truncate != 0: create / truncate the file first)
+ *   fmg_unitig_from_device  the whole assembly on one GPU from merged arrays; 0 = MAG written, 1 = irregular link graph */
+typedef struct fmg_magpart_s fmg_magpart_t;
+int fmg_overlap_shard(const fmg_index_t *idx, int min_match, int max_len, uint64_t row_lo, uint64_t row_hi, void *d_rec, int64_t *d_rank,
                       uint8_t *d_ext, uint64_t ext_cap, void *d_spill, uint64_t spill_cap, uint64_t totals[2]);
-int fmg_overlap_rebase(const fmg_index_t *idx, void *d_pack, const int64_t *d_rank, uint64_t n_rows, uint64_t ext_base, uint64_t spill_base);
+int fmg_overlap_merge(const fmg_index_t *idx, int n_shards, const uint64_t *rows, uint64_t row_pad, uint64_t ext_pad, uint64_t spill_pad,
+                      const void *d_rec_all, const int64_t *d_rank_all, void *d_pack, int64_t *d_rank_of_row);
+int fmg_overlap_left_fix(const fmg_index_t *idx, int min_match, int max_len, void *d_pack, const int64_t *d_rank_of_row, uint64_t *n_left);
+int fmg_unitig_part(const fmg_index_t *idx, int min_match, const void *d_pack, const int64_t *d_rank_of_row, const uint8_t *d_ext, const void *d_spill,
+                    int part, int n_parts, fmg_magpart_t **out, uint64_t *n_unitigs, uint64_t *n_bytes);
+int fmg_magpart_write(const fmg_magpart_t *p, const char *path, uint64_t offset, int truncate);
+void fmg_magpart_free(fmg_magpart_t *p);
 int fmg_unitig_from_device(const fmg_index_t *idx, int min_match, const void *d_pack, const int64_t *d_rank, const uint8_t *d_ext, uint64_t ext_total,
                            const void *d_spill, uint64_t spill_total, const char *out_path, uint64_t *n_unitigs);
 
@@ -150,9 +164,9 @@ int fmg_unitig_from_device(const fmg_index_t *idx, int min_match, const void *d_
  * #contained, #duplicates as fm6_seqsort reports them.  The array is what `fermi unitig -r` / `fermi remap -r` load. */
 int fmg_seqsort(const fmg_index_t *idx, uint64_t *sorted, int64_t stats[3]);
 
-/* CUDA-event durations (ms, summed over the batches) of the kernels of the last fmg_unitig overlap pass on this process:
- * ms[1] fm_retrieve + fm6_is_contained chain, ms[2] fm6_get_nei, ms[3] / ms[4] check_left_simple chain / candidate loop,
- * ms[5] record packing, ms[6] seed rows, ms[0] set-up, ms[7] = number of batches */
+/* CUDA-event durations (ms, summed over the batches) of the kernels of the last overlap pass on this process:
+ * ms[1] fm_retrieve + fm6_is_contained chain, ms[2] fm6_get_nei, ms[3] the deferred check_left_simple pass (selection, all four phases
+ * for the selected rows, patch), ms[4] = rows it evaluated, ms[5] record packing, ms[6] seed rows, ms[7] = number of batches */
 void fmg_overlap_stats(double ms[8]);
 
 /* ------------------------------------------------------------------ `fermi correct`: k-mer collection

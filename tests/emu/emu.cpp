@@ -101,27 +101,39 @@ int emu_overlap(const void *_x, int min_match, int64_t n, const uint64_t *ids, i
                 int64_t *rec, fmg_intv_t *nei, uint32_t *nei_cnt, uint8_t *seq, int32_t *len, uint8_t *ext) {
     const EmuIndex *x = static_cast<const EmuIndex *>(_x);
     std::vector<int64_t> ret(n);
-    // the four phases in the order the product launches them (overlap.cu: launch_phases), over the whole batch
-    const int n_lanes = 3, pcap = (max_len - min_match + 8 > 8 ? max_len - min_match + 8 : 8);
+    // the four phases in the order the product's fmg_overlap_batch launches them, over the whole batch.  Device rows have a
+    // stride that is a multiple of 8 and hold the sequence right-aligned (fmd_overlap.cuh: OverlapArgs::seq_of).
+    const int ml = (max_len + 7) & ~7;
+    const int n_lanes = 3, pcap = (ml - min_match + 8 > 8 ? ml - min_match + 8 : 8);
     std::vector<uint64_t> P0((size_t)n * pcap * 4), A((size_t)n_lanes * cap * 4), B((size_t)n_lanes * cap * 4);
     std::vector<int32_t> cat((size_t)n_lanes * cap * 2), np0(n);
+    std::vector<uint64_t> S0((size_t)n * pcap), S((size_t)n_lanes * cap * 2);
+    std::vector<uint8_t> dseq((size_t)n * ml + 8), dext((size_t)n * ml + 8);
+    // stand-in for the shared-memory part of the level lists of phase 2 (one lane at a time)
+    std::vector<uint64_t> shared(2 * 8 * 6 + 8);
     OverlapArgs O;
-    O.ix = x->view; O.min_match = min_match; O.mode = 0; O.n = n; O.seq = seq; O.len = len; O.max_len = max_len;
+    O.ix = x->view; O.min_match = min_match; O.mode = 0; O.n = n; O.seq = dseq.data(); O.len = len; O.max_len = ml;
     O.ids = ids; O.first = 0; O.step = 1; O.ret = ret.data();
-    O.P0 = P0.data(); O.pcap = pcap; O.np0 = np0.data(); O.A = A.data(); O.B = B.data(); O.cap = cap; O.cat = cat.data();
-    O.rec = rec; O.nei = reinterpret_cast<uint4 *>(nei); O.nei_cap = nei_cap; O.nei_cnt = nei_cnt; O.ext = ext; O.next = nullptr;
+    O.P0 = P0.data(); O.S0 = S0.data(); O.S = S.data(); O.pcap = pcap; O.np0 = np0.data(); O.A = A.data(); O.B = B.data(); O.cap = cap; O.cat = cat.data();
+    O.rec = rec; O.nei = reinterpret_cast<uint4 *>(nei); O.nei_cap = nei_cap; O.nei_cnt = nei_cnt; O.ext = dext.data(); O.next = nullptr;
     auto lists = [&](int phase) {
         for (int t = 0; t < n_lanes; ++t) {
             int64_t cur = t;
             auto fetch = [&]() { int64_t r = cur; cur += n_lanes; return r; };
-            if (wide) { if (phase == 2) overlap_lane_sync<uint64_t, 2>(O, t, fetch); else overlap_lane_sync<uint64_t, 4>(O, t, fetch); }
-            else { if (phase == 2) overlap_lane_sync<uint32_t, 2>(O, t, fetch); else overlap_lane_sync<uint32_t, 4>(O, t, fetch); }
+            if (wide) { if (phase == 2) nei_lane<uint64_t>(O, t, fetch, shared.data(), 1, 0); else overlap_lane_sync<uint64_t, 4>(O, t, fetch); }
+            else { if (phase == 2) nei_lane<uint32_t>(O, t, fetch, shared.data(), 1, 0); else overlap_lane_sync<uint32_t, 4>(O, t, fetch); }
         }
     };
     for (int64_t t = 0; t < n; ++t) { if (wide) overlap_chain<uint64_t, 1>(O, t); else overlap_chain<uint32_t, 1>(O, t); }
     lists(2);
     for (int64_t t = 0; t < n; ++t) { if (wide) overlap_chain<uint64_t, 3>(O, t); else overlap_chain<uint32_t, 3>(O, t); }
     lists(4);
+    for (int64_t t = 0; t < n; ++t) {
+        const int l = len[t] < 0 ? ml : len[t];
+        std::memset(seq + (size_t)t * max_len, 0, max_len);
+        std::memcpy(seq + (size_t)t * max_len, dseq.data() + (size_t)(t + 1) * ml - l, l < max_len ? l : max_len);
+        std::memcpy(ext + (size_t)t * max_len, dext.data() + (size_t)t * ml, max_len);
+    }
     for (int64_t t = 0; t < n; ++t) rec[t * OV_NREC + OV_K] = ret[t];
     return 0;
 }

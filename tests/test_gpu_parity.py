@@ -230,49 +230,88 @@ def test_unitig_20k_reads_vs_reference_binary(fb, tmp_path, monkeypatch, err, co
 
 @pytest.mark.parametrize("err,shards", [(0.0, 2), (0.01, 3)])
 def test_sharded_records_merge_to_the_single_gpu_unitigs(fb, tmp_path, err, shards):
-    """The multi-GPU data path on one GPU: the records of row shards (fmg_overlap_shard) in separate device buffers, offsets
-    rebased, the record arrays merged by summation and the side arrays by concatenation -- what the NCCL all-reduce and
-    all-gather of fermi_b200.parallel.unitig_distributed_device do -- then fmg_unitig_from_device == fm6_unitig."""
+    """The multi-GPU data path on one GPU, stage by stage through the C-ABI: the records of row shards (fmg_overlap_shard) in
+    separate device buffers, laid side by side with padding as the NCCL all-gather of fermi_b200.parallel.unitig_distributed_device
+    leaves them, merged into the rank-indexed array (fmg_overlap_merge), the deferred left check (fmg_overlap_left_fix), and the
+    unitigs assembled part by part (fmg_unitig_part + fmg_magpart_write into one file) == fm6_unitig."""
     import ctypes as C
     import torch
     from fermi_b200._lib import lib
-    from fermi_b200.parallel import shard_range
+    from fermi_b200.parallel import unitig_shard_rows
     L = lib()
     genome = fb.synth_genome(81, 300000)
     reads = fb.synth_reads(82, genome, 30000, 100, err)
     idx = fb.FmdIndex(fb.fm_build(fb.fmd_text(reads), 0), 0)
     n_seq = int(idx.fmd.mcnt[1])
     dev = torch.device("cuda", 0)
-    packs, ranks, exts, spills, tots = [], [], [], [], []
+    recs, ranks, exts, spills, tots, rows = [], [], [], [], [], []
     for r in range(shards):
-        lo, hi = shard_range(n_seq // 2, r, shards)
-        lo, hi = 2 * lo, 2 * hi
-        pack = torch.zeros(n_seq * 8, dtype=torch.int64, device=dev)
+        lo, hi = unitig_shard_rows(n_seq, r, shards)
+        rec = torch.empty((hi - lo) * 8, dtype=torch.int64, device=dev)
         rnk = torch.empty(hi - lo, dtype=torch.int64, device=dev)
         ext_cap, spill_cap = 64, 8                                     # too small on purpose: the call must report the need
         tot = (C.c_uint64 * 2)()
         for attempt in range(3):
             ext = torch.empty(ext_cap, dtype=torch.uint8, device=dev)
             spill = torch.empty(spill_cap * 4, dtype=torch.int64, device=dev)
-            rc = L.fmg_overlap_shard(idx.h, 50, 0, lo, hi, pack.data_ptr(), rnk.data_ptr(), ext.data_ptr(), ext_cap, spill.data_ptr(), spill_cap, tot)
+            rc = L.fmg_overlap_shard(idx.h, 50, 0, lo, hi, rec.data_ptr(), rnk.data_ptr(), ext.data_ptr(), ext_cap, spill.data_ptr(), spill_cap, tot)
             if rc != 1:
                 break
-            pack.zero_()
             ext_cap, spill_cap = int(tot[0]), int(tot[1])
         assert rc == 0 and attempt == 1
-        assert L.fmg_overlap_rebase(idx.h, pack.data_ptr(), rnk.data_ptr(), hi - lo, sum(t[0] for t in tots), sum(t[1] for t in tots)) == 0
-        packs.append(pack); ranks.append(rnk); exts.append(ext[: int(tot[0])]); spills.append(spill[: 4 * int(tot[1])]); tots.append((int(tot[0]), int(tot[1])))
-    pack = torch.stack(packs).sum(0)
-    rank_all, ext_all, spill_all = torch.cat(ranks), torch.cat(exts), torch.cat(spills)
-    assert sorted(rank_all.cpu().tolist()) == list(range(n_seq))
+        recs.append(rec); ranks.append(rnk); exts.append(ext[: int(tot[0])]); spills.append(spill[: 4 * int(tot[1])]); tots.append((int(tot[0]), int(tot[1])))
+        rows.append(hi - lo)
+    row_pad, ext_pad, spill_pad = max(rows) + 3, max(t[0] for t in tots) + 5, max(t[1] for t in tots) + 1
+
+    def side_by_side(parts, pad, width, dtype):
+        out = torch.zeros(shards * pad * width, dtype=dtype, device=dev)
+        for r, p in enumerate(parts):
+            out[r * pad * width: r * pad * width + len(p)] = p
+        return out
+
+    rec_all, rank_all = side_by_side(recs, row_pad, 8, torch.int64), side_by_side(ranks, row_pad, 1, torch.int64)
+    ext_all, spill_all = side_by_side(exts, ext_pad, 1, torch.uint8), side_by_side(spills, spill_pad, 4, torch.int64)
+    assert sorted(torch.cat(ranks).cpu().tolist()) == list(range(n_seq))
+    pack = torch.empty(n_seq * 8, dtype=torch.int64, device=dev)
+    rank_of_row = torch.empty(n_seq, dtype=torch.int64, device=dev)
+    assert L.fmg_overlap_merge(idx.h, shards, (C.c_uint64 * shards)(*rows), row_pad, ext_pad, spill_pad, rec_all.data_ptr(), rank_all.data_ptr(),
+                               pack.data_ptr(), rank_of_row.data_ptr()) == 0
+    assert torch.equal(rank_of_row, torch.cat(ranks))
+    n_left = C.c_uint64()
+    assert L.fmg_overlap_left_fix(idx.h, 50, 0, pack.data_ptr(), rank_of_row.data_ptr(), C.byref(n_left)) == 0
     out, single = str(tmp_path / "m.mag"), str(tmp_path / "s.mag")
-    nu = C.c_uint64()
-    rc = L.fmg_unitig_from_device(idx.h, 50, pack.data_ptr(), rank_all.data_ptr(), ext_all.data_ptr(), len(ext_all), spill_all.data_ptr() if len(spill_all) else 0,
-                                  len(spill_all) // 4, out.encode(), C.byref(nu))
-    assert rc == 0
+    total, offset = 0, 0
+    for part in range(shards):
+        h, nu, nb = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        rc = L.fmg_unitig_part(idx.h, 50, pack.data_ptr(), rank_of_row.data_ptr(), ext_all.data_ptr(), spill_all.data_ptr(), part, shards,
+                               C.byref(h), C.byref(nu), C.byref(nb))
+        assert rc == 0
+        assert L.fmg_magpart_write(h, out.encode(), offset, 1 if part == 0 else 0) == 0
+        L.fmg_magpart_free(h)
+        total += nu.value
+        offset += nb.value
     n = fb.fm6_unitig(idx, 50, single)
-    assert nu.value == n and H.canonical_mag(H.parse_mag(open(out).read())) == H.canonical_mag(H.parse_mag(open(single).read()))
+    assert os.path.getsize(out) == offset
+    assert total == n and H.canonical_mag(H.parse_mag(open(out).read())) == H.canonical_mag(H.parse_mag(open(single).read()))
     idx.close()
+
+
+def test_unitig_over_two_gpus_through_nccl(tmp_path):
+    """The real multi-GPU path (one process per GPU, NCCL all-gather of the record shards, every rank assembling and writing its
+    part of the unitigs): tools/unitig_multi.py --check compares the MAG set with the single-GPU fm6_unitig."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    for err in ("0.0", "0.01"):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29731",
+               os.path.join(H.ROOT, "tools", "unitig_multi.py"), "--reads", "40000", "--err", err, "--check", "--iters", "1"]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+        assert res.returncode == 0, res.stderr[-2000:]
+        line = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+        assert line["n_gpus"] == 2 and line["set_equal_single_gpu"] is True
 
 
 @pytest.mark.skipif(H.ref_fermi_binary() is None, reason="oracle/_ref/fermi did not travel with the repo")

@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--reads", type=int, default=1000000)
 ap.add_argument("--err", type=float, default=0.0)
 ap.add_argument("--check", action="store_true", help="compare with a single-GPU fm6_unitig on rank 0")
+ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--host-gather", action="store_true", help="the round-1 path: records to the host, all-gather, host walk on rank 0")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -22,20 +23,21 @@ if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # keep stdout for
     os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-fn = os.path.join(tempfile.gettempdir(), "unitig_multi_%d.fmd" % a.reads)
+fn = os.path.join(tempfile.gettempdir(), "unitig_multi_%d_%g.fmd" % (a.reads, a.err))
 if rank == 0:
     genome = fb.synth_genome(41, a.reads * 10)
     reads = fb.synth_reads(42, genome, a.reads, 100, a.err)
-    fb.fm_build(fb.fmd_text(reads), local).dump(fn)
+    fb.fm_build(fb.fmd_text(reads), local).dump(fn + ".tmp"); os.replace(fn + ".tmp", fn)
 dist.barrier()
 idx = fb.FmdIndex(fb.Fmd.restore(fn), local)
 out = os.path.join(tempfile.gettempdir(), "unitig_multi.mag")
-for it in range(3):
+tm = {}
+for it in range(a.iters):
     dist.barrier(); torch.cuda.synchronize(); t = time.time()
-    n = parallel.unitig_distributed(idx, 50, out, 108) if a.host_gather else parallel.unitig_distributed_device(idx, 50, out)
+    n = parallel.unitig_distributed(idx, 50, out, 108) if a.host_gather else parallel.unitig_distributed_device(idx, 50, out, timings=tm)
     dist.barrier(); dt = time.time() - t
 if rank == 0:
-    res = {"n_gpus": world, "reads": a.reads, "err": a.err, "path": "host gather" if a.host_gather else "device (NCCL all-reduce + all-gather, GPU assembly)",
+    res = {"n_gpus": world, "reads": a.reads, "err": a.err, "path": "host gather" if a.host_gather else "device (NCCL all-gather of record shards, every rank assembles and writes its part)", "stages_s_rank0": tm,
            "unitigs": n, "seconds": dt, "reads_per_s": a.reads / dt}
     if a.check:
         import helpers as H
