@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--unitig-reads", type=int, default=10_000_000, help="reads of the unitig leg (BASELINE config 3); 0 disables it")
     ap.add_argument("--unitig-ref-reads", type=int, default=500_000, help="reads of the bounded reference sample of the unitig leg")
+    ap.add_argument("--no-unitig-noisy", action="store_true", help="skip the 1 %% substitution variant of the unitig leg")
     return ap.parse_args()
 
 
@@ -163,66 +164,167 @@ def count_locates(fmd_file, reads, cores):
 # ----------------------------------------------------------------------------------- unitig leg (BASELINE config 3)
 UNITIG_GENOME_SEED, UNITIG_READ_SEED, UNITIG_COV, UNITIG_MIN = 41, 42, 10, 50
 # block lookups (rld_locate_blk calls) per input read of `fermi unitig -l50 -t1` on error-free 10x 100 bp reads, measured with
-# a counter in the reference at 1/100 scale: 306 rank2a + ~120 rank1a -> 423 lookups
+# a counter in the reference at 1/100 scale: 306 rank2a + ~120 rank1a -> 423 lookups.  Only the fallback
+# when the instrumented oracle cannot be run on the benchmark input.
 UNITIG_LOCATES_PER_READ = 423.0
 
 
-def unitig_index(fb, n_reads, read_len, device):
+def unitig_index_path(n_reads, err):
+    return os.path.join(tempfile.gettempdir(), "fermi_b200_bench_unitig_%d_%g.fmd" % (n_reads, err))
+
+
+def unitig_build_index(fb, n_reads, read_len, err, device, fn):
     genome = fb.synth_genome(UNITIG_GENOME_SEED, n_reads * read_len // UNITIG_COV)
-    reads = fb.synth_reads(UNITIG_READ_SEED, genome, n_reads, read_len, 0.0)
+    reads = fb.synth_reads(UNITIG_READ_SEED, genome, n_reads, read_len, err)
     t = time.time()
     fmd = fb.fm_build(fb.fmd_text(reads), device)          # suffix sort, BWT and RLD encoding on the GPU
-    return fmd, time.time() - t
+    dt = time.time() - t
+    fmd.dump(fn + ".tmp")
+    os.replace(fn + ".tmp", fn)
+    return dt
 
 
-def unitig_leg(fb, a, device, peak, peak_src):
-    """`fermi unitig -l50` (fm6_unitig, unitig.c:378) over the FMD-index of n x 100 bp error-free 10x reads, end to end through
-    the C-ABI call a user makes: overlap records + unitig assembly on the GPU, results copied to the host and written as MAG
-    text.  Next to it the unmodified reference binary (`fermi unitig -l50 -t<nproc>`) on a bounded sample built the same way."""
+def unitig_count_locates(fn, n_seq, sample=3000):
+    """N_locate per input read from the instrumented oracle on the ACTUAL index: the block lookups of the work the
+    reference's walk does for one read it visits -- fm_retrieve of the seed, overlap_intv + fm6_get_nei, check_left_simple -- over a
+    strided sample of the seed rows (odd rows, unitig.c:333-334)."""
+    import helpers as H
+    O = H.oracle()
+    h = O.load(fn)
+    n_seeds = n_seq // 2
+    step = max(1, n_seeds // sample)
+    seeds = (np.arange(0, n_seeds, step, dtype=np.uint64)[:sample] * 2 + 1)
+    loc, _ = O.unitig_locates(h, UNITIG_MIN, seeds)
+    O.destroy(h)
+    n = len(seeds)
+    return {"locates_per_read": sum(loc) / n, "by_stage": {"fm_retrieve": loc[0] / n, "fm6_is_contained": loc[1] / n, "fm6_get_nei": loc[2] / n,
+                                                          "check_left_simple": loc[3] / n}, "sample_seeds": n}
+
+
+def mag_set(path):
+    import helpers as H
+    with open(path) as fh:
+        return H.canonical_mag(H.parse_mag(fh.read()))
+
+
+def unitig_run(fb, idx, out, world, dist, timings):
+    """one `fermi unitig -l50` over all ranks: the public call on one GPU, the NCCL path (fermi_b200.parallel) on several"""
+    if world == 1:
+        n = fb.fm6_unitig(idx, UNITIG_MIN, out)
+        return n
+    from fermi_b200 import parallel
+    return parallel.unitig_distributed_device(idx, UNITIG_MIN, out, timings=timings)
+
+
+def unitig_leg(fb, a, device, peak, peak_src, rank, world, dist, barrier, err=0.0, iters=3, check_single=True, cpu_baseline=True):
+    """`fermi unitig -l50` (fm6_unitig, unitig.c:378) over the FMD-index of n x 100 bp 10x reads, end to end: overlap records of the
+    rank's share of the sequences, (N > 1) the NCCL all-gather of the record shards, unitig assembly and the MAG text written to
+    one file.  Timed with a barrier + device synchronisation on both sides, max over ranks.  Rank 0 returns the result object."""
+    import torch
     import helpers as H
     L = a.read_len
-    fmd, t_build = unitig_index(fb, a.unitig_reads, L, device)
+    fn = unitig_index_path(a.unitig_reads, err)
+    t_build = None
+    if rank == 0 and not os.path.exists(fn):
+        t_build = unitig_build_index(fb, a.unitig_reads, L, err, device, fn)
+        fb.release_cache()
+    barrier()
+    fmd = fb.Fmd.restore(fn)
     idx = fb.FmdIndex(fmd, device)
+    n_seq, n_sym = int(fmd.mcnt[1]), int(fmd.mcnt[0])
     out = os.path.join(tempfile.gettempdir(), "fermi_b200_bench_unitig.mag")
+    dev = torch.device("cuda", device)
     launches0 = fb.launch_count()
-    fb.fm6_unitig(idx, UNITIG_MIN, out)                    # warm-up: scratch pool, pinned result buffers
+    tm = {}
+    unitig_run(fb, idx, out, world, dist, tm)              # warm-up: scratch pool, pinned result buffers, NCCL channels
     launches = fb.launch_count() - launches0
-    times, n_u = [], 0
-    for _ in range(3):
+    times, stages, n_u = [], [], 0
+    for _ in range(iters):
+        barrier()
         t = time.perf_counter()
-        n_u = fb.fm6_unitig(idx, UNITIG_MIN, out)
-        times.append(time.perf_counter() - t)
+        n_u = unitig_run(fb, idx, out, world, dist, tm)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        times.append(float(dt[0]))
+        stages.append(dict(tm))
     secs = sum(times) / len(times)
     st = fb.overlap_stats()
-    k_ms = st["contained"] + st["neighbours"] + st["left_chain"] + st["left_lists"]
-    bytes_per_read = UNITIG_LOCATES_PER_READ * 128 + L
-    achieved = a.unitig_reads * bytes_per_read / (k_ms / 1e3) / 1e9
-    res = {"workload": "fermi unitig -l%d: FMD-index of %d x %d bp error-free reads (%dx), %d sequences, %d symbols" %
-                       (UNITIG_MIN, a.unitig_reads, L, UNITIG_COV, int(fmd.mcnt[1]), int(fmd.mcnt[0])),
-           "value": a.unitig_reads / secs, "unit": "reads/s", "seconds": secs, "unitigs": int(n_u), "mag_bytes": os.path.getsize(out),
-           "api": "fmg_unitig (records + assembly on the GPU, MAG text written to a file)", "gpu_launches_per_call": int(launches),
-           "setup": {"gpu_build_fmd_s": round(t_build, 2)},
-           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                        "kernel": "k_ov_chain<1> + k_ov_lists<2> + k_ov_chain<3> + k_ov_lists<4>", "kernel_ms": k_ms, "kernel_ms_by_phase": st,
-                        "algorithmic_bytes_per_read": bytes_per_read, "locates_per_read": UNITIG_LOCATES_PER_READ,
-                        "locates_source": "SURVEY.md 8d: counter in the reference's rld_locate_blk, `unitig -l50 -t1`, error-free 10x, 1/100 scale",
-                        "peak_source": peak_src}}
+    k_ms = torch.tensor([st["contained"] + st["neighbours"] + st["left_fix"], st["contained"], st["neighbours"], st["left_fix"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
+    k_ms = [float(x) for x in k_ms.tolist()]
+    res = None
+    if rank == 0:
+        res = {"workload": "fermi unitig -l%d: FMD-index of %d x %d bp reads (%dx, %g%% substitutions), %d sequences, %d symbols" %
+                           (UNITIG_MIN, a.unitig_reads, L, UNITIG_COV, err * 100, n_seq, n_sym),
+               "value": a.unitig_reads / secs, "unit": "reads/s", "seconds": secs, "n_gpus": world, "scaling": "strong", "unitigs": int(n_u),
+               "mag_bytes": os.path.getsize(out),
+               "api": "fmg_unitig (records + assembly on the GPU, MAG text written to a file)" if world == 1 else
+                      "fermi_b200.parallel.unitig_distributed_device: fmg_overlap_shard -> NCCL all-gather of the record shards -> fmg_overlap_merge + "
+                      "fmg_overlap_left_fix -> fmg_unitig_part (every rank assembles, formats and writes the chains it owns)",
+               "gpu_launches_per_call": int(launches)}
+        if t_build is not None:
+            res["setup"] = {"gpu_build_fmd_s": round(t_build, 2)}
+        if world > 1:
+            last = stages[-1]
+            res["stages_ms_rank0"] = {k: round(1e3 * v, 2) for k, v in last.items() if isinstance(v, float)}
+            res["collective_ms"] = round(1e3 * last.get("exchange", 0.0), 2)
+            res["assembly_ms"] = round(1e3 * (last.get("assembly", 0.0) + last.get("write", 0.0)), 2)
+            res["exchange_bytes_per_rank"] = last.get("exchange_bytes")
+            res["host_walk"] = bool(last.get("host_walk"))
+        # roofline of the overlap kernels: algorithmic bytes of the whole job / the slowest rank's kernel time
+        loc = None
+        try:
+            loc = unitig_count_locates(fn, n_seq)
+        except Exception as exc:
+            log("unitig: instrumented oracle unavailable (%r); using the SURVEY constant" % (exc,))
+        n_loc = loc["locates_per_read"] if loc else UNITIG_LOCATES_PER_READ
+        bytes_per_read = n_loc * 128 + L
+        achieved = a.unitig_reads * bytes_per_read / (k_ms[0] / 1e3) / 1e9 if k_ms[0] > 0 else 0.0
+        traffic = None
+        try:
+            import glob
+            tr = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_ov_traffic.json")))[-1]))
+            traffic = tr["traffic_bytes_per_sequence"] * n_seq / world          # DRAM bytes of the phase kernels of one rank's pass (ncu --set full)
+        except Exception:
+            pass
+        res["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": traffic,
+                           "kernel": "k_ov_chain<1> (fm_retrieve + fm6_is_contained) + k_ov_nei (fm6_get_nei) + deferred check_left_simple pass",
+                           "kernel_ms": k_ms[0], "kernel_ms_by_phase_max_over_ranks": {"contained": k_ms[1], "neighbours": k_ms[2], "left_fix": k_ms[3]},
+                           "left_rows": st["left_rows"], "algorithmic_bytes_per_read": bytes_per_read, "locates_per_read": n_loc,
+                           "locates_source": ("instrumented oracle (oracle/fmd_oracle.c: fo_unitig_locates) on %d seed rows of this index: %s" %
+                                              (loc["sample_seeds"], json.dumps({k: round(v, 1) for k, v in loc["by_stage"].items()}))) if loc else
+                                             "SURVEY.md 8d: counter in the reference's rld_locate_blk, `unitig -l50 -t1`, error-free 10x, 1/100 scale",
+                           "peak_source": peak_src + (" x %d GPUs" % world if world > 1 else "")}
+        if check_single and world > 1:
+            single = out + ".single"
+            fb.fm6_unitig(idx, UNITIG_MIN, single)          # untimed: the same index through the single-GPU call
+            res["set_equal_single_gpu"] = mag_set(out) == mag_set(single)
     idx.close()
     del fmd
     fb.release_cache()
     ref_bin = H.ref_fermi_binary()
-    if ref_bin and a.unitig_ref_reads > 0 and not a.no_cpu_baseline:
+    if rank == 0 and cpu_baseline and ref_bin and a.unitig_ref_reads > 0 and not a.no_cpu_baseline:
+        # the unmodified reference on a bounded sample generated the same way, and our MAG set against its own on that sample
         cores = os.cpu_count() or 1
-        rfmd, _ = unitig_index(fb, a.unitig_ref_reads, L, device)
-        fn = os.path.join(tempfile.gettempdir(), "fermi_b200_bench_unitig_ref.fmd")
-        rfmd.dump(fn)
+        rfn = unitig_index_path(a.unitig_ref_reads, err)
+        if not os.path.exists(rfn):
+            unitig_build_index(fb, a.unitig_ref_reads, L, err, device, rfn)
         t = time.perf_counter()
         with open(out + ".ref", "wb") as fh:
-            subprocess.run([ref_bin, "unitig", "-l", str(UNITIG_MIN), "-t", str(cores), fn], stdout=fh, stderr=subprocess.DEVNULL, check=True)
+            subprocess.run([ref_bin, "unitig", "-l", str(UNITIG_MIN), "-t", str(cores), rfn], stdout=fh, stderr=subprocess.DEVNULL, check=True)
         dt = time.perf_counter() - t
         res["cpu_baseline"] = {"value": a.unitig_ref_reads / dt, "unit": "reads/s", "cores": cores, "kind": "reference",
                                "sample": "fermi unitig -l%d -t%d on the index of %d reads generated the same way (incl. loading the .fmd), %.1f s wall"
                                          % (UNITIG_MIN, cores, a.unitig_ref_reads, dt)}
+        ridx = fb.FmdIndex(fb.Fmd.restore(rfn), device)
+        fb.fm6_unitig(ridx, UNITIG_MIN, out + ".ours")
+        ridx.close()
+        res["set_equal_reference_sample"] = mag_set(out + ".ours") == mag_set(out + ".ref")
+        fb.release_cache()
+    barrier()
     return res
 
 
@@ -432,19 +534,32 @@ def run_ours(a):
         if world == 1 and not a.no_cpu_baseline:
             cb, _, _ = cpu_smem_rate(fn, h_reads.numpy(), a.cpu_seconds, cores)
             out["cpu_baseline"] = cb
-        if world == 1 and a.unitig_reads > 0:
-            # the second half of the metric (overlap / unitig): its own index, so the SMEM buffers go first
-            del d_reads, d_off, d_boff, h_reads, h_off
-            if e2e:
-                del h_mem, h_moff
-            idx.close()
-            fb.release_cache()
-            torch.cuda.empty_cache()
+    # ---- the second half of the metric (overlap / unitig, BASELINE config 3): its own index, so the SMEM buffers go first
+    out_line = out if rank == 0 else None
+    if a.unitig_reads > 0:
+        del d_reads, d_off, d_boff, h_reads, h_off
+        if e2e:
+            del h_mem, h_moff
+        else:
+            sess.close()
+        idx.close()
+        fb.release_cache()
+        torch.cuda.empty_cache()
+        pk = float(peaks.get("hbm_gbs", 6650.0)) if rank == 0 else 0.0
+        for key, err, iters in (("unitig", 0.0, 3), ("unitig_err1pct", 0.01, 1)):
+            if err > 0 and a.no_unitig_noisy:
+                continue
             try:
-                out["unitig"] = unitig_leg(fb, a, local, peak, peak_src)
+                r = unitig_leg(fb, a, local, pk, peak_src if rank == 0 else "", rank, world, dist, barrier, err=err, iters=iters,
+                               check_single=(err == 0.0), cpu_baseline=(world == 1 and err == 0.0))
             except Exception as exc:                       # the SMEM line stands on its own
-                out["unitig"] = {"error": repr(exc)}
-        print(json.dumps(out), flush=True)
+                r = {"error": repr(exc)}
+                if world > 1:
+                    raise
+            if rank == 0:
+                out_line[key] = r
+    if rank == 0:
+        print(json.dumps(out_line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

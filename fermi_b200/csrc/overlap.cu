@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(OVLP_BLOCK, MINB) k_ov_nei(const __grid_consta
     nei_lane<U>(A, lane, [&]() -> int64_t { return (int64_t)atomicAdd(A.next, 1ull); }, fmg_ov_shared, (int)blockDim.x, (int)threadIdx.x);
 }
 static int nei_minb() {
-    static const int v = [] { const char *e = std::getenv("FMG_NEI_BLOCKS"); const int x = e ? std::atoi(e) : 5; return x <= 4 ? 4 : x >= 6 ? 6 : 5; }();
+    static const int v = [] { const char *e = std::getenv("FMG_NEI_BLOCKS"); const int x = e ? std::atoi(e) : 4; return x <= 4 ? 4 : x >= 6 ? 6 : 5; }();
     return v;
 }
 template <typename U> static const void *nei_kernel() {

@@ -901,6 +901,68 @@ int fo_overlap_batch(const fo_index_t *e, int min_match, int64_t n, const uint64
 	return 0;
 }
 
+/* check_left_simple, unitig.c:186-204 (U4): 0 = the unique neighbour has no other left neighbour, -1 = potential backward
+ * bifurcation.  s = the consensus grown by get_nei, rbeg = start of the neighbour in it. */
+static int check_left_simple(const fo_index_t *e, int min_match, int beg, int rbeg, const bstr_t *s, ivec_t *prev, ivec_t *curr)
+{
+	fo_intv_t ok[6];
+	ivec_t *swap;
+	int i;
+	size_t j;
+	overlap_intv(e, s->l, s->s, min_match, rbeg, 1, prev, 1);
+	for (i = rbeg - 1; i >= beg; --i) {
+		for (j = 0, curr->n = 0; j < prev->n; ++j) {
+			fo_intv_t *p = &prev->a[j];
+			fo_extend(e, p, ok, 1);
+			if (ok[0].x[2] + ok[s->s[i]].x[2] != p->x[2]) return -1;
+			iv_push(curr, &ok[s->s[i]]);
+		}
+		swap = curr; curr = prev; prev = swap;
+	}
+	return 0;
+}
+
+/* Block lookups (calls of the rld_locate_blk restatement) of the work `fermi unitig` does for ONE sequence that its walk visits
+ * (unitig.c:227-317): locates[0] fm_retrieve of the seed, [1] fm6_is_contained (its overlap_intv is the one fm6_get_nei would run
+ * for a read reached through a neighbour, unitig.c:100-104), [2] fm6_get_nei, [3] check_left_simple when there is exactly one
+ * neighbour; left[i] (optional) = result of check_left_simple (1 = not evaluated).  bench.py sums the four over a sample of the
+ * seed rows of the benchmark index: SURVEY.md 8d's N_locate per input read. */
+int fo_unitig_locates(const fo_index_t *e, int min_match, int64_t n, const uint64_t *seeds, uint64_t locates[4], int8_t *left)
+{
+	bstr_t s = {0, 0, 0};
+	ivec_t a[2] = {{0, 0, 0}, {0, 0, 0}}, nei = {0, 0, 0};
+	cvec_t cat = {0, 0, 0};
+	int64_t i;
+	locates[0] = locates[1] = locates[2] = locates[3] = 0;
+	bs_reserve(&s, 1 << 16);
+	for (i = 0; i < n; ++i) {
+		fo_intv_t intv0;
+		int ret, rbeg, len, k;
+		uint64_t c0;
+		if (left) left[i] = 1;
+		c0 = tl_n_locate = 0;
+		fo_retrieve(e, seeds[i], s.s, s.m - 1, &len);
+		locates[0] += tl_n_locate - c0; c0 = tl_n_locate;
+		s.l = len; s.s[len] = 0;
+		for (k = 0; k < len >> 1; ++k) { uint8_t t = s.s[k]; s.s[k] = s.s[len - 1 - k]; s.s[len - 1 - k] = t; }
+		a[0].n = a[1].n = nei.n = 0;
+		if (len <= min_match) continue;
+		ret = is_contained(e, min_match, &s, &intv0, &a[0]);
+		locates[1] += tl_n_locate - c0; c0 = tl_n_locate;
+		if (ret < 0 || a[0].n == 0) continue;
+		rbeg = get_nei(e, min_match, 0, &s, &nei, &a[0], &a[1], &cat);
+		locates[2] += tl_n_locate - c0; c0 = tl_n_locate;
+		if (rbeg >= 0 && nei.n == 1) {
+			a[0].n = a[1].n = 0;
+			ret = check_left_simple(e, min_match, 0, rbeg, &s, &a[0], &a[1]);
+			locates[3] += tl_n_locate - c0;
+			if (left) left[i] = (int8_t)ret;
+		}
+	}
+	free(s.s); free(a[0].a); free(a[1].a); free(nei.a); free(cat.a);
+	return 0;
+}
+
 /*******************
  * k-mer collection *
  *******************/

@@ -62,6 +62,10 @@ void fo_free(void *p);
 int fo_overlap_batch(const fo_index_t *e, int min_match, int64_t n, const uint64_t *seeds, int64_t *rec,
 					 fo_intv_t **nei_out, uint64_t *nei_off, uint64_t *n_locate);
 
+/* block lookups per stage of the unitig work on one visited sequence (retrieve, is_contained, get_nei, check_left_simple,
+ * unitig.c:77-204): the N_locate of SURVEY.md 8d counted on the benchmark input; left (optional, n) = check_left_simple results */
+int fo_unitig_locates(const fo_index_t *e, int min_match, int64_t n, const uint64_t *seeds, uint64_t locates[4], int8_t *left);
+
 /* k-mer collection of `fermi correct`: fm6_traverse (exact.c:141-171) + ec_collect (correct.c:35-87) over all
  * suffixes; triples = suffix<<40 | key<<8 | val, sorted; returns the k-mer length used (w<0: correct.c:313-318) */
 int fo_ec_collect(const fo_index_t *e, int w, int min_occ, uint64_t **triples, uint64_t *n_triples, int64_t cnt[2]);

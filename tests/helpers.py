@@ -309,6 +309,20 @@ class _Lib:
         return rec, out, no, nl.value
 
 
+    def unitig_locates(self, h, min_match, seeds):
+        """oracle port only: (locates[4] = block lookups of retrieve / is_contained / get_nei / check_left_simple over the seeds,
+        left int8[n] = check_left_simple per seed, 1 = not evaluated)"""
+        assert self.p == "fo_"
+        seeds = np.ascontiguousarray(seeds, np.uint64)
+        loc = (C.c_uint64 * 4)()
+        left = np.ones(len(seeds), np.int8)
+        f = self.lib.fo_unitig_locates
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int64, u64p, C.POINTER(C.c_uint64), C.c_void_p]
+        f(h, min_match, len(seeds), _ptr(seeds, u64p), loc, left.ctypes.data)
+        return [int(x) for x in loc], left
+
+
 _oracle = None
 _ref = None
 
