@@ -263,6 +263,15 @@ FMG_HD bool warp_any(bool v) {
 #endif
 }
 
+// Re-form the full warp.  Lanes that took different branches run as separate groups until a convergence barrier, and a barrier
+// the compiler places ends with the function it is in: after a call, or around a state-machine loop, the groups would execute the
+// same code one after the other.
+FMG_HD void warp_rejoin() {
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+}
+
 // fm6_extend for a CONVERGED warp: every lane calls, `active` lanes get their extension; the blocks come through
 // load_blk_pair (half the L1-miss requests of extend6)
 template <typename U>

@@ -387,7 +387,7 @@ struct OvLane {
 
 // ---------------------------------------------------------------------------------------------
 // Phase 2: fm6_get_nei (unitig.c:93-179, beg = 0, the first `prev` list filled by phase 1) as a flat per-lane state machine with
-// ONE index gather per candidate and level, executed converged by the warp (persistent lanes, like smem_lane).
+// ONE index gather per LEVEL (nearly always), executed converged by the warp (persistent lanes, like smem_lane).
 //
 // The reference spends, per candidate P and level: fm6_extend(P, forward) for the children P.c and |P$|; fm6_extend0(ok[c], back)
 // per non-empty child to learn whether some sequence still STARTS with P.c ($P.c not empty); fm6_extend0(ok[0], back) for $P$ when a
@@ -433,14 +433,14 @@ struct NeiLists {
 
 enum { NP_FETCH = 0, NP_NEXT, NP_END_LEVEL, NP_FINISH, NP_FINISH2, NP_CAND, NP_FIX1, NP_FIX2, NP_DONE };     // >= NP_CAND: wants a gather (or is done)
 
-template <typename U, class FetchFn>
+template <typename U, int TAG, class FetchFn>
 FMG_HD void nei_lane(const OverlapArgs &A, int64_t lane, FetchFn fetch, void *shared, int n_threads, int tid) {
     typedef IntvT<U> Cand;
     typedef OvBits<U> BT;
     NeiLists<U> L(A, lane, shared, n_threads, tid);
     int ph = NP_FETCH;
-    int64_t t = 0;
-    int ori_l = 0, sl = 0, np = 0, npc = 0, np_first = 0, j = 0, nq = 0, pv = 2, cv = 0;
+    int64_t t = 0, t_next = fetch();                                     // the next sequence is claimed one ahead: the atomic's latency hides behind the current one
+    int ori_l = 0, sl = 0, np = 0, npc = 0, np_first = 0, j = 0, nq = 0, pv = 0, cv = 1;
     int first_base = 0, cat_run = 0, nnei = 0, is_forked = 0, cj = 0, fi = 0, rbeg = 0;
     bool sorted = true, ovf = false;
     U last_key = 0, last_hi = 0, ps = 0;
@@ -452,10 +452,12 @@ FMG_HD void nei_lane(const OverlapArgs &A, int64_t lane, FetchFn fetch, void *sh
 
     for (;;) {
         // ---- advance to the next gather request (no index access in here)
+        warp_rejoin();
         while (ph < NP_CAND) {
             if (ph == NP_FETCH) {
-                t = fetch();
+                t = t_next;
                 if (t >= A.n) { ph = NP_DONE; break; }
+                t_next = fetch();
                 np_first = A.np0[t];
                 if (np_first <= 0) continue;
                 A.np0[t] = -1;
@@ -465,23 +467,33 @@ FMG_HD void nei_lane(const OverlapArgs &A, int64_t lane, FetchFn fetch, void *sh
                 xt = A.ext + (size_t)t * A.max_len;
                 nei = A.nei + (size_t)t * A.nei_cap * 2;
                 ovf = false; nnei = 0; is_forked = 0;
-                pv = 2; cv = 0;                                          // `prev` / `curr`: 2 = the list of phase 1 (categories all 0), 0 / 1 = the lane's lists
                 np = np_first; npc = np < A.pcap ? np : A.pcap;
+                {
+                    // the list of phase 1 (its slot was filled from the end: the smallest interval, pushed last, comes first) becomes the
+                    // first `prev` list, all in category 0 (unitig.c:105-106); four entries are requested at a time
+                    const size_t o = (size_t)t * A.pcap + (A.pcap - np_first);
+                    const Cand *src = static_cast<const Cand *>(A.P0) + o;
+                    const U *ssrc = static_cast<const U *>(A.S0) + o;
+                    for (int i = 0; i < npc; i += 4) {
+                        Cand c4[4]; U s4[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) if (i + q < npc) { c4[q] = ld_cand(src + i + q); s4[q] = ssrc[i + q]; }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (i + q < npc) {
+                                c4[q].info = (U)(ori_l - (int)c4[q].info);       // suffix length -> start of the suffix in the read (unitig.c:55)
+                                L.lput(0, i + q, c4[q]); L.sput(0, i + q, s4[q]); L.cput(0, i + q, 0);
+                            }
+                    }
+                }
+                pv = 0; cv = 1;
                 j = 0; nq = 0; first_base = 0; cat_run = 0; sorted = true; last_key = 0; last_hi = 0;
                 ph = NP_NEXT;
             } else if (ph == NP_NEXT) {                                  // the next candidate of `prev` that is still alive (unitig.c:109)
                 if (j >= npc) { ph = NP_END_LEVEL; continue; }
-                if (pv == 2) {
-                    const size_t o = (size_t)t * A.pcap + (A.pcap - np_first + j);      // phase 1 filled its slot from the end, smallest interval last pushed
-                    p = ld_cand(static_cast<const Cand *>(A.P0) + o);
-                    ps = static_cast<const U *>(A.S0)[o];
-                    p.info = (U)(ori_l - (int)p.info);                   // suffix length -> start of the suffix in the read (unitig.c:55)
-                    cj = 0;
-                } else {
-                    cj = L.cget(pv, j);
-                    if (cj < 0) { ++j; continue; }
-                    p = L.lget(pv, j); ps = L.sget(pv, j);
-                }
+                cj = L.cget(pv, j);
+                if (cj < 0) { ++j; continue; }
+                p = L.lget(pv, j); ps = L.sget(pv, j);
                 p.info = (U)((p.info & BT::pos_mask) | ((U)cj << BT::cat_shift));
                 ph = NP_CAND;
             } else if (ph == NP_END_LEVEL) {                             // update categories, unitig.c:137-153
@@ -542,113 +554,114 @@ FMG_HD void nei_lane(const OverlapArgs &A, int64_t lane, FetchFn fetch, void *sh
                 ph = NP_FETCH;
             }
         }
+        // ---- the one gather of this trip (converged): the block(s) around x1 of the lane's candidate -- the candidates of a level are
+        // suffixes of one read, i.e. rc(P) are prefixes of one string, so their x1 lie within a few BWT rows of each other and the
+        // gather nearly always serves the whole level
         const bool active = ph != NP_DONE;
         if (!warp_any(active)) return;
-
-        // ---- the one gather of this trip (converged): ranks at x1, x1 + s and x1 + x2
         const bool cand = ph == NP_CAND;
-        const uint64_t pa = cand ? (uint64_t)p.x1 : (uint64_t)k0.x1;
-        const uint64_t pm = pa + (cand ? (uint64_t)ps : 0), pb = pa + (cand ? (uint64_t)p.x2 : (uint64_t)k0.x2);
-        const uint64_t ba = pa >> kBlkShift, bm = pm >> kBlkShift, bb = pb >> kBlkShift;
-        const bool two = active && bb != ba;
-        const bool any_two = warp_any(two);
+        const uint64_t pa = cand ? (uint64_t)p.x1 : (uint64_t)k0.x1, pb = pa + (cand ? (uint64_t)p.x2 : (uint64_t)k0.x2);
+        const uint64_t b1 = pa >> kBlkShift, b2 = pb >> kBlkShift;
+        const bool two = active && b2 != b1;
+        const bool any_two = warp_any(two);          // one lane in a dozen needs a second block, so most warps do: both gathers are issued before either is waited for
         const PairReq qa = pair_issue(A.ix, pa, active);
         PairReq qb;
         if (any_two) qb = pair_issue(A.ix, pb, two);
-        U ra[6], rm[6], rb[6];                                           // counts relative to the superblock of x1
-        {
-            uint32_t r32[6];
-            {
-                const Blk B = pair_finish(qa);
-                if (active) {
-                    rank_rel(B, pa, r32);
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) ra[c] = r32[c];
-                    if (bm == ba) {
-                        rank_rel(B, pm, r32);
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) rm[c] = r32[c];
-                    }
-                    if (!two) {
-                        rank_rel(B, pb, r32);
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) rb[c] = r32[c];
-                    }
-                }
-            }
-            if (any_two) {
-                const Blk B = pair_finish(qb);
-                if (two) {
-                    rank_rel(B, pb, r32);
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) rb[c] = r32[c];
-                    if (bm == bb) {
-                        rank_rel(B, pm, r32);
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) rm[c] = r32[c];
-                    }
-                }
-            }
-            if (!active) continue;
-            if (bm != ba && bm != bb) {                                  // an interval wider than a block with $P ending in between: rare
-                rank_rel(load_blk(A.ix, pm), pm, r32);
-#pragma unroll
-                for (int c = 0; c < 6; ++c) rm[c] = r32[c];
-            }
-        }
-        const uint64_t sba = pa >> kSuperShift;
+        const uint64_t sba = pa >> kSuperShift;      // C[c] + occurrences before the superblock of x1, requested with the blocks (the row is in L1 / L2)
         const uint64_t *rowa = A.ix.cs + sba * 8;
-        if ((pb >> kSuperShift) != sba) {                                // rare: the interval straddles a superblock boundary
-            const uint64_t *r2 = A.ix.cs + (pb >> kSuperShift) * 8;
+        U csa[6];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) rb[c] += (U)(ld_u64(r2 + c) - ld_u64(rowa + c));
-            if ((pm >> kSuperShift) != sba) {
+        for (int c = 0; c < 6; ++c) csa[c] = active ? (U)ld_u64(rowa + c) : (U)0;
+        const Blk B1 = pair_finish(qa);
+        Blk B2 = B1;
+        if (any_two) { const Blk Bx = pair_finish(qb); if (two) B2 = Bx; }
+        warp_rejoin();
+        if (!active) continue;
+        // rank at position q of one of the two blocks, relative to the superblock of x1 (q's superblock differs: rare)
+        auto rank_at = [&](uint64_t q, U r[6]) {
+            uint32_t r32[6];
+            rank_rel((q >> kBlkShift) == b1 ? B1 : B2, q, r32);
 #pragma unroll
-                for (int c = 0; c < 6; ++c) rm[c] += (U)(ld_u64(r2 + c) - ld_u64(rowa + c));
+            for (int c = 0; c < 6; ++c) r[c] = r32[c];
+            if ((q >> kSuperShift) != sba) {
+                const uint64_t *r2 = A.ix.cs + (q >> kSuperShift) * 8;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) r[c] += (U)(ld_u64(r2 + c) - ld_u64(rowa + c));
             }
-        }
+        };
+        auto have_blk = [&](uint64_t q) { const uint64_t bq = q >> kBlkShift; return bq == b1 || (two && bq == b2); };
 
         // ---- consume
         if (cand) {
-            const U s0 = (U)(rb[0] - ra[0]);                             // |P$|: sequences ending with P
-            const U t0 = (U)(rm[0] - ra[0]);                             // |$P$|: sequences equal to P
-            bool found = false;
-            if (s0 != 0 && ori_l != sl && t0 != 0 && s0 == p.x2 && p.x2 == t0) {     // a full read, not contained in a longer one (unitig.c:112-125)
-                Cand nb;                                                 // fm6_extend0's ok0 (x[0] = tk[0]; cnt[0] is 0)
-                nb.x0 = p.x0; nb.x1 = (U)(ld_u64(rowa) + ra[0]); nb.x2 = t0;
-                nb.info = (U)(ori_l - (int)(p.info & BT::pos_mask));
-                for (int i = j; i < npc && L.cget(pv, i) == cj; ++i) L.cput(pv, i, -1);      // mask out the other intervals of the category (pv != 2: not the first level)
-                if (nnei < A.nei_cap) {
-                    Intv o; o.x0 = nb.x0; o.x1 = nb.x1; o.x2 = nb.x2; o.info = nb.info;
-                    st_intv(nei + 2 * nnei, o);
-                } else ovf = true;
-                if (nnei == 0) nei0 = nb;
-                ++nnei;
-                found = true;
-            }   // a read contained in another one is only marked `used` by the reference
-            if (!found) {                                                // collect the extensible intervals (unitig.c:127-135)
-                U zc[5];                                                 // x0 of $P.c, cumulative in the order $,T,G,C,A (exact.c:81-86)
-                zc[4] = (U)(p.x0 + t0); zc[3] = (U)(zc[4] + (U)(rm[4] - ra[4])); zc[2] = (U)(zc[3] + (U)(rm[3] - ra[3])); zc[1] = (U)(zc[2] + (U)(rm[2] - ra[2]));
+            // candidate j, then the following ones of the level while the fetched blocks hold their three positions
+            for (;;) {
+                const uint64_t qa_ = (uint64_t)p.x1, qm_ = qa_ + ps, qb_ = qa_ + p.x2;
+                U ra[6], rm[6], rb[6];
+                rank_at(qa_, ra);
+                rank_at(qb_, rb);
+                if (have_blk(qm_)) rank_at(qm_, rm);
+                else {                                                   // an interval wider than a block with $P ending in between: rare
+                    uint32_t r32[6];
+                    rank_rel(load_blk(A.ix, qm_), qm_, r32);
 #pragma unroll
-                for (int c = 1; c < 5; ++c) {
-                    const U sc = (U)(rm[c] - ra[c]);                     // |$P.c|: left end still bounded by a sentinel
-                    if (sc == 0) continue;
-                    Cand kc;
-                    kc.x0 = zc[c]; kc.x1 = (U)(ld_u64(rowa + c) + ra[c]); kc.x2 = (U)(rb[c] - ra[c]);
-                    kc.info = (U)((p.info & ~BT::base_mask) | ((U)c << BT::pos_bits));
-                    const U hi = (U)(kc.info >> BT::pos_bits);
-                    if (nq == 0) first_base = c;
-                    else if (kc.info < last_key) sorted = false;
-                    if (nq == 0 || hi != last_hi) { last_hi = hi; cat_run = nq; }
-                    last_key = kc.info;
-                    if (nq < A.cap) { L.cput(cv, nq, cat_run); L.lput(cv, nq, kc); L.sput(cv, nq, sc); } else ovf = true;
-                    ++nq;
+                    for (int c = 0; c < 6; ++c) rm[c] = r32[c];
+                    if ((qm_ >> kSuperShift) != sba) {
+                        const uint64_t *r2 = A.ix.cs + (qm_ >> kSuperShift) * 8;
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) rm[c] += (U)(ld_u64(r2 + c) - ld_u64(rowa + c));
+                    }
                 }
+                const U s0 = (U)(rb[0] - ra[0]);                         // |P$|: sequences ending with P
+                const U t0 = (U)(rm[0] - ra[0]);                         // |$P$|: sequences equal to P
+                bool found = false;
+                if (s0 != 0 && ori_l != sl && t0 != 0 && s0 == p.x2 && p.x2 == t0) {     // a full read, not contained in a longer one (unitig.c:112-125)
+                    Cand nb;                                             // fm6_extend0's ok0 (x[0] = tk[0]; cnt[0] is 0)
+                    nb.x0 = p.x0; nb.x1 = (U)(csa[0] + ra[0]); nb.x2 = t0;
+                    nb.info = (U)(ori_l - (int)(p.info & BT::pos_mask));
+                    for (int i = j; i < npc && L.cget(pv, i) == cj; ++i) L.cput(pv, i, -1);      // mask out the other intervals of the category
+                    if (nnei < A.nei_cap) {
+                        Intv o; o.x0 = nb.x0; o.x1 = nb.x1; o.x2 = nb.x2; o.info = nb.info;
+                        st_intv(nei + 2 * nnei, o);
+                    } else ovf = true;
+                    if (nnei == 0) nei0 = nb;
+                    ++nnei;
+                    found = true;
+                }   // a read contained in another one is only marked `used` by the reference
+                if (!found) {                                            // collect the extensible intervals (unitig.c:127-135)
+                    U zc[5];                                             // x0 of $P.c, cumulative in the order $,T,G,C,A (exact.c:81-86)
+                    zc[4] = (U)(p.x0 + t0); zc[3] = (U)(zc[4] + (U)(rm[4] - ra[4])); zc[2] = (U)(zc[3] + (U)(rm[3] - ra[3])); zc[1] = (U)(zc[2] + (U)(rm[2] - ra[2]));
+#pragma unroll
+                    for (int c = 1; c < 5; ++c) {
+                        const U sc = (U)(rm[c] - ra[c]);                 // |$P.c|: left end still bounded by a sentinel
+                        if (sc == 0) continue;
+                        Cand kc;
+                        kc.x0 = zc[c]; kc.x1 = (U)(csa[c] + ra[c]); kc.x2 = (U)(rb[c] - ra[c]);
+                        kc.info = (U)((p.info & ~BT::base_mask) | ((U)c << BT::pos_bits));
+                        const U hi = (U)(kc.info >> BT::pos_bits);
+                        if (nq == 0) first_base = c;
+                        else if (kc.info < last_key) sorted = false;
+                        if (nq == 0 || hi != last_hi) { last_hi = hi; cat_run = nq; }
+                        last_key = kc.info;
+                        if (nq < A.cap) { L.cput(cv, nq, cat_run); L.lput(cv, nq, kc); L.sput(cv, nq, sc); } else ovf = true;
+                        ++nq;
+                    }
+                }
+                // the next live candidate of the level, if the blocks in registers serve it too
+                ++j;
+                while (j < npc && (cj = L.cget(pv, j)) < 0) ++j;
+                if (j >= npc) break;
+                const Cand pn = L.lget(pv, j);
+                const U sn = L.sget(pv, j);
+                const uint64_t na = (uint64_t)pn.x1;
+                if (!have_blk(na) || !have_blk(na + sn) || !have_blk(na + pn.x2) || (na >> kSuperShift) != sba) break;
+                p = pn; ps = sn;
+                p.info = (U)((p.info & BT::pos_mask) | ((U)cj << BT::cat_shift));
             }
-            ++j;
             ph = NP_NEXT;
         } else {                                                         // the rebuild chain, unitig.c:158-176: forward extension of k0
-            U sz[6], nr[6];
+            U ra[6], rb[6], sz[6], nr[6];
+            rank_at(pa, ra);
+            rank_at(pb, rb);
 #pragma unroll
             for (int c = 0; c < 6; ++c) sz[c] = (U)(rb[c] - ra[c]);
             nr[0] = k0.x0; nr[4] = (U)(nr[0] + sz[0]); nr[3] = (U)(nr[4] + sz[4]); nr[2] = (U)(nr[3] + sz[3]); nr[1] = (U)(nr[2] + sz[2]); nr[5] = (U)(nr[1] + sz[1]);
@@ -664,7 +677,7 @@ FMG_HD void nei_lane(const OverlapArgs &A, int64_t lane, FetchFn fetch, void *sh
                 if (csel < 0) { sl = fi; ph = NP_FINISH2; continue; }
                 xt[fi - ori_l] = (uint8_t)comp6(csel);
             }
-            k0.x0 = pick6(nr, csel); k0.x1 = (U)(ld_u64(rowa + csel) + pick6(ra, csel)); k0.x2 = pick6(sz, csel);
+            k0.x0 = pick6(nr, csel); k0.x1 = (U)(pick6(csa, csel) + pick6(ra, csel)); k0.x2 = pick6(sz, csel);
             ++fi;
             if (ph == NP_FIX1) { if (fi >= ori_l) ph = fi < sl ? NP_FIX2 : NP_FINISH2; }
             else if (fi >= sl) { sl = fi; ph = NP_FINISH2; }

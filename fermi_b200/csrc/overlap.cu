@@ -55,15 +55,15 @@ template <typename U, int MINB>
 __global__ void __launch_bounds__(OVLP_BLOCK, MINB) k_ov_nei(const __grid_constant__ OverlapArgs A) {
     extern __shared__ uint4 fmg_ov_shared[];
     const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    nei_lane<U>(A, lane, [&]() -> int64_t { return (int64_t)atomicAdd(A.next, 1ull); }, fmg_ov_shared, (int)blockDim.x, (int)threadIdx.x);
+    nei_lane<U, MINB>(A, lane, [&]() -> int64_t { return (int64_t)atomicAdd(A.next, 1ull); }, fmg_ov_shared, (int)blockDim.x, (int)threadIdx.x);
 }
 static int nei_minb() {
-    static const int v = [] { const char *e = std::getenv("FMG_NEI_BLOCKS"); const int x = e ? std::atoi(e) : 4; return x <= 4 ? 4 : x >= 6 ? 6 : 5; }();
+    static const int v = [] { const char *e = std::getenv("FMG_NEI_BLOCKS"); const int x = e ? std::atoi(e) : 4; return x <= 3 ? 3 : x >= 5 ? 5 : 4; }();
     return v;
 }
 template <typename U> static const void *nei_kernel() {
     const int m = nei_minb();
-    return m == 4 ? (const void *)k_ov_nei<U, 4> : m == 6 ? (const void *)k_ov_nei<U, 6> : (const void *)k_ov_nei<U, 5>;
+    return m == 3 ? (const void *)k_ov_nei<U, 3> : m == 5 ? (const void *)k_ov_nei<U, 5> : (const void *)k_ov_nei<U, 4>;
 }
 template <typename U> static constexpr size_t lists_shared_bytes() { return NeiLists<U>::shared_bytes(OVLP_BLOCK); }
 
@@ -208,7 +208,15 @@ static cudaError_t launch_records(OverlapArgs O, int grid, unsigned long long *c
     cudaError_t e = cudaMemsetAsync(ctrl2, 0, 16, st);
     if (e != cudaSuccess) return e;
     const unsigned gch = (unsigned)((O.n + OVCH_BLOCK - 1) / OVCH_BLOCK);
-    const int g = (int)std::min<int64_t>(grid, (O.n + OVLP_BLOCK - 1) / OVLP_BLOCK);
+    int g = (int)std::min<int64_t>(grid, (O.n + OVLP_BLOCK - 1) / OVLP_BLOCK);
+    {
+        // persistent lanes: no more blocks than are resident at once (the grid is sized for the roomier of the two list kernels)
+        static int n_sm = 0;
+        if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nei_kernel<U>(), OVLP_BLOCK, lists_shared_bytes<U>());
+        if (per_sm > 0) g = std::min(g, n_sm * per_sm);
+    }
     if (ev) cudaEventRecord(ev[0], st);
     k_ov_chain<U, 1><<<gch, OVCH_BLOCK, 0, st>>>(O);
     if (ev) cudaEventRecord(ev[1], st);
@@ -350,6 +358,9 @@ int fmg_overlap_all(const fmg_index_s *idx, int min_match, int max_len, OvHost *
     return out ? fmg_overlap_pass(idx, min_match, max_len, nullptr, out) : -1;
 }
 
+static inline uint64_t row_lo_arg(const OvShard *shard) { return shard ? shard->row_lo : 0; }
+static inline uint64_t row_hi_arg(const OvShard *shard, uint64_t n_seq) { return shard ? shard->row_hi : n_seq; }
+
 int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevice *dev_out, OvHost *out, OvShard *shard) {
     if (!idx || (!out && !dev_out && !shard) || (shard && (out || dev_out))) return -1;
     int ndev = 0;
@@ -364,8 +375,20 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
     max_len = round8(max_len);
     if (!idx->ovc) idx->ovc = new fmg_ovcache_s;
     fmg_ovcache_s &H = *idx->ovc;
-    const int64_t batch = 1 << 21;                           // even, so that the odd rows of a batch are its local odd rows
-    const int64_t nb_max = (int64_t)std::min<uint64_t>(batch, n_seq ? n_seq : 1);
+    // Rows per batch (even, so that the odd rows of a batch are its local odd rows).  The persistent lanes of the neighbour phase
+    // finish a batch at different times -- the cost of a sequence is heavy-tailed, and a block retires only when its slowest lane
+    // does -- so a batch should hold many sequences per lane: 2 M rows (21 per lane) left the lanes idle half of the time.  Scratch
+    // is ~1.9 KB per row; a batch takes up to a quarter of the free HBM, at most 32 M rows.
+    int64_t batch = 1 << 25;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const int64_t fit = (int64_t)(free_b / 4 / (size_t)(18 * max_len + 256 + 20 * std::max(8, max_len - min_match + 8)));
+            batch = std::max<int64_t>(1 << 20, std::min<int64_t>(batch, fit & ~(int64_t)1));
+        }
+        if (const char *e = std::getenv("FMG_OV_BATCH")) batch = std::max<int64_t>(2, std::atoll(e) & ~1ll);
+    }
+    const int64_t nb_max = (int64_t)std::min<uint64_t>(batch, std::max<uint64_t>(row_hi_arg(shard, n_seq) - row_lo_arg(shard), 2));
     const auto t0 = std::chrono::steady_clock::now();
     auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
 

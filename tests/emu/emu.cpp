@@ -120,8 +120,8 @@ int emu_overlap(const void *_x, int min_match, int64_t n, const uint64_t *ids, i
         for (int t = 0; t < n_lanes; ++t) {
             int64_t cur = t;
             auto fetch = [&]() { int64_t r = cur; cur += n_lanes; return r; };
-            if (wide) { if (phase == 2) nei_lane<uint64_t>(O, t, fetch, shared.data(), 1, 0); else overlap_lane_sync<uint64_t, 4>(O, t, fetch); }
-            else { if (phase == 2) nei_lane<uint32_t>(O, t, fetch, shared.data(), 1, 0); else overlap_lane_sync<uint32_t, 4>(O, t, fetch); }
+            if (wide) { if (phase == 2) nei_lane<uint64_t, 0>(O, t, fetch, shared.data(), 1, 0); else overlap_lane_sync<uint64_t, 4>(O, t, fetch); }
+            else { if (phase == 2) nei_lane<uint32_t, 0>(O, t, fetch, shared.data(), 1, 0); else overlap_lane_sync<uint32_t, 4>(O, t, fetch); }
         }
     };
     for (int64_t t = 0; t < n; ++t) { if (wide) overlap_chain<uint64_t, 1>(O, t); else overlap_chain<uint32_t, 1>(O, t); }
