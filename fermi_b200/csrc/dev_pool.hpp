@@ -108,5 +108,5 @@ struct fmg_ovcache_s {
         }
         ~Pin() { if (p) cudaFreeHost(p); }
         template <class T> T *as() const { return static_cast<T *>(p); }
-    } pack, rank, seq, ext, spill, ctrl, umeta, unei, useq, ucov;
+    } pack, rank, seq, ext, spill, ctrl, text;
 };

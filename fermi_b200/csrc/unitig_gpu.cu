@@ -228,52 +228,115 @@ __global__ void __launch_bounds__(256) k_emit_nodes(G g, OccView ix, const uint3
     }
 }
 
-// depth -> coverage character (unitig.c:253-257: '"' for the first read, +1 per further read, saturating at '~'); bases -> letters
-__global__ void __launch_bounds__(256) k_emit_text(uint64_t total, const int32_t *__restrict__ depth, uint8_t *useq, uint8_t *ucov) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int d = depth[i];
-    ucov[i] = (uint8_t)(33 + (d < 93 ? d : 93));
-    const uint8_t c = useq[i];
-    useq[i] = c == 1 ? 'A' : c == 2 ? 'C' : c == 3 ? 'G' : c == 4 ? 'T' : 'N';
+// ---- MAG text on the device (mag_v_write, mag.c:149-174):  @k0:k1 \t nsr \t nei0 \t nei1 \n SEQ \n + \n COV \n   with nei = "x,ovlp;"...
+// or "." -- sizes per unitig, one scan, then one thread per unitig for the header and one per eight bases for the two strings.
+__device__ __forceinline__ uint32_t dec_digits(uint64_t v) {
+    uint32_t n = 1;
+    while (v >= 10) { v /= 10; ++n; }
+    return n;
+}
+__device__ __forceinline__ uint32_t dec_len_i64(int64_t v) { return v < 0 ? 1 + dec_digits(0 - (uint64_t)v) : dec_digits((uint64_t)v); }
+__device__ __forceinline__ char *put_dec(char *o, int64_t v) {
+    uint64_t u = v < 0 ? 0 - (uint64_t)v : (uint64_t)v;
+    if (v < 0) *o++ = '-';
+    const uint32_t n = dec_digits(u);
+    for (uint32_t i = n; i-- > 0;) { o[i] = (char)('0' + u % 10); u /= 10; }
+    return o + n;
+}
+
+__global__ void __launch_bounds__(256) k_mag_len(uint64_t n_u, const UMeta *__restrict__ meta, const UNei *__restrict__ nei, uint64_t total,
+                                                uint64_t *rec_len, uint32_t *hdr_len, uint64_t *soff) {
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u == n_u) { soff[u] = total; rec_len[u] = 0; }
+    if (u >= n_u) return;
+    const UMeta m = meta[u];
+    uint32_t h = 1 + dec_digits(m.k0) + 1 + dec_digits(m.k1) + 1 + dec_digits(m.nsr);
+    const UNei *e = nei + m.nei_off;
+    for (int j = 0; j < 2; ++j) {
+        const uint32_t c = j ? m.n1 : m.n0;
+        h += 1;
+        for (uint32_t i = 0; i < c; ++i) h += dec_len_i64((int64_t)e[i].x) + 1 + dec_len_i64((int64_t)(int32_t)e[i].ovlp) + 1;
+        if (c == 0) h += 1;
+        e += c;
+    }
+    h += 1;
+    hdr_len[u] = h;
+    soff[u] = m.seq_off;
+    rec_len[u] = (uint64_t)h + 2ull * m.len + 4;                 // header, SEQ, "\n+\n", COV, "\n"
+}
+
+__global__ void __launch_bounds__(256) k_mag_hdr(uint64_t n_u, const UMeta *__restrict__ meta, const UNei *__restrict__ nei, const uint64_t *__restrict__ text_off,
+                                                const uint32_t *__restrict__ hdr_len, char *text) {
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_u) return;
+    const UMeta m = meta[u];
+    char *o = text + text_off[u];
+    *o++ = '@'; o = put_dec(o, (int64_t)m.k0); *o++ = ':'; o = put_dec(o, (int64_t)m.k1); *o++ = '\t'; o = put_dec(o, (int64_t)m.nsr);
+    const UNei *e = nei + m.nei_off;
+    for (int j = 0; j < 2; ++j) {
+        const uint32_t c = j ? m.n1 : m.n0;
+        *o++ = '\t';
+        for (uint32_t i = 0; i < c; ++i) { o = put_dec(o, (int64_t)e[i].x); *o++ = ','; o = put_dec(o, (int64_t)(int32_t)e[i].ovlp); *o++ = ';'; }
+        if (c == 0) *o++ = '.';
+        e += c;
+    }
+    *o++ = '\n';
+    char *q = text + text_off[u] + hdr_len[u] + m.len;
+    q[0] = '\n'; q[1] = '+'; q[2] = '\n';
+    q[3 + m.len] = '\n';
+}
+
+// bases -> letters, depth -> coverage character (unitig.c:253-257: '"' for the first read, +1 per further read, saturating at '~'),
+// both written to their place in the text; a thread takes eight consecutive bases of the flat consensus array
+__global__ void __launch_bounds__(256) k_mag_body(uint64_t total, uint64_t n_u, const int32_t *__restrict__ depth, const uint8_t *__restrict__ useq,
+                                                 const uint64_t *__restrict__ soff, const uint64_t *__restrict__ text_off, const uint32_t *__restrict__ hdr_len,
+                                                 char *text) {
+    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i0 >= total) return;
+    uint64_t lo = 0, hi = n_u;                                    // the unitig of base i0: the last u with soff[u] <= i0
+    while (hi - lo > 1) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (soff[mid] <= i0) lo = mid; else hi = mid;
+    }
+    uint64_t u = lo, end = soff[u + 1], ulen = end - soff[u];
+    char *ps = text + text_off[u] + hdr_len[u] - soff[u];         // + i = place of base i in SEQ; + ulen + 3 in COV
+    const uint64_t i1 = i0 + 8 < total ? i0 + 8 : total;
+    for (uint64_t i = i0; i < i1; ++i) {
+        while (i >= end) { ++u; end = soff[u + 1]; ulen = end - soff[u]; ps = text + text_off[u] + hdr_len[u] - soff[u]; }
+        const uint8_t c = useq[i];
+        const int d = depth[i];
+        ps[i] = c == 1 ? 'A' : c == 2 ? 'C' : c == 3 ? 'G' : c == 4 ? 'T' : 'N';
+        ps[i + ulen + 3] = (char)(33 + (d < 93 ? d : 93));
+    }
 }
 
 inline unsigned nblk(uint64_t n) { return (unsigned)((n + 255) / 256); }
-
-void put_i64(std::string &o, int64_t v) {            // decimal digits without going through printf (several per unitig)
-    char b[24];
-    int n = 24;
-    uint64_t u = v < 0 ? 0 - (uint64_t)v : (uint64_t)v;
-    do { b[--n] = (char)('0' + u % 10); u /= 10; } while (u);
-    if (v < 0) b[--n] = '-';
-    o.append(b + n, 24 - n);
-}
 
 }  // namespace
 
 // MAG text of one part of the unitigs, held by the caller between the two steps of a multi-GPU run (all ranks learn the sizes
 // of all parts before they write them side by side into one file)
-struct fmg_magpart_s { std::vector<std::string> parts; uint64_t bytes = 0; };
+// The text lives in the pinned cache of the index handle (fmg_ovcache_s::text): valid until the next unitig call on that handle.
+struct fmg_magpart_s { const char *text = nullptr; uint64_t bytes = 0; unsigned threads = 1; };
 
-static int write_parts(const std::vector<std::string> &parts, const char *out_path, uint64_t offset, bool truncate, const char *who) {
+// `bytes` of text to `out_path` at `offset`, by `nt` threads with pwrite (the page-cache copy is the cost of the output)
+static int write_text(const char *text, uint64_t bytes, unsigned nt, const char *out_path, uint64_t offset, bool truncate, const char *who) {
     int fd = ::open(out_path, truncate ? (O_WRONLY | O_CREAT | O_TRUNC) : (O_WRONLY | O_CREAT), 0644);
     if (fd < 0) {
         if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] cannot write '%s'\n", who, out_path);
         return -1;
     }
-    const unsigned nt = (unsigned)parts.size();
-    std::vector<uint64_t> off(nt + 1, offset);
-    for (unsigned t = 0; t < nt; ++t) off[t + 1] = off[t] + parts[t].size();
+    if (bytes < (1u << 22)) nt = 1;
     std::atomic<int> io_fail{0};
     auto put = [&](unsigned t) {
-        const std::string &o = parts[t];
-        for (size_t done = 0; done < o.size();) {
-            const ssize_t w = ::pwrite(fd, o.data() + done, o.size() - done, (off_t)(off[t] + done));
+        const uint64_t a = bytes * t / nt, b = bytes * (t + 1) / nt;
+        for (uint64_t done = a; done < b;) {
+            const ssize_t w = ::pwrite(fd, text + done, (size_t)std::min<uint64_t>(b - done, 1u << 26), (off_t)(offset + done));
             if (w <= 0) { io_fail = 1; return; }
-            done += (size_t)w;
+            done += (uint64_t)w;
         }
     };
-    if (nt <= 1) { if (nt) put(0); }
+    if (nt <= 1) put(0);
     else {
         std::vector<std::thread> th;
         for (unsigned t = 0; t < nt; ++t) th.emplace_back(put, t);
@@ -299,7 +362,7 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
     if (!idx->ovc) idx->ovc = new fmg_ovcache_s;
     fmg_ovcache_s &H = *idx->ovc;
     cudaStream_t st = nullptr;                       // legacy default stream: ordered after the pass (which synchronised its streams)
-    Dev d_succ, d_pred, d_row, d_tail, d_flags, d_ptr[2], d_dn[2], d_db[2], d_cnt, d_len, d_nei, d_tmp, d_meta, d_unei, d_useq, d_ucov, d_diff;
+    Dev d_succ, d_pred, d_row, d_tail, d_flags, d_ptr[2], d_dn[2], d_db[2], d_cnt, d_len, d_nei, d_tmp, d_meta, d_unei, d_useq, d_diff;
     UG_TRY(d_succ.alloc(n * 4)); UG_TRY(d_pred.alloc(n * 4)); UG_TRY(d_row.alloc(n * 4)); UG_TRY(d_tail.alloc(n * 4)); UG_TRY(d_flags.alloc(64));
     for (int k = 0; k < 2; ++k) { UG_TRY(d_ptr[k].alloc(n * 4)); UG_TRY(d_dn[k].alloc(n * 4)); UG_TRY(d_db[k].alloc(n * 8)); }
     UG_TRY(d_cnt.alloc((n + 1) * 8)); UG_TRY(d_len.alloc((n + 1) * 8)); UG_TRY(d_nei.alloc((n + 1) * 8));
@@ -375,7 +438,7 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
         return 1;
     }
     UG_TRY(d_meta.alloc(std::max<uint64_t>(n_u, 1) * sizeof(UMeta))); UG_TRY(d_unei.alloc(std::max<uint64_t>(n_nei, 1) * sizeof(UNei)));
-    UG_TRY(d_useq.alloc(total + 1)); UG_TRY(d_ucov.alloc(total + 1)); UG_TRY(d_diff.alloc((total + 1) * 4));
+    UG_TRY(d_useq.alloc(total + 1)); UG_TRY(d_diff.alloc((total + 1) * 4));
     UG_TRY(cudaMemsetAsync(d_diff.p, 0, (total + 1) * 4, st));
     k_emit_meta<<<nblk(n), 256, 0, st>>>(g, dn, db, e_cnt, d_uidx.as<uint64_t>(), d_uoff.as<uint64_t>(), d_noff.as<uint64_t>(), d_meta.as<UMeta>(), d_unei.as<UNei>());
     k_emit_nodes<<<nblk(n), 256, 0, st>>>(g, idx->view, head, db, e_cnt, d_uoff.as<uint64_t>(), d_useq.as<uint8_t>(), d_diff.as<int32_t>());
@@ -386,70 +449,72 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
         UG_TRY(cub::DeviceScan::InclusiveSum(nullptr, need2, d_diff.as<int32_t>(), d_diff.as<int32_t>(), total, st));
         if (need2 > need) UG_TRY(d_tmp.alloc(need2 + 256));
         UG_TRY(cub::DeviceScan::InclusiveSum(d_tmp.p, need2, d_diff.as<int32_t>(), d_diff.as<int32_t>(), total, st));
-        k_emit_text<<<nblk(total), 256, 0, st>>>(total, d_diff.as<int32_t>(), d_useq.as<uint8_t>(), d_ucov.as<uint8_t>());
+        ++g_launches;
+    }
+    // ---- MAG text (mag_v_write, mag.c:149-174) formatted on the device: record sizes, one scan, headers, the two strings
+    Dev d_rlen, d_toff, d_hlen, d_soff, d_text;
+    UG_TRY(d_rlen.alloc((n_u + 1) * 8)); UG_TRY(d_toff.alloc((n_u + 1) * 8)); UG_TRY(d_hlen.alloc((n_u + 1) * 4)); UG_TRY(d_soff.alloc((n_u + 1) * 8));
+    k_mag_len<<<nblk(n_u + 1), 256, 0, st>>>(n_u, d_meta.as<UMeta>(), d_unei.as<UNei>(), total, d_rlen.as<uint64_t>(), d_hlen.as<uint32_t>(), d_soff.as<uint64_t>());
+    {
+        size_t need3 = 0;
+        UG_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need3, d_rlen.as<uint64_t>(), d_toff.as<uint64_t>(), n_u + 1, st));
+        UG_TRY(d_tmp.alloc(need3 + 256));
+        UG_TRY(cub::DeviceScan::ExclusiveSum(d_tmp.p, need3, d_rlen.as<uint64_t>(), d_toff.as<uint64_t>(), n_u + 1, st));
+    }
+    g_launches += 2;
+    UG_TRY(cudaMemcpyAsync(h_tot + 5, d_toff.as<uint64_t>() + n_u, 8, cudaMemcpyDeviceToHost, st));
+    UG_TRY(cudaStreamSynchronize(st));
+    const uint64_t text_bytes = h_tot[5];
+    UG_TRY(d_text.alloc(text_bytes + 1));
+    if (n_u) {
+        k_mag_hdr<<<nblk(n_u), 256, 0, st>>>(n_u, d_meta.as<UMeta>(), d_unei.as<UNei>(), d_toff.as<uint64_t>(), d_hlen.as<uint32_t>(), d_text.as<char>());
+        if (total)
+            k_mag_body<<<nblk((total + 7) / 8), 256, 0, st>>>(total, n_u, d_diff.as<int32_t>(), d_useq.as<uint8_t>(), d_soff.as<uint64_t>(), d_toff.as<uint64_t>(),
+                                                          d_hlen.as<uint32_t>(), d_text.as<char>());
         g_launches += 2;
         UG_TRY(cudaGetLastError());
     }
-    UG_TRY(H.umeta.need(std::max<uint64_t>(n_u, 1) * sizeof(UMeta))); UG_TRY(H.unei.need(std::max<uint64_t>(n_nei, 1) * sizeof(UNei)));
-    UG_TRY(H.useq.need(total + 1)); UG_TRY(H.ucov.need(total + 1));
-    if (n_u) UG_TRY(cudaMemcpyAsync(H.umeta.p, d_meta.p, n_u * sizeof(UMeta), cudaMemcpyDeviceToHost, st));
-    if (n_nei) UG_TRY(cudaMemcpyAsync(H.unei.p, d_unei.p, n_nei * sizeof(UNei), cudaMemcpyDeviceToHost, st));
-    if (total) {
-        UG_TRY(cudaMemcpyAsync(H.useq.p, d_useq.p, total, cudaMemcpyDeviceToHost, st));
-        UG_TRY(cudaMemcpyAsync(H.ucov.p, d_ucov.p, total, cudaMemcpyDeviceToHost, st));
-    }
-    UG_TRY(cudaStreamSynchronize(st));
-    const double t_dev = since(t0);
-
-    // ---- MAG text (mag_v_write, mag.c:149-174), formatted by all host cores in unitig order.  A regular file is written
-    // by the same threads with pwrite at the offsets the part sizes give (the page-cache copy is the cost of the output).
-    const bool to_stdout = !sink && std::strcmp(out_path, "-") == 0;
-    const UMeta *meta = H.umeta.as<UMeta>();
-    const UNei *nei = H.unei.as<UNei>();
-    const char *useq = H.useq.as<char>(), *ucov = H.ucov.as<char>();
+    UG_TRY(H.text.need(text_bytes + 1));
     unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency() / std::max(1u, n_parts), 32u));
     if (const char *e = std::getenv("FMG_THREADS")) nt = (unsigned)std::max(1, std::atoi(e));
-    if (n_u < 4096) nt = 1;
-    std::vector<std::string> local_parts;
-    std::vector<std::string> &parts = sink ? sink->parts : local_parts;
-    parts.assign(nt, std::string());
-    auto fmt = [&](unsigned t) {
-        const uint64_t a = n_u * t / nt, b = n_u * (t + 1) / nt;
-        std::string &o = parts[t];
-        uint64_t bytes = 0;
-        for (uint64_t u = a; u < b; ++u) bytes += 2ull * meta[u].len + 64 + 24ull * (meta[u].n0 + meta[u].n1);
-        o.reserve(bytes);
-        for (uint64_t u = a; u < b; ++u) {
-            const UMeta &m = meta[u];
-            o += '@'; put_i64(o, (int64_t)m.k0); o += ':'; put_i64(o, (int64_t)m.k1); o += '\t'; put_i64(o, m.nsr);
-            const UNei *e = nei + m.nei_off;
-            for (int j = 0; j < 2; ++j) {
-                const uint32_t c = j ? m.n1 : m.n0;
-                o += '\t';
-                for (uint32_t i = 0; i < c; ++i) { put_i64(o, (int64_t)e[i].x); o += ','; put_i64(o, (int32_t)e[i].ovlp); o += ';'; }
-                if (c == 0) o += '.';
-                e += c;
-            }
-            o += '\n';
-            o.append(useq + m.seq_off, m.len);
-            o += "\n+\n";
-            o.append(ucov + m.seq_off, m.len);
-            o += '\n';
+    const bool to_stdout = !sink && std::strcmp(out_path, "-") == 0;
+    double t_dev = 0;
+    if (sink || to_stdout || text_bytes < (1u << 24)) {
+        if (text_bytes) UG_TRY(cudaMemcpyAsync(H.text.p, d_text.p, text_bytes, cudaMemcpyDeviceToHost, st));
+        UG_TRY(cudaStreamSynchronize(st));
+        t_dev = since(t0);
+        if (sink) { sink->text = H.text.as<char>(); sink->bytes = text_bytes; sink->threads = nt; }
+        else if (to_stdout) { std::fwrite(H.text.p, 1, text_bytes, stdout); std::fflush(stdout); }
+        else if (write_text(H.text.as<char>(), text_bytes, nt, out_path, 0, true, __func__) != 0) return -1;
+    } else {
+        // a file: the text leaves the device in slices, and each slice is written while the next one is copied
+        int fd = ::open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (fd < 0) {
+            if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] cannot write '%s'\n", __func__, out_path);
+            return -1;
         }
-    };
-    if (nt == 1) fmt(0u);
-    else {
+        ::close(fd);
+        const unsigned n_slice = std::max(2u, std::min(nt, 16u));
+        std::vector<cudaEvent_t> ev(n_slice);
+        for (auto &e : ev) UG_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (unsigned k = 0; k < n_slice; ++k) {
+            const uint64_t a = text_bytes * k / n_slice, b = text_bytes * (k + 1) / n_slice;
+            UG_TRY(cudaMemcpyAsync(H.text.as<char>() + a, d_text.as<char>() + a, b - a, cudaMemcpyDeviceToHost, st));
+            UG_TRY(cudaEventRecord(ev[k], st));
+        }
+        std::atomic<int> fail{0};
         std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; ++t) th.emplace_back(fmt, t);
+        for (unsigned k = 0; k < n_slice; ++k)
+            th.emplace_back([&, k]() {
+                const uint64_t a = text_bytes * k / n_slice, b = text_bytes * (k + 1) / n_slice;
+                if (cudaEventSynchronize(ev[k]) != cudaSuccess) { fail = 1; return; }
+                if (write_text(H.text.as<char>() + a, b - a, 1, out_path, a, false, "fmg_unitig_device") != 0) fail = 1;
+            });
         for (auto &x : th) x.join();
+        for (auto &e : ev) cudaEventDestroy(e);
+        t_dev = since(t0);
+        if (fail) return -1;
     }
-    if (sink) {
-        sink->bytes = 0;
-        for (const std::string &o : parts) sink->bytes += o.size();
-    } else if (to_stdout) {
-        for (const std::string &o : parts) std::fwrite(o.data(), 1, o.size(), stdout);
-        std::fflush(stdout);
-    } else if (write_parts(parts, out_path, 0, true, __func__) != 0) return -1;
     if (n_unitigs) *n_unitigs = n_u;
     if (fmg_verbose >= 4)
         std::fprintf(stderr, "[M::%s] %llu unitigs, %llu bases from %llu sequences: chains %.3f s (%d jump rounds), assembly + copies %.3f s, text %.3f s\n", __func__,
@@ -600,7 +665,7 @@ int fmg_unitig_part(const fmg_index_t *idx, int min_match, const void *d_pack, c
 
 int fmg_magpart_write(const fmg_magpart_t *p, const char *path, uint64_t offset, int truncate) {
     if (!p || !path) return -1;
-    return write_parts(p->parts, path, offset, truncate != 0, __func__);
+    return write_text(p->text, p->bytes, p->threads, path, offset, truncate != 0, __func__);
 }
 
 void fmg_magpart_free(fmg_magpart_t *p) { delete p; }
