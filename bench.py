@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--unitig-reads", type=int, default=10_000_000, help="reads of the unitig leg (BASELINE config 3); 0 disables it")
     ap.add_argument("--unitig-ref-reads", type=int, default=500_000, help="reads of the bounded reference sample of the unitig leg")
     ap.add_argument("--no-unitig-noisy", action="store_true", help="skip the 1 %% substitution variant of the unitig leg")
+    ap.add_argument("--no-smem-hbm", action="store_true", help="skip the SMEM leg against the index that does not fit L2")
     return ap.parse_args()
 
 
@@ -184,6 +185,70 @@ def unitig_build_index(fb, n_reads, read_len, err, device, fn):
     return dt
 
 
+def smem_hbm_leg(fb, a, idx, fn, device, peak, peak_src):
+    """SMEM where the index does NOT fit L2: fm6_smem(self_match=0) of reads sampled from the unitig genome (1 % substitutions)
+    against the config-3 read index (2.02e9 symbols, 1 GB of occ blocks >> 126 MB L2), reads and results resident in HBM.  The
+    session picks the paired-gather kernel for such an index; the plain-load kernel is timed beside it."""
+    import torch
+    import helpers as H
+    L, n = a.read_len, a.reads
+    genome = fb.synth_genome(UNITIG_GENOME_SEED, a.unitig_reads * L // UNITIG_COV)
+    reads = fb.synth_reads(READ_SEED + 7, genome, n, L, a.err)
+    dev = torch.device("cuda", device)
+    d_reads = torch.from_numpy(reads).to(dev)
+    B = min(a.batch_reads, n)
+    batches = [(s, min(B, n - s)) for s in range(0, n, B)]
+    d_boff = [(torch.arange(m + 1, dtype=torch.int64, device=dev) * L).contiguous() for _, m in batches]
+    stream = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for label, env in (("paired_gathers", None), ("plain_loads", "0")):
+        if env is None:
+            os.environ.pop("FMG_SMEM_PAIR", None)
+        else:
+            os.environ["FMG_SMEM_PAIR"] = env
+        sess = fb.SmemSession(idx, B, L)
+        for _ in range(2):
+            for (s0, m), bo in zip(batches, d_boff):
+                sess.run(m, d_reads[s0:].data_ptr(), bo.data_ptr(), 0, stream)
+        sess.result()
+        sess.set_timing(True)
+        sess.kernel_ms()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 3
+        e0.record()
+        for _ in range(steps):
+            for (s0, m), bo in zip(batches, d_boff):
+                sess.run(m, d_reads[s0:].data_ptr(), bo.data_ptr(), 0, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        k_ms, _ = sess.kernel_ms()
+        res[label] = {"ms_per_step": e0.elapsed_time(e1) / steps, "kernel_ms_per_step": k_ms / steps}
+        sess.close()
+    os.environ.pop("FMG_SMEM_PAIR", None)
+    sample_n = min(n, 10000)
+    n_loc, n_ext, n_out = count_locates(fn, reads[:sample_n], min(os.cpu_count() or 1, 16))
+    bytes_per_read = n_loc * 128 + L + 32 * n_out
+    k = res["paired_gathers"]["kernel_ms_per_step"]
+    achieved = n * bytes_per_read / (k / 1e3) / 1e9
+    traffic = None
+    try:
+        import glob
+        tr = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_smem_hbm_traffic.json")))[-1]))
+        traffic = tr["traffic_bytes_per_launch"] * (B / tr["reads_per_launch"])
+    except Exception:
+        pass
+    return {"workload": "fm6_smem: %d x %d bp reads (%g%% subst) vs the FMD-index of the config-3 reads (%d symbols, %.0f MB of occ blocks: HBM regime)"
+                        % (n, L, a.err * 100, int(idx.fmd.mcnt[0]), idx.nbytes / 1e6),
+            "value": n / (res["paired_gathers"]["ms_per_step"] / 1e3), "unit": "reads/s", "ms_per_step": res["paired_gathers"]["ms_per_step"],
+            "plain_loads_value": n / (res["plain_loads"]["ms_per_step"] / 1e3),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "k_smem<u32, paired gathers>", "kernel_ms_per_step": k, "plain_loads_kernel_ms_per_step": res["plain_loads"]["kernel_ms_per_step"],
+                         "algorithmic_bytes_per_read": bytes_per_read, "algorithmic_bytes_per_launch": bytes_per_read * B,
+                         "n_locate_per_read": round(n_loc, 2), "n_extend_per_read": round(n_ext, 2), "records_per_read": round(n_out, 3),
+                         "counter_sample": "instrumented oracle on the first %d reads" % sample_n, "peak_source": peak_src}}
+
+
 def unitig_count_locates(fn, n_seq, sample=3000):
     """N_locate per input read from the instrumented oracle on the ACTUAL index: the block lookups of the work the
     reference's walk does for one read it visits -- fm_retrieve of the seed, overlap_intv + fm6_get_nei, check_left_simple -- over a
@@ -298,6 +363,11 @@ def unitig_leg(fb, a, device, peak, peak_src, rank, world, dist, barrier, err=0.
                                               (loc["sample_seeds"], json.dumps({k: round(v, 1) for k, v in loc["by_stage"].items()}))) if loc else
                                              "SURVEY.md 8d: counter in the reference's rld_locate_blk, `unitig -l50 -t1`, error-free 10x, 1/100 scale",
                            "peak_source": peak_src + (" x %d GPUs" % world if world > 1 else "")}
+        if world == 1 and err == 0.0 and not a.no_smem_hbm:
+            try:
+                res["smem_hbm"] = smem_hbm_leg(fb, a, idx, fn, device, peak, peak_src)
+            except Exception as exc:
+                res["smem_hbm"] = {"error": repr(exc)}
         if check_single and world > 1:
             single = out + ".single"
             fb.fm6_unitig(idx, UNITIG_MIN, single)          # untimed: the same index through the single-GPU call
@@ -460,32 +530,45 @@ def run_ours(a):
     launches_timed = fb.launch_count() - launches1
     clocks = sampler.stop()
 
-    # ---- e2e: pinned host buffers through the C-ABI (H2D + kernels + D2H inside the timed region)
+    # ---- e2e: pinned host buffers through the C-ABI (H2D + kernels + D2H inside the timed region), with fmintv_t records
+    # (fmg_smem_batch_into) and with the packed 16-byte records (fmg_smem_batch_into16: half the bytes back to the host)
     e2e = None
+    e2e32_s = 0.0
     if not a.no_e2e:
         rec_cap = int(a.reads * 16)
         h_mem = torch.empty((rec_cap, 4), dtype=torch.int64).pin_memory()
         h_moff = torch.empty(a.reads + 1, dtype=torch.int64).pin_memory()
         sess.close()                                   # the host API owns its sessions
-        n_rec = 0
-        times = []
-        for it in range(max(1, min(a.warmup, 2)) + max(1, min(a.steps, 3))):
-            barrier()
-            t = time.perf_counter()
-            n_rec = fb.fm6_smem_raw(idx, a.reads, h_reads.data_ptr(), h_off.data_ptr(), h_mem.data_ptr(), rec_cap, h_moff.data_ptr(),
-                                    0, a.batch_reads)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t
-            if it >= max(1, min(a.warmup, 2)):
-                times.append(dt)
-        e2e_s = sum(times) / len(times)
-        e2e = {"seconds": e2e_s, "n_rec": n_rec, "h2d": a.reads * L + (a.reads + 1) * 8, "d2h": n_rec * 32 + (a.reads + 1) * 8}
+
+        def timed(call):
+            n_rec, times = 0, []
+            n_warm = max(1, min(a.warmup, 2))
+            for it in range(n_warm + max(1, min(a.steps, 3))):
+                barrier()
+                t = time.perf_counter()
+                n_rec = call(idx, a.reads, h_reads.data_ptr(), h_off.data_ptr(), h_mem.data_ptr(), rec_cap, h_moff.data_ptr(), 0, a.batch_reads)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t
+                if it >= n_warm:
+                    times.append(dt)
+            return sum(times) / len(times), n_rec
+
+        e2e32_s, n_rec = timed(fb.fm6_smem_raw)
+        packed = int(fmd.mcnt[0]) < (1 << 32) and L < 32768
+        if packed:
+            e2e_s, n_rec16 = timed(fb.fm6_smem_raw16)
+            assert n_rec16 == n_rec
+        else:
+            e2e_s = e2e32_s
+        rb = 16 if packed else 32
+        e2e = {"seconds": e2e_s, "n_rec": n_rec, "h2d": a.reads * L + (a.reads + 1) * 8, "d2h": n_rec * rb + (a.reads + 1) * 8, "record_bytes": rb,
+               "d2h32": n_rec * 32 + (a.reads + 1) * 8}
 
     # ---- reduce over ranks: max time, summed reads
-    t_dev = torch.tensor([step_ms, k_ms / max(1, a.steps), e2e["seconds"] if e2e else 0.0], dtype=torch.float64, device=dev)
+    t_dev = torch.tensor([step_ms, k_ms / max(1, a.steps), e2e["seconds"] if e2e else 0.0, e2e32_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    step_ms_max, k_ms_step_max, e2e_s_max = [float(x) for x in t_dev.tolist()]
+    step_ms_max, k_ms_step_max, e2e_s_max, e2e32_s_max = [float(x) for x in t_dev.tolist()]
     total_reads = a.reads * world
 
     if rank == 0:
@@ -529,8 +612,12 @@ def run_ours(a):
         }
         if e2e:
             out["e2e"] = {"value": total_reads / e2e_s_max, "unit": "reads/s", "h2d_bytes_per_step": int(e2e["h2d"]),
-                          "d2h_bytes_per_step": int(e2e["d2h"]), "seconds_per_step": e2e_s_max,
-                          "api": "fmg_smem_batch_into (pinned host buffers, 3-stream batch pipeline)"}
+                          "d2h_bytes_per_step": int(e2e["d2h"]), "seconds_per_step": e2e_s_max, "record_bytes": e2e["record_bytes"],
+                          "api": ("fmg_smem_batch_into16 (pinned host buffers, 3-stream batch pipeline, 16-byte records packed on the device; "
+                                  "fmg_intv16_expand gives fmintv_t)") if e2e["record_bytes"] == 16 else
+                                 "fmg_smem_batch_into (pinned host buffers, 3-stream batch pipeline)",
+                          "fmintv_t_records": {"value": total_reads / e2e32_s_max, "unit": "reads/s", "seconds_per_step": e2e32_s_max,
+                                               "d2h_bytes_per_step": int(e2e["d2h32"]), "api": "fmg_smem_batch_into (32-byte fmintv_t records)"}}
         if world == 1 and not a.no_cpu_baseline:
             cb, _, _ = cpu_smem_rate(fn, h_reads.numpy(), a.cpu_seconds, cores)
             out["cpu_baseline"] = cb

@@ -38,6 +38,9 @@ _PROTOS = {
     "fmg_smem_batch": (C.c_int, [C.c_void_p, C.c_int64, u8p, u64p, C.c_int, vpp, u64p]),
     "fmg_smem_batch_into": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64,
                                       C.c_void_p, u64p, C.c_int64]),
+    "fmg_smem_batch_into16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64,
+                                        C.c_void_p, u64p, C.c_int64]),
+    "fmg_intv16_expand": (None, [C.c_uint64, C.c_void_p, C.c_void_p]),
     "fmg_free": (None, [C.c_void_p]),
     # device-resident session
     "fmg_smem_session_create": (C.c_void_p, [C.c_void_p, C.c_int64, C.c_int]),

@@ -171,6 +171,25 @@ def fm6_smem_raw(idx, n, seq_ptr, off_ptr, mem_ptr, mem_cap, mem_off_ptr, self_m
     return got.value
 
 
+def fm6_smem_raw16(idx, n, seq_ptr, off_ptr, mem_ptr, mem_cap, mem_off_ptr, self_match=0, batch_reads=0):
+    """fmg_smem_batch_into16 on raw host pointers: packed 16-byte records (x0, x1, x2, end | start << 16 | closed << 31)."""
+    got = C.c_uint64()
+    rc = lib().fmg_smem_batch_into16(idx.h, n, seq_ptr, off_ptr, int(self_match), mem_ptr, mem_cap, mem_off_ptr,
+                                     C.byref(got), batch_reads)
+    if rc == 1:
+        raise RuntimeError("fermi_b200: record buffer too small (%d needed)" % got.value)
+    _check(rc, "fm6_smem (packed)")
+    return got.value
+
+
+def intv16_expand(packed):
+    """uint32[n,4] packed records -> INTV[n] (fmg_intv16_expand)"""
+    packed = np.ascontiguousarray(packed, np.uint32).reshape(-1, 4)
+    out = np.zeros(len(packed), INTV)
+    lib().fmg_intv16_expand(len(packed), packed.ctypes.data, out.ctypes.data)
+    return out
+
+
 class SmemSession:
     """Device-resident SMEM session (fmg_smem_session_*): reads and results stay in HBM."""
 

@@ -398,6 +398,8 @@ struct SmemArgs {
     int out_cap;
     uint32_t *rec_cnt;
     unsigned long long *next_read;
+    int max_len;                      // reads longer than this do not fit F / W: they are skipped and counted in *too_long
+    unsigned long long *too_long;
 };
 
 enum { PH_FETCH = 0, PH_BEGIN, PH_START_BWD, PH_FWD, PH_FWD_TAIL, PH_BWD, PH_DONE };
@@ -406,7 +408,9 @@ enum { PH_FETCH = 0, PH_BEGIN, PH_START_BWD, PH_FWD, PH_FWD_TAIL, PH_BWD, PH_DON
 //                         [warp vote]         leave when no lane has a request; reconverges the warp
 //                         [converged, long]   extend6: two line loads + popcounts for all requesting lanes
 //                         [divergent, short]  consume the result according to the lane's phase
-template <typename U, class FetchFn>
+// PAIR: the blocks come through the paired gather (extend6_conv) -- for indexes that do not fit L2, where the rate of L1-miss
+// requests bounds the kernel; an L2-resident index is served as fast by plain loads with fewer instructions.
+template <typename U, bool PAIR = false, class FetchFn>
 FMG_HD void smem_lane(const SmemArgs &A, int64_t lane_slot, FetchFn fetch) {
     typedef IntvT<U> Cand;
     Cand *F = static_cast<Cand *>(A.F) + (size_t)lane_slot * A.cap;
@@ -430,6 +434,15 @@ FMG_HD void smem_lane(const SmemArgs &A, int64_t lane_slot, FetchFn fetch) {
                 const uint64_t o = A.off[r];
                 len = (int)(A.off[r + 1] - o);
                 if (len <= 0) { A.rec_cnt[r] = 0; continue; }
+                if (len > A.max_len) {                  // would overrun the lane's lists: report it, never corrupt memory
+                    A.rec_cnt[r] = 0;
+#if defined(__CUDA_ARCH__)
+                    atomicAdd(A.too_long, 1ull);
+#else
+                    ++*A.too_long;
+#endif
+                    continue;
+                }
                 q = A.seq + o;
                 out = A.out + (size_t)r * A.out_cap * 2;
                 nmem = 0; x = 0;
@@ -457,18 +470,21 @@ FMG_HD void smem_lane(const SmemArgs &A, int64_t lane_slot, FetchFn fetch) {
         }
         const bool active = ph != PH_DONE;
         if (!warp_any(active)) return;
-        if (!active) continue;
+        if (!PAIR && !active) continue;
 
         // ---- the one extension of this trip (converged across the warp).  The query base it will be
         // consumed with and the next candidate of the backward pass are requested first, so that their
         // latency overlaps the two block loads instead of following them.
         const int back = (ph == PH_BWD);
-        const int qc = (ph == PH_FWD_TAIL || i < 0) ? 0 : (int)ld_u8(q + i);
-        const bool have_nxt = back && j + 1 < nprev;       // entry j+1 of the list being read is final (writes go to <= j)
+        const int qc = (!active || ph == PH_FWD_TAIL || i < 0) ? 0 : (int)ld_u8(q + i);
+        const bool have_nxt = active && back && j + 1 < nprev;       // entry j+1 of the list being read is final (writes go to <= j)
         Cand nxt = ik;
         if (have_nxt) nxt = ld_cand(first_pass ? F + (nF - 2 - j) : W + (j + 1));
         Ext6T<U> e;
-        extend6(A.ix, back ? ik.x1 : ik.x0, back ? ik.x0 : ik.x1, ik.x2, e);
+        if (PAIR) {
+            extend6_conv<U>(A.ix, active, back ? ik.x1 : ik.x0, back ? ik.x0 : ik.x1, ik.x2, e);
+            if (!active) continue;
+        } else extend6(A.ix, back ? ik.x1 : ik.x0, back ? ik.x0 : ik.x1, ik.x2, e);
 
         // ---- consume it
         // x[0]/x[1] of ok[c]: the far side is x[1] for a forward, x[0] for a backward extension

@@ -112,10 +112,15 @@ __global__ void __launch_bounds__(256) k_backward_search(OccView ix, int64_t n, 
 }
 
 // U = coordinate type: k_smem<uint32_t> for indexes of < 2^32 symbols, k_smem<uint64_t> beyond
-template <typename U>
+// PAIR = paired block gathers (fmd_device.cuh: load_blk_pair), chosen for indexes that do not fit L2
+template <typename U, bool PAIR>
 __global__ void __launch_bounds__(SMEM_BLOCK, sizeof(U) == 4 ? SMEM_MIN_BLOCKS_U32 : SMEM_MIN_BLOCKS_U64) k_smem(SmemArgs A) {
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    smem_lane<U>(A, slot, [&]() -> int64_t { return (int64_t)atomicAdd(A.next_read, 1ull); });
+    smem_lane<U, PAIR>(A, slot, [&]() -> int64_t { return (int64_t)atomicAdd(A.next_read, 1ull); });
+}
+static const void *smem_kernel(bool wide, bool pair) {
+    if (wide) return pair ? (const void *)k_smem<uint64_t, true> : (const void *)k_smem<uint64_t, false>;
+    return pair ? (const void *)k_smem<uint32_t, true> : (const void *)k_smem<uint32_t, false>;
 }
 
 // ---- compaction of the per-read record slots -------------------------------------------------
@@ -360,6 +365,7 @@ struct fmg_smem_session_s {
     void *F = nullptr, *W = nullptr;
     uint4 *slots = nullptr, *mem = nullptr;
     bool wide = true;                          // 64-bit coordinates (index of >= 2^32 symbols)
+    bool pair = false;                         // paired block gathers (index larger than L2)
     uint32_t *rec_cnt = nullptr;
     uint64_t *mem_off = nullptr, *tile_sum = nullptr;
     unsigned long long *ctrl = nullptr;        // [0] next read, [1] overflow count, [2] total records
@@ -396,9 +402,11 @@ fmg_smem_session_t *fmg_smem_session_create(const fmg_index_t *idx, int64_t max_
     s->idx = idx; s->max_reads = max_reads; s->max_len = max_len;
     s->cap = 2 * max_len + 2;
     s->wide = idx->view.n_sym + 256 >= (1ull << 32) || std::getenv("FMG_FORCE_WIDE") != nullptr;
+    // paired gathers when the index does not fit L2 (126 MB on B200): there the L1-miss request rate bounds the kernel
+    s->pair = idx->bytes > ((size_t)112 << 20);
+    if (const char *e = std::getenv("FMG_SMEM_PAIR")) s->pair = std::atoi(e) != 0;
     int per_sm = 0;
-    if (s->wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_smem<uint64_t>, SMEM_BLOCK, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_smem<uint32_t>, SMEM_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smem_kernel(s->wide, s->pair), SMEM_BLOCK, 0);
     if (per_sm < 1) per_sm = 1;
     s->grid = idx->n_sm * per_sm;
     // long queries (contigs, unitigs: fm6_remap, `exact` on assemblies): every lane needs 2 x (2 len + 2) candidate slots, so
@@ -451,7 +459,7 @@ static int session_enqueue(fmg_smem_session_t *s, int64_t n, const uint8_t *d_se
     SmemArgs A;
     A.ix = s->idx->view; A.seq = d_seq; A.off = d_off; A.n_reads = n; A.self_match = self_match;
     A.F = s->F; A.W = s->W; A.cap = s->cap; A.out = s->slots; A.out_cap = s->out_cap;
-    A.rec_cnt = s->rec_cnt; A.next_read = s->ctrl;
+    A.rec_cnt = s->rec_cnt; A.next_read = s->ctrl; A.max_len = s->max_len; A.too_long = s->ctrl + 3;
     const int64_t need_blocks = (n + SMEM_BLOCK - 1) / SMEM_BLOCK;
     const int grid = (int)std::min<int64_t>(s->grid, need_blocks);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -462,9 +470,11 @@ static int session_enqueue(fmg_smem_session_t *s, int64_t n, const uint8_t *d_se
         }
         CUDA_TRY(cudaEventRecord(e0, st), return -1);
     }
-    if (s->wide) k_smem<uint64_t><<<grid, SMEM_BLOCK, 0, st>>>(A);
-    else k_smem<uint32_t><<<grid, SMEM_BLOCK, 0, st>>>(A);
-    LAUNCH_CHECK(return -1);
+    {
+        void *kargs[] = {(void *)&A};
+        CUDA_TRY(cudaLaunchKernel(smem_kernel(s->wide, s->pair), dim3((unsigned)grid), dim3(SMEM_BLOCK), kargs, 0, st), return -1);
+        ++g_launches;
+    }
     if (s->timing) {
         CUDA_TRY(cudaEventRecord(e1, st), return -1);
         s->ev.push_back(e0); s->ev.push_back(e1);
@@ -490,6 +500,11 @@ int fmg_smem_session_result(fmg_smem_session_t *s, uint64_t *n_records, const fm
     if (!s) return -1;
     if (use_device(s->idx->device, __func__)) return -1;
     CUDA_TRY(cudaStreamSynchronize(s->last_stream), return -1);
+    if (s->last_n > 0 && s->h_ctrl[3] != 0) {
+        if (fmg_verbose >= 1)
+            std::fprintf(stderr, "[E::%s] %llu reads are longer than the %d bases this session was created for; they were skipped\n", __func__, s->h_ctrl[3], s->max_len);
+        return -2;
+    }
     while (s->last_n > 0 && s->h_ctrl[1] != 0) {
         // some read produced more records than its slot holds: grow the slots and run the batch again
         const int bigger = s->out_cap * 4;
@@ -615,8 +630,47 @@ __global__ void k_rebase_offsets(uint64_t *off, int64_t n, uint64_t sub) {
     if (i < n) off[i] -= sub;
 }
 
+// fmintv_t records (32 bytes) -> fmg_intv16_t (16 bytes): x[0..2] as 32-bit values, info = end | start << 16 | left_closed << 31
+__global__ void __launch_bounds__(256) k_pack16(uint64_t n, const uint4 *__restrict__ in, uint4 *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 a = in[2 * i], b = in[2 * i + 1];              // a = x0 lo, x0 hi, x1 lo, x1 hi;  b = x2 lo, x2 hi, info lo (end), info hi (start | flag << 31)
+    uint4 o;
+    o.x = a.x; o.y = a.z; o.z = b.x;
+    o.w = (b.z & 0xffffu) | (b.w & 0x7fffu) << 16 | (b.w & 0x80000000u);
+    out[i] = o;
+}
+
+static int smem_batch_into_impl(const fmg_index_t *idx, int64_t n, const uint8_t *seq, const uint64_t *off, int self_match,
+                                void *mem_v, int rec_bytes, uint64_t mem_cap, uint64_t *mem_off, uint64_t *n_records, int64_t batch_reads);
+
 int fmg_smem_batch_into(const fmg_index_t *idx, int64_t n, const uint8_t *seq, const uint64_t *off, int self_match,
                         fmg_intv_t *mem, uint64_t mem_cap, uint64_t *mem_off, uint64_t *n_records, int64_t batch_reads) {
+    return smem_batch_into_impl(idx, n, seq, off, self_match, mem, 32, mem_cap, mem_off, n_records, batch_reads);
+}
+
+int fmg_smem_batch_into16(const fmg_index_t *idx, int64_t n, const uint8_t *seq, const uint64_t *off, int self_match,
+                          fmg_intv16_t *mem, uint64_t mem_cap, uint64_t *mem_off, uint64_t *n_records, int64_t batch_reads) {
+    if (idx && idx->view.n_sym >= (1ull << 32)) {
+        if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] packed records need an index of < 2^32 symbols\n", __func__);
+        return -3;
+    }
+    return smem_batch_into_impl(idx, n, seq, off, self_match, mem, 16, mem_cap, mem_off, n_records, batch_reads);
+}
+
+void fmg_intv16_expand(uint64_t n, const fmg_intv16_t *in, fmg_intv_t *out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t w = in[i].info;
+        out[i].x[0] = in[i].x[0]; out[i].x[1] = in[i].x[1]; out[i].x[2] = in[i].x[2];
+        out[i].info = (uint64_t)(w & 0xffffu) | (uint64_t)(w >> 16 & 0x7fffu) << 32 | (uint64_t)(w >> 31) << 63;
+    }
+}
+
+static int smem_batch_into_impl(const fmg_index_t *idx, int64_t n, const uint8_t *seq, const uint64_t *off, int self_match,
+                                void *mem_v, int rec_bytes, uint64_t mem_cap, uint64_t *mem_off, uint64_t *n_records, int64_t batch_reads) {
+    const char *const __func__name = rec_bytes == 16 ? "fmg_smem_batch_into16" : "fmg_smem_batch_into";
+    (void)__func__name;
+    uint8_t *const mem = static_cast<uint8_t *>(mem_v);
     if (!idx || use_device(idx->device, __func__)) return -1;
     if (n_records) *n_records = 0;
     mem_off[0] = 0;
@@ -648,6 +702,12 @@ int fmg_smem_batch_into(const fmg_index_t *idx, int64_t n, const uint8_t *seq, c
         return m;
     };
     int max_len = batch_max_len(0);
+    auto fits16 = [&](int ml) {                       // packed records hold the start in 15 bits and the end in 16
+        if (rec_bytes == 32 || ml < 32768) return true;
+        if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] packed records need reads shorter than 32768 bases (one has %d)\n", __func__name, ml);
+        return false;
+    };
+    if (!fits16(max_len)) return -3;
 
     // one pipeline per index, rebuilt only when a call needs larger batches or longer reads
     std::lock_guard<std::mutex> guard(idx->pipe_lock);
@@ -697,8 +757,15 @@ int fmg_smem_batch_into(const fmg_index_t *idx, int64_t n, const uint8_t *seq, c
                 k_rebase_offsets<<<(unsigned)((B.count + 1 + 255) / 256), 256, 0, s_out>>>(S->mem_off, B.count + 1, 0 - B.rec_base);
                 LAUNCH_CHECK(return -1);
             }
-            if (!short_cap && B.n_rec)
-                CUDA_TRY(cudaMemcpyAsync(mem + B.rec_base, S->mem, B.n_rec * 32, cudaMemcpyDeviceToHost, s_out), return -1);
+            if (!short_cap && B.n_rec) {
+                const void *src = S->mem;
+                if (rec_bytes == 16) {                                   // pack into the slot array, which the compaction has finished with
+                    k_pack16<<<(unsigned)((B.n_rec + 255) / 256), 256, 0, s_out>>>(B.n_rec, S->mem, S->slots);
+                    LAUNCH_CHECK(return -1);
+                    src = S->slots;
+                }
+                CUDA_TRY(cudaMemcpyAsync(mem + B.rec_base * (uint64_t)rec_bytes, src, B.n_rec * (uint64_t)rec_bytes, cudaMemcpyDeviceToHost, s_out), return -1);
+            }
             CUDA_TRY(cudaMemcpyAsync(mem_off + B.first, S->mem_off, (size_t)(B.count + 1) * 8, cudaMemcpyDeviceToHost, s_out), return -1);
             CUDA_TRY(cudaEventRecord(B.d2h_done, s_out), return -1);
             return 0;
@@ -708,6 +775,7 @@ int fmg_smem_batch_into(const fmg_index_t *idx, int64_t n, const uint8_t *seq, c
             bool drained = false;
             if (b >= 1 && b < n_batches) {
                 const int ml = batch_max_len(b);
+                if (!fits16(ml)) { fail = true; break; }
                 if (ml > idx->pipe->max_len) {
                     // a longer read than any before: finish what is in flight, then rebuild the sessions for it
                     if (drain(b - 1)) { fail = true; break; }

@@ -80,6 +80,13 @@ int fmg_smem_batch(const fmg_index_t *idx, int64_t n, const uint8_t *seq, const 
  * Returns 0, or 1 when mem_cap is too small (*n_records then holds the required capacity). */
 int fmg_smem_batch_into(const fmg_index_t *idx, int64_t n, const uint8_t *seq, const uint64_t *off, int self_match,
                         fmg_intv_t *mem, uint64_t mem_cap, uint64_t *mem_off, uint64_t *n_records, int64_t batch_reads);
+/* The same with packed 16-byte records, for indexes of < 2^32 symbols and reads shorter than 32768 bases (else -3): half the bytes
+ * on the way back to the host, which is what bounds the call when several GPUs share the host's memory system.  Records are
+ * packed on the device after the kernels; fmg_intv16_expand turns them into fmintv_t where the caller needs that layout. */
+typedef struct { uint32_t x[3]; uint32_t info; } fmg_intv16_t;    /* info = end | start << 16 | left_closed << 31 (smem.c:63) */
+int fmg_smem_batch_into16(const fmg_index_t *idx, int64_t n, const uint8_t *seq, const uint64_t *off, int self_match,
+                          fmg_intv16_t *mem, uint64_t mem_cap, uint64_t *mem_off, uint64_t *n_records, int64_t batch_reads);
+void fmg_intv16_expand(uint64_t n, const fmg_intv16_t *in, fmg_intv_t *out);
 void fmg_free(void *p);
 
 /* ------------------------------------------------------------------ device-resident SMEM session

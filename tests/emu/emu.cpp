@@ -76,7 +76,8 @@ int emu_smem(const void *_x, int64_t n, const uint8_t *seq, const uint64_t *off,
     SmemArgs A;
     A.ix = x->view; A.seq = seq; A.off = off; A.n_reads = n; A.self_match = self_match;
     A.F = F.data(); A.W = W.data(); A.cap = cap; A.out = out.data(); A.out_cap = out_cap;
-    A.rec_cnt = cnt.data(); A.next_read = &next;
+    unsigned long long too_long = 0;
+    A.rec_cnt = cnt.data(); A.next_read = &next; A.max_len = max_len; A.too_long = &too_long;
     // interleave the lanes' reads like concurrent lanes would: lane t takes reads t, t+n_lanes, ...
     for (int t = 0; t < n_lanes; ++t) {
         int64_t cur = t;

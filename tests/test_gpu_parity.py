@@ -133,6 +133,42 @@ def test_ragged_empty_and_multibatch(fb, oracle):
     idx.close()
 
 
+def test_packed_records_paired_gathers_and_session_guard(fb, oracle, monkeypatch):
+    """fmg_smem_batch_into16 (16-byte records packed on the device) expands to the records of fmg_smem_batch_into; the paired-gather
+    kernel (chosen for indexes larger than L2, forced here) gives the same records; a read longer than a session was created
+    for is reported, not run (it would overrun the lane's candidate lists)."""
+    import torch
+    fmd_path = os.path.join(H.GOLDEN_DIR, "noisy.fmd")
+    g = np.load(os.path.join(H.GOLDEN_DIR, "noisy.npz"))
+    seq, off = H.reads_to_flat(g["q"])
+    h = oracle.load(fmd_path)
+    idx = fb.FmdIndex(fb.Fmd.restore(fmd_path), 0)
+    for pair in ("0", "1"):
+        monkeypatch.setenv("FMG_SMEM_PAIR", pair)
+        for sm in (0, 1):
+            orec, omo, _, _, _ = oracle.smem(h, seq, off, sm, 4)
+            mem = np.zeros((len(orec) + 8, 4), np.uint32)
+            mo = np.zeros(len(off), np.uint64)
+            n = fb.fm6_smem_raw16(idx, len(off) - 1, seq.ctypes.data, off.ctypes.data, mem.ctypes.data, len(mem), mo.ctypes.data, sm, batch_reads=97)
+            assert n == len(orec) and np.array_equal(mo, omo)
+            assert np.array_equal(fb.intv16_expand(mem[:n]), orec)
+            rec, mo2 = fb.fm6_smem(idx, seq, off, sm)
+            assert np.array_equal(mo2, omo) and np.array_equal(rec, orec)
+        idx.close()                                            # the pipeline (and its kernel choice) lives with the handle
+        idx = fb.FmdIndex(fb.Fmd.restore(fmd_path), 0)
+    monkeypatch.delenv("FMG_SMEM_PAIR")
+    oracle.destroy(h)
+    L = g["q"].shape[1]
+    sess = fb.SmemSession(idx, 16, L - 1)                       # one base too short for these reads
+    d_seq = torch.from_numpy(seq[: 16 * L].copy()).cuda()
+    d_off = torch.from_numpy(off[:17].astype(np.int64)).cuda()
+    sess.run(16, d_seq.data_ptr(), d_off.data_ptr(), 0, 0)
+    with pytest.raises(RuntimeError):
+        sess.result()
+    sess.close()
+    idx.close()
+
+
 def test_record_slot_overflow_is_rerun_not_truncated(fb, oracle, tmp_path):
     """a read with more SMEMs than the default 64 record slots: the session must grow and re-run."""
     rng = np.random.RandomState(2)
