@@ -108,31 +108,92 @@ __device__ __forceinline__ uint64_t count_acgt(uint32_t w) {       // packed 4 x
     return r;
 }
 
-__global__ void __launch_bounds__(kThreads) k_bcr_merge(const uint8_t *__restrict__ old_bwt, uint64_t m_new, const Item *__restrict__ item,
+// ---- bulk asynchronous copies (TMA unit, 1-D) and their mbarriers: the old symbols of the next tiles travel to shared memory while
+// the block merges the current one
+constexpr int kStages = 4;
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar)) : "memory");
+}
+
+// PERSISTENT: blocks walk over the tiles (blockIdx.x, + gridDim.x, ...); thread 0 keeps kStages bulk copies of old symbols in
+// flight per block, each completing on its own mbarrier.
+__global__ void __launch_bounds__(kThreads, 4) k_bcr_merge(const uint8_t *__restrict__ old_bwt, uint64_t m_new, const Item *__restrict__ item,
                                                         const uint8_t *__restrict__ sym, const uint64_t *__restrict__ tile_lo, uint8_t *__restrict__ new_bwt,
-                                                        Vec4 *__restrict__ tile_hist, uint32_t *__restrict__ rank_in_tile) {
+                                                        Vec4 *__restrict__ tile_hist, uint32_t *__restrict__ rank_in_tile, uint64_t n_tiles) {
     __shared__ __align__(16) uint8_t s_sym[kTile];
-    __shared__ __align__(16) uint8_t s_src[kTile + 32];
+    __shared__ __align__(128) uint8_t s_srcs[kStages][kTile + 64];
     __shared__ __align__(16) uint8_t s_flag[kTile];
     __shared__ uint32_t s_warp_ins[kThreads / 32];
     __shared__ uint64_t s_warp_cnt[kThreads / 32];
-    const uint64_t q0 = (uint64_t)blockIdx.x * kTile;
+    __shared__ __align__(8) uint64_t s_bar[kStages];
     const int tid = threadIdx.x;
-    const uint64_t k_lo = tile_lo[blockIdx.x], k_hi = tile_lo[blockIdx.x + 1];
+    // source range of a tile: old symbols [src_lo, src_lo + n_src), fetched from the 16-byte boundary below src_lo
+    auto issue = [&](uint64_t tile, int stage) {
+        const uint64_t tq0 = tile * kTile, lo = tile_lo[tile], hi = tile_lo[tile + 1];
+        const uint64_t len = tq0 + kTile <= m_new ? (uint64_t)kTile : m_new - tq0;
+        const uint64_t ns = len - (hi - lo), sl = tq0 - lo, al = sl & ~15ull;
+        const uint32_t bytes = ns ? (uint32_t)((ns + (sl - al) + 15) & ~15ull) : 0u;
+        if (bytes) { mbar_expect_tx(&s_bar[stage], bytes); bulk_g2s(s_srcs[stage], old_bwt + al, bytes, &s_bar[stage]); }
+        else mbar_arrive(&s_bar[stage]);
+    };
+    if (tid == 0) {
+        for (int q = 0; q < kStages; ++q) mbar_init(&s_bar[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int q = 0; q < kStages; ++q) { const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)q * gridDim.x; if (t < n_tiles) issue(t, q); }
+    // Software pipeline of the metadata: the insert range of a tile is requested two tiles ahead and the thread's first insert of
+    // it (position, symbol) one tile ahead, so that no tile waits for a chain of dependent global loads
+    const uint64_t stride = gridDim.x;
+    auto range_of = [&](uint64_t t, uint64_t &lo, uint64_t &hi) { if (t < n_tiles) { lo = tile_lo[t]; hi = tile_lo[t + 1]; } else lo = hi = 0; };
+    uint64_t k_lo, k_hi, n_lo, n_hi, nn_lo, nn_hi;
+    range_of(blockIdx.x, k_lo, k_hi);
+    range_of(blockIdx.x + stride, n_lo, n_hi);
+    uint64_t my_f = 0, nx_f = 0;
+    uint8_t my_s = 0, nx_s = 0;
+    if (k_lo + tid < k_hi) { my_f = item[k_lo + tid].f; my_s = sym[k_lo + tid]; }
+    for (uint64_t it = 0;; ++it) {
+    const uint64_t tile = (uint64_t)blockIdx.x + it * stride;
+    if (tile >= n_tiles) break;
+    const int stage = (int)(it % kStages);
+    const uint8_t *s_src = s_srcs[stage];
+    const uint64_t q0 = tile * kTile;
+    range_of(tile + 2 * stride, nn_lo, nn_hi);                          // requested now, used two tiles on
+    if (n_lo + tid < n_hi) { nx_f = item[n_lo + tid].f; nx_s = sym[n_lo + tid]; }      // the next tile's insert of this thread
     reinterpret_cast<uint4 *>(s_flag)[tid] = make_uint4(0, 0, 0, 0);
     // the old symbols this tile keeps
     const uint64_t src_lo = q0 - k_lo;            // old symbols before this tile
-    const uint64_t tile_len = q0 + kTile <= m_new ? (uint64_t)kTile : m_new - q0;
-    const uint64_t n_src = tile_len - (k_hi - k_lo);
     const uint64_t a0 = src_lo & ~15ull;
     const int shift = (int)(src_lo - a0);
-    for (uint64_t v = tid; v * 16 < n_src + shift; v += kThreads)
-        reinterpret_cast<uint4 *>(s_src)[v] = *reinterpret_cast<const uint4 *>(old_bwt + a0 + v * 16);
     __syncthreads();
-    for (uint64_t k = k_lo + tid; k < k_hi; k += kThreads) {
+    if (k_lo + tid < k_hi) { const int j = (int)(my_f - q0); s_flag[j] = 1; s_sym[j] = my_s; }
+    for (uint64_t k = k_lo + tid + kThreads; k < k_hi; k += kThreads) {  // more than 256 inserts in the tile: the first cycles only
         const int j = (int)(item[k].f - q0);
         s_flag[j] = 1; s_sym[j] = sym[k];
     }
+    mbar_wait(&s_bar[stage], (uint32_t)((it / kStages) & 1));        // the bulk copy of this tile's old symbols has landed
     __syncthreads();
     // inserts before each thread's 16 positions
     const int j0 = tid * kPer;
@@ -182,7 +243,7 @@ __global__ void __launch_bounds__(kThreads) k_bcr_merge(const uint8_t *__restric
         const uint64_t tot = cnt_before + my_cnt;
         Vec4 h;
         for (int c = 0; c < 4; ++c) h.v[c] = (tot >> (16 * c)) & 0xffff;
-        tile_hist[blockIdx.x] = h;
+        tile_hist[tile] = h;
     }
     // rank of every insert among equal symbols inside the tile
     if (my_ins) {
@@ -202,6 +263,16 @@ __global__ void __launch_bounds__(kThreads) k_bcr_merge(const uint8_t *__restric
     // write the tile (16 bytes per thread)
     if (full) *reinterpret_cast<uint4 *>(new_bwt + q0 + j0) = make_uint4(o[0], o[1], o[2], o[3]);
     else for (int t = 0; t < kPer; ++t) if (q0 + j0 + t < m_new) new_bwt[q0 + j0 + t] = (uint8_t)(o[t >> 2] >> (8 * (t & 3)));
+    __syncthreads();                              // every thread is done with this stage's bytes, the flags and the warp sums
+    if (tid == 0) {
+        const uint64_t nxt = tile + (uint64_t)kStages * gridDim.x;
+        if (nxt < n_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy reads of the buffer precede the async-proxy write
+            issue(nxt, stage);
+        }
+    }
+    k_lo = n_lo; k_hi = n_hi; n_lo = nn_lo; n_hi = nn_hi; my_f = nx_f; my_s = nx_s;
+    }
 }
 
 // LF mapping of every insert: position of the extended suffix in the next cycle's BWT (bcr.c:442 + set_bwt bookkeeping)
@@ -267,6 +338,14 @@ static int bcr_build_device(fmg_bcr_s *b) {
     }
     BCR_TRY(d_tmp.reserve(tmp_scan > tmp_sort ? tmp_scan : tmp_sort));
 
+    uint64_t merge_grid = 148 * 6;
+    {
+        int n_sm = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, b->device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bcr_merge, kThreads, 0);
+        if (n_sm > 0 && per_sm > 0) merge_grid = (uint64_t)n_sm * per_sm;
+        if (const char *e = std::getenv("FMG_BCR_BLOCKS")) merge_grid = (uint64_t)n_sm * std::max(1, std::atoi(e));
+    }
     const double t_in = since();
     cub::DoubleBuffer<uint8_t> syms(d_sym[0].as<uint8_t>(), d_sym[1].as<uint8_t>());
     cub::DoubleBuffer<Item> items(d_item[0].as<Item>(), d_item[1].as<Item>());
@@ -278,8 +357,8 @@ static int bcr_build_device(fmg_bcr_s *b) {
         const uint64_t m_new = m + n_act, n_tiles = (m_new + kTile - 1) / kTile;
         k_bcr_symbols<<<blocks_for(n_act, 256), 256>>>(items.Current(), n_act, d_seq.as<uint8_t>(), d_off.as<uint64_t>(), pos, syms.Current()); ++g_launches;
         k_bcr_bounds<<<blocks_for(n_act, 256), 256>>>(items.Current(), n_act, n_tiles, d_lo.as<uint64_t>()); ++g_launches;
-        k_bcr_merge<<<(unsigned)n_tiles, kThreads>>>(d_bwt[cur].as<uint8_t>(), m_new, items.Current(), syms.Current(), d_lo.as<uint64_t>(), d_bwt[cur ^ 1].as<uint8_t>(),
-                                                     d_hist.as<Vec4>(), d_rank.as<uint32_t>()); ++g_launches;
+        k_bcr_merge<<<(unsigned)std::min<uint64_t>(n_tiles, merge_grid), kThreads>>>(d_bwt[cur].as<uint8_t>(), m_new, items.Current(), syms.Current(), d_lo.as<uint64_t>(),
+                                                     d_bwt[cur ^ 1].as<uint8_t>(), d_hist.as<Vec4>(), d_rank.as<uint32_t>(), n_tiles); ++g_launches;
         size_t need = d_tmp.cap;
         Vec4 zero{};
         BCR_TRY(cub::DeviceScan::ExclusiveScan(d_tmp.p, need, d_hist.as<Vec4>(), d_pref.as<Vec4>(), Vec4Add(), zero, (int64_t)n_tiles));

@@ -219,6 +219,11 @@ int        fmg_bcr_want_fmd(fmg_bcr_t *b, int on);
 fmg_fmd_t *fmg_bcr_fmd(fmg_bcr_t *b);
 void       fmg_bcr_destroy(fmg_bcr_t *b);                               /* bcr_destroy, bcr.c:342 */
 
+/* The library also exports the reference's own BCR symbols with the reference's signatures (bcr.h:43-49: bcr_init, bcr_append,
+ * bcr_build, bcr_itr_init, bcr_itr_next, bcr_destroy, bcr_verbose; fermi_b200/csrc/bcr_compat.cpp) so that ropebwt.c links against
+ * it unmodified in place of bcr.c: `make -C oracle drop` builds the reference with its bcr.c left out and cmd.c patched by
+ * integration/main_exact.patch, and tests/test_gpu_parity.py compares that binary's output with the reference's own. */
+
 /* ------------------------------------------------------------------ synthetic data
  * Deterministic, seed-addressed generators shared by the GPU run, the CPU baseline and the tests. */
 void fmg_synth_genome(uint64_t seed, int64_t n, uint8_t *nt6);

@@ -196,6 +196,16 @@ class _Lib:
         self._free(p)
         return out, (int(cnt[0]), int(cnt[1])), w
 
+    def ec_fix_from_triples(self, h, w, min_occ, triples, fq, out_path):
+        """reference harness only: the fix phase of `fermi correct` (the reference's worker2 / ec_fix) on the reads of `fq` with the
+        hash tables filled from `triples`; corrected FASTQ to out_path; returns the k-mer length used"""
+        assert self.p == "refh_"
+        f = self.lib.refh_ec_fix_from_triples
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, u64p, C.c_char_p, C.c_char_p]
+        t = np.ascontiguousarray(triples, np.uint64)
+        return f(h, w, min_occ, len(t), _ptr(t, u64p), fq.encode(), out_path.encode())
+
     # --- index lifecycle
     def load(self, fn):
         h = self._load(fn.encode())
@@ -354,6 +364,14 @@ def ref_fermi_binary():
 
 
 # ----------------------------------------------------------------------------- MAG records (mag.c:149-174)
+def write_fastq(path, reads, qual_char="I"):
+    """nt6 reads [n, L] -> FASTQ with constant qualities"""
+    tab = np.array(list("$ACGTN"))
+    with open(path, "w") as fh:
+        for i, r in enumerate(reads):
+            fh.write("@r%d\n%s\n+\n%s\n" % (i, "".join(tab[r]), qual_char * len(r)))
+
+
 def parse_mag(text):
     """MAG text -> list of (k0, k1, nsr, nei0, nei1, seq, cov); nei = tuple of (id, ovlp)."""
     out = []

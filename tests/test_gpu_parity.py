@@ -485,6 +485,68 @@ def test_ec_collect_parts_add_up(fb):
     idx.close()
 
 
+DROP_BIN = os.path.join(H.ORACLE_DIR, "_ref", "fermi_drop")
+
+
+@pytest.mark.skipif(not os.path.exists(DROP_BIN), reason="oracle/_ref/fermi_drop did not travel with the repo (make -C oracle drop)")
+def test_reference_binary_with_the_library_dropped_in(fb, tmp_path):
+    """The drop-in boundary, compiled: oracle/_ref/fermi_drop is the reference's own main.c, ropebwt.c (UNMODIFIED, linked against
+    the bcr_* symbols of libfermi_b200 instead of bcr.c) and cmd.c with integration/main_exact.patch applied.  `exact` must print the
+    bytes the reference printed (golden files), `ropebwt -a bcr` the BWT the reference prints."""
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(H.ROOT, "fermi_b200", "lib") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    for case in ("genome", "noisy", "reads10x"):
+        fmd, fa = os.path.join(H.GOLDEN_DIR, case + ".fmd"), os.path.join(H.GOLDEN_DIR, case + ".query.fa")
+        res = subprocess.run([DROP_BIN, "exact", fmd, fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=300)
+        assert res.returncode == 0, res.stderr.decode()[-1500:]
+        assert res.stdout == open(os.path.join(H.GOLDEN_DIR, case + ".exact.txt"), "rb").read(), case
+    ref_bin = H.ref_fermi_binary()
+    if ref_bin is None:
+        pytest.skip("oracle/_ref/fermi did not travel with the repo")
+    genome = fb.synth_genome(91, 60000)
+    reads = fb.synth_reads(92, genome, 6000, 100, 0.005)
+    reads[17, 40] = 5                                          # an N: ropebwt -N cuts the read there (ropebwt.c:107-116)
+    fa = str(tmp_path / "r.fa")
+    tab = np.array(list("$ACGTN"))
+    with open(fa, "w") as fh:
+        for i, r in enumerate(reads):
+            fh.write(">%d\n%s\n" % (i, "".join(tab[r])))
+    for flags in (["-a", "bcr", "-N"], ["-a", "bcr", "-N", "-b"], ["-a", "bcr", "-N", "-R"]):
+        ours = subprocess.run([DROP_BIN, "ropebwt"] + flags + [fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=300)
+        ref = subprocess.run([ref_bin, "ropebwt"] + flags + [fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+        assert ours.returncode == 0 and ref.returncode == 0, ours.stderr.decode()[-1500:]
+        if "-b" in flags:                                      # binary run-length bytes: the runs may be cut differently, the BWT they spell may not
+            def spell(b):
+                assert b[:4] == b"RLE\6"
+                a = np.frombuffer(b[4:], np.uint8)
+                return np.repeat(a & 7, a >> 3)
+            assert np.array_equal(spell(ours.stdout), spell(ref.stdout))
+        else:
+            assert ours.stdout == ref.stdout
+
+
+@pytest.mark.skipif(H.reference() is None or H.ref_fermi_binary() is None, reason="needs the compiled reference (oracle/_ref)")
+def test_gpu_kmers_drive_the_reference_fix_phase_to_the_same_fastq(fb, tmp_path):
+    """`fermi correct` with the collect phase on the GPU: fmg_ec_collect's triples are loaded into the
+    reference's solid[] tables, the reference's own ec_fix corrects the reads (oracle/ref_harness_correct.c), and the FASTQ is
+    byte-identical to `fermi correct -t1`."""
+    R = H.reference()
+    genome = fb.synth_genome(33, 30000)
+    reads = fb.synth_reads(34, genome, 12000, 100, 0.01)
+    fq, fn = str(tmp_path / "r.fq"), str(tmp_path / "r.fmd")
+    H.write_fastq(fq, reads)
+    fmd = fb.fm_build(fb.fmd_text(reads), 0)
+    fmd.dump(fn)
+    idx = fb.FmdIndex(fmd, 0)
+    tri, cnt = fb.fm6_ec_collect(idx, -1, 3)
+    idx.close()
+    h = R.load(fn)
+    out = str(tmp_path / "fixed.fq")
+    R.ec_fix_from_triples(h, -1, 3, tri, fq, out)
+    R.destroy(h)
+    ref = subprocess.run([H.ref_fermi_binary(), "correct", "-t", "1", fn, fq], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+    assert len(ref) > 100000 and open(out, "rb").read() == ref
+
+
 def test_ec_collect_100k_reads_vs_oracle(fb, oracle, tmp_path):
     genome = fb.synth_genome(71, 500000)
     reads = fb.synth_reads(72, genome, 50000, 100, 0.01)

@@ -97,3 +97,27 @@ def test_oracle_vs_compiled_reference_fresh_inputs(oracle, tmp_path):
     assert all(np.array_equal(x, y) for x, y in zip(ra[:3], oa[:3]))
     R.destroy(hr)
     oracle.destroy(ho)
+
+
+@pytest.mark.skipif(H.reference() is None or H.ref_fermi_binary() is None, reason="needs the compiled reference (oracle/_ref)")
+def test_fix_phase_driver_reproduces_fermi_correct(tmp_path):
+    """oracle/ref_harness_correct.c: refh_ec_fix_from_triples runs the reference's own worker2 / ec_fix from a given set of k-mer
+    triples.  With the triples of the reference's own ec_collect its output must be `fermi correct -t1` byte for byte: that pins
+    the driver the GPU hand-off test (tests/test_gpu_parity.py) relies on."""
+    import subprocess
+    import fermi_b200 as fb
+    R = H.reference()
+    genome = fb.synth_genome(31, 20000)
+    reads = fb.synth_reads(32, genome, 8000, 100, 0.01)            # 40x, 1 % substitutions
+    fq, fmd = str(tmp_path / "r.fq"), str(tmp_path / "r.fmd")
+    H.write_fastq(fq, reads)
+    h = R.build_text(fb.fmd_text(reads))
+    R.dump(h, fmd)
+    tri, _, w = R.ec_collect(h, -1, 3)
+    out = str(tmp_path / "fixed.fq")
+    assert R.ec_fix_from_triples(h, -1, 3, tri, fq, out) == w
+    R.destroy(h)
+    ref = subprocess.run([H.ref_fermi_binary(), "correct", "-t", "1", fmd, fq], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+    ours = open(out, "rb").read()
+    assert len(ref) > 100000 and ours == ref
+    assert b"a" in ref or b"c" in ref or b"g" in ref or b"t" in ref   # some base was corrected (lower case, correct.c:247)
