@@ -64,7 +64,7 @@ _PROTOS = {
     "fmg_overlap_left_fix": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "fmg_unitig_part": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
-    "fmg_magpart_write": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int]),
+    "fmg_magpart_write": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64]),
     "fmg_magpart_free": (None, [C.c_void_p]),
     "fmg_unitig_from_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                          C.c_char_p, u64p]),

@@ -22,6 +22,7 @@
 #include <cstring>
 #include <fcntl.h>
 #include <unistd.h>
+#include <sys/mman.h>
 #include <atomic>
 #include <chrono>
 #include <mutex>
@@ -114,25 +115,40 @@ __global__ void __launch_bounds__(256) k_pred(G g) {
     if (f) atomicOr(g.flags, f);
 }
 
-// pointer jumping along pred: ptr -> head, dn = reads before this one in the chain, db = start of the read in the consensus
-__global__ void __launch_bounds__(256) k_jump_init(G g, uint32_t *ptr, uint32_t *dn, uint64_t *db) {
+// pointer jumping along pred: ptr -> head, dn = reads before this one in the chain, db = start of the read in the consensus.
+// The three travel as ONE 16-byte record: a round is one random 16-byte gather per read instead of three.
+struct alignas(16) Jmp { uint32_t ptr, dn; uint64_t db; };
+__device__ __forceinline__ Jmp ld_jmp(const Jmp *p) { const uint4 a = *reinterpret_cast<const uint4 *>(p); Jmp j; j.ptr = a.x; j.dn = a.y; j.db = (uint64_t)a.w << 32 | a.z; return j; }
+__device__ __forceinline__ void st_jmp(Jmp *p, const Jmp &j) { *reinterpret_cast<uint4 *>(p) = make_uint4(j.ptr, j.dn, (uint32_t)j.db, (uint32_t)(j.db >> 32)); }
+
+__global__ void __launch_bounds__(256) k_jump_init(G g, Jmp *J) {
     const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= g.n) return;
     const uint32_t p = g.pred[v];
-    ptr[v] = p == kNone ? (uint32_t)v : p;
-    dn[v] = p == kNone ? 0u : 1u;
-    db[v] = p == kNone ? 0ull : (uint64_t)g.pack[p].rbeg;
+    Jmp j;
+    j.ptr = p == kNone ? (uint32_t)v : p;
+    j.dn = p == kNone ? 0u : 1u;
+    j.db = p == kNone ? 0ull : (uint64_t)g.pack[p].rbeg;
+    st_jmp(J + v, j);
 }
 
-__global__ void __launch_bounds__(256) k_jump(uint64_t n, const uint32_t *__restrict__ ptr, const uint32_t *__restrict__ dn, const uint64_t *__restrict__ db,
-                                             uint32_t *__restrict__ ptr2, uint32_t *__restrict__ dn2, uint64_t *__restrict__ db2, uint32_t *flags) {
+__global__ void __launch_bounds__(256) k_jump(uint64_t n, const Jmp *__restrict__ J, Jmp *__restrict__ J2, uint32_t *flags) {
     const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
-    const uint32_t p = ptr[v], q = ptr[p];
-    ptr2[v] = q;
-    dn2[v] = dn[v] + (p != v ? dn[p] : 0u);
-    db2[v] = db[v] + (p != v ? db[p] : 0ull);
-    if (q != p) atomicOr(flags, (uint32_t)UGF_CHANGED);
+    const Jmp a = ld_jmp(J + v), b = ld_jmp(J + a.ptr);
+    Jmp o;
+    o.ptr = b.ptr;
+    o.dn = a.dn + (a.ptr != v ? b.dn : 0u);
+    o.db = a.db + (a.ptr != v ? b.db : 0ull);
+    st_jmp(J2 + v, o);
+    if (b.ptr != a.ptr) atomicOr(flags, (uint32_t)UGF_CHANGED);
+}
+
+__global__ void __launch_bounds__(256) k_jump_unpack(uint64_t n, const Jmp *__restrict__ J, uint32_t *__restrict__ head, uint32_t *__restrict__ dn, uint64_t *__restrict__ db) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const Jmp a = ld_jmp(J + v);
+    head[v] = a.ptr; dn[v] = a.dn; db[v] = a.db;
 }
 
 __global__ void __launch_bounds__(256) k_tails(G g, const uint32_t *__restrict__ head) {
@@ -319,17 +335,41 @@ inline unsigned nblk(uint64_t n) { return (unsigned)((n + 255) / 256); }
 // The text lives in the pinned cache of the index handle (fmg_ovcache_s::text): valid until the next unitig call on that handle.
 struct fmg_magpart_s { const char *text = nullptr; uint64_t bytes = 0; unsigned threads = 1; };
 
-// `bytes` of text to `out_path` at `offset`, by `nt` threads with pwrite (the page-cache copy is the cost of the output)
-static int write_text(const char *text, uint64_t bytes, unsigned nt, const char *out_path, uint64_t offset, bool truncate, const char *who) {
-    int fd = ::open(out_path, truncate ? (O_WRONLY | O_CREAT | O_TRUNC) : (O_WRONLY | O_CREAT), 0644);
+// `bytes` of text to `out_path` at `offset` by `nt` threads.  The file must already have its final size (ensure_size): the
+// threads copy into a shared mapping of their own slices, which -- unlike write() on one inode -- neither serialises the threads
+// of a process nor the processes of a multi-GPU run that fill one file side by side.  pwrite is the fallback where a mapping is
+// not possible (pipes, devices).
+static int ensure_size(const char *out_path, uint64_t total, const char *who) {
+    // no O_TRUNC: dropping the pages of a previous output of the same size costs more than overwriting them
+    int fd = ::open(out_path, O_RDWR | O_CREAT, 0644);
+    if (fd < 0 || ::ftruncate(fd, (off_t)total) != 0) {
+        if (fd >= 0) ::close(fd);
+        if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] cannot write '%s'\n", who, out_path);
+        return -1;
+    }
+    ::close(fd);
+    return 0;
+}
+
+static int write_text(const char *text, uint64_t bytes, unsigned nt, const char *out_path, uint64_t offset, const char *who) {
+    int fd = ::open(out_path, O_RDWR | O_CREAT, 0644);
     if (fd < 0) {
         if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] cannot write '%s'\n", who, out_path);
         return -1;
     }
     if (bytes < (1u << 22)) nt = 1;
     std::atomic<int> io_fail{0};
+    const uint64_t page = (uint64_t)::sysconf(_SC_PAGESIZE);
     auto put = [&](unsigned t) {
         const uint64_t a = bytes * t / nt, b = bytes * (t + 1) / nt;
+        if (b <= a) return;
+        const uint64_t f0 = (offset + a) & ~(page - 1), span = offset + b - f0;
+        void *m = ::mmap(nullptr, span, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)f0);
+        if (m != MAP_FAILED) {
+            std::memcpy(static_cast<char *>(m) + (offset + a - f0), text + a, b - a);
+            ::munmap(m, span);
+            return;
+        }
         for (uint64_t done = a; done < b;) {
             const ssize_t w = ::pwrite(fd, text + done, (size_t)std::min<uint64_t>(b - done, 1u << 26), (off_t)(offset + done));
             if (w <= 0) { io_fail = 1; return; }
@@ -362,9 +402,10 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
     if (!idx->ovc) idx->ovc = new fmg_ovcache_s;
     fmg_ovcache_s &H = *idx->ovc;
     cudaStream_t st = nullptr;                       // legacy default stream: ordered after the pass (which synchronised its streams)
-    Dev d_succ, d_pred, d_row, d_tail, d_flags, d_ptr[2], d_dn[2], d_db[2], d_cnt, d_len, d_nei, d_tmp, d_meta, d_unei, d_useq, d_diff;
+    Dev d_succ, d_pred, d_row, d_tail, d_flags, d_jmp[2], d_ptr, d_dn, d_db, d_cnt, d_len, d_nei, d_tmp, d_meta, d_unei, d_useq, d_diff;
     UG_TRY(d_succ.alloc(n * 4)); UG_TRY(d_pred.alloc(n * 4)); UG_TRY(d_row.alloc(n * 4)); UG_TRY(d_tail.alloc(n * 4)); UG_TRY(d_flags.alloc(64));
-    for (int k = 0; k < 2; ++k) { UG_TRY(d_ptr[k].alloc(n * 4)); UG_TRY(d_dn[k].alloc(n * 4)); UG_TRY(d_db[k].alloc(n * 8)); }
+    for (int k = 0; k < 2; ++k) UG_TRY(d_jmp[k].alloc(n * sizeof(Jmp)));
+    UG_TRY(d_ptr.alloc(n * 4)); UG_TRY(d_dn.alloc(n * 4)); UG_TRY(d_db.alloc(n * 8));
     UG_TRY(d_cnt.alloc((n + 1) * 8)); UG_TRY(d_len.alloc((n + 1) * 8)); UG_TRY(d_nei.alloc((n + 1) * 8));
     UG_TRY(H.ctrl.need(64));
     uint32_t *h_flags = H.ctrl.as<uint32_t>();
@@ -378,7 +419,7 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
     UG_TRY(cudaMemsetAsync(d_tail.p, 0xff, n * 4, st));
     k_links<<<nblk(n), 256, 0, st>>>(g);
     k_pred<<<nblk(n), 256, 0, st>>>(g);
-    k_jump_init<<<nblk(n), 256, 0, st>>>(g, d_ptr[0].as<uint32_t>(), d_dn[0].as<uint32_t>(), d_db[0].as<uint64_t>());
+    k_jump_init<<<nblk(n), 256, 0, st>>>(g, d_jmp[0].as<Jmp>());
     g_launches += 3;
     UG_TRY(cudaGetLastError());
     int cur = 0, rounds = 0;
@@ -398,15 +439,16 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
         UG_TRY(cudaMemsetAsync(d_flags.p, 0, 4, st));
         // two jumps per flag read-back (a converged jump is the identity)
         for (int r = 0; r < 2; ++r) {
-            k_jump<<<nblk(n), 256, 0, st>>>(n, d_ptr[cur].as<uint32_t>(), d_dn[cur].as<uint32_t>(), d_db[cur].as<uint64_t>(),
-                                            d_ptr[cur ^ 1].as<uint32_t>(), d_dn[cur ^ 1].as<uint32_t>(), d_db[cur ^ 1].as<uint64_t>(), g.flags);
+            k_jump<<<nblk(n), 256, 0, st>>>(n, d_jmp[cur].as<Jmp>(), d_jmp[cur ^ 1].as<Jmp>(), g.flags);
             ++g_launches;
             cur ^= 1;
         }
         UG_TRY(cudaGetLastError());
     }
-    const uint32_t *head = d_ptr[cur].as<uint32_t>(), *dn = d_dn[cur].as<uint32_t>();
-    const uint64_t *db = d_db[cur].as<uint64_t>();
+    k_jump_unpack<<<nblk(n), 256, 0, st>>>(n, d_jmp[cur].as<Jmp>(), d_ptr.as<uint32_t>(), d_dn.as<uint32_t>(), d_db.as<uint64_t>());
+    ++g_launches;
+    const uint32_t *head = d_ptr.as<uint32_t>(), *dn = d_dn.as<uint32_t>();
+    const uint64_t *db = d_db.as<uint64_t>();
     const double t_rank = since(t0);
     k_tails<<<nblk(n), 256, 0, st>>>(g, head);
     uint64_t *e_cnt = d_cnt.as<uint64_t>(), *e_len = d_len.as<uint64_t>(), *e_nei = d_nei.as<uint64_t>();
@@ -485,15 +527,10 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
         t_dev = since(t0);
         if (sink) { sink->text = H.text.as<char>(); sink->bytes = text_bytes; sink->threads = nt; }
         else if (to_stdout) { std::fwrite(H.text.p, 1, text_bytes, stdout); std::fflush(stdout); }
-        else if (write_text(H.text.as<char>(), text_bytes, nt, out_path, 0, true, __func__) != 0) return -1;
+        else if (ensure_size(out_path, text_bytes, __func__) != 0 || write_text(H.text.as<char>(), text_bytes, nt, out_path, 0, __func__) != 0) return -1;
     } else {
         // a file: the text leaves the device in slices, and each slice is written while the next one is copied
-        int fd = ::open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
-        if (fd < 0) {
-            if (fmg_verbose >= 1) std::fprintf(stderr, "[E::%s] cannot write '%s'\n", __func__, out_path);
-            return -1;
-        }
-        ::close(fd);
+        if (ensure_size(out_path, text_bytes, __func__) != 0) return -1;
         const unsigned n_slice = std::max(2u, std::min(nt, 16u));
         std::vector<cudaEvent_t> ev(n_slice);
         for (auto &e : ev) UG_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -508,7 +545,7 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
             th.emplace_back([&, k]() {
                 const uint64_t a = text_bytes * k / n_slice, b = text_bytes * (k + 1) / n_slice;
                 if (cudaEventSynchronize(ev[k]) != cudaSuccess) { fail = 1; return; }
-                if (write_text(H.text.as<char>() + a, b - a, 1, out_path, a, false, "fmg_unitig_device") != 0) fail = 1;
+                if (write_text(H.text.as<char>() + a, b - a, 1, out_path, a, "fmg_unitig_device") != 0) fail = 1;
             });
         for (auto &x : th) x.join();
         for (auto &e : ev) cudaEventDestroy(e);
@@ -663,9 +700,10 @@ int fmg_unitig_part(const fmg_index_t *idx, int min_match, const void *d_pack, c
     return 0;
 }
 
-int fmg_magpart_write(const fmg_magpart_t *p, const char *path, uint64_t offset, int truncate) {
+int fmg_magpart_write(const fmg_magpart_t *p, const char *path, uint64_t offset, uint64_t total_bytes) {
     if (!p || !path) return -1;
-    return write_text(p->text, p->bytes, p->threads, path, offset, truncate != 0, __func__);
+    if (total_bytes && ensure_size(path, total_bytes, __func__) != 0) return -1;
+    return write_text(p->text, p->bytes, p->threads, path, offset, __func__);
 }
 
 void fmg_magpart_free(fmg_magpart_t *p) { delete p; }

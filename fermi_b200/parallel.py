@@ -189,18 +189,24 @@ def unitig_distributed_device(idx, min_match, out_path, max_len=0, group=None, t
                            left_rows=int(n_left.value))
         return int(res[0])
     sizes_b = all_state[:, 2].tolist()
+    t_sizes = time.perf_counter()
     path = str(out_path).encode()
-    if rank == 0:
-        with open(out_path, "wb") as fh:                      # the file exists and is empty before anyone writes into it
-            fh.truncate(sum(sizes_b))
+    if rank == 0:                                             # the file has its final size before anyone writes into it (no truncation to
+        import os                                             # zero first: dropping the pages of a previous output costs more than reusing them)
+        fd = os.open(out_path, os.O_RDWR | os.O_CREAT, 0o644)
+        os.ftruncate(fd, sum(sizes_b))
+        os.close(fd)
     dist.barrier(group=group)
+    t_sized = time.perf_counter()
     if L.fmg_magpart_write(part, path, sum(sizes_b[:rank]), 0) != 0:
         raise RuntimeError("fermi_b200: fmg_magpart_write failed")
     L.fmg_magpart_free(part)
+    t_copied = time.perf_counter()
     dist.barrier(group=group)
     lap()
     if timings is not None:
         timings.update(records=t[1] - t[0], exchange=t[2] - t[1], merge_left=t[3] - t[2], assembly=t[4] - t[3], write=t[5] - t[4], host_walk=False,
+                       write_wait_for_all_parts=t_sizes - t[4], write_size_file=t_sized - t_sizes, write_copy=t_copied - t_sized, write_final_barrier=t[5] - t_copied,
                        left_rows=int(n_left.value), exchange_bytes=int(8 * (world - 1) * (row_pad * 9) + (world - 1) * (ext_pad + spill_pad * 32)))
     return int(all_state[:, 1].sum())
 

@@ -151,7 +151,9 @@ int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *o
  *   fmg_unitig_part     link graph + pointer jumping over all records, then emission + MAG text (mag_v_write, mag.c:149-174) of the chains
  *                       with head rank % n_parts == part, kept in memory; 0 = ok, 1 = irregular link graph (run fmg_unitig on one GPU)
  *   -- all-gather of the text sizes --
- *   fmg_magpart_write   the text of this part at `offset` of the output file (truncate != 0: create / truncate the file first)
+ *   fmg_magpart_write   the text of this part at `offset` of the output file, which must have its final size: ONE caller passes
+ *                       total_bytes != 0 first (the file is created / resized), the others 0 after a barrier; the parts are copied
+ *                       into a shared mapping, so the ranks fill the file side by side without serialising on it
  *   fmg_unitig_from_device  the whole assembly on one GPU from merged arrays; 0 = MAG written, 1 = irregular link graph */
 typedef struct fmg_magpart_s fmg_magpart_t;
 int fmg_overlap_shard(const fmg_index_t *idx, int min_match, int max_len, uint64_t row_lo, uint64_t row_hi, void *d_rec, int64_t *d_rank,
@@ -161,7 +163,7 @@ int fmg_overlap_merge(const fmg_index_t *idx, int n_shards, const uint64_t *rows
 int fmg_overlap_left_fix(const fmg_index_t *idx, int min_match, int max_len, void *d_pack, const int64_t *d_rank_of_row, uint64_t *n_left);
 int fmg_unitig_part(const fmg_index_t *idx, int min_match, const void *d_pack, const int64_t *d_rank_of_row, const uint8_t *d_ext, const void *d_spill,
                     int part, int n_parts, fmg_magpart_t **out, uint64_t *n_unitigs, uint64_t *n_bytes);
-int fmg_magpart_write(const fmg_magpart_t *p, const char *path, uint64_t offset, int truncate);
+int fmg_magpart_write(const fmg_magpart_t *p, const char *path, uint64_t offset, uint64_t total_bytes);
 void fmg_magpart_free(fmg_magpart_t *p);
 int fmg_unitig_from_device(const fmg_index_t *idx, int min_match, const void *d_pack, const int64_t *d_rank, const uint8_t *d_ext, uint64_t ext_total,
                            const void *d_spill, uint64_t spill_total, const char *out_path, uint64_t *n_unitigs);
