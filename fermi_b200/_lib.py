@@ -33,6 +33,8 @@ _PROTOS = {
     "fmg_index_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, u64p, u64p]),
     # batched queries
     "fmg_rank2a_batch": (C.c_int, [C.c_void_p, C.c_int64, u64p, u64p, u64p, u64p]),
+    "fmg_rank1a_batch": (C.c_int, [C.c_void_p, C.c_int64, u64p, u64p, C.c_void_p]),
+    "fmg_check_rank": (C.c_int, [C.c_void_p, u64p, u64p]),
     "fmg_extend_batch": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, u8p, C.c_void_p]),
     "fmg_backward_search_batch": (C.c_int, [C.c_void_p, C.c_int64, u8p, u64p, u64p, u64p, u64p]),
     "fmg_smem_batch": (C.c_int, [C.c_void_p, C.c_int64, u8p, u64p, C.c_int, vpp, u64p]),
@@ -68,6 +70,8 @@ _PROTOS = {
     "fmg_magpart_free": (None, [C.c_void_p]),
     "fmg_unitig_from_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                          C.c_char_p, u64p]),
+    "fmg_gap_bits": (C.c_int, [C.c_void_p, C.c_void_p, u64p]),
+    "fmg_merge": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int]),
     "fmg_ec_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, vpp, u64p, C.POINTER(C.c_int64)]),
     "fmg_ec_collect_part": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, vpp, u64p, C.POINTER(C.c_int64)]),
     "fmg_ec_kmer_length": (C.c_int, [C.c_uint64]),

@@ -171,6 +171,35 @@ def fm6_smem_raw(idx, n, seq_ptr, off_ptr, mem_ptr, mem_cap, mem_off_ptr, self_m
     return got.value
 
 
+def fm_merge(fmd0, fmd1, device=0):
+    """fm_merge (merge.c:100-137) / `fermi merge`: the gap vector, the interleaving and the RLD encoding on the GPU"""
+    return Fmd(lib().fmg_merge(fmd0.h, fmd1.h, device))
+
+
+def fm_gap_bits(idx0, idx1):
+    """fm_compute_gap_bits (merge.c:68-94): uint64 words, bit q set when symbol q of the merged BWT comes from idx1"""
+    n = int(idx0.mcnt[0]) + int(idx1.mcnt[0])
+    bits = np.zeros((n + 63) // 64, np.uint64)
+    _check(lib().fmg_gap_bits(idx0.h, idx1.h, _p(bits, u64p)), "fm_compute_gap_bits")
+    return bits
+
+
+def rld_rank1a(idx, k):
+    """rld_rank1a (rld.c:424-446) for an array of positions: (ok[n,6], symbol[n]); k = 2^64-1 gives zeros and -1"""
+    k = np.ascontiguousarray(k, np.uint64)
+    ok = np.zeros((len(k), 6), np.uint64)
+    sym = np.zeros(len(k), np.int32)
+    _check(lib().fmg_rank1a_batch(idx.h, len(k), _p(k, u64p), _p(ok, u64p), sym.ctypes.data), "rld_rank1a")
+    return ok, sym
+
+
+def check_rank(idx):
+    """`fermi chkbwt -r` on the device: (number of positions where the rank function disagrees with the BWT, first such position)"""
+    bad, first = C.c_uint64(), C.c_uint64()
+    _check(lib().fmg_check_rank(idx.h, C.byref(bad), C.byref(first)), "chkbwt -r")
+    return int(bad.value), int(first.value)
+
+
 def fm6_smem_raw16(idx, n, seq_ptr, off_ptr, mem_ptr, mem_cap, mem_off_ptr, self_match=0, batch_reads=0):
     """fmg_smem_batch_into16 on raw host pointers: packed 16-byte records (x0, x1, x2, end | start << 16 | closed << 31)."""
     got = C.c_uint64()

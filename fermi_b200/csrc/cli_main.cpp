@@ -166,6 +166,31 @@ int main_ropebwt(int argc, char *argv[]) {
     return 0;
 }
 
+// `fermi merge` (cmd.c:335-373): the indexes are merged left to right on the GPU (gap vector + interleave + RLD encoding)
+int main_merge(int argc, char *argv[]) {
+    int c, force = 0, device = 0;
+    const char *out = "-";
+    while ((c = getopt(argc, argv, "fo:t:d:")) >= 0) { if (c == 'f') force = 1; else if (c == 'o') out = optarg; else if (c == 'd') device = atoi(optarg); }
+    if (optind + 2 > argc) { std::fprintf(stderr, "Usage: fermi-b200 merge [-f] [-o out.fmd] [-d device] <in0.fmd> <in1.fmd> [...]\n"); return 1; }
+    if (!force && std::strcmp(out, "-") != 0) {
+        if (FILE *fp = std::fopen(out, "r")) { std::fclose(fp); std::fprintf(stderr, "[E::%s] File `%s' exists. Please use `-f' to overwrite.\n", __func__, out); return 1; }
+    }
+    fmg_fmd_t *e0 = fmg_fmd_restore(argv[optind]);
+    if (!e0) return 1;
+    for (int i = optind + 1; i < argc; ++i) {
+        fmg_fmd_t *e1 = fmg_fmd_restore(argv[i]);
+        fmg_fmd_t *m = e1 ? fmg_merge(e0, e1, device) : nullptr;
+        fmg_fmd_destroy(e0);
+        if (e1) fmg_fmd_destroy(e1);
+        if (!m) return 1;
+        e0 = m;
+        std::fprintf(stderr, "[M::%s] Merged file `%s' to the existing index.\n", __func__, argv[i]);
+    }
+    const int rc = fmg_fmd_dump(e0, out);
+    fmg_fmd_destroy(e0);
+    return rc != 0;
+}
+
 int main_recode(int argc, char *argv[]) {
     if (argc < 2) { std::fprintf(stderr, "Usage: fermi-b200 recode <in.rld|in.rle> [out.fmd]\n"); return 1; }
     fmg_fmd_t *e = fmg_fmd_restore(argv[1]);
@@ -176,9 +201,9 @@ int main_recode(int argc, char *argv[]) {
 }
 
 int main_chkbwt(int argc, char *argv[]) {
-    int c, print = 0;
-    while ((c = getopt(argc, argv, "p")) >= 0) if (c == 'p') print = 1;
-    if (optind == argc) { std::fprintf(stderr, "Usage: fermi-b200 chkbwt [-p] <idx.fmd>\n"); return 1; }
+    int c, print = 0, check_rank = 0, device = 0;
+    while ((c = getopt(argc, argv, "prd:")) >= 0) { if (c == 'p') print = 1; else if (c == 'r') check_rank = 1; else if (c == 'd') device = atoi(optarg); }
+    if (optind == argc) { std::fprintf(stderr, "Usage: fermi-b200 chkbwt [-p] [-r] [-d device] <idx.fmd>\n         -r  check the rank function at every position (on the GPU)\n"); return 1; }
     fmg_fmd_t *e = fmg_fmd_restore(argv[optind]);
     if (!e) return 1;
     uint64_t info[17];
@@ -186,6 +211,14 @@ int main_chkbwt(int argc, char *argv[]) {
     std::printf("Marginal counts:");
     for (int i = 0; i < 7; ++i) std::printf(" %llu", (unsigned long long)info[i]);
     std::printf("\n");
+    if (check_rank) {                                        // cmd.c:90-116: rank1a(k) against the symbols themselves, every k
+        fmg_index_t *idx = fmg_index_upload(e, device);
+        uint64_t bad = 0, first = 0;
+        if (!idx || fmg_check_rank(idx, &bad, &first) != 0) return 1;
+        fmg_index_free(idx);
+        if (bad) { std::fprintf(stderr, "[E::%s] rank disagrees with the BWT at %llu positions, first at %llu\n", __func__, (unsigned long long)bad, (unsigned long long)first); return 1; }
+        std::fprintf(stderr, "[M::%s] Checked the rank function at %llu positions.\n", __func__, (unsigned long long)info[0]);
+    }
     if (print) {
         std::vector<uint8_t> bwt(info[0]);
         fmg_fmd_decode_bwt(e, bwt.data());
@@ -322,7 +355,8 @@ int usage() {
     std::fprintf(stderr, "Command: build      generate the FMD-index (GPU suffix sort)\n");
     std::fprintf(stderr, "         ropebwt    BWT of a read set by BCR on the GPU\n");
     std::fprintf(stderr, "         recode     convert RLE\\6 / RLD to RLD\n");
-    std::fprintf(stderr, "         chkbwt     marginal counts / print the BWT\n");
+    std::fprintf(stderr, "         merge      merge FMD-indexes (gap vector on the GPU)\n");
+    std::fprintf(stderr, "         chkbwt     marginal counts / print the BWT / check the rank function\n");
     std::fprintf(stderr, "         exact      find supermaximal exact matches\n");
     std::fprintf(stderr, "         unitig     construct unitigs\n");
     std::fprintf(stderr, "         seqrank    compute the rank of sequences\n");
@@ -340,6 +374,7 @@ int main(int argc, char *argv[]) {                    // main.c:63-138
     if (cmd == "build") ret = main_build(argc - 1, argv + 1);
     else if (cmd == "ropebwt") ret = main_ropebwt(argc - 1, argv + 1);
     else if (cmd == "recode") ret = main_recode(argc - 1, argv + 1);
+    else if (cmd == "merge") ret = main_merge(argc - 1, argv + 1);
     else if (cmd == "chkbwt") ret = main_chkbwt(argc - 1, argv + 1);
     else if (cmd == "exact") ret = main_exact(argc - 1, argv + 1);
     else if (cmd == "unitig") ret = main_unitig(argc - 1, argv + 1);

@@ -66,6 +66,42 @@ __global__ void __launch_bounds__(256) k_rank2a(OccView ix, int64_t n, const uin
     }
 }
 
+// rld_rank1a (rld.c:424-446): ok[c] = #c in BWT[0..k] and the symbol BWT[k]; k == -1 -> zeros and -1.  ks == nullptr: k = first + i
+__global__ void __launch_bounds__(256) k_rank1a(OccView ix, int64_t n, const uint64_t *__restrict__ ks, uint64_t first, uint64_t *__restrict__ ok,
+                                                int32_t *__restrict__ sym) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k = ks ? ks[i] : first + (uint64_t)i;
+    const uint64_t p = k + 1;                              // counts of BWT[0, k]
+    const Blk b = load_blk(ix, p);
+    uint32_t a[6];
+    rank_rel(b, p, a);
+    const uint64_t *ck = ix.cs + (p >> kSuperShift) * 8;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ok[6 * i + c] = ck[c] - ix.C[c] + a[c];
+    if (sym) sym[i] = k == ~0ull ? -1 : blk_symbol((k >> kBlkShift) == (p >> kBlkShift) ? b : load_blk(ix, k), k);
+}
+
+// the check of `fermi chkbwt -r` (cmd.c:90-105) for every position at once: rank1a(k)[c] must equal the number of c among
+// BWT[0..k] counted directly.  The direct count is a scan of the symbols; here it is checked incrementally, which is equivalent:
+// rank(k) - rank(k-1) must be exactly the one-hot vector of BWT[k] (rank(-1) = 0), and rank(n-1) must equal the marginal counts.
+__global__ void __launch_bounds__(256) k_chk_rank(OccView ix, uint64_t n, unsigned long long *bad, unsigned long long *first_bad) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t a[6], b[6];
+    const uint64_t p1 = k + 1;
+    const Blk B1 = load_blk(ix, p1);
+    rank_rel(B1, p1, a);
+    const Blk B0 = (k >> kBlkShift) == (p1 >> kBlkShift) ? B1 : load_blk(ix, k);
+    rank_rel(B0, k, b);
+    const int c0 = blk_symbol(B0, k);
+    const uint64_t *c1 = ix.cs + (p1 >> kSuperShift) * 8, *cz = ix.cs + (k >> kSuperShift) * 8;
+    bool ok = c0 >= 0 && c0 < 6;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ok = ok && (c1[c] + a[c]) - (cz[c] + b[c]) == (uint64_t)(c == c0);
+    if (!ok) { atomicAdd(bad, 1ull); atomicMin(first_bad, (unsigned long long)k); }
+}
+
 __global__ void __launch_bounds__(256) k_extend(OccView ix, int64_t n, const uint4 *__restrict__ ik,
                                                 const uint8_t *__restrict__ is_back, uint4 *__restrict__ ok6) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -306,6 +342,52 @@ int fmg_rank2a_batch(const fmg_index_t *idx, int64_t n, const uint64_t *k, const
         rc = 0;
     } while (0);
     cudaFree(dk); cudaFree(dl); cudaFree(dok); cudaFree(dol);
+    return rc;
+}
+
+int fmg_rank1a_batch(const fmg_index_t *idx, int64_t n, const uint64_t *k, uint64_t *ok, int32_t *sym) {
+    if (!idx || !k || !ok || use_device(idx->device, __func__)) return -1;
+    if (n <= 0) return 0;
+    uint64_t *dk = nullptr, *dok = nullptr;
+    int32_t *ds = nullptr;
+    int rc = -1;
+    do {
+        CUDA_TRY(cudaMalloc(&dk, n * 8), break);
+        CUDA_TRY(cudaMalloc(&dok, n * 48), break);
+        CUDA_TRY(cudaMalloc(&ds, n * 4), break);
+        CUDA_TRY(cudaMemcpy(dk, k, n * 8, cudaMemcpyHostToDevice), break);
+        k_rank1a<<<(unsigned)((n + 255) / 256), 256>>>(idx->view, n, dk, 0, dok, ds);
+        LAUNCH_CHECK(break);
+        CUDA_TRY(cudaMemcpy(ok, dok, n * 48, cudaMemcpyDeviceToHost), break);
+        if (sym) CUDA_TRY(cudaMemcpy(sym, ds, n * 4, cudaMemcpyDeviceToHost), break);
+        rc = 0;
+    } while (0);
+    cudaFree(dk); cudaFree(dok); cudaFree(ds);
+    return rc;
+}
+
+int fmg_check_rank(const fmg_index_t *idx, uint64_t *n_bad, uint64_t *first_bad) {
+    if (!idx || use_device(idx->device, __func__)) return -1;
+    const uint64_t n = idx->view.n_sym;
+    unsigned long long *d = nullptr, h[2] = {0, ~0ull};
+    int rc = -1;
+    do {
+        CUDA_TRY(cudaMalloc(&d, 16), break);
+        CUDA_TRY(cudaMemcpy(d, h, 16, cudaMemcpyHostToDevice), break);
+        if (n) {
+            k_chk_rank<<<(unsigned)((n + 255) / 256), 256>>>(idx->view, n, d, d + 1);
+            LAUNCH_CHECK(break);
+        }
+        CUDA_TRY(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost), break);
+        // the last position must reproduce the marginal counts (cmd.c:108-116)
+        uint64_t last = n - 1, ok[6];
+        if (n && fmg_rank1a_batch(idx, 1, &last, ok, nullptr) == 0)
+            for (int c = 0; c < 6; ++c) if (ok[c] != idx->mcnt[c + 1]) { ++h[0]; if (h[1] == ~0ull) h[1] = last; }
+        rc = 0;
+    } while (0);
+    cudaFree(d);
+    if (n_bad) *n_bad = h[0];
+    if (first_bad) *first_bad = h[1];
     return rc;
 }
 

@@ -65,6 +65,13 @@ int          fmg_index_export(const fmg_index_t *idx, uint32_t *blocks, uint64_t
 
 /* n x rld_rank2a (rld.c:457-492): ok/ol = n*6 counts; k = (uint64_t)-1 allowed */
 int fmg_rank2a_batch(const fmg_index_t *idx, int64_t n, const uint64_t *k, const uint64_t *l, uint64_t *ok, uint64_t *ol);
+/* n x rld_rank1a (rld.c:424-446): ok = n*6 counts of BWT[0..k]; sym[i] (may be NULL) = the value rld_rank1a returns, BWT[k]
+ * (-1 for k = (uint64_t)-1, whose counts are 0) */
+int fmg_rank1a_batch(const fmg_index_t *idx, int64_t n, const uint64_t *k, uint64_t *ok, int32_t *sym);
+/* the self-check of `fermi chkbwt -r` (cmd.c:90-116) for every position of the BWT at once, on the device layout: rank1a(k) -
+ * rank1a(k-1) must be the one-hot vector of BWT[k] and rank1a(n-1) the marginal counts; *n_bad = violations (0 = the rank
+ * function is consistent with the BWT), *first_bad = the first offending position */
+int fmg_check_rank(const fmg_index_t *idx, uint64_t *n_bad, uint64_t *first_bad);
 /* n x fm6_extend (exact.c:72-88): ok6 = n*6 intervals; ok6[].info is set to 0 */
 int fmg_extend_batch(const fmg_index_t *idx, int64_t n, const fmg_intv_t *ik, const uint8_t *is_back, fmg_intv_t *ok6);
 /* n x fm_backward_search (exact.c:7-23): reads are nt6 bytes, read i = seq[off[i]..off[i+1]) */
@@ -201,6 +208,13 @@ int fmg_build_bwt(int device, int64_t n, const uint8_t *text, uint8_t *bwt);
 fmg_fmd_t *fmg_build_fmd(int device, int64_t n, const uint8_t *text);
 /* fm_bwtenc (build.c:11-31) on the device for a BWT held by the host (n nt6 symbols) */
 fmg_fmd_t *fmg_fmd_from_bwt_device(int device, int64_t n, const uint8_t *bwt);
+
+/* `fermi merge` (cmd.c:335-373): fm_compute_gap_bits (merge.c:31-94) -- bits = (n0 + n1 + 63) / 64 words, bit q set when symbol q of
+ * the merged BWT comes from the second index -- as one LF chain per sequence of the second index on the GPU, and fm_merge
+ * (merge.c:100-137): the two BWTs interleaved by the gap vector and RLD-encoded on the device; the image is byte-identical to
+ * what `fermi merge` writes.  Both indexes of fmg_gap_bits live on the same device. */
+int fmg_gap_bits(const fmg_index_t *idx0, const fmg_index_t *idx1, uint64_t *bits);
+fmg_fmd_t *fmg_merge(const fmg_fmd_t *e0, const fmg_fmd_t *e1, int device);
 
 /* BCR construction (bcr.h:43-49: bcr_init / bcr_append / bcr_build / bcr_itr_next / bcr_destroy), for collections of
  * any total size that fits HBM.  Sequences are nt6 codes 1..4 (no N, like bcr_append, ropebwt.c:98); they are

@@ -36,6 +36,17 @@ def test_golden_rank_extend_smem_search(fb, case):
         assert np.array_equal(mo, g[ok_]) and np.array_equal(rec, g[rk])
     b, e, s = fb.fm_backward_search(idx, seq, off)
     assert np.array_equal(b, g["sa_beg"]) and np.array_equal(e, g["sa_end"]) and np.array_equal(s, g["sa_size"])
+    # rld_rank1a with its returned symbol (rld.c:424-446) against the oracle, incl. k = -1, and the `chkbwt -r` self-check (cmd.c:90-116)
+    O = H.oracle()
+    h = O.load(fmd)
+    n_sym = int(idx.fmd.mcnt[0])
+    rng = np.random.RandomState(3)
+    ks = np.concatenate([rng.randint(0, n_sym, 5000).astype(np.uint64), np.array([0, n_sym - 1, 2**64 - 1], np.uint64)])
+    ook, osym = O.rank1a(h, ks)
+    ok1, sym1 = fb.rld_rank1a(idx, ks)
+    assert np.array_equal(ok1, ook) and np.array_equal(sym1, osym)
+    O.destroy(h)
+    assert fb.check_rank(idx) == (0, 2**64 - 1)
     idx.close()
 
 
@@ -485,6 +496,37 @@ def test_ec_collect_parts_add_up(fb):
     idx.close()
 
 
+@pytest.mark.skipif(H.ref_fermi_binary() is None, reason="oracle/_ref/fermi did not travel with the repo")
+def test_merge_is_byte_identical_to_fermi_merge(fb, tmp_path):
+    """`fermi merge a.fmd b.fmd` (fm_compute_gap_bits + fm_merge, merge.c:31-137): gap vector, interleaving and RLD encoding on the
+    GPU give the reference's bytes; the merged index is the index of the concatenated collection (cmd.c:366-370); the command-line
+    front end writes the same file."""
+    genome = fb.synth_genome(95, 80000)
+    a = fb.synth_reads(96, genome, 5000, 100, 0.01)
+    b = fb.synth_reads(97, genome, 3000, 73, 0.0)                     # another read length, fewer reads
+    fa, fbn, ref_out = str(tmp_path / "a.fmd"), str(tmp_path / "b.fmd"), str(tmp_path / "ref.fmd")
+    ea, eb = fb.fm_build(fb.fmd_text(a), 0), fb.fm_build(fb.fmd_text(b), 0)
+    ea.dump(fa); eb.dump(fbn)
+    with open(ref_out, "wb") as fh:
+        subprocess.run([H.ref_fermi_binary(), "merge", fa, fbn], stdout=fh, stderr=subprocess.DEVNULL, check=True)
+    ours = str(tmp_path / "ours.fmd")
+    fb.fm_merge(ea, eb, 0).dump(ours)
+    assert open(ours, "rb").read() == open(ref_out, "rb").read()
+    # the gap vector itself: as many set bits as the second index has symbols, and consistent with the merged BWT
+    ia, ib = fb.FmdIndex(ea, 0), fb.FmdIndex(eb, 0)
+    bits = fb.fm_gap_bits(ia, ib)
+    n0, n1 = int(ea.mcnt[0]), int(eb.mcnt[0])
+    flat = np.unpackbits(bits.view(np.uint8), bitorder="little")[: n0 + n1].astype(bool)
+    assert flat.sum() == n1
+    merged = fb.Fmd.restore(ours).decode_bwt()
+    assert np.array_equal(merged[flat], eb.decode_bwt()) and np.array_equal(merged[~flat], ea.decode_bwt())
+    ia.close(); ib.close()
+    cli = os.path.join(H.ROOT, "fermi_b200", "bin", "fermi-b200")
+    out2 = str(tmp_path / "cli.fmd")
+    subprocess.run([cli, "merge", "-o", out2, fa, fbn], stderr=subprocess.DEVNULL, check=True)
+    assert open(out2, "rb").read() == open(ref_out, "rb").read()
+
+
 DROP_BIN = os.path.join(H.ORACLE_DIR, "_ref", "fermi_drop")
 
 
@@ -522,6 +564,15 @@ def test_reference_binary_with_the_library_dropped_in(fb, tmp_path):
             assert np.array_equal(spell(ours.stdout), spell(ref.stdout))
         else:
             assert ours.stdout == ref.stdout
+    # `fermi correct`: collect phase on the GPU (integration/correct_collect.patch), the reference's own fix phase
+    reads = fb.synth_reads(93, genome[:25000], 10000, 100, 0.01)
+    fq, fn = str(tmp_path / "c.fq"), str(tmp_path / "c.fmd")
+    H.write_fastq(fq, reads)
+    fb.fm_build(fb.fmd_text(reads), 0).dump(fn)
+    ours = subprocess.run([DROP_BIN, "correct", "-t", "1", fn, fq], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=600)
+    ref = subprocess.run([ref_bin, "correct", "-t", "1", fn, fq], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert ours.returncode == 0 and ref.returncode == 0, ours.stderr.decode()[-1500:]
+    assert len(ref.stdout) > 100000 and ours.stdout == ref.stdout
 
 
 @pytest.mark.skipif(H.reference() is None or H.ref_fermi_binary() is None, reason="needs the compiled reference (oracle/_ref)")
