@@ -70,6 +70,7 @@ _PROTOS = {
     "fmg_magpart_free": (None, [C.c_void_p]),
     "fmg_unitig_from_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                          C.c_char_p, u64p]),
+    "fmg_contrast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, u64p, u64p]),
     "fmg_gap_bits": (C.c_int, [C.c_void_p, C.c_void_p, u64p]),
     "fmg_merge": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int]),
     "fmg_ec_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, vpp, u64p, C.POINTER(C.c_int64)]),

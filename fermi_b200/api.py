@@ -171,6 +171,14 @@ def fm6_smem_raw(idx, n, seq_ptr, off_ptr, mem_ptr, mem_cap, mem_off_ptr, self_m
     return got.value
 
 
+def fm6_contrast(idx0, idx1, k, min_occ):
+    """fm6_contrast (cmp.c:94-126): (sub0, sub1) bitmaps over the sequence ranks of the two indexes (uint64 words)"""
+    s0 = np.zeros((int(idx0.mcnt[1]) + 63) // 64, np.uint64)
+    s1 = np.zeros((int(idx1.mcnt[1]) + 63) // 64, np.uint64)
+    _check(lib().fmg_contrast(idx0.h, idx1.h, int(k), int(min_occ), _p(s0, u64p), _p(s1, u64p)), "fm6_contrast")
+    return s0, s1
+
+
 def fm_merge(fmd0, fmd1, device=0):
     """fm_merge (merge.c:100-137) / `fermi merge`: the gap vector, the interleaving and the RLD encoding on the GPU"""
     return Fmd(lib().fmg_merge(fmd0.h, fmd1.h, device))

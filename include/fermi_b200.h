@@ -216,6 +216,12 @@ fmg_fmd_t *fmg_fmd_from_bwt_device(int device, int64_t n, const uint8_t *bwt);
 int fmg_gap_bits(const fmg_index_t *idx0, const fmg_index_t *idx1, uint64_t *bits);
 fmg_fmd_t *fmg_merge(const fmg_fmd_t *e0, const fmg_fmd_t *e1, int device);
 
+/* `fermi contrast` (cmd.c:567-638): fm6_contrast (cmp.c:94-126) -- the lock-step walk of the backward-extension tries of two indexes
+ * down to k-mers, children with < min_occ occurrences in both pruned -- as a breadth-first expansion on the GPU.  sub0 / sub1 =
+ * (mcnt[1] + 63) / 64 words each: bit x set when sequence rank x of that index starts with a string absent from the other index
+ * (collect_tips, cmp.c:22-43).  The bitmaps equal the reference's (a set: the order of the walk does not matter).  k > 4. */
+int fmg_contrast(const fmg_index_t *idx0, const fmg_index_t *idx1, int k, int min_occ, uint64_t *sub0, uint64_t *sub1);
+
 /* BCR construction (bcr.h:43-49: bcr_init / bcr_append / bcr_build / bcr_itr_next / bcr_destroy), for collections of
  * any total size that fits HBM.  Sequences are nt6 codes 1..4 (no N, like bcr_append, ropebwt.c:98); they are
  * indexed in the order appended, so `fermi ropebwt` semantics = append the read, then its reverse complement

@@ -208,3 +208,28 @@ int refh_overlap_batch(const void *_e, int min_match, int64_t n, const uint64_t 
 	free(s.s); free(a[0].a); free(a[1].a); free(nei.a); free(cat.a);
 	return 0;
 }
+
+/* fm6_contrast (cmp.c:94-126) of the reference on two loaded indexes: sub0 / sub1 receive (mcnt[1] + 63) / 64 words each */
+void fm6_contrast(rld_t *const e[2], int k, int min_occ, int n_threads, uint64_t *sub[2]);
+int refh_contrast(const void *_e0, const void *_e1, int k, int min_occ, int n_threads, uint64_t *sub0, uint64_t *sub1)
+{
+	rld_t *e[2];
+	uint64_t *sub[2];
+	e[0] = (rld_t*)_e0; e[1] = (rld_t*)_e1;
+	fm6_contrast(e, k, min_occ, n_threads, sub);
+	memcpy(sub0, sub[0], (e[0]->mcnt[1] + 63) / 64 * 8);
+	memcpy(sub1, sub[1], (e[1]->mcnt[1] + 63) / 64 * 8);
+	free(sub[0]); free(sub[1]);
+	return 0;
+}
+
+/* fm_compute_gap_bits (merge.c:68-94) of the reference: bits receives (n0 + n1 + 63) / 64 words */
+uint64_t *fm_compute_gap_bits(const rld_t *e0, const rld_t *e1, int n_threads);
+int refh_gap_bits(const void *_e0, const void *_e1, int n_threads, uint64_t *bits)
+{
+	const rld_t *e0 = (const rld_t*)_e0, *e1 = (const rld_t*)_e1;
+	uint64_t *b = fm_compute_gap_bits(e0, e1, n_threads);
+	memcpy(bits, b, (e0->mcnt[0] + e1->mcnt[0] + 63) / 64 * 8);
+	free(b);
+	return 0;
+}

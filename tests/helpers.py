@@ -206,6 +206,26 @@ class _Lib:
         t = np.ascontiguousarray(triples, np.uint64)
         return f(h, w, min_occ, len(t), _ptr(t, u64p), fq.encode(), out_path.encode())
 
+    def contrast(self, h0, h1, n_seq0, n_seq1, k, min_occ, n_threads=1):
+        """reference harness only: fm6_contrast (cmp.c:94-126) -> (sub0, sub1) uint64 bitmaps over sequence ranks"""
+        assert self.p == "refh_"
+        f = self.lib.refh_contrast
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, u64p, u64p]
+        s0, s1 = np.zeros((n_seq0 + 63) // 64, np.uint64), np.zeros((n_seq1 + 63) // 64, np.uint64)
+        f(h0, h1, k, min_occ, n_threads, _ptr(s0, u64p), _ptr(s1, u64p))
+        return s0, s1
+
+    def gap_bits(self, h0, h1, n_total, n_threads=1):
+        """reference harness only: fm_compute_gap_bits (merge.c:68-94)"""
+        assert self.p == "refh_"
+        f = self.lib.refh_gap_bits
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, u64p]
+        bits = np.zeros((n_total + 63) // 64, np.uint64)
+        f(h0, h1, n_threads, _ptr(bits, u64p))
+        return bits
+
     # --- index lifecycle
     def load(self, fn):
         h = self._load(fn.encode())

@@ -527,6 +527,34 @@ def test_merge_is_byte_identical_to_fermi_merge(fb, tmp_path):
     assert open(out2, "rb").read() == open(ref_out, "rb").read()
 
 
+@pytest.mark.skipif(H.reference() is None, reason="needs the compiled reference (oracle/_ref)")
+def test_contrast_and_gap_bits_equal_the_reference_functions(fb, tmp_path):
+    """fm6_contrast (cmp.c:94-126) on two read sets from genomes that differ by a few substitutions, and fm_compute_gap_bits
+    (merge.c:68-94): the bitmaps of the GPU equal those of the reference's own functions (oracle/ref_harness.c)."""
+    R = H.reference()
+    g0 = fb.synth_genome(101, 40000)
+    g1 = g0.copy()
+    rng = np.random.RandomState(5)
+    for p in rng.choice(len(g1), 25, replace=False):
+        g1[p] = 1 + (g1[p] % 4)                                       # another base
+    r0 = fb.synth_reads(102, g0, 12000, 100, 0.002)
+    r1 = fb.synth_reads(103, g1, 12000, 100, 0.002)
+    f0, f1 = str(tmp_path / "0.fmd"), str(tmp_path / "1.fmd")
+    e0, e1 = fb.fm_build(fb.fmd_text(r0), 0), fb.fm_build(fb.fmd_text(r1), 0)
+    e0.dump(f0); e1.dump(f1)
+    i0, i1 = fb.FmdIndex(e0, 0), fb.FmdIndex(e1, 0)
+    h0, h1 = R.load(f0), R.load(f1)
+    for k, min_occ in ((25, 3), (31, 2)):
+        s0, s1 = fb.fm6_contrast(i0, i1, k, min_occ)
+        o0, o1 = R.contrast(h0, h1, int(e0.mcnt[1]), int(e1.mcnt[1]), k, min_occ, 3)
+        assert np.array_equal(s0, o0) and np.array_equal(s1, o1)
+        assert int(np.unpackbits(s0.view(np.uint8)).sum()) > 0 and int(np.unpackbits(s1.view(np.uint8)).sum()) > 0
+    bits = fb.fm_gap_bits(i0, i1)
+    assert np.array_equal(bits, R.gap_bits(h0, h1, int(e0.mcnt[0]) + int(e1.mcnt[0]), 2))
+    R.destroy(h0); R.destroy(h1)
+    i0.close(); i1.close()
+
+
 DROP_BIN = os.path.join(H.ORACLE_DIR, "_ref", "fermi_drop")
 
 
