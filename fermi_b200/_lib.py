@@ -31,6 +31,12 @@ _PROTOS = {
     "fmg_index_bytes": (C.c_uint64, [C.c_void_p]),
     "fmg_index_device": (C.c_int, [C.c_void_p]),
     "fmg_index_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, u64p, u64p]),
+    # rank on the .fmd stream itself
+    "fmg_rldx_upload": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "fmg_rldx_free": (None, [C.c_void_p]),
+    "fmg_rldx_bytes": (C.c_uint64, [C.c_void_p]),
+    "fmg_rldx_rank2a_batch": (C.c_int, [C.c_void_p, C.c_int64, u64p, u64p, u64p, u64p]),
+    "fmg_rldx_extend_batch": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, u8p, C.c_void_p]),
     # batched queries
     "fmg_rank2a_batch": (C.c_int, [C.c_void_p, C.c_int64, u64p, u64p, u64p, u64p]),
     "fmg_rank1a_batch": (C.c_int, [C.c_void_p, C.c_int64, u64p, u64p, C.c_void_p]),

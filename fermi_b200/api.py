@@ -171,6 +171,40 @@ def fm6_smem_raw(idx, n, seq_ptr, off_ptr, mem_ptr, mem_cap, mem_off_ptr, self_m
     return got.value
 
 
+class RldIndex:
+    """The .fmd stream itself in HBM + a dense block directory (fmg_rldx_*): rank by one warp per query (rldx.cu)."""
+
+    def __init__(self, fmd, device=0):
+        self.fmd = fmd
+        self.h = lib().fmg_rldx_upload(fmd.h, device)
+        if not self.h:
+            raise RuntimeError("fermi_b200: RLD index upload failed (no CUDA device? see stderr); there is no CPU fallback")
+
+    @property
+    def nbytes(self):
+        return int(lib().fmg_rldx_bytes(self.h))
+
+    def rank2a(self, k, l):
+        k = np.ascontiguousarray(k, np.uint64)
+        l = np.ascontiguousarray(l, np.uint64)
+        ok = np.zeros((len(k), 6), np.uint64)
+        ol = np.zeros((len(k), 6), np.uint64)
+        _check(lib().fmg_rldx_rank2a_batch(self.h, len(k), _p(k, u64p), _p(l, u64p), _p(ok, u64p), _p(ol, u64p)), "rld_rank2a (RLD index)")
+        return ok, ol
+
+    def extend(self, ik, is_back):
+        ik = np.ascontiguousarray(ik, INTV)
+        is_back = np.ascontiguousarray(is_back, np.uint8)
+        out = np.zeros((len(ik), 6), INTV)
+        _check(lib().fmg_rldx_extend_batch(self.h, len(ik), ik.ctypes.data, _p(is_back, u8p), out.ctypes.data), "fm6_extend (RLD index)")
+        return out
+
+    def close(self):
+        if self.h:
+            lib().fmg_rldx_free(self.h)
+            self.h = None
+
+
 def fm6_contrast(idx0, idx1, k, min_occ):
     """fm6_contrast (cmp.c:94-126): (sub0, sub1) bitmaps over the sequence ranks of the two indexes (uint64 words)"""
     s0 = np.zeros((int(idx0.mcnt[1]) + 63) // 64, np.uint64)

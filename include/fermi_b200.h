@@ -60,6 +60,21 @@ int          fmg_index_device(const fmg_index_t *idx);
 /* copy the query layout back to the host: blocks = n_blocks x 16 u32, cs = n_super x 8 u64 (either may be NULL to query sizes) */
 int          fmg_index_export(const fmg_index_t *idx, uint32_t *blocks, uint64_t *cs, uint64_t *n_blocks, uint64_t *n_super);
 
+/* ------------------------------------------------------------------ rank on the .fmd stream itself (memory-lean mode)
+ * fmg_rldx_upload keeps the run-length / Elias-delta blocks of the .fmd as they are in HBM plus a dense block directory: one 64-byte
+ * line per 64-byte block with its first BWT coordinate and the six cumulative counts (together about twice the .fmd file: 1.6-4.4
+ * bits per symbol for read sets, against 4 for the occ blocks), and a coarse position -> block table.  One WARP serves a query: ballot search of the block,
+ * the block and its directory line staged by bulk asynchronous copies (TMA) on an mbarrier, the codes located by pointer doubling
+ * over the payload bit offsets and summed with warp prefix sums / reductions (fermi_b200/csrc/rldx.cu).  Same results as
+ * rld_rank2a / fm6_extend; far fewer ranks per second than the occ-block path -- the layout north_star sketches, kept as the
+ * alternative for highly repetitive (deep-coverage) indexes that must fit a smaller share of HBM. */
+typedef struct fmg_rldx_s fmg_rldx_t;
+fmg_rldx_t *fmg_rldx_upload(const fmg_fmd_t *e, int device);
+void        fmg_rldx_free(fmg_rldx_t *x);
+uint64_t    fmg_rldx_bytes(const fmg_rldx_t *x);
+int fmg_rldx_rank2a_batch(const fmg_rldx_t *x, int64_t n, const uint64_t *k, const uint64_t *l, uint64_t *ok, uint64_t *ol);   /* rld_rank2a, rld.c:457-492 */
+int fmg_rldx_extend_batch(const fmg_rldx_t *x, int64_t n, const fmg_intv_t *ik, const uint8_t *is_back, fmg_intv_t *ok6);     /* fm6_extend, exact.c:72-88 */
+
 /* ------------------------------------------------------------------ batched queries, HOST buffers
  * (host->device and device->host copies happen inside the call) */
 

@@ -527,6 +527,34 @@ def test_merge_is_byte_identical_to_fermi_merge(fb, tmp_path):
     assert open(out2, "rb").read() == open(ref_out, "rb").read()
 
 
+def test_rank_on_the_rld_stream_itself(fb):
+    """fmg_rldx_*: the .fmd blocks stay run-length / Elias-delta coded in HBM and a warp decodes them (ballot search of the block,
+    TMA-staged block + directory line, pointer doubling over the bit offsets, warp prefix sums): rank2a and fm6_extend equal the
+    reference's golden vectors; on streams with 7 x u32 block headers (runs >= 0x8000), 4-bit codes only and a stream longer than
+    one 2^23-word chunk (shortened chunk-end blocks) the ranks equal those of the occ-block path at random and boundary positions."""
+    for case in golden_cases():
+        g, fmd = _load(case)
+        x = fb.RldIndex(fb.Fmd.restore(fmd), 0)
+        ok, ol = x.rank2a(g["k"], g["l"])
+        assert np.array_equal(ok, g["ok"]) and np.array_equal(ol, g["ol"]), case
+        assert np.array_equal(x.extend(g["ik"], g["is_back"]), g["ext"]), case
+        x.close()
+    rng = np.random.RandomState(13)
+    long_runs = np.concatenate([np.full(l, s, np.uint8) for l, s in zip(rng.choice([1, 5, 300, 40000, 70000, 1 << 20], size=300), rng.randint(0, 6, size=300))])
+    cases = [long_runs, np.tile(np.array([1, 2, 3, 4, 0, 5], np.uint8), 100000), rng.randint(1, 5, size=150_000_000).astype(np.uint8)]
+    for bwt in cases:
+        e = fb.Fmd.from_bwt_device(bwt, 0)
+        n = len(bwt)
+        x, idx = fb.RldIndex(e, 0), fb.FmdIndex(e, 0)
+        k = np.concatenate([rng.randint(0, n, 20000).astype(np.uint64), np.array([2**64 - 1, 0, 1, n - 2, n - 1], np.uint64)])
+        l = np.minimum(k + rng.randint(0, 3000, len(k)).astype(np.uint64), np.uint64(n - 1))
+        l[k == np.uint64(2**64 - 1)] = 17
+        ok, ol = x.rank2a(k, l)
+        ok2, ol2 = fb.rld_rank2a(idx, k, l)
+        assert np.array_equal(ok, ok2) and np.array_equal(ol, ol2), n
+        x.close(); idx.close()
+
+
 @pytest.mark.skipif(H.reference() is None, reason="needs the compiled reference (oracle/_ref)")
 def test_contrast_and_gap_bits_equal_the_reference_functions(fb, tmp_path):
     """fm6_contrast (cmp.c:94-126) on two read sets from genomes that differ by a few substitutions, and fm_compute_gap_bits
