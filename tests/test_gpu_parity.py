@@ -620,6 +620,32 @@ def test_reference_binary_with_the_library_dropped_in(fb, tmp_path):
             assert np.array_equal(spell(ours.stdout), spell(ref.stdout))
         else:
             assert ours.stdout == ref.stdout
+    # `fermi remap` (fm6_remap / paircov, smem.c:139-394) with the SMEMs of the contigs from the GPU (integration/remap_smem.patch):
+    # unpaired, paired with the rank table of seqrank, and paired + broken at low paired coverage (-c)
+    frag = 300
+    starts = np.random.RandomState(8).randint(0, len(genome) - frag, 4000)
+    pe = np.empty((8000, 100), np.uint8)
+    for i, st in enumerate(starts):                            # mates of a pair are consecutive reads, facing each other
+        pe[2 * i] = genome[st: st + 100]
+        pe[2 * i + 1] = (5 - genome[st + frag - 100: st + frag][::-1])
+    pfmd, prank, pmag = str(tmp_path / "pe.fmd"), str(tmp_path / "pe.rank"), str(tmp_path / "pe.mag")
+    fb.fm_build(fb.fmd_text(pe), 0).dump(pfmd)
+    with open(prank, "wb") as fh:
+        subprocess.run([ref_bin, "seqrank", pfmd], stdout=fh, stderr=subprocess.DEVNULL, check=True)
+    with open(pmag, "wb") as fh:
+        subprocess.run([ref_bin, "unitig", "-l", "40", pfmd], stdout=fh, stderr=subprocess.DEVNULL, check=True)
+    assert os.path.getsize(pmag) > 50000
+    for opts in ([], ["-r", prank], ["-r", prank, "-c", "2", "-D", "600"], ["-r", prank, "-t", "3"]):
+        ours = subprocess.run([DROP_BIN, "remap"] + opts + [pfmd, pmag], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=600)
+        ref = subprocess.run([ref_bin, "remap"] + opts + [pfmd, pmag], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+        assert ours.returncode == 0 and ref.returncode == 0, ours.stderr.decode()[-1500:]
+        if "-t" in opts:                                       # several threads write whole records in any order
+            split = lambda b: sorted(b.split(b"\n@"))
+            assert split(ours.stdout) == split(ref.stdout)
+        else:
+            assert len(ref.stdout) > 50000 and ours.stdout == ref.stdout, opts
+        pick = lambda e: [l for l in e.decode().splitlines() if "fm6_remap" in l]
+        assert pick(ours.stderr) == pick(ref.stderr)           # "[M::fm6_remap] avg = ... std = ... cap = ..."
     # `fermi correct`: collect phase on the GPU (integration/correct_collect.patch), the reference's own fix phase
     reads = fb.synth_reads(93, genome[:25000], 10000, 100, 0.01)
     fq, fn = str(tmp_path / "c.fq"), str(tmp_path / "c.fmd")
