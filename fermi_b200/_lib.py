@@ -86,7 +86,6 @@ _PROTOS = {
     "fmg_build_bwt": (C.c_int, [C.c_int, C.c_int64, u8p, u8p]),
     "fmg_build_fmd": (C.c_void_p, [C.c_int, C.c_int64, u8p]),
     "fmg_fmd_from_bwt_device": (C.c_void_p, [C.c_int, C.c_int64, u8p]),
-    "fmg_bcr_want_fmd": (C.c_int, [C.c_void_p, C.c_int]),
     "fmg_bcr_fmd": (C.c_void_p, [C.c_void_p]),
     "fmg_bcr_init": (C.c_void_p, [C.c_int]),
     "fmg_bcr_append": (C.c_int, [C.c_void_p, C.c_int, u8p]),

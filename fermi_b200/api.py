@@ -411,7 +411,6 @@ class Bcr:
 
     def build_fmd(self):
         """`fermi ropebwt | fermi recode`: BCR and the RLD encoder on the GPU; returns the Fmd (the BWT itself is not copied out)."""
-        _check(lib().fmg_bcr_want_fmd(self.h, 1), "bcr_want_fmd")
         _check(lib().fmg_bcr_build(self.h), "bcr_build")
         return Fmd(lib().fmg_bcr_fmd(self.h))
 

@@ -307,7 +307,6 @@ struct fmg_bcr_s {
     int max_len = 0;
     DevBuf d_bwt;                    // result: one nt6 byte per symbol, kept in HBM; copied out / RLD-encoded on request
     bool built = false;
-    bool want_fmd = false;           // kept for callers of fmg_bcr_want_fmd (the image is encoded on request either way)
     uint64_t n_sym = 0;
 };
 
@@ -446,9 +445,6 @@ int fmg_bcr_build(fmg_bcr_t *b) {
 }
 
 int64_t fmg_bcr_size(const fmg_bcr_t *b) { return b && b->built ? (int64_t)b->n_sym : -1; }
-
-// kept for source compatibility: the image is encoded on request from the BWT that stays in HBM
-int fmg_bcr_want_fmd(fmg_bcr_t *b, int on) { if (!b) return -1; b->want_fmd = on != 0; return 0; }
 
 // `fermi ropebwt | fermi recode` in one step: the BWT in HBM through the RLD encoder on the device; the caller owns the image
 fmg_fmd_t *fmg_bcr_fmd(fmg_bcr_t *b) {

@@ -137,7 +137,6 @@ int main_ropebwt(int argc, char *argv[]) {
             if (j == rd.seq.size() || rd.seq[j] == 5 || rd.seq[j] == 0) { if (j > st) insert1(rd.seq.substr(st, j - st)); st = j + 1; }
     }
     if (fmd) {
-        fmg_bcr_want_fmd(b, 1);
         if (fmg_bcr_build(b)) return 1;
         fmg_fmd_t *e = fmg_bcr_fmd(b);
         const int rc = e ? fmg_fmd_dump(e, out) : 1;

@@ -250,9 +250,7 @@ int64_t    fmg_bcr_size(const fmg_bcr_t *b);                            /* symbo
 int        fmg_bcr_bwt(const fmg_bcr_t *b, uint8_t *bwt);               /* one nt6 byte per symbol */
 int        fmg_bcr_rle(const fmg_bcr_t *b, uint8_t **rle, int64_t *n);  /* bcr_itr_next stream: bytes len<<3|sym (ropebwt.c:127-144) */
 /* `fermi ropebwt | fermi recode` in one step: the BWT stays in HBM with the handle after fmg_bcr_build; fmg_bcr_fmd runs the
- * RLD encoder on it there and hands the image to the caller (fmg_bcr_bwt / fmg_bcr_rle copy it out instead).
- * fmg_bcr_want_fmd is accepted for source compatibility and changes nothing. */
-int        fmg_bcr_want_fmd(fmg_bcr_t *b, int on);
+ * RLD encoder on it there and hands the image to the caller (fmg_bcr_bwt / fmg_bcr_rle copy it out instead). */
 fmg_fmd_t *fmg_bcr_fmd(fmg_bcr_t *b);
 void       fmg_bcr_destroy(fmg_bcr_t *b);                               /* bcr_destroy, bcr.c:342 */
 
