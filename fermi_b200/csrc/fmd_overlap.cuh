@@ -52,6 +52,7 @@ struct OverlapArgs {
     uint32_t *nei_cnt;
     uint8_t *ext;               // n x max_len: bases fm6_get_nei appends to the read (s[len .. s_len), unitig.c:141)
     unsigned long long *next;
+    const uint32_t *order;      // phase 2: the sequences of the batch in the order the lanes take them (see k_nei_key), or nullptr
     // row t of seq, given the (clipped) length of the sequence
     FMG_HD const uint8_t *seq_of(int64_t t, int len) const { return seq + (size_t)(t + 1) * max_len - (len < max_len ? len : max_len); }
 };

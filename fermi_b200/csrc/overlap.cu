@@ -3,6 +3,7 @@
 //   k_ov_lists<U,2|4>  fm6_get_nei / the candidate loop of check_left_simple (unitig.c:93-179,191-203), persistent lanes
 //   k_ov_pack          batch records -> rank-indexed 64-byte records + compact ext / spill arrays (whole-index pass)
 #include <cuda_runtime.h>
+#include <cub/cub.cuh>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -55,7 +56,28 @@ template <typename U, int MINB>
 __global__ void __launch_bounds__(OVLP_BLOCK, MINB) k_ov_nei(const __grid_constant__ OverlapArgs A) {
     extern __shared__ uint4 fmg_ov_shared[];
     const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    nei_lane<U, MINB>(A, lane, [&]() -> int64_t { return (int64_t)atomicAdd(A.next, 1ull); }, fmg_ov_shared, (int)blockDim.x, (int)threadIdx.x);
+    nei_lane<U, MINB>(A, lane, [&]() -> int64_t {
+        const int64_t j = (int64_t)atomicAdd(A.next, 1ull);
+        return A.order && j < A.n ? (int64_t)A.order[j] : j;
+    }, fmg_ov_shared, (int)blockDim.x, (int)threadIdx.x);
+}
+
+// The lanes of a warp stay in step only while their sequences take the same trips: a sequence costs (levels) trips of (candidates)
+// rank triples each, levels = length - longest overlap.  The batch is therefore handed out sorted by that pair (heaviest first), so
+// that the 32 sequences a warp works on at any time are alike: key = levels << 8 | candidates, 0 for sequences without work.
+template <typename U>
+__global__ void __launch_bounds__(256) k_nei_key(OverlapArgs A, uint32_t *__restrict__ key, uint32_t *__restrict__ idx) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= A.n) return;
+    const int np = A.np0[t];
+    uint32_t k = 0;
+    if (np > 0) {
+        const int npc = np < A.pcap ? np : A.pcap;
+        const IntvT<U> first = ld_cand(static_cast<const IntvT<U> *>(A.P0) + (size_t)t * A.pcap + (A.pcap - npc));     // the longest overlap
+        const int levels = A.len[t] - (int)first.info;
+        k = (uint32_t)(levels < 1 ? 1 : levels > 4095 ? 4095 : levels) << 8 | (uint32_t)(np > 255 ? 255 : np);
+    }
+    key[t] = k; idx[t] = (uint32_t)t;
 }
 static int nei_minb() {
     static const int v = [] { const char *e = std::getenv("FMG_NEI_BLOCKS"); const int x = e ? std::atoi(e) : 4; return x <= 3 ? 3 : x >= 5 ? 5 : 4; }();
@@ -204,7 +226,8 @@ int64_t fmg_compact_tiles(int64_t n);
 // phases 1 + 2 (the record without the left check) and phases 3 + 4 (check_left_simple) over one batch, back to back on `st`;
 // ctrl2 = two work counters (zeroed by launch_records)
 template <typename U>
-static cudaError_t launch_records(OverlapArgs O, int grid, unsigned long long *ctrl2, cudaStream_t st, cudaEvent_t *ev = nullptr) {
+static cudaError_t launch_records(OverlapArgs O, int grid, unsigned long long *ctrl2, cudaStream_t st, cudaEvent_t *ev = nullptr,
+                                  uint32_t *ord = nullptr, void *ord_tmp = nullptr, size_t ord_tmp_bytes = 0) {
     cudaError_t e = cudaMemsetAsync(ctrl2, 0, 16, st);
     if (e != cudaSuccess) return e;
     const unsigned gch = (unsigned)((O.n + OVCH_BLOCK - 1) / OVCH_BLOCK);
@@ -221,6 +244,16 @@ static cudaError_t launch_records(OverlapArgs O, int grid, unsigned long long *c
     k_ov_chain<U, 1><<<gch, OVCH_BLOCK, 0, st>>>(O);
     if (ev) cudaEventRecord(ev[1], st);
     O.next = ctrl2;
+    O.order = nullptr;
+    if (ord && O.n > 4096) {                     // hand the sequences out sorted by their cost (k_nei_key)
+        uint32_t *k0 = ord, *k1 = ord + O.n, *i0 = ord + 2 * O.n, *i1 = ord + 3 * O.n;
+        k_nei_key<U><<<(unsigned)((O.n + 255) / 256), 256, 0, st>>>(O, k0, i0);
+        size_t need = ord_tmp_bytes;
+        e = cub::DeviceRadixSort::SortPairsDescending(ord_tmp, need, k0, k1, i0, i1, (int64_t)O.n, 0, 20, st);
+        if (e != cudaSuccess) return e;
+        O.order = i1;
+        g_launches += 2;
+    }
     {
         void *kargs[] = {(void *)&O};
         e = cudaLaunchKernel(nei_kernel<U>(), dim3((unsigned)g), dim3(OVLP_BLOCK), kargs, lists_shared_bytes<U>(), st);
@@ -266,7 +299,8 @@ namespace fmg { Pool g_pool; }
 
 // device scratch of the phase kernels for batches of up to `nb` rows
 struct OvScratch {
-    Dev seq, len, rec, ext, cnt, slots, P0, S0, np0, A, B, cat, S;
+    Dev seq, len, rec, ext, cnt, slots, P0, S0, np0, A, B, cat, S, ord, ord_tmp;
+    size_t ord_tmp_bytes = 0;
     int max_len = 0, pcap = 0, cap = 0, nei_cap = 0, grid = 0;
     bool wide = false;
     cudaError_t alloc(int64_t nb, int max_len_, int pcap_, int cap_, int nei_cap_, bool wide_, int grid_) {
@@ -280,6 +314,13 @@ struct OvScratch {
         OVS_A(P0.alloc((size_t)nb * pcap * esz)); OVS_A(S0.alloc((size_t)nb * pcap * (esz / 4))); OVS_A(np0.alloc((size_t)nb * 4));
         OVS_A(A.alloc((size_t)n_lanes * cap * esz)); OVS_A(B.alloc((size_t)n_lanes * cap * esz)); OVS_A(cat.alloc((size_t)n_lanes * cap * 8));
         OVS_A(S.alloc((size_t)n_lanes * cap * 2 * (esz / 4)));
+        OVS_A(ord.alloc((size_t)nb * 16));                           // keys and sequence numbers, two buffers each (k_nei_key + radix sort)
+        {
+            size_t need = 0;
+            OVS_A(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr, nb, 0, 20));
+            ord_tmp_bytes = need + 256;
+            OVS_A(ord_tmp.alloc(ord_tmp_bytes));
+        }
 #undef OVS_A
         return cudaSuccess;
     }
@@ -289,7 +330,7 @@ struct OvScratch {
         O.ids = nullptr; O.first = 0; O.step = 1; O.ret = nullptr;
         O.P0 = P0.p; O.S0 = S0.p; O.pcap = pcap; O.np0 = np0.as<int32_t>(); O.A = A.p; O.B = B.p; O.cap = cap; O.cat = cat.as<int32_t>(); O.S = S.p;
         O.rec = rec.as<int64_t>(); O.nei = slots.as<uint4>(); O.nei_cap = nei_cap; O.nei_cnt = cnt.as<uint32_t>();
-        O.ext = ext.as<uint8_t>(); O.next = nullptr;
+        O.ext = ext.as<uint8_t>(); O.next = nullptr; O.order = nullptr;
         return O;
     }
 };
@@ -333,7 +374,8 @@ static int left_fix(const fmg_index_s *idx, int min_match, const OvScratch &S, i
         OverlapArgs O = S.args(idx, min_match, m);
         O.ids = d_ids.as<uint64_t>() + o; O.ret = d_ret.as<int64_t>();
         unsigned long long *c2 = d_ctrl + OVC_NEXT;
-        OV_TRY(S.wide ? launch_records<uint64_t>(O, S.grid, c2, st) : launch_records<uint32_t>(O, S.grid, c2, st));
+        OV_TRY(S.wide ? launch_records<uint64_t>(O, S.grid, c2, st, nullptr, S.ord.as<uint32_t>(), S.ord_tmp.p, S.ord_tmp_bytes)
+                      : launch_records<uint32_t>(O, S.grid, c2, st, nullptr, S.ord.as<uint32_t>(), S.ord_tmp.p, S.ord_tmp_bytes));
         OV_TRY(S.wide ? launch_left<uint64_t>(O, S.grid, c2, st) : launch_left<uint32_t>(O, S.grid, c2, st));
         k_left_patch<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(m, S.rec.as<int64_t>(), d_ret.as<int64_t>(), S.cnt.as<uint32_t>(), S.nei_cap, pack, d_ctrl);
         ++g_launches;
@@ -453,7 +495,8 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
             OverlapArgs O = S.args(idx, min_match, m);
             O.first = row0; O.ret = o_ret + row0;
             unsigned long long *c2 = d_ctrl.as<unsigned long long>() + OVC_NEXT;       // OVC_NEXT, OVC_NEXT2: the work counters
-            OV_TRY(wide ? launch_records<uint64_t>(O, grid, c2, s_run, ev) : launch_records<uint32_t>(O, grid, c2, s_run, ev));
+            OV_TRY(wide ? launch_records<uint64_t>(O, grid, c2, s_run, ev, S.ord.as<uint32_t>(), S.ord_tmp.p, S.ord_tmp_bytes)
+                        : launch_records<uint32_t>(O, grid, c2, s_run, ev, S.ord.as<uint32_t>(), S.ord_tmp.p, S.ord_tmp_bytes));
             PackArgs P;
             P.n = m; P.rec = S.rec.as<int64_t>(); P.ret = o_ret + row0; P.len = S.len.as<int32_t>(); P.nei_cnt = S.cnt.as<uint32_t>();
             P.nei_slots = S.slots.as<uint4>(); P.nei_cap = nei_cap; P.ext = S.ext.as<uint8_t>(); P.max_len = max_len;

@@ -116,7 +116,7 @@ int emu_overlap(const void *_x, int min_match, int64_t n, const uint64_t *ids, i
     O.ix = x->view; O.min_match = min_match; O.mode = 0; O.n = n; O.seq = dseq.data(); O.len = len; O.max_len = ml;
     O.ids = ids; O.first = 0; O.step = 1; O.ret = ret.data();
     O.P0 = P0.data(); O.S0 = S0.data(); O.S = S.data(); O.pcap = pcap; O.np0 = np0.data(); O.A = A.data(); O.B = B.data(); O.cap = cap; O.cat = cat.data();
-    O.rec = rec; O.nei = reinterpret_cast<uint4 *>(nei); O.nei_cap = nei_cap; O.nei_cnt = nei_cnt; O.ext = dext.data(); O.next = nullptr;
+    O.rec = rec; O.nei = reinterpret_cast<uint4 *>(nei); O.nei_cap = nei_cap; O.nei_cnt = nei_cnt; O.ext = dext.data(); O.next = nullptr; O.order = nullptr;
     auto lists = [&](int phase) {
         for (int t = 0; t < n_lanes; ++t) {
             int64_t cur = t;
