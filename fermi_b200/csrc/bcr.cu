@@ -44,9 +44,7 @@ namespace {
         }                                                                                               \
     } while (0)
 
-constexpr int kTile = 4096;          // output symbols per block of the merge pass
-constexpr int kThreads = 256;
-constexpr int kPer = kTile / kThreads;   // 16 symbols per thread: one 16-byte vector
+constexpr int kPer = 16;             // output symbols per thread of the merge pass: one 16-byte vector; a tile = kPer x block size symbols
 
 struct Vec4 { uint64_t v[4]; };      // occurrences of A,C,G,T
 struct Vec4Add { __host__ __device__ Vec4 operator()(const Vec4 &a, const Vec4 &b) const { Vec4 r; for (int i = 0; i < 4; ++i) r.v[i] = a.v[i] + b.v[i]; return r; } };
@@ -84,7 +82,7 @@ __global__ void k_bcr_iota(Item *item, uint64_t n) {
 // tile_lo[t] = first insert whose position falls into output tile t or later (the inserts are sorted by position): every
 // insert fills the entries between its predecessor's tile and its own -- one coalesced pass instead of a binary search
 // over the whole insert list at the start of every tile
-__global__ void k_bcr_bounds(const Item *__restrict__ item, uint64_t n_act, uint64_t n_tiles, uint64_t *__restrict__ tile_lo) {
+__global__ void k_bcr_bounds(const Item *__restrict__ item, uint64_t n_act, uint64_t n_tiles, uint64_t *__restrict__ tile_lo, uint32_t kTile) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_act) return;
     const uint64_t t1 = item[k].f / kTile;
@@ -98,16 +96,6 @@ __global__ void k_bcr_bounds(const Item *__restrict__ item, uint64_t n_act, uint
 // one contiguous piece of the old array, staged in shared memory with aligned 16-byte loads; a thread whose 16 positions
 // hold no insert (most of them: one insert per pos symbols in cycle pos) copies 16 staged bytes with word operations, and
 // every thread writes one 16-byte vector.
-__device__ __forceinline__ uint64_t count_acgt(uint32_t w) {       // packed 4 x 16-bit counts of A,C,G,T among 4 symbol bytes
-    uint64_t r = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t c = (w >> (8 * i)) & 0xffu;
-        if (c >= 1 && c <= 4) r += 1ull << (16 * (c - 1));
-    }
-    return r;
-}
-
 // ---- bulk asynchronous copies (TMA unit, 1-D) and their mbarriers: the old symbols of the next tiles travel to shared memory while
 // the block merges the current one
 constexpr int kStages = 4;
@@ -137,15 +125,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 
 // PERSISTENT: blocks walk over the tiles (blockIdx.x, + gridDim.x, ...); thread 0 keeps kStages bulk copies of old symbols in
 // flight per block, each completing on its own mbarrier.
-__global__ void __launch_bounds__(kThreads, 4) k_bcr_merge(const uint8_t *__restrict__ old_bwt, uint64_t m_new, const Item *__restrict__ item,
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_bcr_merge(const uint8_t *__restrict__ old_bwt, uint64_t m_new, const Item *__restrict__ item,
                                                         const uint8_t *__restrict__ sym, const uint64_t *__restrict__ tile_lo, uint8_t *__restrict__ new_bwt,
                                                         Vec4 *__restrict__ tile_hist, uint32_t *__restrict__ rank_in_tile, uint64_t n_tiles) {
+    constexpr int kTile = kThreads * kPer;
     __shared__ __align__(16) uint8_t s_sym[kTile];
     __shared__ __align__(128) uint8_t s_srcs[kStages][kTile + 64];
     __shared__ __align__(16) uint8_t s_flag[kTile];
     __shared__ uint32_t s_warp_ins[kThreads / 32];
     __shared__ uint64_t s_warp_cnt[kThreads / 32];
     __shared__ __align__(8) uint64_t s_bar[kStages];
+    __shared__ uint32_t s_spread[16];              // byte-permute selector that spreads consecutive bytes over the non-insert positions of a word
     const int tid = threadIdx.x;
     // source range of a tile: old symbols [src_lo, src_lo + n_src), fetched from the 16-byte boundary below src_lo
     auto issue = [&](uint64_t tile, int stage) {
@@ -156,6 +147,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_bcr_merge(const uint8_t *__rest
         if (bytes) { mbar_expect_tx(&s_bar[stage], bytes); bulk_g2s(s_srcs[stage], old_bwt + al, bytes, &s_bar[stage]); }
         else mbar_arrive(&s_bar[stage]);
     };
+    if (tid < 16) {
+        uint32_t sel = 0, nxt = 0;
+        for (int t = 0; t < 4; ++t) if (!((tid >> t) & 1)) sel |= (nxt++) << (4 * t);
+        s_spread[tid] = sel;
+    }
     if (tid == 0) {
         for (int q = 0; q < kStages; ++q) mbar_init(&s_bar[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -198,6 +194,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_bcr_merge(const uint8_t *__rest
     // inserts before each thread's 16 positions
     const int j0 = tid * kPer;
     const uint4 fl = reinterpret_cast<const uint4 *>(s_flag)[tid];
+    const uint32_t flw[4] = {fl.x, fl.y, fl.z, fl.w};
     const uint32_t my_ins = (((fl.x + fl.y + fl.z + fl.w) * 0x01010101u) >> 24);      // flag bytes are 0/1: at most 16
     uint32_t incl = my_ins;
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
@@ -205,34 +202,38 @@ __global__ void __launch_bounds__(kThreads, 4) k_bcr_merge(const uint8_t *__rest
     __syncthreads();
     uint32_t ins_before = incl - my_ins;
     for (int w = 0; w < (tid >> 5); ++w) ins_before += s_warp_ins[w];
-    // the thread's 16 output symbols in four words
+    // The thread's 16 output symbols in four words, a word at a time and without a branch per symbol (every warp holds a few
+    // inserts, so a per-symbol path taken by the threads that hold one is a path the whole warp waits for): the old symbols of a
+    // word are consecutive staged bytes; a byte permute spreads them over the positions that are not inserts (selector from a
+    // 16-entry table indexed by the word's four flags) and the inserted symbols are blended in under the flag mask.
     uint32_t o[4];
     const bool full = q0 + j0 + kPer <= m_new;
-    if (my_ins == 0 && full) {                     // plain copy of 16 staged bytes starting at an arbitrary byte offset
-        const int sb = shift + j0 - (int)ins_before;
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(s_src) + (sb >> 2);
-        const int sh = (sb & 3) * 8;
-        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-        o[0] = __funnelshift_r(w0, w1, sh); o[1] = __funnelshift_r(w1, w2, sh);
-        o[2] = __funnelshift_r(w2, w3, sh); o[3] = __funnelshift_r(w3, w4, sh);
-    } else {
+    {
         const uint4 sy = reinterpret_cast<const uint4 *>(s_sym)[tid];
-        const uint32_t syw[4] = {sy.x, sy.y, sy.z, sy.w}, flw[4] = {fl.x, fl.y, fl.z, fl.w};
+        const uint32_t syw[4] = {sy.x, sy.y, sy.z, sy.w};
         uint32_t ib = ins_before;
 #pragma unroll
-        for (int t = 0; t < kPer; ++t) {
-            const int j = j0 + t;
-            uint32_t c = 7;
-            if (q0 + j < m_new) {
-                if ((flw[t >> 2] >> (8 * (t & 3))) & 1u) { c = (syw[t >> 2] >> (8 * (t & 3))) & 0xffu; ++ib; }
-                else c = s_src[shift + (j - (int)ib)];
-            }
-            if ((t & 3) == 0) o[t >> 2] = 0;
-            o[t >> 2] |= c << (8 * (t & 3));
+        for (int w = 0; w < 4; ++w) {
+            const int sb = shift + j0 + 4 * w - (int)ib;             // staged byte of the word's first old symbol
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(s_src) + (sb >> 2);
+            const uint32_t sel = s_spread[(flw[w] * 0x01020408u) >> 24] + (uint32_t)(sb & 3) * 0x1111u;
+            const uint32_t ins = flw[w] * 0xffu;
+            o[w] = (__byte_perm(src[0], src[1], sel) & ~ins) | (syw[w] & ins);
+            ib += (flw[w] * 0x01010101u) >> 24;
+        }
+        if (!full) {                                                 // the last tile: positions past the end count as no symbol
+#pragma unroll
+            for (int t = 0; t < kPer; ++t) if (q0 + j0 + t >= m_new) o[t >> 2] |= 7u << (8 * (t & 3));
         }
     }
-    // packed A/C/G/T counts of the thread's symbols (4 x 16 bit) and their block-wide exclusive prefix
-    const uint64_t my_cnt = count_acgt(o[0]) + count_acgt(o[1]) + count_acgt(o[2]) + count_acgt(o[3]);
+    // Bit planes of the 16 symbols (symbol 4w+b at bit 8b+w of each plane) and from them one mask per base: packed A/C/G/T counts
+    // of the thread (4 x 16 bit) by population count, then their block-wide exclusive prefix
+    const uint32_t kLsb = 0x01010101u;
+    const uint32_t p0 = (o[0] & kLsb) | ((o[1] & kLsb) << 1) | ((o[2] & kLsb) << 2) | ((o[3] & kLsb) << 3);
+    const uint32_t p1 = ((o[0] >> 1) & kLsb) | (o[1] & (kLsb << 1)) | ((o[2] & (kLsb << 1)) << 1) | ((o[3] & (kLsb << 1)) << 2);
+    const uint32_t p2 = ((o[0] >> 2) & kLsb) | ((o[1] >> 1) & (kLsb << 1)) | (o[2] & (kLsb << 2)) | ((o[3] & (kLsb << 2)) << 1);
+    const uint32_t eq[4] = {p0 & ~p1 & ~p2, ~p0 & p1 & ~p2, p0 & p1 & ~p2, ~p0 & ~p1 & p2};      // A = 1, C = 2, G = 3, T = 4
+    const uint64_t my_cnt = (uint64_t)(__popc(eq[0]) | (__popc(eq[1]) << 16)) | ((uint64_t)(__popc(eq[2]) | (__popc(eq[3]) << 16)) << 32);
     uint64_t cincl = my_cnt;
     for (int q = 1; q < 32; q <<= 1) { const uint64_t v = __shfl_up_sync(0xffffffffu, cincl, q); if ((tid & 31) >= q) cincl += v; }
     if ((tid & 31) == 31) s_warp_cnt[tid >> 5] = cincl;
@@ -245,19 +246,26 @@ __global__ void __launch_bounds__(kThreads, 4) k_bcr_merge(const uint8_t *__rest
         for (int c = 0; c < 4; ++c) h.v[c] = (tot >> (16 * c)) & 0xffff;
         tile_hist[tile] = h;
     }
-    // rank of every insert among equal symbols inside the tile
+    // rank of every insert among equal symbols inside the tile: the prefix of the thread plus the equal symbols at earlier
+    // positions of its 16 (a population count under the mask of those positions)
     if (my_ins) {
-        const uint32_t flw[4] = {fl.x, fl.y, fl.z, fl.w};
-        uint64_t run = cnt_before;
         uint32_t ib = ins_before;
 #pragma unroll
-        for (int t = 0; t < kPer; ++t) {
-            const uint32_t c = (o[t >> 2] >> (8 * (t & 3))) & 0xffu;
-            if ((flw[t >> 2] >> (8 * (t & 3))) & 1u) {
-                rank_in_tile[k_lo + ib] = (c >= 1 && c <= 4) ? (uint32_t)((run >> (16 * (c - 1))) & 0xffff) : 0u;
+        for (int w = 0; w < 4; ++w) {
+            uint32_t f = flw[w];
+            while (f) {
+                const int sh = (__ffs(f) - 1) & ~7;                  // 8 x byte of the insert in the word
+                f &= f - 1;
+                const uint32_t c = (o[w] >> sh) & 0xffu;
+                uint32_t r = 0;
+                if (c >= 1 && c <= 4) {
+                    const uint32_t earlier = (kLsb * ((1u << w) - 1u)) | ((kLsb << w) & ((1u << sh) - 1u));
+                    const uint32_t e = c == 1 ? eq[0] : c == 2 ? eq[1] : c == 3 ? eq[2] : eq[3];
+                    r = (uint32_t)((cnt_before >> (16 * (c - 1))) & 0xffff) + __popc(e & earlier);
+                }
+                rank_in_tile[k_lo + ib] = r;
                 ++ib;
             }
-            if (c >= 1 && c <= 4) run += 1ull << (16 * (c - 1));
         }
     }
     // write the tile (16 bytes per thread)
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_bcr_merge(const uint8_t *__rest
 
 // LF mapping of every insert: position of the extended suffix in the next cycle's BWT (bcr.c:442 + set_bwt bookkeeping)
 __global__ void k_bcr_lf(Item *__restrict__ item, const uint8_t *__restrict__ sym, const uint32_t *__restrict__ rank_in_tile,
-                         const Vec4 *__restrict__ tile_pref, const Vec4 *__restrict__ total, uint64_t n_act, uint64_t n_seq) {
+                         const Vec4 *__restrict__ tile_pref, const Vec4 *__restrict__ total, uint64_t n_act, uint64_t n_seq, uint32_t kTile) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_act) return;
     const uint32_t a = sym[k];
@@ -324,6 +332,12 @@ static int bcr_build_device(fmg_bcr_s *b) {
     BCR_TRY(d_bwt[0].reserve(total + 64)); BCR_TRY(d_bwt[1].reserve(total + 64));         // the merge stages whole 16-byte words
     BCR_TRY(d_item[0].reserve(n_seq * sizeof(Item))); BCR_TRY(d_item[1].reserve(n_seq * sizeof(Item)));
     BCR_TRY(d_sym[0].reserve(n_seq)); BCR_TRY(d_sym[1].reserve(n_seq)); BCR_TRY(d_rank.reserve(n_seq * 4));
+    // block size of the merge pass: small blocks put more tiles in flight per SM (a tile is a chain of barriers and dependent
+    // loads: its latency, not its work, bounds the pass)
+    int merge_threads = 128;             // measured, 10 M x 150 bp: 64 -> 1.065 s, 128 -> 1.046 s, 256 -> 1.272 s
+    if (const char *e = std::getenv("FMG_BCR_THREADS")) merge_threads = std::atoi(e) >= 256 ? 256 : std::atoi(e) >= 128 ? 128 : 64;
+    const uint32_t kTile = (uint32_t)merge_threads * kPer;
+    const void *merge_kernel = merge_threads == 256 ? (const void *)k_bcr_merge<256, 4> : merge_threads == 128 ? (const void *)k_bcr_merge<128, 8> : (const void *)k_bcr_merge<64, 16>;
     const uint64_t max_tiles = (total + kTile - 1) / kTile;
     BCR_TRY(d_lo.reserve((max_tiles + 2) * 8));
     BCR_TRY(d_hist.reserve(max_tiles * sizeof(Vec4))); BCR_TRY(d_pref.reserve(max_tiles * sizeof(Vec4))); BCR_TRY(d_total.reserve(sizeof(Vec4)));
@@ -341,7 +355,7 @@ static int bcr_build_device(fmg_bcr_s *b) {
     {
         int n_sm = 0, per_sm = 0;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, b->device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bcr_merge, kThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_kernel, merge_threads, 0);
         if (n_sm > 0 && per_sm > 0) merge_grid = (uint64_t)n_sm * per_sm;
         if (const char *e = std::getenv("FMG_BCR_BLOCKS")) merge_grid = (uint64_t)n_sm * std::max(1, std::atoi(e));
     }
@@ -355,14 +369,20 @@ static int bcr_build_device(fmg_bcr_s *b) {
     for (int pos = 0; n_act > 0; ++pos) {
         const uint64_t m_new = m + n_act, n_tiles = (m_new + kTile - 1) / kTile;
         k_bcr_symbols<<<blocks_for(n_act, 256), 256>>>(items.Current(), n_act, d_seq.as<uint8_t>(), d_off.as<uint64_t>(), pos, syms.Current()); ++g_launches;
-        k_bcr_bounds<<<blocks_for(n_act, 256), 256>>>(items.Current(), n_act, n_tiles, d_lo.as<uint64_t>()); ++g_launches;
-        k_bcr_merge<<<(unsigned)std::min<uint64_t>(n_tiles, merge_grid), kThreads>>>(d_bwt[cur].as<uint8_t>(), m_new, items.Current(), syms.Current(), d_lo.as<uint64_t>(),
-                                                     d_bwt[cur ^ 1].as<uint8_t>(), d_hist.as<Vec4>(), d_rank.as<uint32_t>(), n_tiles); ++g_launches;
+        k_bcr_bounds<<<blocks_for(n_act, 256), 256>>>(items.Current(), n_act, n_tiles, d_lo.as<uint64_t>(), kTile); ++g_launches;
+        {
+            const uint8_t *a_old = d_bwt[cur].as<uint8_t>(); uint64_t a_m = m_new; const Item *a_item = items.Current(); const uint8_t *a_sym = syms.Current();
+            const uint64_t *a_lo = d_lo.as<uint64_t>(); uint8_t *a_new = d_bwt[cur ^ 1].as<uint8_t>(); Vec4 *a_hist = d_hist.as<Vec4>(); uint32_t *a_rank = d_rank.as<uint32_t>();
+            uint64_t a_tiles = n_tiles;
+            void *kargs[] = {&a_old, &a_m, &a_item, &a_sym, &a_lo, &a_new, &a_hist, &a_rank, &a_tiles};
+            BCR_TRY(cudaLaunchKernel(merge_kernel, dim3((unsigned)std::min<uint64_t>(n_tiles, merge_grid)), dim3(merge_threads), kargs, 0, nullptr));
+            ++g_launches;
+        }
         size_t need = d_tmp.cap;
         Vec4 zero{};
         BCR_TRY(cub::DeviceScan::ExclusiveScan(d_tmp.p, need, d_hist.as<Vec4>(), d_pref.as<Vec4>(), Vec4Add(), zero, (int64_t)n_tiles));
         k_bcr_total<<<1, 32>>>(d_hist.as<Vec4>(), d_pref.as<Vec4>(), n_tiles, d_total.as<Vec4>()); ++g_launches;
-        k_bcr_lf<<<blocks_for(n_act, 256), 256>>>(items.Current(), syms.Current(), d_rank.as<uint32_t>(), d_pref.as<Vec4>(), d_total.as<Vec4>(), n_act, n_seq); ++g_launches;
+        k_bcr_lf<<<blocks_for(n_act, 256), 256>>>(items.Current(), syms.Current(), d_rank.as<uint32_t>(), d_pref.as<Vec4>(), d_total.as<Vec4>(), n_act, n_seq, kTile); ++g_launches;
         // next order = stable partition by the inserted symbol; finished sequences (symbol 0) sort first and are dropped
         need = d_tmp.cap;
         BCR_TRY(cub::DeviceRadixSort::SortPairs(d_tmp.p, need, syms, items, (int64_t)n_act, 0, 3));

@@ -16,6 +16,7 @@ ap.add_argument("--len", type=int, default=150)
 ap.add_argument("--cov", type=float, default=30.0)
 ap.add_argument("--ref-reads", type=int, default=500000)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--iters", type=int, default=4)
 ap.add_argument("--fmd", action="store_true", help="also time BCR + RLD encoding on the GPU (`ropebwt | recode` in one step)")
 a = ap.parse_args()
 L = a.len | 1 if False else a.len
@@ -24,11 +25,14 @@ reads = fb.synth_reads(62, genome, a.reads, L, 0.0)
 rc = (5 - reads[:, ::-1]).astype(np.uint8)
 both = np.empty((2 * a.reads, L), np.uint8); both[0::2] = reads; both[1::2] = rc       # r, rc(r), ... (ropebwt.c:30-44); no palindromes at random
 res = {"reads": a.reads, "len": L, "symbols": int(2 * a.reads * (L + 1))}
-for it in range(2):
+builds = []
+for it in range(a.iters):
     b = fb.Bcr(0)
     t = time.time(); b.append_batch(both); t_app = time.time() - t
-    t = time.time(); b.build(); t_build = time.time() - t
-    if it == 1:
+    t = time.time(); b.build(); builds.append(time.time() - t)
+    if it == a.iters - 1:
+        t_build = min(builds[1:] or builds)          # the first build pays for the allocations; boxes are shared, so the best of the rest
+        res["build_s_all"] = builds
         res.update({"append_s": t_app, "build_s": t_build, "symbols_per_s": res["symbols"] / t_build, "reads_per_s": a.reads / t_build})
         if a.check:
             res["equals_suffix_sort"] = bool(np.array_equal(b.bwt(), fb.fm_build_bwt(fb.fmd_text(reads), 0)))
