@@ -44,7 +44,7 @@ namespace {
         }                                                                                               \
     } while (0)
 
-constexpr int kPer = 16;             // output symbols per thread of the merge pass: one 16-byte vector; a tile = kPer x block size symbols
+// the merge pass: kPer output symbols per thread (16 or 32: one or two 16-byte vectors), a tile = kPer x block size symbols
 
 struct Vec4 { uint64_t v[4]; };      // occurrences of A,C,G,T
 struct Vec4Add { __host__ __device__ Vec4 operator()(const Vec4 &a, const Vec4 &b) const { Vec4 r; for (int i = 0; i < 4; ++i) r.v[i] = a.v[i] + b.v[i]; return r; } };
@@ -125,11 +125,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 
 // PERSISTENT: blocks walk over the tiles (blockIdx.x, + gridDim.x, ...); thread 0 keeps kStages bulk copies of old symbols in
 // flight per block, each completing on its own mbarrier.
-template <int kThreads, int kMinBlocks>
+template <int kThreads, int kMinBlocks, int kPer>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_bcr_merge(const uint8_t *__restrict__ old_bwt, uint64_t m_new, const Item *__restrict__ item,
                                                         const uint8_t *__restrict__ sym, const uint64_t *__restrict__ tile_lo, uint8_t *__restrict__ new_bwt,
                                                         Vec4 *__restrict__ tile_hist, uint32_t *__restrict__ rank_in_tile, uint64_t n_tiles) {
-    constexpr int kTile = kThreads * kPer;
+    constexpr int kTile = kThreads * kPer, kWords = kPer / 4, kVecs = kPer / 16;
+    static_assert(kPer == 16 || kPer == 32, "the bit planes below hold one bit per word in every byte");
     __shared__ __align__(16) uint8_t s_sym[kTile];
     __shared__ __align__(128) uint8_t s_srcs[kStages][kTile + 64];
     __shared__ __align__(16) uint8_t s_flag[kTile];
@@ -178,7 +179,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_bcr_merge(const uint8_
     const uint64_t q0 = tile * kTile;
     range_of(tile + 2 * stride, nn_lo, nn_hi);                          // requested now, used two tiles on
     if (n_lo + tid < n_hi) { nx_f = item[n_lo + tid].f; nx_s = sym[n_lo + tid]; }      // the next tile's insert of this thread
-    reinterpret_cast<uint4 *>(s_flag)[tid] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int v = 0; v < kVecs; ++v) reinterpret_cast<uint4 *>(s_flag)[tid * kVecs + v] = make_uint4(0, 0, 0, 0);
     // the old symbols this tile keeps
     const uint64_t src_lo = q0 - k_lo;            // old symbols before this tile
     const uint64_t a0 = src_lo & ~15ull;
@@ -191,11 +193,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_bcr_merge(const uint8_
     }
     mbar_wait(&s_bar[stage], (uint32_t)((it / kStages) & 1));        // the bulk copy of this tile's old symbols has landed
     __syncthreads();
-    // inserts before each thread's 16 positions
+    // inserts before each thread's kPer positions
     const int j0 = tid * kPer;
-    const uint4 fl = reinterpret_cast<const uint4 *>(s_flag)[tid];
-    const uint32_t flw[4] = {fl.x, fl.y, fl.z, fl.w};
-    const uint32_t my_ins = (((fl.x + fl.y + fl.z + fl.w) * 0x01010101u) >> 24);      // flag bytes are 0/1: at most 16
+    uint32_t flw[kWords], syw[kWords];
+#pragma unroll
+    for (int v = 0; v < kVecs; ++v) {
+        const uint4 fl = reinterpret_cast<const uint4 *>(s_flag)[tid * kVecs + v], sy = reinterpret_cast<const uint4 *>(s_sym)[tid * kVecs + v];
+        flw[4 * v] = fl.x; flw[4 * v + 1] = fl.y; flw[4 * v + 2] = fl.z; flw[4 * v + 3] = fl.w;
+        syw[4 * v] = sy.x; syw[4 * v + 1] = sy.y; syw[4 * v + 2] = sy.z; syw[4 * v + 3] = sy.w;
+    }
+    uint32_t fl_sum = 0;
+#pragma unroll
+    for (int w = 0; w < kWords; ++w) fl_sum += flw[w];
+    const uint32_t my_ins = (fl_sum * 0x01010101u) >> 24;                // flag bytes are 0/1: at most kWords per byte lane
     uint32_t incl = my_ins;
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
     if ((tid & 31) == 31) s_warp_ins[tid >> 5] = incl;
@@ -206,14 +216,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_bcr_merge(const uint8_
     // inserts, so a per-symbol path taken by the threads that hold one is a path the whole warp waits for): the old symbols of a
     // word are consecutive staged bytes; a byte permute spreads them over the positions that are not inserts (selector from a
     // 16-entry table indexed by the word's four flags) and the inserted symbols are blended in under the flag mask.
-    uint32_t o[4];
+    uint32_t o[kWords];
     const bool full = q0 + j0 + kPer <= m_new;
     {
-        const uint4 sy = reinterpret_cast<const uint4 *>(s_sym)[tid];
-        const uint32_t syw[4] = {sy.x, sy.y, sy.z, sy.w};
         uint32_t ib = ins_before;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+        for (int w = 0; w < kWords; ++w) {
             const int sb = shift + j0 + 4 * w - (int)ib;             // staged byte of the word's first old symbol
             const uint32_t *src = reinterpret_cast<const uint32_t *>(s_src) + (sb >> 2);
             const uint32_t sel = s_spread[(flw[w] * 0x01020408u) >> 24] + (uint32_t)(sb & 3) * 0x1111u;
@@ -226,12 +234,16 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_bcr_merge(const uint8_
             for (int t = 0; t < kPer; ++t) if (q0 + j0 + t >= m_new) o[t >> 2] |= 7u << (8 * (t & 3));
         }
     }
-    // Bit planes of the 16 symbols (symbol 4w+b at bit 8b+w of each plane) and from them one mask per base: packed A/C/G/T counts
-    // of the thread (4 x 16 bit) by population count, then their block-wide exclusive prefix
+    // Bit planes of the thread's symbols (symbol 4w+b at bit 8b+w of each plane) and from them one mask per base: packed A/C/G/T
+    // counts of the thread (4 x 16 bit) by population count, then their block-wide exclusive prefix
     const uint32_t kLsb = 0x01010101u;
-    const uint32_t p0 = (o[0] & kLsb) | ((o[1] & kLsb) << 1) | ((o[2] & kLsb) << 2) | ((o[3] & kLsb) << 3);
-    const uint32_t p1 = ((o[0] >> 1) & kLsb) | (o[1] & (kLsb << 1)) | ((o[2] & (kLsb << 1)) << 1) | ((o[3] & (kLsb << 1)) << 2);
-    const uint32_t p2 = ((o[0] >> 2) & kLsb) | ((o[1] >> 1) & (kLsb << 1)) | (o[2] & (kLsb << 2)) | ((o[3] & (kLsb << 2)) << 1);
+    uint32_t p0 = 0, p1 = 0, p2 = 0;
+#pragma unroll
+    for (int w = 0; w < kWords; ++w) {
+        p0 |= (o[w] & kLsb) << w;
+        p1 |= w >= 1 ? (o[w] & (kLsb << 1)) << (w - 1) : (o[w] >> 1) & kLsb;
+        p2 |= w >= 2 ? (o[w] & (kLsb << 2)) << (w - 2) : (o[w] >> (2 - w)) & (kLsb << w);
+    }
     const uint32_t eq[4] = {p0 & ~p1 & ~p2, ~p0 & p1 & ~p2, p0 & p1 & ~p2, ~p0 & ~p1 & p2};      // A = 1, C = 2, G = 3, T = 4
     const uint64_t my_cnt = (uint64_t)(__popc(eq[0]) | (__popc(eq[1]) << 16)) | ((uint64_t)(__popc(eq[2]) | (__popc(eq[3]) << 16)) << 32);
     uint64_t cincl = my_cnt;
@@ -251,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_bcr_merge(const uint8_
     if (my_ins) {
         uint32_t ib = ins_before;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+        for (int w = 0; w < kWords; ++w) {
             uint32_t f = flw[w];
             while (f) {
                 const int sh = (__ffs(f) - 1) & ~7;                  // 8 x byte of the insert in the word
@@ -269,7 +281,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_bcr_merge(const uint8_
         }
     }
     // write the tile (16 bytes per thread)
-    if (full) *reinterpret_cast<uint4 *>(new_bwt + q0 + j0) = make_uint4(o[0], o[1], o[2], o[3]);
+    if (full) {
+#pragma unroll
+        for (int v = 0; v < kVecs; ++v) *reinterpret_cast<uint4 *>(new_bwt + q0 + j0 + 16 * v) = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+    }
     else for (int t = 0; t < kPer; ++t) if (q0 + j0 + t < m_new) new_bwt[q0 + j0 + t] = (uint8_t)(o[t >> 2] >> (8 * (t & 3)));
     __syncthreads();                              // every thread is done with this stage's bytes, the flags and the warp sums
     if (tid == 0) {
@@ -334,10 +349,15 @@ static int bcr_build_device(fmg_bcr_s *b) {
     BCR_TRY(d_sym[0].reserve(n_seq)); BCR_TRY(d_sym[1].reserve(n_seq)); BCR_TRY(d_rank.reserve(n_seq * 4));
     // block size of the merge pass: small blocks put more tiles in flight per SM (a tile is a chain of barriers and dependent
     // loads: its latency, not its work, bounds the pass)
-    int merge_threads = 128;             // measured, 10 M x 150 bp: 64 -> 1.065 s, 128 -> 1.046 s, 256 -> 1.272 s
+    // measured (10 M x 150 bp, best of three builds on a shared box): 64 x 32 -> 0.77 s, 64 x 16 -> 0.82 s, 128 x 16 -> 1.01 s, 128 x 32 -> 1.04 s
+    int merge_threads = 64, merge_per = 32;
     if (const char *e = std::getenv("FMG_BCR_THREADS")) merge_threads = std::atoi(e) >= 256 ? 256 : std::atoi(e) >= 128 ? 128 : 64;
-    const uint32_t kTile = (uint32_t)merge_threads * kPer;
-    const void *merge_kernel = merge_threads == 256 ? (const void *)k_bcr_merge<256, 4> : merge_threads == 128 ? (const void *)k_bcr_merge<128, 8> : (const void *)k_bcr_merge<64, 16>;
+    if (const char *e = std::getenv("FMG_BCR_PER")) merge_per = std::atoi(e) >= 32 ? 32 : 16;
+    const void *merge_kernel = merge_per == 16
+        ? (merge_threads == 256 ? (const void *)k_bcr_merge<256, 4, 16> : merge_threads == 128 ? (const void *)k_bcr_merge<128, 8, 16> : (const void *)k_bcr_merge<64, 16, 16>)
+        : (merge_threads >= 128 ? (const void *)k_bcr_merge<128, 5, 32> : (const void *)k_bcr_merge<64, 10, 32>);       // static shared memory: no 8192-symbol tile
+    if (merge_per == 32 && merge_threads > 128) merge_threads = 128;
+    const uint32_t kTile = (uint32_t)(merge_threads * merge_per);
     const uint64_t max_tiles = (total + kTile - 1) / kTile;
     BCR_TRY(d_lo.reserve((max_tiles + 2) * 8));
     BCR_TRY(d_hist.reserve(max_tiles * sizeof(Vec4))); BCR_TRY(d_pref.reserve(max_tiles * sizeof(Vec4))); BCR_TRY(d_total.reserve(sizeof(Vec4)));

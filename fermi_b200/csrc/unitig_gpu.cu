@@ -71,6 +71,7 @@ struct G {
     uint64_t n;
     int min_match;
     uint32_t *succ, *pred, *row_of_rank, *tail_of;
+    uint2 *step;                // (succ, rbeg) of every row in one 8-byte record: what a walk along a chain reads per read
     uint32_t *flags;
     unsigned long long *counts;     // [0] nodes, [1] nodes reachable from a head (they differ when the graph has a cycle)
 };
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256) k_links(G g) {
     uint32_t s = kNone;
     const bool node = in && is_node(p, v, g.min_match);
     if (node && links(g, p)) s = (uint32_t)p.nx0;
-    if (in) g.succ[v] = s;
+    if (in) { g.succ[v] = s; g.step[v] = make_uint2(s, (uint32_t)p.rbeg); }
     const int c = __syncthreads_count(node);
     if (threadIdx.x == 0 && c) atomicAdd(g.counts, (unsigned long long)c);
 }
@@ -115,21 +116,61 @@ __global__ void __launch_bounds__(256) k_pred(G g) {
     if (f) atomicOr(g.flags, f);
 }
 
-// pointer jumping along pred: ptr -> head, dn = reads before this one in the chain, db = start of the read in the consensus.
-// The three travel as ONE 16-byte record: a round is one random 16-byte gather per read instead of three.
+// Rank of every read in its chain: head, dn = reads before this one, db = start of the read in the consensus.
+//
+// Pointer jumping over all reads costs a random gather per read and round (log2 of the longest chain: 14 rounds on 10x reads);
+// here it runs on SPLITTERS only, list ranking with linear work:
+//   k_rank_init    splitters = the heads and one read in 16 by a hash of its row; each gets an ordinal
+//   k_rank_walk    a thread per splitter follows succ up to the next splitter (16 reads on average, one 8-byte gather each): the
+//                  reads passed get (ordinal, dn, db) relative to the splitter, the splitter reached gets its jump record
+//   k_jump         pointer jumping over the splitters (a 16th of the reads, L2-resident records)
+//   k_rank_final   every read adds the totals of its splitter
+// Reads on a cycle without a head are either never reached by a walk or keep the jumps from converging; both end in the host walk
+// (the count check after k_select, the round limit).
 struct alignas(16) Jmp { uint32_t ptr, dn; uint64_t db; };
 __device__ __forceinline__ Jmp ld_jmp(const Jmp *p) { const uint4 a = *reinterpret_cast<const uint4 *>(p); Jmp j; j.ptr = a.x; j.dn = a.y; j.db = (uint64_t)a.w << 32 | a.z; return j; }
 __device__ __forceinline__ void st_jmp(Jmp *p, const Jmp &j) { *reinterpret_cast<uint4 *>(p) = make_uint4(j.ptr, j.dn, (uint32_t)j.db, (uint32_t)(j.db >> 32)); }
+__device__ __forceinline__ bool hashed_splitter(uint32_t v) { return (v * 0x9E3779B1u) >> 28 == 0; }
 
-__global__ void __launch_bounds__(256) k_jump_init(G g, Jmp *J) {
+// rec[v]: (kNone, 0, 0) for a read that waits for a walk, (ordinal, 0, 0) for a splitter; reads without links are their own chain
+__global__ void __launch_bounds__(256) k_rank_init(G g, Jmp *rec, uint32_t *list, Jmp *sj, unsigned long long *n_split) {
     const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= g.n) return;
-    const uint32_t p = g.pred[v];
-    Jmp j;
-    j.ptr = p == kNone ? (uint32_t)v : p;
-    j.dn = p == kNone ? 0u : 1u;
-    j.db = p == kNone ? 0ull : (uint64_t)g.pack[p].rbeg;
-    st_jmp(J + v, j);
+    const bool in = v < g.n;
+    bool linked = false, split = false;
+    if (in) {
+        const uint32_t p = g.pred[v];
+        linked = p != kNone || g.succ[v] != kNone;
+        split = linked && (p == kNone || hashed_splitter((uint32_t)v));
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, split);
+    uint32_t base = 0;
+    if ((threadIdx.x & 31) == 0 && m) base = (uint32_t)atomicAdd(n_split, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!in) return;
+    Jmp r; r.ptr = kNone; r.dn = 0; r.db = 0;
+    if (split) {
+        const uint32_t i = base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+        list[i] = (uint32_t)v;
+        Jmp j; j.ptr = i; j.dn = 0; j.db = 0;       // a head; a hashed splitter is overwritten by the walk that reaches it
+        st_jmp(sj + i, j);
+        r.ptr = i;
+    }
+    if (linked) st_jmp(rec + v, r);
+}
+
+__global__ void __launch_bounds__(256) k_rank_walk(G g, uint64_t n_split, const uint32_t *__restrict__ list, Jmp *rec, Jmp *sj) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_split) return;
+    uint32_t cur = list[i];
+    Jmp r; r.ptr = (uint32_t)i; r.dn = 0; r.db = 0;
+    for (;;) {
+        const uint2 s = g.step[cur];
+        if (s.x == kNone) break;                    // the tail of the chain
+        ++r.dn; r.db += s.y;
+        cur = s.x;
+        if (hashed_splitter(cur)) { st_jmp(sj + rec[cur].ptr, r); break; }       // its ordinal was stored by k_rank_init
+        st_jmp(rec + cur, r);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_jump(uint64_t n, const Jmp *__restrict__ J, Jmp *__restrict__ J2, uint32_t *flags) {
@@ -144,11 +185,20 @@ __global__ void __launch_bounds__(256) k_jump(uint64_t n, const Jmp *__restrict_
     if (b.ptr != a.ptr) atomicOr(flags, (uint32_t)UGF_CHANGED);
 }
 
-__global__ void __launch_bounds__(256) k_jump_unpack(uint64_t n, const Jmp *__restrict__ J, uint32_t *__restrict__ head, uint32_t *__restrict__ dn, uint64_t *__restrict__ db) {
+__global__ void __launch_bounds__(256) k_rank_final(G g, const Jmp *__restrict__ rec, const Jmp *__restrict__ sj, const uint32_t *__restrict__ list,
+                                                   uint32_t *__restrict__ head, uint32_t *__restrict__ dn, uint64_t *__restrict__ db) {
     const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n) return;
-    const Jmp a = ld_jmp(J + v);
-    head[v] = a.ptr; dn[v] = a.dn; db[v] = a.db;
+    if (v >= g.n) return;
+    uint32_t h = (uint32_t)v, n = 0;
+    uint64_t b = 0;
+    if (g.pred[v] != kNone || g.succ[v] != kNone) {
+        const Jmp r = ld_jmp(rec + v);
+        if (r.ptr != kNone) {                       // kNone: no walk came by (a cycle without a splitter); the read stays its own head
+            const Jmp j = ld_jmp(sj + r.ptr);
+            h = list[j.ptr]; n = r.dn + j.dn; b = r.db + j.db;
+        }
+    }
+    head[v] = h; dn[v] = n; db[v] = b;
 }
 
 __global__ void __launch_bounds__(256) k_tails(G g, const uint32_t *__restrict__ head) {
@@ -402,9 +452,12 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
     if (!idx->ovc) idx->ovc = new fmg_ovcache_s;
     fmg_ovcache_s &H = *idx->ovc;
     cudaStream_t st = nullptr;                       // legacy default stream: ordered after the pass (which synchronised its streams)
-    Dev d_succ, d_pred, d_row, d_tail, d_flags, d_jmp[2], d_ptr, d_dn, d_db, d_cnt, d_len, d_nei, d_tmp, d_meta, d_unei, d_useq, d_diff;
+    Dev d_succ, d_pred, d_row, d_tail, d_step, d_flags, d_jmp[2], d_rec, d_list, d_ptr, d_dn, d_db, d_cnt, d_len, d_nei, d_tmp, d_meta, d_unei, d_useq, d_diff;
     UG_TRY(d_succ.alloc(n * 4)); UG_TRY(d_pred.alloc(n * 4)); UG_TRY(d_row.alloc(n * 4)); UG_TRY(d_tail.alloc(n * 4)); UG_TRY(d_flags.alloc(64));
+    // jump records of the splitters (a 16th of the linked reads plus the heads: n / 2 bounds them, a chain has two reads or more and
+    // the hash takes a 16th) -- sized for the worst case all the same
     for (int k = 0; k < 2; ++k) UG_TRY(d_jmp[k].alloc(n * sizeof(Jmp)));
+    UG_TRY(d_rec.alloc(n * sizeof(Jmp))); UG_TRY(d_list.alloc(n * 4)); UG_TRY(d_step.alloc(n * 8));
     UG_TRY(d_ptr.alloc(n * 4)); UG_TRY(d_dn.alloc(n * 4)); UG_TRY(d_db.alloc(n * 8));
     UG_TRY(d_cnt.alloc((n + 1) * 8)); UG_TRY(d_len.alloc((n + 1) * 8)); UG_TRY(d_nei.alloc((n + 1) * 8));
     UG_TRY(H.ctrl.need(64));
@@ -413,23 +466,31 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
     g.pack = static_cast<const OvPack *>(D.pack); g.spill = static_cast<const uint4 *>(D.spill); g.ext = D.ext; g.rank_of_row = D.rank;
     g.n = n; g.min_match = min_match;
     g.succ = d_succ.as<uint32_t>(); g.pred = d_pred.as<uint32_t>(); g.row_of_rank = d_row.as<uint32_t>(); g.tail_of = d_tail.as<uint32_t>();
+    g.step = d_step.as<uint2>();
     g.flags = d_flags.as<uint32_t>(); g.counts = d_flags.as<unsigned long long>() + 1;
     UG_TRY(cudaMemsetAsync(d_flags.p, 0, 64, st));
     UG_TRY(cudaMemsetAsync(d_pred.p, 0xff, n * 4, st));
     UG_TRY(cudaMemsetAsync(d_tail.p, 0xff, n * 4, st));
     k_links<<<nblk(n), 256, 0, st>>>(g);
     k_pred<<<nblk(n), 256, 0, st>>>(g);
-    k_jump_init<<<nblk(n), 256, 0, st>>>(g, d_jmp[0].as<Jmp>());
+    k_rank_init<<<nblk(n), 256, 0, st>>>(g, d_rec.as<Jmp>(), d_list.as<uint32_t>(), d_jmp[0].as<Jmp>(), g.counts + 2);
     g_launches += 3;
     UG_TRY(cudaGetLastError());
     int cur = 0, rounds = 0;
+    uint64_t n_split = 0;
     for (;; ++rounds) {
-        UG_TRY(cudaMemcpyAsync(h_flags, d_flags.p, 4, cudaMemcpyDeviceToHost, st));
+        UG_TRY(cudaMemcpyAsync(h_flags, d_flags.p, 32, cudaMemcpyDeviceToHost, st));
         UG_TRY(cudaStreamSynchronize(st));
         const uint32_t f = *h_flags;
         if (f & (UGF_NONINJ | UGF_ASYM | UGF_NOTNODE)) {
             if (fmg_verbose >= 3) std::fprintf(stderr, "[M::%s] irregular link graph (flags %x): falling back to the host walk\n", __func__, f);
             return 1;
+        }
+        if (rounds == 0) {
+            n_split = reinterpret_cast<const uint64_t *>(h_flags)[3];      // counts[2]
+            if (n_split == 0) break;                                       // no links at all: every read is its own chain
+            k_rank_walk<<<nblk(n_split), 256, 0, st>>>(g, n_split, d_list.as<uint32_t>(), d_rec.as<Jmp>(), d_jmp[0].as<Jmp>());
+            ++g_launches;
         }
         if (rounds > 0 && !(f & UGF_CHANGED)) break;
         if (rounds >= 40) {
@@ -439,13 +500,13 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
         UG_TRY(cudaMemsetAsync(d_flags.p, 0, 4, st));
         // two jumps per flag read-back (a converged jump is the identity)
         for (int r = 0; r < 2; ++r) {
-            k_jump<<<nblk(n), 256, 0, st>>>(n, d_jmp[cur].as<Jmp>(), d_jmp[cur ^ 1].as<Jmp>(), g.flags);
+            k_jump<<<nblk(n_split), 256, 0, st>>>(n_split, d_jmp[cur].as<Jmp>(), d_jmp[cur ^ 1].as<Jmp>(), g.flags);
             ++g_launches;
             cur ^= 1;
         }
         UG_TRY(cudaGetLastError());
     }
-    k_jump_unpack<<<nblk(n), 256, 0, st>>>(n, d_jmp[cur].as<Jmp>(), d_ptr.as<uint32_t>(), d_dn.as<uint32_t>(), d_db.as<uint64_t>());
+    k_rank_final<<<nblk(n), 256, 0, st>>>(g, d_rec.as<Jmp>(), d_jmp[cur].as<Jmp>(), d_list.as<uint32_t>(), d_ptr.as<uint32_t>(), d_dn.as<uint32_t>(), d_db.as<uint64_t>());
     ++g_launches;
     const uint32_t *head = d_ptr.as<uint32_t>(), *dn = d_dn.as<uint32_t>();
     const uint64_t *db = d_db.as<uint64_t>();
