@@ -1,6 +1,8 @@
 /* Plain C99 client of include/fermi_b200.h: proves that the header is valid C, that every declared entry point links, and
  * exercises the host-only part of the C-ABI (container build / info / decode / dump) -- what fermi's own C mains would do.
- * Built and run by tests/test_host_logic.py with gcc; no GPU needed. */
+ * Built and run by tests/test_host_logic.py with gcc; no GPU needed.  With a second argument "gpu" it also drives the device
+ * entry points the way a C main would (upload, fmg_rank1a_batch against counts taken from the BWT here, fmg_check_rank,
+ * fmg_backward_search_batch) and fails if no device answers: tests/test_gpu_parity.py runs that on the GPU box. */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -39,6 +41,30 @@ int main(int argc, char *argv[])
 	if (info[0] != sizeof(bwt) || info[1] != 3 || info[2] != 4 || info[6] != 1) return 4;       /* mcnt: total, $, A, ..., N */
 	if (fmg_fmd_decode_bwt(e, back) != (int64_t)sizeof(bwt) || memcmp(back, bwt, sizeof(bwt)) != 0) return 5;
 	if (argc > 1 && fmg_fmd_dump(e, argv[1]) != 0) return 6;
+	if (argc > 2 && strcmp(argv[2], "gpu") == 0) {
+		fmg_index_t *idx = fmg_index_upload(e, 0);
+		uint64_t k[sizeof(bwt)], ok[6 * sizeof(bwt)], cnt[6] = {0, 0, 0, 0, 0, 0}, n_bad = 1, first_bad = 0;
+		int32_t sym[sizeof(bwt)];
+		/* the read "3" (G) as nt6: its interval is the G bucket, C(G) = #$ + #A + #C, size = #G */
+		const uint8_t q[1] = {3};
+		const uint64_t off[2] = {0, 1};
+		uint64_t sa_beg = 0, sa_end = 0, size = 0;
+		int c;
+		if (idx == 0) return 20;
+		if (fmg_index_device(idx) != 0 || fmg_index_bytes(idx) == 0) return 21;
+		for (i = 0; i < sizeof(bwt); ++i) k[i] = i;
+		if (fmg_rank1a_batch(idx, (int64_t)sizeof(bwt), k, ok, sym) != 0) return 22;
+		for (i = 0; i < sizeof(bwt); ++i) {             /* rld_rank1a: counts of BWT[0..k] and the symbol at k */
+			++cnt[bwt[i]];
+			if (sym[i] != bwt[i]) return 23;
+			for (c = 0; c < 6; ++c) if (ok[6 * i + c] != cnt[c]) return 24;
+		}
+		if (fmg_check_rank(idx, &n_bad, &first_bad) != 0 || n_bad != 0) return 25;
+		if (fmg_backward_search_batch(idx, 1, q, off, &sa_beg, &sa_end, &size) != 0) return 26;
+		if (size != cnt[3] || sa_beg != cnt[0] + cnt[1] + cnt[2]) return 27;
+		fmg_index_free(idx);
+		printf("gpu ok: %d ranks, %ld kernel launches\n", (int)sizeof(bwt), (long)fmg_launch_count());
+	}
 	fmg_fmd_destroy(e);
 	if (argc > 1) {                                  /* the file reads back to the same container */
 		e = fmg_fmd_restore(argv[1]);

@@ -792,3 +792,19 @@ def test_full_size_smem_properties(fb, oracle, tmp_path):
     b, e, sz = fb.fm_backward_search(idx, sub, sub_off)
     assert np.array_equal(b, rec["x0"][pick]) and np.array_equal(sz, rec["x2"][pick])
     idx.close()
+
+
+def test_plain_c_client_drives_the_device(tmp_path):
+    """tests/c_abi/abi_check.c with "gpu": a C99 program (no Python, no torch in the process) uploads an index and calls
+    fmg_rank1a_batch / fmg_check_rank / fmg_backward_search_batch through include/fermi_b200.h; the expected counts are taken
+    from the BWT inside the C program."""
+    import subprocess
+    src = os.path.join(H.ROOT, "tests", "c_abi", "abi_check.c")
+    exe = str(tmp_path / "abi_check")
+    libdir = os.path.join(H.ROOT, "fermi_b200", "lib")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + os.path.join(H.ROOT, "include"), "-o", exe, src,
+                    "-L" + libdir, "-lfermi_b200", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe, str(tmp_path / "t.fmd"), "gpu"], stdout=subprocess.PIPE)
+    assert r.returncode == 0, "abi_check exit %d" % r.returncode
+    out = r.stdout.decode()
+    assert "gpu ok: 18 ranks" in out and " 0 kernel launches" not in out, out
