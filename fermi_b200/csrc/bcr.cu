@@ -24,7 +24,9 @@
 #include <vector>
 #include <memory>
 #include <chrono>
+#include <thread>
 #include "fmd_host.hpp"
+#include "dev_pool.hpp"
 #include "../../include/fermi_b200.h"
 
 int fmg_rld_encode_device(const uint8_t *d_bwt, uint64_t n, fmg::FmdImage *out);     // rld_enc.cu
@@ -50,19 +52,63 @@ struct Vec4 { uint64_t v[4]; };      // occurrences of A,C,G,T
 struct Vec4Add { __host__ __device__ Vec4 operator()(const Vec4 &a, const Vec4 &b) const { Vec4 r; for (int i = 0; i < 4; ++i) r.v[i] = a.v[i] + b.v[i]; return r; } };
 struct Item { uint64_t f; uint32_t id; uint32_t pad; };      // (position of the suffix in the current BWT, sequence)
 
+// Device buffers come from the pool the overlap pass uses (dev_pool.hpp): a build allocates and frees tens of gigabytes, and
+// cudaMalloc / cudaFree of those cost as much as several cycles.  fmg_release_cache hands the pool back to the driver.
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
-    ~DevBuf() { cudaFree(p); }
+    int dev = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) fmg::g_pool.put(p, cap, dev); p = nullptr; cap = 0; }
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        cudaFree(p); p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
-        if (e == cudaSuccess) cap = bytes;
-        return e;
+        release();
+        cudaGetDevice(&dev);
+        return fmg::g_pool.get(bytes ? bytes : 1, dev, &p, &cap);
     }
     template <class T> T *as() const { return static_cast<T *>(p); }
 };
+
+// Pageable host memory -> device through pinned staging buffers filled by several threads: a plain cudaMemcpy of pageable memory is
+// one thread copying into the driver's staging buffer (~10 GB/s); the reads of a build are gigabytes.
+struct Stager {
+    static constexpr int kThreads = 4, kBufs = 2;
+    static constexpr size_t kChunk = 32u << 20;
+    uint8_t *pin = nullptr;                  // kept until the process exits
+    std::mutex lock;
+    cudaError_t upload(void *dst, const void *src, size_t bytes) {
+        if (bytes < 4 * kChunk) return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+        std::lock_guard<std::mutex> guard(lock);
+        if (!pin) { const cudaError_t e = cudaHostAlloc((void **)&pin, kThreads * kBufs * kChunk, cudaHostAllocDefault); if (e != cudaSuccess) { pin = nullptr; cudaGetLastError(); return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice); } }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const size_t n_chunks = (bytes + kChunk - 1) / kChunk;
+        std::atomic<int> fail{0};
+        auto work = [&](int t) {
+            cudaSetDevice(dev);
+            cudaStream_t st; cudaEvent_t ev[kBufs];
+            if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { fail = 1; return; }
+            for (auto &e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            int k = 0;
+            for (size_t c = (size_t)t; c < n_chunks && !fail; c += kThreads, ++k) {
+                uint8_t *buf = pin + ((size_t)t * kBufs + (k % kBufs)) * kChunk;
+                const size_t o = c * kChunk, len = std::min(kChunk, bytes - o);
+                if (k >= kBufs) cudaEventSynchronize(ev[k % kBufs]);                  // the copy that last used this buffer
+                std::memcpy(buf, static_cast<const uint8_t *>(src) + o, len);
+                if (cudaMemcpyAsync(static_cast<uint8_t *>(dst) + o, buf, len, cudaMemcpyHostToDevice, st) != cudaSuccess) fail = 1;
+                cudaEventRecord(ev[k % kBufs], st);
+            }
+            if (cudaStreamSynchronize(st) != cudaSuccess) fail = 1;
+            for (auto &e : ev) cudaEventDestroy(e);
+            cudaStreamDestroy(st);
+        };
+        std::vector<std::thread> th;
+        for (int t = 0; t < kThreads; ++t) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+        return fail ? cudaErrorUnknown : cudaSuccess;
+    }
+};
+Stager g_stager;
 
 // symbol each active sequence inserts in cycle `pos`: its base at distance pos from the end, 0 when exhausted (bcr.c:430)
 __global__ void k_bcr_symbols(const Item *__restrict__ item, uint64_t n_act, const uint8_t *__restrict__ seq, const uint64_t *__restrict__ off,
@@ -72,6 +118,20 @@ __global__ void k_bcr_symbols(const Item *__restrict__ item, uint64_t n_act, con
     const uint32_t id = item[k].id;
     const uint64_t b = off[id], e = off[id + 1];
     sym[k] = (uint64_t)pos < e - b ? seq[e - 1 - pos] : 0;
+}
+
+// The same from the sequences transposed by cycle (what bcr_append keeps, bcr.c:358-376): col[pos][id] = the base of sequence id
+// at distance pos from its end, 0 past its start.  A cycle then gathers single bytes from ONE row of n_seq bytes (L2-resident up to
+// ~10^8 sequences) instead of an offset pair and a byte from the whole read set.
+__global__ void k_bcr_transpose(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ off, uint64_t n_seq, int max_len, uint8_t *__restrict__ col) {
+    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_seq) return;
+    const uint64_t b = off[id], e = off[id + 1];
+    for (int pos = 0; pos < max_len; ++pos) col[(uint64_t)pos * n_seq + id] = (uint64_t)pos < e - b ? seq[e - 1 - pos] : 0;
+}
+__global__ void k_bcr_symbols_col(const Item *__restrict__ item, uint64_t n_act, const uint8_t *__restrict__ row, uint8_t *__restrict__ sym) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_act) sym[k] = row[item[k].id];
 }
 
 __global__ void k_bcr_iota(Item *item, uint64_t n) {
@@ -342,8 +402,19 @@ static int bcr_build_device(fmg_bcr_s *b) {
     auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
     DevBuf d_seq, d_off, d_bwt[2], d_item[2], d_sym[2], d_rank, d_hist, d_pref, d_total, d_tmp, d_lo;
     BCR_TRY(d_seq.reserve(b->seq.size())); BCR_TRY(d_off.reserve((n_seq + 1) * 8));
-    BCR_TRY(cudaMemcpy(d_seq.p, b->seq.data(), b->seq.size(), cudaMemcpyHostToDevice));
-    BCR_TRY(cudaMemcpy(d_off.p, b->off.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice));
+    BCR_TRY(g_stager.upload(d_seq.p, b->seq.data(), b->seq.size()));
+    BCR_TRY(g_stager.upload(d_off.p, b->off.data(), (n_seq + 1) * 8));
+    const double t_copy = since();
+    // reads of (nearly) one length: transposed by cycle; a ragged set keeps the gather through the offsets
+    DevBuf d_col;
+    const bool by_cycle = (uint64_t)b->max_len * n_seq <= b->seq.size() + b->seq.size() / 4 + (1u << 20) && !std::getenv("FMG_BCR_NO_TRANSPOSE");
+    if (by_cycle) {
+        BCR_TRY(d_col.reserve((uint64_t)b->max_len * n_seq + 1));
+        k_bcr_transpose<<<blocks_for(n_seq, 128), 128>>>(d_seq.as<uint8_t>(), d_off.as<uint64_t>(), n_seq, b->max_len, d_col.as<uint8_t>()); ++g_launches;
+        BCR_TRY(cudaGetLastError());
+        BCR_TRY(cudaDeviceSynchronize());
+        d_seq.release(); d_off.release();               // every cycle reads the columns; the last one (all exhausted) needs neither
+    }
     BCR_TRY(d_bwt[0].reserve(total + 64)); BCR_TRY(d_bwt[1].reserve(total + 64));         // the merge stages whole 16-byte words
     BCR_TRY(d_item[0].reserve(n_seq * sizeof(Item))); BCR_TRY(d_item[1].reserve(n_seq * sizeof(Item)));
     BCR_TRY(d_sym[0].reserve(n_seq)); BCR_TRY(d_sym[1].reserve(n_seq)); BCR_TRY(d_rank.reserve(n_seq * 4));
@@ -388,7 +459,10 @@ static int bcr_build_device(fmg_bcr_s *b) {
     Vec4 h_total{}, h_prev{};
     for (int pos = 0; n_act > 0; ++pos) {
         const uint64_t m_new = m + n_act, n_tiles = (m_new + kTile - 1) / kTile;
-        k_bcr_symbols<<<blocks_for(n_act, 256), 256>>>(items.Current(), n_act, d_seq.as<uint8_t>(), d_off.as<uint64_t>(), pos, syms.Current()); ++g_launches;
+        if (by_cycle && pos < b->max_len) k_bcr_symbols_col<<<blocks_for(n_act, 256), 256>>>(items.Current(), n_act, d_col.as<uint8_t>() + (uint64_t)pos * n_seq, syms.Current());
+        else if (by_cycle) BCR_TRY(cudaMemsetAsync(syms.Current(), 0, n_act));       // cycle max_len: every sequence left inserts its sentinel
+        else k_bcr_symbols<<<blocks_for(n_act, 256), 256>>>(items.Current(), n_act, d_seq.as<uint8_t>(), d_off.as<uint64_t>(), pos, syms.Current());
+        ++g_launches;
         k_bcr_bounds<<<blocks_for(n_act, 256), 256>>>(items.Current(), n_act, n_tiles, d_lo.as<uint64_t>(), kTile); ++g_launches;
         {
             const uint8_t *a_old = d_bwt[cur].as<uint8_t>(); uint64_t a_m = m_new; const Item *a_item = items.Current(); const uint8_t *a_sym = syms.Current();
@@ -426,11 +500,11 @@ static int bcr_build_device(fmg_bcr_s *b) {
     BCR_TRY(cudaDeviceSynchronize());
     const double t_cycles = since();
     b->n_sym = m;
-    std::swap(b->d_bwt.p, d_bwt[cur].p); std::swap(b->d_bwt.cap, d_bwt[cur].cap);     // the BWT stays in HBM with the handle
+    std::swap(b->d_bwt.p, d_bwt[cur].p); std::swap(b->d_bwt.cap, d_bwt[cur].cap); std::swap(b->d_bwt.dev, d_bwt[cur].dev);     // the BWT stays in HBM with the handle
     b->built = true;
     if (fmg_verbose >= 3)
-        std::fprintf(stderr, "[M::fmg_bcr_build] %llu sequences, %llu symbols: allocation + copy in %.3f s, %d cycles %.3f s\n", (unsigned long long)n_seq,
-                     (unsigned long long)m, t_in, b->max_len + 1, t_cycles - t_in);
+        std::fprintf(stderr, "[M::fmg_bcr_build] %llu sequences, %llu symbols: allocation + copy in %.3f s, %d cycles %.3f s (copy in alone %.3f s)\n", (unsigned long long)n_seq,
+                     (unsigned long long)m, t_in, b->max_len + 1, t_cycles - t_in, t_copy);
     return 0;
 }
 

@@ -25,18 +25,39 @@ reads = fb.synth_reads(62, genome, a.reads, L, 0.0)
 rc = (5 - reads[:, ::-1]).astype(np.uint8)
 both = np.empty((2 * a.reads, L), np.uint8); both[0::2] = reads; both[1::2] = rc       # r, rc(r), ... (ropebwt.c:30-44); no palindromes at random
 res = {"reads": a.reads, "len": L, "symbols": int(2 * a.reads * (L + 1))}
-builds = []
+import ctypes, re
+from fermi_b200 import _lib
+ctypes.c_int.in_dll(_lib.lib(), "fmg_verbose").value = 3        # "[M::fmg_bcr_build] ...: allocation + copy in X s, N cycles Y s" per build
+builds, cycles, copy_in = [], [], []
 for it in range(a.iters):
     b = fb.Bcr(0)
     t = time.time(); b.append_batch(both); t_app = time.time() - t
-    t = time.time(); b.build(); builds.append(time.time() - t)
+    err = tempfile.TemporaryFile(); saved = os.dup(2); sys.stderr.flush(); os.dup2(err.fileno(), 2)
+    try:
+        t = time.time(); b.build(); builds.append(time.time() - t)
+    finally:
+        os.dup2(saved, 2); os.close(saved)
+    err.seek(0); m = re.search(r"allocation \+ copy in ([0-9.]+) s, \d+ cycles ([0-9.]+) s", err.read().decode())
+    if m: copy_in.append(float(m.group(1))); cycles.append(float(m.group(2)))
     if it == a.iters - 1:
         t_build = min(builds[1:] or builds)          # the first build pays for the allocations; boxes are shared, so the best of the rest
         res["build_s_all"] = builds
+        # the cycles alone (all kernels, device-synchronised): the box's host side (shared, pageable 3 GB copy in) is the noisy part
+        if cycles: res["cycles_s_all"] = cycles; res["copy_in_s_all"] = copy_in; res["cycles_s"] = min(cycles); res["cycle_symbols_per_s"] = res["symbols"] / min(cycles)
         res.update({"append_s": t_app, "build_s": t_build, "symbols_per_s": res["symbols"] / t_build, "reads_per_s": a.reads / t_build})
         if a.check:
             res["equals_suffix_sort"] = bool(np.array_equal(b.bwt(), fb.fm_build_bwt(fb.fmd_text(reads), 0)))
     b.close()
+# SURVEY.md 8(d), BCR: sum over cycles of (partial BWT read + written; one byte per symbol here) + 16 B per active sequence and cycle x
+# (2 x 1 sort passes of the 3-bit key + 2 classify + 2 update) + the reads at 2 bits per base
+n_seq = 2 * a.reads
+bytes_8d = n_seq * (L + 1) ** 2 + n_seq * (L + 1) * 16 * 6 + n_seq * L // 4
+res["bytes_8d"] = int(bytes_8d); res["achieved_gbs"] = bytes_8d / res["build_s"] / 1e9
+try:
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    res["frac_of_measured_hbm_peak"] = res["achieved_gbs"] / peak
+except Exception:
+    pass
 if a.fmd:
     b = fb.Bcr(0)
     b.append_batch(both)

@@ -9,7 +9,7 @@ OBJ = os.path.join(ROOT, "build", "obj")
 KERNELS = [("overlap.cu.o", "k_ov_chainIjLi1"), ("overlap.cu.o", "k_ov_neiIjLi4"), ("overlap.cu.o", "k_ov_chainImLi1"), ("overlap.cu.o", "k_ov_neiImLi4"),
            ("fmg_cuda.cu.o", "k_smemIjLb0"), ("fmg_cuda.cu.o", "k_smemIjLb1"), ("fmg_cuda.cu.o", "k_smemImLb1"), ("bcr.cu.o", "k_bcr_merge"),
            ("ec.cu.o", "k_trie_expand"), ("unitig_gpu.cu.o", "k_mag_body")]
-MARK = ["LDG.E.ENL2.256", "LDG.E.128", "SHFL.BFLY", "SHFL.IDX", "VOTE", "POPC", "UBLKCP", "SYNCS", "ATOMG", "LDS", "STS", "BAR.SYNC", "WARPSYNC", "LDL", "STL"]
+MARK = ["LDG.E.ENL2.256", "LDG.E.128", "SHFL.BFLY", "SHFL.IDX", "VOTE", "POPC", "UBLKCP", "SYNCS", "PRMT", "ATOMG", "LDS", "STS", "BAR.SYNC", "WARPSYNC", "LDL", "STL"]
 for obj, pat in KERNELS:
     txt = subprocess.run(["cuobjdump", "-sass", os.path.join(OBJ, obj)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode(errors="replace")
     cur, hist, name = None, None, None
