@@ -70,6 +70,8 @@ _PROTOS = {
                                     C.c_void_p, C.c_uint64, u64p]),
     "fmg_overlap_merge": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fmg_overlap_left_fix": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "fmg_overlap_left_fix_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "fmg_overlap_left_flags": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]),
     "fmg_unitig_part": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fmg_magpart_write": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64]),

@@ -601,8 +601,28 @@ int fmg_overlap_pass(const fmg_index_s *idx, int min_match, int max_len, OvDevic
 
 // the left check over ALL rows of a merged, rank-indexed record array in caller-owned device memory (multi-GPU path: every rank
 // runs it on its copy after the exchange; fmg_overlap_pass does the same internally for a single GPU)
-int fmg_overlap_left_fix_dev(const fmg_index_s *idx, int min_match, int max_len, void *d_pack, const int64_t *d_rank_of_row, uint64_t *n_left_out) {
-    if (!idx || !d_pack || !d_rank_of_row) return -1;
+// OV_LEFT of rows [row_lo, row_lo + n) read out of (apply = 0) or written into (apply = 1) the rank-indexed records: the exchange of the
+// sharded left fix
+__global__ void __launch_bounds__(256) k_left_flags(OvPack *pack, const int64_t *__restrict__ rank_of_row, uint64_t row_lo, uint64_t n, int8_t *flags, int apply) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    OvPack &p = pack[rank_of_row[row_lo + i]];
+    if (apply) p.left = flags[i];
+    else flags[i] = p.left;
+}
+int fmg_overlap_left_flags_dev(const fmg_index_s *idx, void *d_pack, const int64_t *d_rank_of_row, uint64_t row_lo, uint64_t row_hi, int8_t *d_flags, int apply) {
+    if (!idx || !d_pack || !d_rank_of_row || !d_flags || row_hi < row_lo || row_hi > idx->mcnt[1]) return -1;
+    OV_TRY(cudaSetDevice(idx->device));
+    const uint64_t n = row_hi - row_lo;
+    if (n == 0) return 0;
+    k_left_flags<<<(unsigned)((n + 255) / 256), 256>>>(static_cast<OvPack *>(d_pack), d_rank_of_row, row_lo, n, d_flags, apply);
+    ++g_launches;
+    OV_TRY(cudaGetLastError());
+    return 0;
+}
+
+int fmg_overlap_left_fix_dev(const fmg_index_s *idx, int min_match, int max_len, void *d_pack, const int64_t *d_rank_of_row, uint64_t row_lo, uint64_t row_hi, uint64_t *n_left_out) {
+    if (!idx || !d_pack || !d_rank_of_row || row_hi < row_lo || row_hi > idx->mcnt[1]) return -1;
     OV_TRY(cudaSetDevice(idx->device));
     std::lock_guard<std::mutex> ov_guard(idx->ov_lock);
     const uint64_t n_seq = idx->mcnt[1];
@@ -625,7 +645,7 @@ int fmg_overlap_left_fix_dev(const fmg_index_s *idx, int min_match, int max_len,
         OV_TRY(S.alloc(nb_max, max_len, std::max(8, max_len - min_match + 8) * pcap_mul, cap, nei_cap, wide, grid));
         OV_TRY(cudaMemset(d_ctrl.p, 0, OVC_N * 8));
         double ms = 0;
-        const int rc = left_fix(idx, min_match, S, nb_max, static_cast<OvPack *>(d_pack), d_rank_of_row, 0, n_seq, d_ctrl.as<unsigned long long>(), h_ctrl, nullptr, &n_left, &ms);
+        const int rc = left_fix(idx, min_match, S, nb_max, static_cast<OvPack *>(d_pack), d_rank_of_row, row_lo, row_hi, d_ctrl.as<unsigned long long>(), h_ctrl, nullptr, &n_left, &ms);
         if (rc < 0) return -1;
         {
             std::lock_guard<std::mutex> g(g_stats_lock);

@@ -8,7 +8,8 @@
 // rc(vm) > ... > rc(v1) -- and the reference emits whichever orientation its first unused seed happens to walk.
 // Here:   k_links        succ(v) for every primary, non-contained sequence
 //         k_pred         pred = inverse of succ (must be injective) and the check that rc(k) links back to rc(v)
-//         k_jump         pointer jumping along pred: head, number of reads and base offset of every read in its chain
+//         k_rank_*, k_jump  head, number of reads and base offset of every read in its chain: list ranking over splitters
+//                        (walks between splitters, pointer jumping over the splitters only)
 //         k_tails/k_select  one orientation per chain (head <= rc(tail)), sizes for the output scans
 //         k_emit_*       consensus = head sequence (LF walk, exact.c:59-70) + appended bases of every link (unitig.c:141),
 //                        coverage = 33 + min(93, reads covering the base) via a difference array + scan (unitig.c:253-257),
@@ -410,11 +411,12 @@ static int write_text(const char *text, uint64_t bytes, unsigned nt, const char 
     if (bytes < (1u << 22)) nt = 1;
     std::atomic<int> io_fail{0};
     const uint64_t page = (uint64_t)::sysconf(_SC_PAGESIZE);
+    static const bool use_pwrite = [] { const char *e = std::getenv("FMG_MAG_WRITE"); return e && std::strcmp(e, "pwrite") == 0; }();
     auto put = [&](unsigned t) {
         const uint64_t a = bytes * t / nt, b = bytes * (t + 1) / nt;
         if (b <= a) return;
         const uint64_t f0 = (offset + a) & ~(page - 1), span = offset + b - f0;
-        void *m = ::mmap(nullptr, span, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)f0);
+        void *m = use_pwrite ? MAP_FAILED : ::mmap(nullptr, span, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)f0);
         if (m != MAP_FAILED) {
             std::memcpy(static_cast<char *>(m) + (offset + a - f0), text + a, b - a);
             ::munmap(m, span);
@@ -695,7 +697,8 @@ __global__ void __launch_bounds__(256) k_ov_merge(MergeArgs M, const OvPack *__r
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
 }
 
-int fmg_overlap_left_fix_dev(const fmg_index_s *idx, int min_match, int max_len, void *d_pack, const int64_t *d_rank_of_row, uint64_t *n_left_out);
+int fmg_overlap_left_fix_dev(const fmg_index_s *idx, int min_match, int max_len, void *d_pack, const int64_t *d_rank_of_row, uint64_t row_lo, uint64_t row_hi, uint64_t *n_left_out);
+int fmg_overlap_left_flags_dev(const fmg_index_s *idx, void *d_pack, const int64_t *d_rank_of_row, uint64_t row_lo, uint64_t row_hi, int8_t *d_flags, int apply);
 
 extern "C" {
 
@@ -734,7 +737,14 @@ int fmg_overlap_merge(const fmg_index_t *idx, int n_shards, const uint64_t *rows
 }
 
 int fmg_overlap_left_fix(const fmg_index_t *idx, int min_match, int max_len, void *d_pack, const int64_t *d_rank_of_row, uint64_t *n_left) {
-    return fmg_overlap_left_fix_dev(idx, min_match, max_len, d_pack, d_rank_of_row, n_left);
+    return idx ? fmg_overlap_left_fix_dev(idx, min_match, max_len, d_pack, d_rank_of_row, 0, idx->mcnt[1], n_left) : -1;
+}
+int fmg_overlap_left_fix_rows(const fmg_index_t *idx, int min_match, int max_len, void *d_pack, const int64_t *d_rank_of_row, uint64_t row_lo, uint64_t row_hi,
+                              uint64_t *n_left) {
+    return fmg_overlap_left_fix_dev(idx, min_match, max_len, d_pack, d_rank_of_row, row_lo, row_hi, n_left);
+}
+int fmg_overlap_left_flags(const fmg_index_t *idx, void *d_pack, const int64_t *d_rank_of_row, uint64_t row_lo, uint64_t row_hi, int8_t *d_flags, int apply) {
+    return fmg_overlap_left_flags_dev(idx, d_pack, d_rank_of_row, row_lo, row_hi, d_flags, apply);
 }
 
 int fmg_unitig_from_device(const fmg_index_t *idx, int min_match, const void *d_pack, const int64_t *d_rank, const uint8_t *d_ext, uint64_t ext_total,

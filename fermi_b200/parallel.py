@@ -160,9 +160,23 @@ def unitig_distributed_device(idx, min_match, out_path, max_len=0, group=None, t
                            rank_of_row.data_ptr()) != 0:
         raise RuntimeError("fermi_b200: fmg_overlap_merge failed")
     del rec_all, rank_all
+    # the deferred left check, shared: every rank evaluates its own rows on the merged array, one all-gather of a byte per row
+    # hands the flags round (the check of a row reads the records of other rows but patches only its own)
     n_left = C.c_uint64()
-    if L.fmg_overlap_left_fix(idx.h, int(min_match), int(max_len), pack.data_ptr(), rank_of_row.data_ptr(), C.byref(n_left)) != 0:
-        raise RuntimeError("fermi_b200: fmg_overlap_left_fix failed")
+    if L.fmg_overlap_left_fix_rows(idx.h, int(min_match), int(max_len), pack.data_ptr(), rank_of_row.data_ptr(), lo, hi, C.byref(n_left)) != 0:
+        raise RuntimeError("fermi_b200: fmg_overlap_left_fix_rows failed")
+    if world > 1:
+        flags = torch.zeros(row_pad, dtype=torch.int8, device=dev)
+        if L.fmg_overlap_left_flags(idx.h, pack.data_ptr(), rank_of_row.data_ptr(), lo, hi, flags.data_ptr(), 0) != 0:
+            raise RuntimeError("fermi_b200: fmg_overlap_left_flags failed")
+        flags_all = torch.empty(world * row_pad, dtype=torch.int8, device=dev)
+        dist.all_gather_into_tensor(flags_all, flags, group=group)
+        first = 0
+        for s in range(world):
+            if s != rank and rows[s] and L.fmg_overlap_left_flags(idx.h, pack.data_ptr(), rank_of_row.data_ptr(), first, first + rows[s],
+                                                                 flags_all.data_ptr() + s * row_pad, 1) != 0:
+                raise RuntimeError("fermi_b200: fmg_overlap_left_flags failed")
+            first += rows[s]
     lap()
     part, nu, nb = C.c_void_p(), C.c_uint64(), C.c_uint64()
     rc = L.fmg_unitig_part(idx.h, int(min_match), pack.data_ptr(), rank_of_row.data_ptr(), ext_all.data_ptr(), spill_all.data_ptr(), rank, world,

@@ -169,7 +169,10 @@ int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *o
  *                       indexed by sequence rank (the layout the assembly chases), d_rank_of_row = n_seq ranks; offsets are rebased onto
  *                       the padded gathered ext / spill arrays, which stay as they are
  *   fmg_overlap_left_fix  check_left_simple (unitig.c:186-204) for the records where it decides a link (the reverse complement of the
- *                       unique neighbour has several neighbours): needs the merged array, patches OV_LEFT in it; *n_left = rows evaluated
+ *                       unique neighbour has several neighbours): needs the merged array, patches OV_LEFT in it; *n_left = rows evaluated.
+ *                       fmg_overlap_left_fix_rows does it for rows [row_lo, row_hi) only, so that N GPUs share the work: each fixes its
+ *                       own rows, fmg_overlap_left_flags(apply = 0) reads the row_hi - row_lo flags out, one all-gather of those bytes,
+ *                       fmg_overlap_left_flags(apply = 1) writes the flags of the other shards into the local array
  *   fmg_unitig_part     link graph + pointer jumping over all records, then emission + MAG text (mag_v_write, mag.c:149-174) of the chains
  *                       with head rank % n_parts == part, kept in memory; 0 = ok, 1 = irregular link graph (run fmg_unitig on one GPU)
  *   -- all-gather of the text sizes --
@@ -183,6 +186,9 @@ int fmg_overlap_shard(const fmg_index_t *idx, int min_match, int max_len, uint64
 int fmg_overlap_merge(const fmg_index_t *idx, int n_shards, const uint64_t *rows, uint64_t row_pad, uint64_t ext_pad, uint64_t spill_pad,
                       const void *d_rec_all, const int64_t *d_rank_all, void *d_pack, int64_t *d_rank_of_row);
 int fmg_overlap_left_fix(const fmg_index_t *idx, int min_match, int max_len, void *d_pack, const int64_t *d_rank_of_row, uint64_t *n_left);
+int fmg_overlap_left_fix_rows(const fmg_index_t *idx, int min_match, int max_len, void *d_pack, const int64_t *d_rank_of_row, uint64_t row_lo, uint64_t row_hi,
+                              uint64_t *n_left);
+int fmg_overlap_left_flags(const fmg_index_t *idx, void *d_pack, const int64_t *d_rank_of_row, uint64_t row_lo, uint64_t row_hi, int8_t *d_flags, int apply);
 int fmg_unitig_part(const fmg_index_t *idx, int min_match, const void *d_pack, const int64_t *d_rank_of_row, const uint8_t *d_ext, const void *d_spill,
                     int part, int n_parts, fmg_magpart_t **out, uint64_t *n_unitigs, uint64_t *n_bytes);
 int fmg_magpart_write(const fmg_magpart_t *p, const char *path, uint64_t offset, uint64_t total_bytes);

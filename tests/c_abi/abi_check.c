@@ -18,7 +18,7 @@ static const anyfn_t all_symbols[] = {
 	(anyfn_t)fmg_smem_batch_into, (anyfn_t)fmg_free, (anyfn_t)fmg_smem_session_create, (anyfn_t)fmg_smem_session_destroy,
 	(anyfn_t)fmg_smem_session_run, (anyfn_t)fmg_smem_session_result, (anyfn_t)fmg_smem_session_set_timing, (anyfn_t)fmg_smem_session_kernel_ms,
 	(anyfn_t)fmg_release_cache, (anyfn_t)fmg_launch_count, (anyfn_t)fmg_overlap_batch, (anyfn_t)fmg_unitig_assemble, (anyfn_t)fmg_unitig,
-	(anyfn_t)fmg_overlap_shard, (anyfn_t)fmg_rldx_upload, (anyfn_t)fmg_rldx_free, (anyfn_t)fmg_rldx_bytes, (anyfn_t)fmg_rldx_rank2a_batch, (anyfn_t)fmg_rldx_extend_batch, (anyfn_t)fmg_contrast, (anyfn_t)fmg_gap_bits, (anyfn_t)fmg_merge, (anyfn_t)fmg_rank1a_batch, (anyfn_t)fmg_check_rank, (anyfn_t)fmg_smem_batch_into16, (anyfn_t)fmg_intv16_expand, (anyfn_t)fmg_overlap_merge, (anyfn_t)fmg_overlap_left_fix, (anyfn_t)fmg_unitig_part, (anyfn_t)fmg_magpart_write, (anyfn_t)fmg_magpart_free, (anyfn_t)fmg_unitig_from_device, (anyfn_t)fmg_seqsort, (anyfn_t)fmg_overlap_stats,
+	(anyfn_t)fmg_overlap_shard, (anyfn_t)fmg_rldx_upload, (anyfn_t)fmg_rldx_free, (anyfn_t)fmg_rldx_bytes, (anyfn_t)fmg_rldx_rank2a_batch, (anyfn_t)fmg_rldx_extend_batch, (anyfn_t)fmg_contrast, (anyfn_t)fmg_gap_bits, (anyfn_t)fmg_merge, (anyfn_t)fmg_rank1a_batch, (anyfn_t)fmg_check_rank, (anyfn_t)fmg_smem_batch_into16, (anyfn_t)fmg_intv16_expand, (anyfn_t)fmg_overlap_merge, (anyfn_t)fmg_overlap_left_fix, (anyfn_t)fmg_overlap_left_fix_rows, (anyfn_t)fmg_overlap_left_flags, (anyfn_t)fmg_unitig_part, (anyfn_t)fmg_magpart_write, (anyfn_t)fmg_magpart_free, (anyfn_t)fmg_unitig_from_device, (anyfn_t)fmg_seqsort, (anyfn_t)fmg_overlap_stats,
 	(anyfn_t)fmg_ec_collect, (anyfn_t)fmg_ec_collect_part, (anyfn_t)fmg_ec_kmer_length, (anyfn_t)fmg_build_bwt, (anyfn_t)fmg_build_fmd, (anyfn_t)fmg_fmd_from_bwt_device,
 	(anyfn_t)fmg_bcr_init, (anyfn_t)fmg_bcr_append, (anyfn_t)fmg_bcr_append_batch, (anyfn_t)fmg_bcr_build, (anyfn_t)fmg_bcr_size,
 	(anyfn_t)fmg_bcr_bwt, (anyfn_t)fmg_bcr_rle, (anyfn_t)fmg_bcr_fmd, (anyfn_t)fmg_bcr_destroy,
