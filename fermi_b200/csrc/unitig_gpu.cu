@@ -230,21 +230,26 @@ __device__ __forceinline__ uint32_t stop_nei(const G &g, uint64_t u, UNei *out) 
 // one orientation per chain: the head h emits when h <= rc(tail)
 __global__ void __launch_bounds__(256) k_select(G g, const uint32_t *__restrict__ dn, const uint64_t *__restrict__ db,
                                                uint64_t *e_cnt, uint64_t *e_len, uint64_t *e_nei, uint32_t part, uint32_t n_parts) {
-    const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= g.n) return;
+    const uint64_t h0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = h0 < g.n;
+    const uint64_t h = in ? h0 : 0;
     uint64_t c = 0, l = 0, m = 0;
+    uint32_t reads = 0;                              // reads of the chain this thread is the head of
     const OvPack ph = g.pack[h];
-    if (g.pred[h] == kNone && is_node(ph, h, g.min_match)) {
+    if (in && g.pred[h] == kNone && is_node(ph, h, g.min_match)) {
         const uint32_t t = g.tail_of[h];
         const OvPack pt = g.pack[t];
-        atomicAdd(g.counts + 1, (unsigned long long)dn[t] + 1);
+        reads = dn[t] + 1;
         if (h <= pt.x1 && (n_parts <= 1 || (uint32_t)(h % n_parts) == part)) {      // several GPUs: the chains are dealt out by head rank
             c = 1;
             l = db[t] + pt.len;
             m = stop_nei(g, ph.x1, nullptr) + stop_nei(g, t, nullptr);
         }
     }
-    e_cnt[h] = c; e_len[h] = l; e_nei[h] = m;
+    // one atomic per warp: with noisy reads most sequences are heads, and 10^7 atomics on one address serialise
+    const uint32_t warp_reads = __reduce_add_sync(0xffffffffu, reads);
+    if ((threadIdx.x & 31) == 0 && warp_reads) atomicAdd(g.counts + 1, (unsigned long long)warp_reads);
+    if (in) { e_cnt[h] = c; e_len[h] = l; e_nei[h] = m; }
 }
 
 __global__ void __launch_bounds__(256) k_emit_meta(G g, const uint32_t *__restrict__ dn, const uint64_t *__restrict__ db, const uint64_t *__restrict__ e_cnt,
