@@ -275,6 +275,32 @@ def test_unitig_20k_reads_vs_reference_binary(fb, tmp_path, monkeypatch, err, co
     idx.close()
 
 
+def test_unitig_small_cycles_take_the_host_walk(fb, tmp_path, monkeypatch):
+    """Forty 300 bp plasmids tiled by reads every 25 bp, next to an ordinary linear genome: link-graph cycles of 12 reads.  Some hold
+    a splitter of the list ranking (one read in 16) and keep the pointer jumping from converging, some hold none and are never
+    reached by a walk (unitig_gpu.cu: k_rank_walk); either way the device assembly must notice (count check / round limit) and the
+    records go to the host walk, whose result equals the reference's."""
+    rng = np.random.RandomState(5)
+    reads = [fb.synth_reads(52, fb.synth_genome(51, 40000), 4000, 100, 0.0)]
+    for _ in range(40):
+        pl = rng.randint(1, 5, 300).astype(np.uint8)
+        ring = np.concatenate([pl, pl[:100]])
+        reads.append(np.stack([ring[s: s + 100] for s in range(0, 300, 25)]))
+    reads = np.concatenate(reads)
+    fmd = fb.fm_build(fb.fmd_text(reads), 0)
+    fn = str(tmp_path / "p.fmd")
+    fmd.dump(fn)
+    ref = H.parse_mag(H.reference_unitig(fn, 50, 1))
+    idx = fb.FmdIndex(fmd, 0)
+    out = str(tmp_path / "p.mag")
+    monkeypatch.setenv("FMG_THREADS", "1")
+    monkeypatch.setenv("FMG_UNITIG_HOST", "0")
+    n = fb.fm6_unitig(idx, 50, out)
+    assert n == len(ref)
+    assert H.canonical_mag(H.parse_mag(open(out).read())) == H.canonical_mag(ref)
+    idx.close()
+
+
 @pytest.mark.parametrize("err,shards", [(0.0, 2), (0.01, 3)])
 def test_sharded_records_merge_to_the_single_gpu_unitigs(fb, tmp_path, err, shards):
     """The multi-GPU data path on one GPU, stage by stage through the C-ABI: the records of row shards (fmg_overlap_shard) in
@@ -324,8 +350,28 @@ def test_sharded_records_merge_to_the_single_gpu_unitigs(fb, tmp_path, err, shar
     assert L.fmg_overlap_merge(idx.h, shards, (C.c_uint64 * shards)(*rows), row_pad, ext_pad, spill_pad, rec_all.data_ptr(), rank_all.data_ptr(),
                                pack.data_ptr(), rank_of_row.data_ptr()) == 0
     assert torch.equal(rank_of_row, torch.cat(ranks))
+    # the deferred left check shared between the ranks: each fixes its own rows on ITS copy of the merged array and hands one byte
+    # per row round (fmg_overlap_left_fix_rows + fmg_overlap_left_flags) == the whole-array call
+    merged = pack.clone()
     n_left = C.c_uint64()
     assert L.fmg_overlap_left_fix(idx.h, 50, 0, pack.data_ptr(), rank_of_row.data_ptr(), C.byref(n_left)) == 0
+    flags, n_rows_fixed, first = [], 0, 0
+    for r in range(shards):
+        mine = merged.clone()
+        k = C.c_uint64()
+        assert L.fmg_overlap_left_fix_rows(idx.h, 50, 0, mine.data_ptr(), rank_of_row.data_ptr(), first, first + rows[r], C.byref(k)) == 0
+        n_rows_fixed += int(k.value)
+        f = torch.zeros(rows[r], dtype=torch.int8, device=dev)
+        assert L.fmg_overlap_left_flags(idx.h, mine.data_ptr(), rank_of_row.data_ptr(), first, first + rows[r], f.data_ptr(), 0) == 0
+        flags.append(f)
+        first += rows[r]
+    assert n_rows_fixed == int(n_left.value) and (err == 0.0 or n_rows_fixed > 0)
+    first = 0
+    for r in range(shards):
+        assert L.fmg_overlap_left_flags(idx.h, merged.data_ptr(), rank_of_row.data_ptr(), first, first + rows[r], flags[r].data_ptr(), 1) == 0
+        first += rows[r]
+    torch.cuda.synchronize()
+    assert torch.equal(merged, pack)
     out, single = str(tmp_path / "m.mag"), str(tmp_path / "s.mag")
     total, offset = 0, 0
     for part in range(shards):
