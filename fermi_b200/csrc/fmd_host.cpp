@@ -8,6 +8,8 @@
 #include <memory>
 
 int fmg_verbose = 3;
+// FMG_VERBOSE in the environment overrides the default when the library is loaded (fm_verbose has no such hook: utils.c:8)
+static const int fmg_verbose_from_env = [] { const char *e = std::getenv("FMG_VERBOSE"); if (e && *e) fmg_verbose = std::atoi(e); return 0; }();
 
 namespace fmg {
 
