@@ -96,19 +96,15 @@ FMG_HD bool ov_pack(const int64_t *rec, uint64_t nx0, uint64_t nx1, uint64_t nx2
     return (uint64_t)rec[OV_X2] < (1ull << 32) && nx2 < (1ull << 32) && rec[OV_NNEI] < 65536 && rec[OV_LEN] < (1ll << 31) && rec[OV_SLEN] < (1ll << 31);
 }
 
-// Result intervals of fm6_extend (exact.c:72-88) indexed by symbol, info = 0: storage for the ok[1..4] a call site walks over.
-template <typename U> struct Ok6 { IntvT<U> v[6]; };
-
-// What most call sites need of an extension: the size of ok[0] and the interval of ONE selected symbol.  These come back in
-// registers together with a mask of the non-empty base extensions; the intervals of those (ok[1..4], usually one) are only
-// written -- through `kids`, to the caller's stack -- where a call site walks over them.  Everything is computed inside
-// ext_sync, i.e. while the warp is converged, so that the (divergent) callers only pick values.
+// What the call sites of the list phase need of an extension (fm6_extend, exact.c:72-88): the size of ok[0] and the interval of ONE
+// selected symbol.  These come back in registers together with a mask of the non-empty base extensions.  Everything is computed
+// inside ext_sync, i.e. while the warp is converged, so that the (divergent) callers only pick values.
 template <typename U> struct ExtSel { U s0, ssel, x0, x1; int flags; };       // flags: bit 0 = some lane of the warp was active, bits 1..4 = ok[c] is not empty
 
 // TAG gives every kernel its own copy of the function (ptxas 12.9 crashes on a noinline function shared by two entries)
 
 template <typename U, int TAG>
-FMG_NOINLINE ExtSel<U> ext_sync(const OccView &ix, bool active, U x0, U x1, U x2, int back, int csel, Ok6<U> *kids) {
+FMG_NOINLINE ExtSel<U> ext_sync(const OccView &ix, bool active, U x0, U x1, U x2, int back, int csel) {
     ExtSel<U> R;
     R.s0 = R.ssel = R.x0 = R.x1 = 0;
 #if defined(__CUDA_ARCH__)
@@ -125,17 +121,7 @@ FMG_NOINLINE ExtSel<U> ext_sync(const OccView &ix, bool active, U x0, U x1, U x2
         R.s0 = e.size[0]; R.ssel = pick6(e.size, csel);
         R.x0 = back ? fr : nr; R.x1 = back ? nr : fr;
 #pragma unroll
-        for (int c = 1; c < 5; ++c) {
-            if (e.size[c] == 0) continue;
-            R.flags |= 1 << c;
-            if (kids) {
-                const U f6 = (U)(ld_u64(row + c) + e.relk[c]);
-                kids->v[c].x0 = back ? f6 : e.near[c];
-                kids->v[c].x1 = back ? e.near[c] : f6;
-                kids->v[c].x2 = e.size[c];
-                kids->v[c].info = 0;
-            }
-        }
+        for (int c = 1; c < 5; ++c) if (e.size[c] != 0) R.flags |= 1 << c;
     }
     return R;
 }
@@ -173,7 +159,6 @@ struct OvLane {
     Cand *P, *Q;      // lane lists (phases 2 and 4)
     int32_t *cat;
     bool ovf;
-    Ok6<U> em;        // SYNC: the non-empty ok[1..4] of the last extension that asked for them (phase 2)
     ExtSel<U> rs;     // SYNC: size of ok[0], the selected interval and the mask of non-empty ok[1..4] of the last extension (registers)
     Ext6T<U> e;       // !SYNC: the same, before the far coordinates are formed
     int eback;
@@ -182,9 +167,8 @@ struct OvLane {
         : A(a), P(static_cast<Cand *>(a.A) + (size_t)lane * a.cap), Q(static_cast<Cand *>(a.B) + (size_t)lane * a.cap),
           cat(a.cat + (size_t)lane * a.cap * 2), ovf(false), eback(0) {}
 
-    // SYNC phases: rs for the selected symbol, with (ext_kids) or without (extend_sel) the non-empty ok[1..4] in `em`
-    FMG_HD void ext_kids(const Cand &k, int back, int csel) { rs = ext_sync<U, TAG>(A.ix, true, k.x0, k.x1, k.x2, back, csel, &em); }
-    FMG_HD void extend_sel(const Cand &k, int back, int csel) { rs = ext_sync<U, TAG>(A.ix, true, k.x0, k.x1, k.x2, back, csel, nullptr); }
+    // SYNC phases: rs for the selected symbol
+    FMG_HD void extend_sel(const Cand &k, int back, int csel) { rs = ext_sync<U, TAG>(A.ix, true, k.x0, k.x1, k.x2, back, csel); }
     FMG_HD Cand sel() const { Cand o; o.x0 = rs.x0; o.x1 = rs.x1; o.x2 = rs.ssel; o.info = 0; return o; }
     // chain phases (!SYNC): the plain inlined extension
     FMG_HD void extend(const Cand &k, int back) { extend6<U>(A.ix, back ? k.x1 : k.x0, back ? k.x0 : k.x1, k.x2, e); eback = back; }
@@ -695,7 +679,7 @@ FMG_HD void overlap_lane_sync(const OverlapArgs &A, int64_t lane, FetchFn fetch)
         if (t >= A.n) break;
         ln.phase_left2(t);
     }
-    while (ext_sync<U, PHASE>(A.ix, false, 0, 0, 0, 0, 0, nullptr).flags & 1) {}
+    while (ext_sync<U, PHASE>(A.ix, false, 0, 0, 0, 0, 0).flags & 1) {}
 }
 
 // chain phases: one sequence per thread; phase 1 is run by whole warps (`live` = this lane has a sequence)
