@@ -389,7 +389,22 @@ inline unsigned nblk(uint64_t n) { return (unsigned)((n + 255) / 256); }
 // MAG text of one part of the unitigs, held by the caller between the two steps of a multi-GPU run (all ranks learn the sizes
 // of all parts before they write them side by side into one file)
 // The text lives in the pinned cache of the index handle (fmg_ovcache_s::text): valid until the next unitig call on that handle.
-struct fmg_magpart_s { const char *text = nullptr; uint64_t bytes = 0; unsigned threads = 1; };
+// The MAG text of one part (multi-GPU: the chains a rank owns).  The text leaves the device in slices on a stream of its own while
+// the caller exchanges the part sizes; fmg_magpart_write waits for a slice, copies it into the file, waits for the next.
+struct fmg_magpart_s {
+    const char *text = nullptr;      // pinned host buffer of the index handle
+    uint64_t bytes = 0;
+    unsigned threads = 1;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> landed; // slice k = [bytes * k / n, bytes * (k + 1) / n) is on the host once landed[k] completed
+    fmg::Dev d_text;                 // the device copy lives until the slices have landed
+    ~fmg_magpart_s() {
+        if (stream) { cudaSetDevice(device); cudaStreamSynchronize(stream); }
+        for (auto e : landed) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
 
 // `bytes` of text to `out_path` at `offset` by `nt` threads.  The file must already have its final size (ensure_size): the
 // threads copy into a shared mapping of their own slices, which -- unlike write() on one inode -- neither serialises the threads
@@ -589,12 +604,31 @@ int fmg_unitig_device(const fmg_index_s *idx, const OvDevView &D, int min_match,
     if (const char *e = std::getenv("FMG_THREADS")) nt = (unsigned)std::max(1, std::atoi(e));
     const bool to_stdout = !sink && std::strcmp(out_path, "-") == 0;
     double t_dev = 0;
-    if (sink || to_stdout || text_bytes < (1u << 24)) {
+    if (sink) {
+        // asynchronous hand-over: slices on the part's own stream, ordered after the formatting kernels
+        sink->text = H.text.as<char>(); sink->bytes = text_bytes; sink->threads = nt; sink->device = idx->device;
+        UG_TRY(cudaStreamCreateWithFlags(&sink->stream, cudaStreamNonBlocking));
+        cudaEvent_t formatted;
+        UG_TRY(cudaEventCreateWithFlags(&formatted, cudaEventDisableTiming));
+        UG_TRY(cudaEventRecord(formatted, st));
+        UG_TRY(cudaStreamWaitEvent(sink->stream, formatted, 0));
+        cudaEventDestroy(formatted);
+        const unsigned n_slice = text_bytes < (1u << 24) ? 1u : std::max(2u, std::min(nt, 8u));
+        sink->landed.resize(n_slice);
+        for (auto &e : sink->landed) UG_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (unsigned k = 0; k < n_slice; ++k) {
+            const uint64_t a = text_bytes * k / n_slice, b = text_bytes * (k + 1) / n_slice;
+            if (b > a) UG_TRY(cudaMemcpyAsync(H.text.as<char>() + a, d_text.as<char>() + a, b - a, cudaMemcpyDeviceToHost, sink->stream));
+            UG_TRY(cudaEventRecord(sink->landed[k], sink->stream));
+        }
+        sink->d_text.swap(d_text);
+        UG_TRY(cudaStreamSynchronize(st));          // the scratch of this call returns to the pool when it ends: its kernels must be done
+        t_dev = since(t0);
+    } else if (to_stdout || text_bytes < (1u << 24)) {
         if (text_bytes) UG_TRY(cudaMemcpyAsync(H.text.p, d_text.p, text_bytes, cudaMemcpyDeviceToHost, st));
         UG_TRY(cudaStreamSynchronize(st));
         t_dev = since(t0);
-        if (sink) { sink->text = H.text.as<char>(); sink->bytes = text_bytes; sink->threads = nt; }
-        else if (to_stdout) { std::fwrite(H.text.p, 1, text_bytes, stdout); std::fflush(stdout); }
+        if (to_stdout) { std::fwrite(H.text.p, 1, text_bytes, stdout); std::fflush(stdout); }
         else if (ensure_size(out_path, text_bytes, __func__) != 0 || write_text(H.text.as<char>(), text_bytes, nt, out_path, 0, __func__) != 0) return -1;
     } else {
         // a file: the text leaves the device in slices, and each slice is written while the next one is copied
@@ -779,7 +813,23 @@ int fmg_unitig_part(const fmg_index_t *idx, int min_match, const void *d_pack, c
 int fmg_magpart_write(const fmg_magpart_t *p, const char *path, uint64_t offset, uint64_t total_bytes) {
     if (!p || !path) return -1;
     if (total_bytes && ensure_size(path, total_bytes, __func__) != 0) return -1;
-    return write_text(p->text, p->bytes, p->threads, path, offset, __func__);
+    if (cudaSetDevice(p->device) != cudaSuccess) return -1;
+    const unsigned n_slice = (unsigned)p->landed.size();
+    if (n_slice <= 1) {
+        if (n_slice == 1 && cudaEventSynchronize(p->landed[0]) != cudaSuccess) return -1;
+        return write_text(p->text, p->bytes, p->threads, path, offset, __func__);
+    }
+    // a thread per slice: each waits for its slice to land and copies it into the file while the later ones are still in flight
+    std::atomic<int> fail{0};
+    std::vector<std::thread> th;
+    for (unsigned k = 0; k < n_slice; ++k)
+        th.emplace_back([&, k]() {
+            const uint64_t a = p->bytes * k / n_slice, b = p->bytes * (k + 1) / n_slice;
+            if (cudaSetDevice(p->device) != cudaSuccess || cudaEventSynchronize(p->landed[k]) != cudaSuccess) { fail = 1; return; }
+            if (b > a && write_text(p->text + a, b - a, 1, path, offset + a, "fmg_magpart_write") != 0) fail = 1;
+        });
+    for (auto &x : th) x.join();
+    return fail ? -1 : 0;
 }
 
 void fmg_magpart_free(fmg_magpart_t *p) { delete p; }

@@ -173,10 +173,12 @@ int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *o
  *                       fmg_overlap_left_fix_rows does it for rows [row_lo, row_hi) only, so that N GPUs share the work: each fixes its
  *                       own rows, fmg_overlap_left_flags(apply = 0) reads the row_hi - row_lo flags out, one all-gather of those bytes,
  *                       fmg_overlap_left_flags(apply = 1) writes the flags of the other shards into the local array
- *   fmg_unitig_part     link graph + pointer jumping over all records, then emission + MAG text (mag_v_write, mag.c:149-174) of the chains
- *                       with head rank % n_parts == part, kept in memory; 0 = ok, 1 = irregular link graph (run fmg_unitig on one GPU)
+ *   fmg_unitig_part     link graph + list ranking over all records, then emission + MAG text (mag_v_write, mag.c:149-174) of the chains
+ *                       with head rank % n_parts == part; 0 = ok, 1 = irregular link graph (run fmg_unitig on one GPU).  The text
+ *                       travels to a pinned buffer of the index handle in slices on a stream of its own while the caller exchanges
+ *                       the sizes (*n_bytes is known at return): ONE part per index handle may be outstanding, until fmg_magpart_free
  *   -- all-gather of the text sizes --
- *   fmg_magpart_write   the text of this part at `offset` of the output file, which must have its final size: ONE caller passes
+ *   fmg_magpart_write   the text of this part (each slice as it lands) at `offset` of the output file, which must have its final size: ONE caller passes
  *                       total_bytes != 0 first (the file is created / resized), the others 0 after a barrier; the parts are copied
  *                       into a shared mapping, so the ranks fill the file side by side without serialising on it
  *   fmg_unitig_from_device  the whole assembly on one GPU from merged arrays; 0 = MAG written, 1 = irregular link graph */
