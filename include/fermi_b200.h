@@ -159,7 +159,7 @@ int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *o
 
 /* Multi-GPU `fermi unitig`: the sequences (BWT rows) are sharded over the GPUs the way fm6_unitig stripes its threads
  * (unitig.c:394-404), every GPU holding the whole index.  All pointers are DEVICE pointers owned by the caller, who also runs
- * the exchanges of the path (INTEGRATION.md section 5; fermi_b200/parallel.py does it with NCCL through torch.distributed):
+ * the exchanges of the path (INTEGRATION.md section 4; fermi_b200/parallel.py does it with NCCL through torch.distributed):
  *   fmg_overlap_shard   records of rows [row_lo, row_hi) (row_lo even), in ROW order: d_rec = (row_hi - row_lo) x 64-byte records,
  *                       d_rank[row - row_lo] = rank of the row; d_ext / d_spill (32-byte entries) = appended bases / neighbour lists of
  *                       forks, addressed by the records with shard-local offsets; totals = {ext bytes, spill entries} used.  Returns 1
