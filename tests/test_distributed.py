@@ -56,6 +56,18 @@ def test_shard_range_covers_everything():
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
 
 
+def test_unitig_row_shards_are_whole_reads():
+    """fmg_overlap_shard wants shards of whole reads (row 2i = the read, 2i+1 = its reverse complement): even boundaries, every
+    row exactly once, the last shard takes an odd tail (an index whose last read was given without its complement)."""
+    from fermi_b200.parallel import unitig_shard_rows
+    for n_seq in (0, 2, 6, 14, 15, 2000006, 2000007):
+        for world in (1, 2, 3, 8):
+            spans = [unitig_shard_rows(n_seq, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n_seq
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(l % 2 == 0 for l, _ in spans) and all(h % 2 == 0 for _, h in spans[:-1])
+
+
 def test_two_rank_unitig_equals_reference(product_lib, emu, tmp_path):
     case = "noisy"
     out = str(tmp_path / "u.mag")
