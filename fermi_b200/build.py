@@ -15,7 +15,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfermi_b200.so")
 
 SOURCES = ["fmg_cuda.cu", "overlap.cu", "unitig_gpu.cu", "rld_enc.cu", "occ_build.cu", "build_bwt.cu", "bcr.cu", "ec.cu", "merge.cu", "contrast.cu", "rldx.cu", "fmd_host.cpp", "occ_build_host.cpp", "unitig_host.cpp", "synth.cpp", "bcr_compat.cpp"]
-HEADERS = ["cli_main.cpp", "fmd_device.cuh", "fmd_overlap.cuh", "fmd_host.hpp", "occ_layout.hpp", "fmg_internal.hpp", "ov_records.hpp", "dev_pool.hpp", "../../include/fermi_b200.h"]
+HEADERS = ["cli_main.cpp", "fmd_device.cuh", "fmd_overlap.cuh", "fmd_host.hpp", "occ_layout.hpp", "fmg_internal.hpp", "ov_records.hpp", "dev_pool.hpp", "bcr_tile.cuh", "../../include/fermi_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -27,6 +27,7 @@
 #include <thread>
 #include "fmd_host.hpp"
 #include "dev_pool.hpp"
+#include "bcr_tile.cuh"
 #include "../../include/fermi_b200.h"
 
 int fmg_rld_encode_device(const uint8_t *d_bwt, uint64_t n, fmg::FmdImage *out);     // rld_enc.cu
@@ -208,11 +209,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_bcr_merge(const uint8_
         if (bytes) { mbar_expect_tx(&s_bar[stage], bytes); bulk_g2s(s_srcs[stage], old_bwt + al, bytes, &s_bar[stage]); }
         else mbar_arrive(&s_bar[stage]);
     };
-    if (tid < 16) {
-        uint32_t sel = 0, nxt = 0;
-        for (int t = 0; t < 4; ++t) if (!((tid >> t) & 1)) sel |= (nxt++) << (4 * t);
-        s_spread[tid] = sel;
-    }
+    if (tid < 16) s_spread[tid] = fmg::bcr_spread_selector((uint32_t)tid);
     if (tid == 0) {
         for (int q = 0; q < kStages; ++q) mbar_init(&s_bar[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -265,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_bcr_merge(const uint8_
     uint32_t fl_sum = 0;
 #pragma unroll
     for (int w = 0; w < kWords; ++w) fl_sum += flw[w];
-    const uint32_t my_ins = (fl_sum * 0x01010101u) >> 24;                // flag bytes are 0/1: at most kWords per byte lane
+    const uint32_t my_ins = fmg::bcr_flag_count(fl_sum);                 // flag bytes are 0/1: at most kWords per byte lane
     uint32_t incl = my_ins;
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
     if ((tid & 31) == 31) s_warp_ins[tid >> 5] = incl;
@@ -282,12 +279,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_bcr_merge(const uint8_
         uint32_t ib = ins_before;
 #pragma unroll
         for (int w = 0; w < kWords; ++w) {
-            const int sb = shift + j0 + 4 * w - (int)ib;             // staged byte of the word's first old symbol
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(s_src) + (sb >> 2);
-            const uint32_t sel = s_spread[(flw[w] * 0x01020408u) >> 24] + (uint32_t)(sb & 3) * 0x1111u;
-            const uint32_t ins = flw[w] * 0xffu;
-            o[w] = (__byte_perm(src[0], src[1], sel) & ~ins) | (syw[w] & ins);
-            ib += (flw[w] * 0x01010101u) >> 24;
+            // staged byte of the word's first old symbol: the thread's first position less the inserts before the word
+            o[w] = fmg::bcr_merge_word(reinterpret_cast<const uint32_t *>(s_src), shift + j0 + 4 * w - (int)ib, flw[w], syw[w], s_spread);
+            ib += fmg::bcr_flag_count(flw[w]);
         }
         if (!full) {                                                 // the last tile: positions past the end count as no symbol
 #pragma unroll
@@ -296,16 +290,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_bcr_merge(const uint8_
     }
     // Bit planes of the thread's symbols (symbol 4w+b at bit 8b+w of each plane) and from them one mask per base: packed A/C/G/T
     // counts of the thread (4 x 16 bit) by population count, then their block-wide exclusive prefix
-    const uint32_t kLsb = 0x01010101u;
-    uint32_t p0 = 0, p1 = 0, p2 = 0;
-#pragma unroll
-    for (int w = 0; w < kWords; ++w) {
-        p0 |= (o[w] & kLsb) << w;
-        p1 |= w >= 1 ? (o[w] & (kLsb << 1)) << (w - 1) : (o[w] >> 1) & kLsb;
-        p2 |= w >= 2 ? (o[w] & (kLsb << 2)) << (w - 2) : (o[w] >> (2 - w)) & (kLsb << w);
-    }
-    const uint32_t eq[4] = {p0 & ~p1 & ~p2, ~p0 & p1 & ~p2, p0 & p1 & ~p2, ~p0 & ~p1 & p2};      // A = 1, C = 2, G = 3, T = 4
-    const uint64_t my_cnt = (uint64_t)(__popc(eq[0]) | (__popc(eq[1]) << 16)) | ((uint64_t)(__popc(eq[2]) | (__popc(eq[3]) << 16)) << 32);
+    uint32_t eq[4];                                                      // A = 1, C = 2, G = 3, T = 4
+    fmg::bcr_base_masks<kWords>(o, eq);
+    const uint64_t my_cnt = fmg::bcr_pack_counts(eq);
     uint64_t cincl = my_cnt;
     for (int q = 1; q < 32; q <<= 1) { const uint64_t v = __shfl_up_sync(0xffffffffu, cincl, q); if ((tid & 31) >= q) cincl += v; }
     if ((tid & 31) == 31) s_warp_cnt[tid >> 5] = cincl;
@@ -328,14 +315,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_bcr_merge(const uint8_
             while (f) {
                 const int sh = (__ffs(f) - 1) & ~7;                  // 8 x byte of the insert in the word
                 f &= f - 1;
-                const uint32_t c = (o[w] >> sh) & 0xffu;
-                uint32_t r = 0;
-                if (c >= 1 && c <= 4) {
-                    const uint32_t earlier = (kLsb * ((1u << w) - 1u)) | ((kLsb << w) & ((1u << sh) - 1u));
-                    const uint32_t e = c == 1 ? eq[0] : c == 2 ? eq[1] : c == 3 ? eq[2] : eq[3];
-                    r = (uint32_t)((cnt_before >> (16 * (c - 1))) & 0xffff) + __popc(e & earlier);
-                }
-                rank_in_tile[k_lo + ib] = r;
+                rank_in_tile[k_lo + ib] = fmg::bcr_insert_rank(o[w], w, sh, eq, cnt_before);
                 ++ib;
             }
         }

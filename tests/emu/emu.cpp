@@ -10,6 +10,7 @@
 #include "../../fermi_b200/csrc/fmd_device.cuh"
 #include "../../fermi_b200/csrc/fmd_overlap.cuh"
 #include "../../fermi_b200/csrc/occ_layout.hpp"
+#include "../../fermi_b200/csrc/bcr_tile.cuh"
 #include "../../include/fermi_b200.h"
 
 using namespace fmg;
@@ -137,6 +138,44 @@ int emu_overlap(const void *_x, int min_match, int64_t n, const uint64_t *ids, i
     }
     for (int64_t t = 0; t < n; ++t) rec[t * OV_NREC + OV_K] = ret[t];
     return 0;
+}
+
+// One tile of the BCR merge pass (bcr.cu: k_bcr_merge) with the kernel's per-thread arithmetic (bcr_tile.cuh) and its block scans
+// replaced by a serial loop over the threads.  tile_len <= n_threads * k_per output positions; flags / syms per position (syms valid
+// where flagged); staged = the old symbols of the tile starting at byte `shift` of a word-aligned buffer (8 bytes of slack after
+// the last one).  Out: the merged symbols, the A,C,G,T histogram and the in-tile rank of every insert in position order.
+int emu_bcr_tile(int k_per, int n_threads, int tile_len, const uint8_t *flags_in, const uint8_t *syms_in, const uint32_t *staged, int shift,
+                 uint8_t *out, uint64_t hist[4], uint32_t *ranks) {
+    if ((k_per != 16 && k_per != 32) || tile_len > n_threads * k_per) return -1;
+    const int words = k_per / 4, tile = n_threads * k_per;
+    std::vector<uint8_t> flags(tile, 0), syms(tile, 0xee);           // garbage where no insert: the kernel's s_sym is stale there too
+    std::memcpy(flags.data(), flags_in, tile_len);
+    for (int i = 0; i < tile_len; ++i) if (flags[i]) syms[i] = syms_in[i];
+    uint32_t spread[16];
+    for (uint32_t f = 0; f < 16; ++f) spread[f] = bcr_spread_selector(f);
+    uint32_t ins_before = 0;
+    uint64_t cnt_before = 0;
+    for (int tid = 0; tid < n_threads; ++tid) {
+        const int j0 = tid * k_per;
+        uint32_t flw[8], syw[8], o[8], eq[4];
+        std::memcpy(flw, flags.data() + j0, k_per); std::memcpy(syw, syms.data() + j0, k_per);
+        uint32_t ib = ins_before;
+        for (int w = 0; w < words; ++w) {
+            o[w] = bcr_merge_word(staged, shift + j0 + 4 * w - (int)ib, flw[w], syw[w], spread);
+            ib += bcr_flag_count(flw[w]);
+        }
+        for (int t = 0; t < k_per; ++t) if (j0 + t >= tile_len) o[t >> 2] |= 7u << (8 * (t & 3));
+        if (words == 4) bcr_base_masks<4>(o, eq); else bcr_base_masks<8>(o, eq);
+        const uint64_t my_cnt = bcr_pack_counts(eq);
+        uint32_t k = ins_before;
+        for (int w = 0; w < words; ++w)
+            for (int b = 0; b < 4; ++b)
+                if ((flw[w] >> (8 * b)) & 1u) ranks[k++] = bcr_insert_rank(o[w], w, 8 * b, eq, cnt_before);
+        for (int t = 0; t < k_per; ++t) if (j0 + t < tile_len) out[j0 + t] = (uint8_t)(o[t >> 2] >> (8 * (t & 3)));
+        ins_before = ib; cnt_before += my_cnt;
+    }
+    for (int c = 0; c < 4; ++c) hist[c] = (cnt_before >> (16 * c)) & 0xffff;
+    return (int)ins_before;
 }
 
 } // extern "C"

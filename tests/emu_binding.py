@@ -13,7 +13,7 @@ OUT = os.path.join(ROOT, "build", "libemu.so")
 SRC = [os.path.join(ROOT, "tests", "emu", "emu.cpp"),
        os.path.join(ROOT, "fermi_b200", "csrc", "fmd_host.cpp"),
        os.path.join(ROOT, "fermi_b200", "csrc", "occ_build_host.cpp")]
-DEPS = SRC + [os.path.join(ROOT, "fermi_b200", "csrc", f) for f in ("fmd_device.cuh", "fmd_overlap.cuh", "fmd_host.hpp", "occ_layout.hpp")]
+DEPS = SRC + [os.path.join(ROOT, "fermi_b200", "csrc", f) for f in ("fmd_device.cuh", "fmd_overlap.cuh", "fmd_host.hpp", "occ_layout.hpp", "bcr_tile.cuh")]
 
 
 class Emu:
@@ -30,6 +30,8 @@ class Emu:
         L.emu_smem.argtypes = [C.c_void_p, C.c_int64, H.u8p, H.u64p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), H.u64p]
         L.emu_smem.restype = C.c_int
         L.fmg_free.argtypes = [C.c_void_p]
+        L.emu_bcr_tile.argtypes = [C.c_int, C.c_int, C.c_int, H.u8p, H.u8p, C.c_void_p, C.c_int, H.u8p, H.u64p, C.c_void_p]
+        L.emu_bcr_tile.restype = C.c_int
         L.emu_overlap.argtypes = [C.c_void_p, C.c_int, C.c_int64, H.u64p, C.c_int, C.c_int, C.c_int, C.c_int,
                                   H.i64p, C.c_void_p, C.c_void_p, H.u8p, H.i32p, H.u8p]
 
@@ -83,6 +85,21 @@ class Emu:
         off = np.concatenate([[0], np.cumsum(np.minimum(cnt, nei_cap))]).astype(np.uint64)
         flat = np.concatenate([nei[i, :min(int(cnt[i]), nei_cap)] for i in range(n)]) if n else np.zeros(0, H.INTV)
         return rec, flat, off, seq, ln, ext
+
+
+    def bcr_tile(self, k_per, n_threads, flags, syms, old, shift):
+        """one tile of the BCR merge: flags / syms per output position, old = the old symbols in order -> (out, hist[4], ranks)"""
+        flags = np.ascontiguousarray(flags, np.uint8)
+        syms = np.ascontiguousarray(syms, np.uint8)
+        staged = np.full(shift + len(old) + 8 + (-(shift + len(old)) % 4), 0xdd, np.uint8)
+        staged[shift: shift + len(old)] = old
+        out = np.zeros(len(flags), np.uint8)
+        hist = np.zeros(4, np.uint64)
+        ranks = np.zeros(max(1, int(flags.sum())), np.uint32)
+        n = self.lib.emu_bcr_tile(k_per, n_threads, len(flags), H._ptr(flags, H.u8p), H._ptr(syms, H.u8p), staged.view(np.uint32).ctypes.data, shift,
+                                  H._ptr(out, H.u8p), H._ptr(hist, H.u64p), ranks.ctypes.data)
+        assert n == int(flags.sum())
+        return out, hist, ranks[:n]
 
 
 def load():

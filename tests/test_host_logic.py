@@ -162,3 +162,30 @@ def test_device_core_ragged_and_empty_reads(emu, oracle):
         assert ov == 0 and np.array_equal(mo, omo) and np.array_equal(rec, orec)
     oracle.destroy(h)
     emu.lib.emu_index_free(x)
+
+
+@pytest.mark.parametrize("k_per,n_threads", [(16, 64), (32, 64), (16, 256), (32, 128)])
+def test_bcr_merge_tile_arithmetic_on_host(emu, k_per, n_threads):
+    """The per-thread arithmetic of k_bcr_merge (fermi_b200/csrc/bcr_tile.cuh: byte-permute spread of the old symbols, blend of the
+    inserts, bit-plane base counts, in-tile insert ranks) compiled for the host, against the obvious per-symbol merge: tiles
+    without inserts, sparse, dense, nothing but inserts, a short last tile, every byte offset of the staged symbols."""
+    rng = np.random.RandomState(k_per * 1000 + n_threads)
+    tile = k_per * n_threads
+    cases = []
+    for density in (0.0, 0.004, 0.05, 0.5, 1.0):
+        for tile_len in (tile, tile - 1, tile // 2 + 3, 5):
+            cases.append((density, tile_len, int(rng.randint(0, 16))))
+    for density, tile_len, shift in cases:
+        flags = (rng.rand(tile_len) < density).astype(np.uint8)
+        n_ins = int(flags.sum())
+        syms = np.where(flags == 1, rng.randint(0, 6, tile_len), 0xaa).astype(np.uint8)      # inserts: $ A C G T N
+        old = rng.randint(0, 6, tile_len - n_ins).astype(np.uint8)
+        out, hist, ranks = emu.bcr_tile(k_per, n_threads, flags, syms, old, shift)
+        want = np.empty(tile_len, np.uint8)
+        want[flags == 1] = syms[flags == 1]
+        want[flags == 0] = old
+        assert np.array_equal(out, want), (density, tile_len, shift)
+        assert [int(h) for h in hist] == [int((want == c).sum()) for c in (1, 2, 3, 4)]
+        pos = np.flatnonzero(flags)
+        want_rank = [int((want[:p] == want[p]).sum()) if 1 <= want[p] <= 4 else 0 for p in pos]
+        assert ranks.tolist() == want_rank, (density, tile_len, shift)
