@@ -604,7 +604,8 @@ def run_ours(a):
                 "l2": "each step streams %.2f GB of reads and %.2f GB of records (>> 126 MB L2); the %.0f MB index is re-read within a step by design"
                       % (a.reads * L / 1e9, n_out * a.reads * 32 / 1e9, idx.nbytes / 1e6),
                 "records_per_read": round(n_out, 3), "n_locate_per_read": round(n_loc, 2), "n_extend_per_read": round(n_ext, 2),
-                "counter_sample": "instrumented oracle on the first %d reads" % sample_n},
+                "counter_sample": "instrumented oracle on the first %d reads" % sample_n,
+                "coordinates": "records are fmintv_t (u64), bit-exact; the kernels are instantiated with 32-bit coordinates when the index has < 2^32 symbols (this one), with 64-bit ones otherwise"},
             "clocks": clocks,
             "gpu_launches": int(launches_timed),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
