@@ -406,7 +406,8 @@ static int bcr_build_device(fmg_bcr_s *b) {
     if (const char *e = std::getenv("FMG_BCR_PER")) merge_per = std::atoi(e) >= 32 ? 32 : 16;
     const void *merge_kernel = merge_per == 16
         ? (merge_threads == 256 ? (const void *)k_bcr_merge<256, 4, 16> : merge_threads == 128 ? (const void *)k_bcr_merge<128, 8, 16> : (const void *)k_bcr_merge<64, 16, 16>)
-        : (merge_threads >= 128 ? (const void *)k_bcr_merge<128, 5, 32> : (const void *)k_bcr_merge<64, 10, 32>);       // static shared memory: no 8192-symbol tile
+        : (merge_threads >= 128 ? (const void *)k_bcr_merge<128, 8, 32> : (const void *)k_bcr_merge<64, 16, 32>);       // static shared memory: no 8192-symbol tile
+    // (64 x 32 at 16 blocks per SM: 62 registers without spills, half the warp slots; at 12 blocks and 80 registers the cycles took 6 % longer)
     if (merge_per == 32 && merge_threads > 128) merge_threads = 128;
     const uint32_t kTile = (uint32_t)(merge_threads * merge_per);
     const uint64_t max_tiles = (total + kTile - 1) / kTile;
