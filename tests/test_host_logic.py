@@ -189,3 +189,39 @@ def test_bcr_merge_tile_arithmetic_on_host(emu, k_per, n_threads):
         pos = np.flatnonzero(flags)
         want_rank = [int((want[:p] == want[p]).sum()) if 1 <= want[p] <= 4 else 0 for p in pos]
         assert ranks.tolist() == want_rank, (density, tile_len, shift)
+
+
+def test_committed_traffic_figures_follow_from_the_committed_launch_list(tmp_path):
+    """roofline.traffic in the bench lines is read from profiles/r02_k_*_traffic.json; those files must be what tools/ncu_traffic.py
+    derives from the committed ncu launch list (profiles/r02_launches.csv: 4 unitig passes of 20 M sequences in the capture)."""
+    import json, subprocess, sys
+    prof = os.path.join(H.ROOT, "profiles")
+    subprocess.run([sys.executable, os.path.join(H.ROOT, "tools", "ncu_traffic.py"), os.path.join(prof, "r02_launches.csv"), str(tmp_path), "r02",
+                    "20000000", "80000000"], check=True, stdout=subprocess.DEVNULL)
+    for name in ("r02_k_smem_traffic.json", "r02_k_smem_hbm_traffic.json", "r02_k_ov_traffic.json"):
+        assert json.load(open(os.path.join(str(tmp_path), name))) == json.load(open(os.path.join(prof, name))), name
+    assert open(os.path.join(str(tmp_path), "r02_launch_shares.csv")).read() == open(os.path.join(prof, "r02_launch_shares.csv")).read()
+    # and the bench line of the same round quotes them
+    line = json.load(open(os.path.join(prof, "r02_bench_n1.json")))
+    assert line["roofline"]["traffic"] == pytest.approx(json.load(open(os.path.join(prof, "r02_k_smem_traffic.json")))["traffic_bytes_per_launch"], rel=1e-3)
+    ov = json.load(open(os.path.join(prof, "r02_k_ov_traffic.json")))["traffic_bytes_per_sequence"]
+    assert line["unitig"]["roofline"]["traffic"] == pytest.approx(ov * 20000000, rel=1e-6)
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8])
+def test_committed_bench_lines_keep_the_contract(n):
+    """The bench lines under profiles/ are what bench.py printed: they must carry every key of the measurement contract."""
+    import json
+    d = json.load(open(os.path.join(H.ROOT, "profiles", "r02_bench_n%d.json" % n)))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "clocks", "gpu_launches", "roofline", "e2e", "unitig", "unitig_err1pct"):
+        assert k in d, k
+    assert d["n_gpus"] == n and d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["vs_baseline"] is None and "workload" in d["config"]
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"]) and 0 < d["roofline"]["frac"] <= 1.0
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if n == 1:
+        assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "reference"
+        assert d["unitig"]["set_equal_reference_sample"] is True
+    else:
+        assert d["unitig"]["set_equal_single_gpu"] is True and d["unitig"]["collective_ms"] > 0
