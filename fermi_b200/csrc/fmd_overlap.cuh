@@ -143,12 +143,13 @@ struct SeqView {
 // The per-sequence record is computed in FOUR phases, each its own kernel over the batch, handing the
 // candidate list of overlap_intv from one to the next through P0 / np0:
 //   1 phase_contained  fm6_is_contained (unitig.c:77-91): a chain of len+1 extensions, no lists read    [SYNC = false]
-//   2 phase_nei        fm6_get_nei (unitig.c:93-179): breadth-first over the candidate list             [SYNC = true]
+//   2 nei_lane         fm6_get_nei (unitig.c:93-179): breadth-first over the candidate list, one gather per level (below)
 //   3 phase_left1      overlap_intv of check_left_simple (unitig.c:186-190): a chain of extensions      [SYNC = false]
 //   4 phase_left2      the candidate loop of check_left_simple (unitig.c:191-203)                       [SYNC = true]
 // Phases 1 and 3 are the same straight loop for every lane of a warp (equal-length reads: exactly the same trip
 // count), so they run converged without help and with few registers.  Phases 2 and 4 have data-dependent nested
-// loops; there every extension goes through ext_sync (warp vote + one shared copy of the code).  Splitting them
+// loops: phase 2 is a flat state machine of its own (nei_lane), in phase 4 every extension goes through ext_sync (warp vote +
+// one shared copy of the code).  Splitting them
 // keeps the lanes of a warp in the same phase: one fused kernel had lanes in all four at once, and every distinct
 // path between two votes costs the warp its own serialized round trips to the scratch lists.
 template <typename U, bool SYNC, int TAG>

@@ -708,8 +708,9 @@ int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *o
 //   fmg_overlap_shard      every GPU: records of its rows, in row order, into caller-owned device buffers
 //   -- one all-gather of the record / rank / ext / spill shards, each padded to the largest shard --
 //   fmg_overlap_merge      every GPU: gathered shards -> the rank-indexed record array the assembly chases
-//   fmg_overlap_left_fix   every GPU: the deferred left check (overlap.cu: left_fix) on the merged array
-//   fmg_unitig_part        every GPU: link graph + pointer jumping over all records, then emission and MAG text of the chains
+//   fmg_overlap_left_fix_rows / _flags  every GPU: the deferred left check (overlap.cu: left_fix) for its own rows of the merged
+//                          array, then one all-gather of a byte per row (fmg_overlap_left_fix does all rows on one GPU)
+//   fmg_unitig_part        every GPU: link graph + list ranking over all records, then emission and MAG text of the chains
 //                          it owns (head rank % n_parts == part)
 //   -- all-gather of the text sizes --
 //   fmg_magpart_write      every GPU: its text at its offset of the one output file

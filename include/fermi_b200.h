@@ -152,7 +152,7 @@ int fmg_overlap_batch(const fmg_index_t *idx, int min_match, int64_t n, const ui
 int fmg_unitig_assemble(uint64_t n_seq, int max_len, int min_match, const int64_t *rec, const fmg_intv_t *nei,
                         const uint64_t *nei_off, const uint8_t *seq, const uint8_t *ext, const char *out_path, uint64_t *n_unitigs);
 /* fm6_unitig (unitig.c:378-407) / `fermi unitig -l min_match`: overlap records of every sequence and the unitigs themselves
- * (link graph + pointer jumping) on the GPU; an irregular link graph (cycle, one-sided link) or FMG_UNITIG_HOST=1 takes
+ * (link graph + list ranking) on the GPU; an irregular link graph (cycle, one-sided link) or FMG_UNITIG_HOST=1 takes
  * the records to the host and walks them in the reference's seed order (fmg_unitig_assemble).  The set of MAG records
  * equals that of the reference after canonicalisation. max_len 0 = estimate. */
 int fmg_unitig(const fmg_index_t *idx, int min_match, int max_len, const char *out_path, uint64_t *n_unitigs);
